@@ -1,0 +1,442 @@
+// Implicit-GEMM convolution / inner-product on the sm_100a tensor cores.
+//
+// Replaces, for the MNC inference path, Caffe's Convolution layer
+// (caffe-mnc/src/caffe/layers/cudnn_conv_layer.cu:11-54, conv_layer.cu:8-23 +
+// util/im2col.cu:9-39) and InnerProduct layer (inner_product_layer.cu:21-27).
+//
+// Design (B200-first, not a port):
+//  * activations live in HBM as NHWC, split into two bf16 planes (hi, lo) with
+//    x ~= hi + lo (16 mantissa bits).  Weights likewise, stored [Cout][tap][Cin].
+//  * one persistent CTA per SM; warp 0 = TMA producer, warp 1 = MMA issuer
+//    (single elected thread, tcgen05.mma), warp 2 owns TMEM, warps 4..7 = epilogue.
+//  * im2col is folded into the TMA descriptor: the A tile for filter tap (dy,dx)
+//    is the 4-D box [1, TH, TW, 64ch] at (h0+dy, w0+dx); out-of-image rows/cols
+//    are zero-filled by TMA, which *is* the conv zero padding.
+//  * fp32-class accuracy on bf16 tensor cores: D += Ahi*Bhi + Ahi*Blo + Alo*Bhi
+//    (the dropped Alo*Blo term is ~2^-18 relative).  Accumulators are fp32 in
+//    TMEM, double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1.
+//  * epilogue: tcgen05.ld -> +bias -> ReLU -> re-split to (hi, lo) bf16 NHWC, or
+//    raw fp32 (split-K partials / final logits).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+
+#include "mnc_b200.h"
+#include "ptx.cuh"
+
+namespace mnc {
+
+struct IgemmArgs {
+  int batch, H, W;
+  int Cin, Cout;
+  int taps;  // 1 (inner product / 1x1) or 9 (3x3, pad 1, stride 1)
+  int tiles_h, tiles_w, tiles_n;
+  int k_steps;  // taps * Cin / 64
+  int split_k;
+  int relu;
+  int out_mode;  // 0: split bf16 (hi, lo); 1: fp32
+  const float* bias;
+  __nv_bfloat16* out_hi;
+  __nv_bfloat16* out_lo;
+  float* out_f32;
+  long long out_pix_stride;  // elements between consecutive pixels (rows)
+  int out_ch_offset;
+  long long split_stride;  // elements between split-K partial planes (fp32 mode)
+  int vec_ok;              // 16-byte vector stores are aligned
+};
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;
+constexpr int kABytes = kBlockM * kBlockK * 2;  // one bf16 plane of the A tile
+
+template <int BN>
+struct IgemmCfg {
+  static constexpr int kBBytes = BN * kBlockK * 2;
+  static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+  static constexpr int kStages = (BN == 64) ? 4 : (BN == 128 ? 3 : 2);
+  static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ void decode_tile(const IgemmArgs& p, int t, int& img, int& h0, int& w0,
+                                            int& n0, int& k_begin, int& k_end, int TH, int TW,
+                                            int BN) {
+  const int per_img = p.tiles_h * p.tiles_w;
+  const int spatial = p.batch * per_img;
+  const int sp = t % spatial;
+  const int rest = t / spatial;
+  const int nt = rest % p.tiles_n;
+  const int ks = rest / p.tiles_n;
+  img = sp / per_img;
+  const int r = sp % per_img;
+  h0 = (r / p.tiles_w) * TH;
+  w0 = (r % p.tiles_w) * TW;
+  n0 = nt * BN;
+  k_begin = static_cast<int>(static_cast<long long>(p.k_steps) * ks / p.split_k);
+  k_end = static_cast<int>(static_cast<long long>(p.k_steps) * (ks + 1) / p.split_k);
+}
+
+template <int TH, int TW, int BN>
+__global__ void __launch_bounds__(256, 1)
+igemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                const IgemmArgs p) {
+  static_assert(TH * TW == kBlockM, "pixel tile must have 128 rows");
+  using Cfg = IgemmCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tfull_bar = empty_bar + kStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.split_k * p.tiles_n * p.batch * p.tiles_h * p.tiles_w;
+  const int kchunks = p.Cin / kBlockK;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tm_a_hi);
+    ptx::prefetch_tmap(&tm_a_lo);
+    ptx::prefetch_tmap(&tm_b_hi);
+    ptx::prefetch_tmap(&tm_b_lo);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tfull_bar[a], 1);
+      ptx::mbar_init(&tempty_bar[a], 128);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int img, h0, w0, n0, kb, ke;
+        decode_tile(p, t, img, h0, w0, n0, kb, ke, TH, TW, BN);
+        for (int k = kb; k < ke; ++k) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* st = smem + stage * Cfg::kStageBytes;
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          const int tap = k / kchunks;
+          const int kc = k - tap * kchunks;
+          int dy = 0, dx = 0;
+          if (p.taps == 9) {
+            dy = tap / 3 - 1;
+            dx = tap % 3 - 1;
+          }
+          ptx::tma_load_4d(st, &tm_a_hi, &full_bar[stage], kc * kBlockK, w0 + dx, h0 + dy, img);
+          ptx::tma_load_4d(st + kABytes, &tm_a_lo, &full_bar[stage], kc * kBlockK, w0 + dx,
+                           h0 + dy, img);
+          ptx::tma_load_2d(st + 2 * kABytes, &tm_b_hi, &full_bar[stage],
+                           tap * p.Cin + kc * kBlockK, n0);
+          ptx::tma_load_2d(st + 2 * kABytes + Cfg::kBBytes, &tm_b_lo, &full_bar[stage],
+                           tap * p.Cin + kc * kBlockK, n0);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // -------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16_m128(BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
+        int img, h0, w0, n0, kb, ke;
+        decode_tile(p, t, img, h0, w0, n0, kb, ke, TH, TW, BN);
+        const int acc = local & 1;
+        const uint32_t acc_phase = (local >> 1) & 1;
+        ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int k = kb; k < ke; ++k) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t a_hi = ptx::smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t a_lo = a_hi + kABytes;
+          const uint32_t b_hi = a_hi + 2 * kABytes;
+          const uint32_t b_lo = b_hi + Cfg::kBBytes;
+#pragma unroll
+          for (int kk = 0; kk < kBlockK / 16; ++kk) {
+            const uint64_t da_hi = ptx::umma_desc_sw128(a_hi + kk * 32);
+            const uint64_t da_lo = ptx::umma_desc_sw128(a_lo + kk * 32);
+            const uint64_t db_hi = ptx::umma_desc_sw128(b_hi + kk * 32);
+            const uint64_t db_lo = ptx::umma_desc_sw128(b_lo + kk * 32);
+            // small cross terms first, then the dominant product
+            ptx::umma_bf16_ss(tmem_d, da_lo, db_hi, idesc, (k > kb || kk > 0) ? 1u : 0u);
+            ptx::umma_bf16_ss(tmem_d, da_hi, db_lo, idesc, 1u);
+            ptx::umma_bf16_ss(tmem_d, da_hi, db_hi, idesc, 1u);
+          }
+          ptx::umma_commit(&empty_bar[stage]);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        ptx::umma_commit(&tfull_bar[acc]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ---------------------------------------------------------------- epilogue
+    const int q = warp - 4;  // TMEM lane quarter == warp_id % 4
+    const int row = q * 32 + lane;
+    int local = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
+      int img, h0, w0, n0, kb, ke;
+      decode_tile(p, t, img, h0, w0, n0, kb, ke, TH, TW, BN);
+      const int ks = (t / (p.batch * p.tiles_h * p.tiles_w)) / p.tiles_n;
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      const int h = h0 + row / TW;
+      const int w = w0 + row % TW;
+      const bool valid = (h < p.H) && (w < p.W);
+      const long long pix = (static_cast<long long>(img) * p.H + h) * p.W + w;
+      ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+      ptx::tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c0;
+        ptx::tmem_ld_32x32b_x32(taddr, r);
+        ptx::tmem_ld_wait();
+        const int ch0 = n0 + c0;
+        if (valid && ch0 < p.Cout) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = __uint_as_float(r[j]);
+            if (p.bias != nullptr && ch0 + j < p.Cout) x += __ldg(p.bias + ch0 + j);
+            if (p.relu) x = fmaxf(x, 0.f);
+            v[j] = x;
+          }
+          const bool fullchunk = (ch0 + 32 <= p.Cout) && p.vec_ok;
+          if (p.out_mode == 0) {
+            __nv_bfloat16* ph = p.out_hi + pix * p.out_pix_stride + p.out_ch_offset + ch0;
+            __nv_bfloat16* pl = p.out_lo + pix * p.out_pix_stride + p.out_ch_offset + ch0;
+            if (fullchunk) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                uint32_t hw[4], lw[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float x0 = v[g * 8 + 2 * e], x1 = v[g * 8 + 2 * e + 1];
+                  const __nv_bfloat16 h0b = __float2bfloat16_rn(x0);
+                  const __nv_bfloat16 h1b = __float2bfloat16_rn(x1);
+                  const __nv_bfloat16 l0b = __float2bfloat16_rn(x0 - __bfloat162float(h0b));
+                  const __nv_bfloat16 l1b = __float2bfloat16_rn(x1 - __bfloat162float(h1b));
+                  hw[e] = static_cast<uint32_t>(__bfloat16_as_ushort(h0b)) |
+                          (static_cast<uint32_t>(__bfloat16_as_ushort(h1b)) << 16);
+                  lw[e] = static_cast<uint32_t>(__bfloat16_as_ushort(l0b)) |
+                          (static_cast<uint32_t>(__bfloat16_as_ushort(l1b)) << 16);
+                }
+                *reinterpret_cast<uint4*>(ph + g * 8) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                *reinterpret_cast<uint4*>(pl + g * 8) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+              }
+            } else {
+              for (int j = 0; j < 32 && ch0 + j < p.Cout; ++j) {
+                const __nv_bfloat16 hb = __float2bfloat16_rn(v[j]);
+                ph[j] = hb;
+                pl[j] = __float2bfloat16_rn(v[j] - __bfloat162float(hb));
+              }
+            }
+          } else {
+            float* po = p.out_f32 + ks * p.split_stride + pix * p.out_pix_stride +
+                        p.out_ch_offset + ch0;
+            if (fullchunk) {
+#pragma unroll
+              for (int g = 0; g < 8; ++g)
+                *reinterpret_cast<float4*>(po + g * 4) =
+                    make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+            } else {
+              for (int j = 0; j < 32 && ch0 + j < p.Cout; ++j) po[j] = v[j];
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) !=
+            cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess) {
+      return nullptr;
+    }
+    fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// bf16 [N][H][W][C] activation plane, box [1][TH][TW][64], 128B swizzle, zero OOB fill.
+static int make_act_map(CUtensorMap* m, const void* base, int N, int H, int W, int C, int TH,
+                        int TW) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return MNC_ERR_DRIVER;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)TW, (cuuint32_t)TH, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MNC_OK : MNC_ERR_DRIVER;
+}
+
+// bf16 [Cout][Ktot] weight plane, box [BN][64].
+static int make_wgt_map(CUtensorMap* m, const void* base, int Cout, long long Ktot, int BN) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return MNC_ERR_DRIVER;
+  cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)Cout};
+  cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)BN};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MNC_OK : MNC_ERR_DRIVER;
+}
+
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+template <int TH, int TW, int BN>
+static int launch_igemm(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo,
+                        const CUtensorMap& tb_hi, const CUtensorMap& tb_lo, const IgemmArgs& a,
+                        int max_ctas, cudaStream_t stream) {
+  using Cfg = IgemmCfg<BN>;
+  auto kern = igemm_tc_kernel<TH, TW, BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e =
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return MNC_ERR_CUDA;
+    attr_set = true;
+  }
+  const int total = a.split_k * a.tiles_n * a.batch * a.tiles_h * a.tiles_w;
+  int grid = sm_count();
+  if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
+  if (total < grid) grid = total;
+  kern<<<grid, 256, Cfg::kSmemBytes, stream>>>(ta_hi, ta_lo, tb_hi, tb_lo, a);
+  return cudaGetLastError() == cudaSuccess ? MNC_OK : MNC_ERR_CUDA;
+}
+
+}  // namespace mnc
+
+using namespace mnc;
+
+extern "C" int mnc_igemm_tc(const void* a_hi, const void* a_lo, int batch, int H, int W, int Cin,
+                            const void* w_hi, const void* w_lo, int Cout, int taps,
+                            const float* bias, int relu, int out_mode, void* out0, void* out1,
+                            long long out_pix_stride, int out_ch_offset, int split_k,
+                            long long split_stride, int bn, int max_ctas, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (Cin % 64 != 0 || (taps != 1 && taps != 9) || batch <= 0 || H <= 0 || W <= 0 || Cout <= 0)
+    return MNC_ERR_ARG;
+  if (split_k < 1) split_k = 1;
+  if (split_k > 1 && out_mode != 1) return MNC_ERR_ARG;
+  const bool conv = (taps == 9);
+  const int TH = conv ? 8 : 1, TW = conv ? 16 : 128;
+  if (bn == 0) bn = (Cout <= 64) ? 64 : (Cout <= 128 ? 128 : 256);
+  if (bn != 64 && bn != 128 && bn != 256) return MNC_ERR_ARG;
+
+  IgemmArgs a;
+  a.batch = batch;
+  a.H = H;
+  a.W = W;
+  a.Cin = Cin;
+  a.Cout = Cout;
+  a.taps = taps;
+  a.tiles_h = (H + TH - 1) / TH;
+  a.tiles_w = (W + TW - 1) / TW;
+  a.tiles_n = (Cout + bn - 1) / bn;
+  a.k_steps = taps * (Cin / 64);
+  if (split_k > a.k_steps) split_k = a.k_steps;
+  a.split_k = split_k;
+  a.relu = relu;
+  a.out_mode = out_mode;
+  a.bias = bias;
+  a.out_hi = static_cast<__nv_bfloat16*>(out0);
+  a.out_lo = static_cast<__nv_bfloat16*>(out1);
+  a.out_f32 = static_cast<float*>(out0);
+  a.out_pix_stride = out_pix_stride;
+  a.out_ch_offset = out_ch_offset;
+  a.split_stride = split_stride;
+  const int vec = (out_mode == 0) ? 8 : 4;
+  a.vec_ok = (out_pix_stride % vec == 0) && (out_ch_offset % vec == 0) &&
+             (reinterpret_cast<uintptr_t>(out0) % 16 == 0) &&
+             (out_mode == 1 || reinterpret_cast<uintptr_t>(out1) % 16 == 0) &&
+             (split_stride % vec == 0);
+
+  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+  int rc;
+  if ((rc = make_act_map(&ta_hi, a_hi, batch, H, W, Cin, TH, TW)) != MNC_OK) return rc;
+  if ((rc = make_act_map(&ta_lo, a_lo, batch, H, W, Cin, TH, TW)) != MNC_OK) return rc;
+  const long long ktot = static_cast<long long>(taps) * Cin;
+  if ((rc = make_wgt_map(&tb_hi, w_hi, Cout, ktot, bn)) != MNC_OK) return rc;
+  if ((rc = make_wgt_map(&tb_lo, w_lo, Cout, ktot, bn)) != MNC_OK) return rc;
+
+#define MNC_LAUNCH(TH_, TW_, BN_) \
+  return launch_igemm<TH_, TW_, BN_>(ta_hi, ta_lo, tb_hi, tb_lo, a, max_ctas, stream)
+  if (conv) {
+    if (bn == 64) MNC_LAUNCH(8, 16, 64);
+    if (bn == 128) MNC_LAUNCH(8, 16, 128);
+    MNC_LAUNCH(8, 16, 256);
+  } else {
+    if (bn == 64) MNC_LAUNCH(1, 128, 64);
+    if (bn == 128) MNC_LAUNCH(1, 128, 128);
+    MNC_LAUNCH(1, 128, 256);
+  }
+#undef MNC_LAUNCH
+}

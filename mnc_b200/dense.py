@@ -1,0 +1,104 @@
+"""Host-side wrappers of the dense (conv / inner-product) C-ABI entry points.
+
+Activations and weights are "split" tensors: a torch bf16 tensor of shape [2, ...] holding the
+(hi, lo) planes with x ~= hi + lo.
+"""
+import torch
+
+from ._lib import lib, ptr, cur_stream, check, c_int, c_ll
+
+
+def split(x):
+    """fp32 tensor -> bf16 [2, *x.shape] (hi, lo) with hi = rn(x), lo = rn(x - hi)."""
+    x = x.float()
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.float()).to(torch.bfloat16)
+    return torch.stack([hi, lo]).contiguous()
+
+
+def merge(s):
+    return s[0].float() + s[1].float()
+
+
+def conv_weight_to_split(w):
+    """Caffe conv weight (Cout, Cin, 3, 3) -> split [2, Cout, 9*Cin], K index = tap*Cin + c."""
+    cout, cin, kh, kw = w.shape
+    return split(w.permute(0, 2, 3, 1).reshape(cout, kh * kw * cin))
+
+
+def fc_weight_to_split(w, chw=None):
+    """Caffe InnerProduct weight (N, K) with K flattened as (c, h, w)
+    (inner_product_layer.cpp:14-34) -> split [2, N, K'] with K' flattened as (h, w, c), the
+    order our NHWC RoI features use.  chw=None keeps K as is."""
+    if chw is not None:
+        c, h, wd = chw
+        w = w.reshape(w.shape[0], c, h, wd).permute(0, 2, 3, 1).reshape(w.shape[0], -1)
+    return split(w)
+
+
+def igemm(a, batch, H, W, cin, w, cout, taps, bias=None, relu=False, out=None, out_f32=None,
+          out_pix_stride=None, out_ch_offset=0, split_k=1, split_stride=0, bn=0, max_ctas=0,
+          impl="tc"):
+    """a: split [2, batch, H, W, cin]; w: split [2, cout, taps*cin].
+    Writes split `out` ([2, ..., stride]) or fp32 `out_f32`."""
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+    if out_f32 is not None:
+        mode, o0, o1 = 1, out_f32, None
+        stride = out_pix_stride if out_pix_stride is not None else cout
+    else:
+        mode, o0, o1 = 0, out[0], out[1]
+        stride = out_pix_stride if out_pix_stride is not None else cout
+    if impl == "tc":
+        rc = lib.mnc_igemm_tc(ptr(a[0]), ptr(a[1]), c_int(batch), c_int(H), c_int(W), c_int(cin),
+                              ptr(w[0]), ptr(w[1]), c_int(cout), c_int(taps), ptr(bias),
+                              c_int(int(relu)), c_int(mode), ptr(o0), ptr(o1), c_ll(stride),
+                              c_int(out_ch_offset), c_int(split_k), c_ll(split_stride), c_int(bn),
+                              c_int(max_ctas), cur_stream())
+        check(rc, "mnc_igemm_tc")
+    else:
+        assert split_k == 1
+        rc = lib.mnc_igemm_simt(ptr(a[0]), ptr(a[1]), c_int(batch), c_int(H), c_int(W),
+                                c_int(cin), ptr(w[0]), ptr(w[1]), c_int(cout), c_int(taps),
+                                ptr(bias), c_int(int(relu)), c_int(mode), ptr(o0), ptr(o1),
+                                c_ll(stride), c_int(out_ch_offset), cur_stream())
+        check(rc, "mnc_igemm_simt")
+
+
+def splitk_reduce(partial, splits, split_stride, rows, cols, bias=None, relu=False, out=None,
+                  out_f32=None, out_row_stride=None, out_ch_offset=0):
+    if out_f32 is not None:
+        mode, o0, o1 = 1, out_f32, None
+    else:
+        mode, o0, o1 = 0, out[0], out[1]
+    stride = out_row_stride if out_row_stride is not None else cols
+    rc = lib.mnc_splitk_reduce(ptr(partial), c_int(splits), c_ll(split_stride), c_ll(rows),
+                               c_int(cols), ptr(bias), c_int(int(relu)), c_int(mode), ptr(o0),
+                               ptr(o1), c_ll(stride), c_int(out_ch_offset), cur_stream())
+    check(rc, "mnc_splitk_reduce")
+
+
+def conv1_1(data, weight, bias, out):
+    b, c, H, W = data.shape
+    assert c == 3 and data.dtype == torch.float32
+    rc = lib.mnc_conv1_1(ptr(data), c_int(b), c_int(H), c_int(W), ptr(weight), ptr(bias),
+                         c_int(weight.shape[0]), ptr(out[0]), ptr(out[1]), cur_stream())
+    check(rc, "mnc_conv1_1")
+
+
+def maxpool2x2(a, batch, H, W, C, out):
+    rc = lib.mnc_maxpool2x2_split(ptr(a[0]), ptr(a[1]), c_int(batch), c_int(H), c_int(W), c_int(C),
+                                  ptr(out[0]), ptr(out[1]), cur_stream())
+    check(rc, "mnc_maxpool2x2_split")
+
+
+def split_to_nchw(a, batch, H, W, C, out):
+    rc = lib.mnc_split_to_nchw(ptr(a[0]), ptr(a[1]), c_int(batch), c_int(H), c_int(W), c_int(C),
+                               ptr(out), cur_stream())
+    check(rc, "mnc_split_to_nchw")
+
+
+def nchw_to_split(x, out):
+    b, C, H, W = x.shape
+    rc = lib.mnc_nchw_to_split(ptr(x), c_int(b), c_int(C), c_int(H), c_int(W), ptr(out[0]),
+                               ptr(out[1]), cur_stream())
+    check(rc, "mnc_nchw_to_split")
