@@ -83,6 +83,120 @@ int mnc_nchw_to_split(const float* in_nchw, int batch, int C, int H, int W, void
 int mnc_f32_to_split(const float* in, long long n, void* out_hi, void* out_lo, void* stream);
 int mnc_split_to_f32(const void* in_hi, const void* in_lo, long long n, float* out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * NMS.  mnc_nms_host is the drop-in for the reference's `_nms` (lib/nms/gpu_nms.hpp:1-2,
+ * lib/nms/nms_kernel.cu:91-144): caller-owned HOST buffers, boxes already sorted by score
+ * (descending), keep_out holds >= boxes_num ints, suppression when IoU > thresh (strict, :71),
+ * synchronous.  Differences: returns a status instead of printing CUDA errors (:12-19); the
+ * suppression matrix stays on the device (only the keep list crosses PCIe).
+ */
+int mnc_nms_host(int* keep_out, int* num_out, const float* boxes_host, int boxes_num,
+                 int boxes_dim, float nms_overlap_thresh, int device_id);
+
+/* Device form, batched over `problems` independent box lists (images x classes):
+ *   boxes + p*problem_stride : n_max x box_stride floats (x1,y1,x2,y2,...), score-sorted
+ *   counts[p] (device, may be NULL = n_max) : number of valid boxes of problem p
+ *   keep_out + p*keep_stride : kept positions (into the sorted list), num_out[p] of them,
+ *   stopping after max_keep (<= 0: no limit).  workspace: mnc_nms_workspace_bytes(n_max, problems). */
+long long mnc_nms_workspace_bytes(int n_max, int problems);
+int mnc_nms_sorted(const float* boxes, int box_stride, long long problem_stride, const int* counts,
+                   int n_max, int problems, float thresh, int max_keep, void* workspace,
+                   int* keep_out, int keep_stride, int* num_out, void* stream);
+
+/* `scores.argsort()[::-1]` (lib/pylayer/proposal_layer.py:139, lib/nms/gpu_nms.pyx:25-26) with the
+ * tie rule (score desc, index asc).  Problem p reads keys at
+ * keys + (p / inner)*outer_stride + (p % inner)*inner_stride + i*key_stride, i < n; entries with
+ * valid[p*n + i] == 0 are dropped (valid may be NULL).  order[p*n + rank] = i, n_valid[p] = count. */
+int mnc_rank_sort_desc(const float* keys, long long outer_stride, long long inner_stride, int inner,
+                       int key_stride, const unsigned char* valid, int n, int problems, int* order,
+                       int* n_valid, void* stream);
+/* dst[p][k][0..3] = src[(p / inner)][order[p*order_stride + k]][0..3], k < min(counts[p], n_out);
+ * out_counts[p] = that minimum. */
+int mnc_gather_boxes(const float* src, int src_stride, long long src_outer_stride, int inner,
+                     const int* order, int order_stride, const int* counts, int n_out, int problems,
+                     float* dst, int* out_counts, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * ProposalLayer pieces (lib/pylayer/proposal_layer.py:52-175), StageBridgeLayer.forward_test
+ * (lib/pylayer/stage_bridge_layer.py:237-255), Caffe Softmax (softmax_layer.cu:86-120) and the
+ * im_detect tail (tools/demo.py:92-95), all on device.
+ */
+int mnc_generate_anchors(float* out36); /* lib/transform/anchors.py:38-49, 9x4 */
+/* Element (img, ch, pixel) of cls at cls + img*img_stride + ch*ch_stride + pixel*pix_stride
+ * (so both NCHW blobs and the engine's NHWC buffer work); channels [bg a0..a8 | fg a0..a8]
+ * (test.prototxt:440-462) and [4a..4a+3]; apply_softmax: cls holds logits.
+ * Outputs per image: proposals [H*W*9][4], scores [H*W*9], valid [H*W*9] (min-size filter). */
+int mnc_rpn_decode(const float* cls, long long cls_img_stride, long long cls_ch_stride,
+                   long long cls_pix_stride, const float* bbox, long long bb_img_stride,
+                   long long bb_ch_stride, long long bb_pix_stride, const float* im_info, int batch,
+                   int H, int W, int feat_stride, float min_size, int apply_softmax,
+                   float* proposals, float* scores, unsigned char* valid, void* stream);
+int mnc_write_rois(const float* sorted_boxes, int n_sorted, const int* keep, int keep_stride,
+                   const int* num_keep, int max_rois, int batch, int batch_index_mode, float* rois,
+                   int* roi_counts, void* stream);
+int mnc_stage_bridge(const float* rois, const float* bbox_pred, int bbox_stride,
+                     const float* seg_cls_prob, int prob_stride, int ncls, const float* im_info,
+                     int rois_per_img, int total, float* rois_out, void* stream);
+int mnc_softmax_rows(const float* in, int in_stride, int rows, int cols, float* out,
+                     int out_stride, void* stream);
+int mnc_unscale_clip(const float* rois, int total, int rois_per_img, const float* im_scale,
+                     const float* im_hw, float* boxes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * The three MNC Caffe layers, Forward_gpu contract (fp32 NCHW device blobs):
+ *   ROIWarping  roi_warping_layer.cu:110-122 : feat (B,C,H,W), rois (R,5) -> out (R,C,ph,pw)
+ *   MaskResize  mask_resize_layer.cu:76-84   : in (N,C,ih,iw) -> out (N,C,oh,ow)
+ *   MaskPooling mask_pooling_layer.cu:29-41  : feat (N,C,H,W), mask (N,1,H,W) -> out (N,C,H,W)
+ */
+int mnc_roi_warp_nchw(const float* feat, int C, int H, int W, const float* rois, int R,
+                      int pooled_h, int pooled_w, float spatial_scale, float* out, void* stream);
+int mnc_mask_resize_nchw(const float* in, int N, int C, int in_h, int in_w, int out_h, int out_w,
+                         float* out, void* stream);
+int mnc_mask_pool_nchw(const float* feat, const float* mask, int N, int C, int H, int W,
+                       float* out, void* stream);
+/* Fused engine forms on split NHWC: RoI warp (+2x2 max when sub == 2) to [R][14][14][C] plus the
+ * 7x7 box pool [R][7][7][C]; sigmoid + 21->14 mask resize; mask pooling + 2x2 max. */
+int mnc_roi_warp_split(const void* f_hi, const void* f_lo, int C, int H, int W, const float* rois,
+                       int R, int sub, float spatial_scale, void* o14_hi, void* o14_lo, void* o7_hi,
+                       void* o7_lo, void* stream);
+int mnc_sigmoid_mask_resize(const float* logits, int stride, int R, int mask_size, int out_size,
+                            float* mask_proposal, float* mask_resized, void* stream);
+int mnc_mask_pool_split(const void* f_hi, const void* f_lo, const float* mask14, int R, int C,
+                        void* o_hi, void* o_lo, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Mask voting.  mnc_mv_host is the drop-in for the reference's `_mv` (lib/nms/gpu_mv.hpp:1-4,
+ * lib/nms/mv_kernel.cu:242-348): HOST buffers, candidate_start holds END offsets (:101-102),
+ * outputs result_num x mask_size^2 floats and result_num x 4 ints [x1,y1,x2,y2]; synchronous.
+ * Differences: returns a status; honours device_id; needs no nb*H*W render buffer.
+ * mnc_bbox_overlaps_host: utils.cython_bbox.bbox_overlaps (lib/utils/bbox.pyx:15-55), float64.
+ */
+int mnc_mv_host(const float* all_boxes, const float* all_masks, int all_boxes_num,
+                const int* candidate_inds, const int* candidate_start,
+                const float* candidate_weights, int candidate_num, int image_height,
+                int image_width, int box_dim, int mask_size, int result_num,
+                float* finalize_output_mask, int* finalize_output_box, int device_id);
+int mnc_bbox_overlaps_host(const double* boxes, int N, const double* query, int K, double* out);
+
+/* Device pipeline of gpu_mask_voting (lib/transform/mask_transform.py:213-286), batched:
+ * after per-class rank sort + NMS (mnc_rank_sort_desc / mnc_gather_boxes / mnc_nms_sorted with
+ * problems = batch*(ncls-1)), vote_select picks the global threshold and enumerates results,
+ * vote_candidates builds the (inds, weights) lists, mv_device renders/aggregates/resizes. */
+int mnc_vote_select(const float* scores, int nb, int ncls, const int* order, const int* keep,
+                    int keep_stride, const int* num_keep, int max_per_image, int max_results,
+                    int batch, int* res_box_idx, int* res_class, float* res_score, int* n_res,
+                    int* class_bar, int* overflow, void* stream);
+int mnc_vote_candidates(const float* boxes, const float* scores,
+                        const unsigned char* box_valid /* [batch][nb], NULL = all */, int nb,
+                        int ncls, const int* res_box_idx, const int* res_class, const int* n_res,
+                        int max_results, int batch, double iou_thresh, int* cand_inds,
+                        float* cand_weights, int* cand_begin, int* cand_end, void* stream);
+int mnc_mv_device(const float* boxes, const float* masks, int nb, int box_dim, int mask_size,
+                  const int* cand_inds, const float* cand_weights, long long cand_img_stride,
+                  const int* cand_begin, const int* cand_end, const int* n_res, int max_results,
+                  int batch, const int* im_hw, int* bbox_ws, float* out_mask, int* out_box,
+                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,7 +34,14 @@ c_ll = ctypes.c_longlong
 c_float = ctypes.c_float
 
 
+# kernels launched by each C-ABI entry point (for bench.py's `gpu_launches` claim)
+_LAUNCHES = {"mnc_nms_sorted": 2, "mnc_mv_device": 3}
+launch_count = 0
+
+
 def check(rc, what):
+    global launch_count
+    launch_count += _LAUNCHES.get(what, 1)
     if rc != MNC_OK:
         detail = ""
         if rc == 2:

@@ -1,0 +1,63 @@
+"""Public host-buffer API of the batched engine: the call a user makes.
+
+`Detector.im_detect_batch(host_blob)` is the batched form of the reference's `im_detect`
+(tools/demo.py:79-100 == lib/caffeWrapper/TesterWrapper.py:239-260): network inputs in HOST memory
+(fp32 NCHW blobs exactly as `prepare_mnc_args` builds them, tools/demo.py:54-76), results back in
+HOST memory -- boxes (B,600,4), masks (B,600,1,21,21), scores (B,600,21), valid (B,600).
+Host<->device copies go through pinned staging buffers on the engine's stream.
+`Detector.mask_voting` is the batched `gpu_mask_voting` (lib/transform/mask_transform.py:213-286).
+"""
+import numpy as np
+import torch
+
+from . import ops
+from .engine import MNCEngine, ROIS_PER_IMAGE, MASK_SIZE, NUM_CLASSES
+
+
+class Detector:
+    def __init__(self, weights, device="cuda", max_batch=8, height=600, width=1000):
+        self.device = torch.device(device)
+        self.engine = MNCEngine(weights, device=self.device)
+        self.max_batch = max_batch
+        B, n = max_batch, 2 * ROIS_PER_IMAGE
+        self._h_in = torch.empty((B, 3, height, width), dtype=torch.float32).pin_memory()
+        self._h_boxes = torch.empty((B, n, 4), dtype=torch.float32).pin_memory()
+        self._h_masks = torch.empty((B, n, 1, MASK_SIZE, MASK_SIZE), dtype=torch.float32).pin_memory()
+        self._h_scores = torch.empty((B, n, NUM_CLASSES), dtype=torch.float32).pin_memory()
+        self._h_valid = torch.empty((B, n), dtype=torch.uint8).pin_memory()
+        self._d_in = torch.empty((B, 3, height, width), dtype=torch.float32, device=self.device)
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def im_detect_batch(self, blob, im_info=None, im_scales=None, im_shapes=None):
+        """blob: (B,3,H,W) fp32 numpy / CPU tensor (mean-subtracted BGR, as `im_list_to_blob`
+        returns).  im_info: (B,3) [H, W, scale] (default: blob size, scale 1).  Synchronous."""
+        blob = torch.as_tensor(blob)
+        B, _, H, W = blob.shape
+        assert B <= self.max_batch and tuple(self._h_in.shape[2:]) == (H, W)
+        dev = self.device
+        if im_info is None:
+            im_info = np.tile(np.array([[H, W, 1.0]], dtype=np.float32), (B, 1))
+        info_h = torch.as_tensor(np.asarray(im_info, dtype=np.float32))
+        scale_h = info_h[:, 2].contiguous() if im_scales is None else torch.as_tensor(np.asarray(im_scales, np.float32))
+        hw_h = info_h[:, :2].contiguous() if im_shapes is None else torch.as_tensor(np.asarray(im_shapes, np.float32))
+        self._h_in[:B].copy_(blob)                       # user memory -> pinned staging
+        with torch.cuda.device(dev):
+            self._d_in[:B].copy_(self._h_in[:B], non_blocking=True)
+            info = info_h.to(dev, non_blocking=True)
+            boxes, masks, scores, valid, _ = self.engine.detect(
+                self._d_in[:B], info, hw_h.to(dev), scale_h.to(dev))
+            self._h_boxes[:B].copy_(boxes, non_blocking=True)
+            self._h_masks[:B].copy_(masks, non_blocking=True)
+            self._h_scores[:B].copy_(scores, non_blocking=True)
+            self._h_valid[:B].copy_(valid, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        self.h2d_bytes = blob.numel() * 4 + info_h.numel() * 4 + scale_h.numel() * 4 + hw_h.numel() * 4
+        self.d2h_bytes = (boxes.numel() + masks.numel() + scores.numel()) * 4 + valid.numel()
+        return (self._h_boxes[:B].numpy(), self._h_masks[:B].numpy(), self._h_scores[:B].numpy(),
+                self._h_valid[:B].numpy())
+
+    def mask_voting(self, boxes, masks, scores, valid, im_hw, max_per_image=100):
+        """Device-resident batched gpu_mask_voting on `engine.detect` outputs (device tensors)."""
+        hw = torch.as_tensor(np.asarray(im_hw, dtype=np.int32)).to(self.device)
+        return ops.mask_voting(boxes, masks, scores, hw, max_per_image=max_per_image, box_valid=valid)

@@ -1,0 +1,615 @@
+// GPU mask voting.
+//
+// Replaces `_mv` (lib/nms/mv_kernel.cu: kernels :36-240, host wrapper :242-348) and the host loop
+// of gpu_mask_voting that feeds it (lib/transform/mask_transform.py:242-274, with
+// lib/utils/bbox.pyx:15-55 for the float64 IoU).
+//
+// The reference renders every one of the nb input masks to image size (nb*H*W floats: 1.44 GB at
+// 600x1000, nb = 600) and then aggregates.  Here nothing image-sized is ever stored:
+//   mv_aggregate : for each result instance, CTAs sweep the union bounding region of its
+//                  candidates, evaluate  sum_i w_i * render_i(h, w)  on the fly in candidate-list
+//                  order, and reduce the tight bounding box of {agg > 0.4} with warp shuffles +
+//                  atomicMin/Max (4 ints per result);
+//   mv_finalize  : resamples the aggregate back to MxM, evaluating it at the <= 4 pixels each
+//                  output needs.
+// Per-pixel arithmetic mirrors the reference expression by expression (same last-row / last-col
+// nearest rule, same W/2, H/2 defaults for an empty mask).
+#include <cuda_runtime.h>
+#include <climits>
+#include <cstdint>
+
+#include "mnc_b200.h"
+
+namespace mnc {
+
+constexpr float kBinarizeThresh = 0.4f;  // mv_kernel.cu:13
+constexpr int kMaxBoxes = 1024;          // nb limit of the device pipeline (2 stages x 300 = 600)
+
+// mask_render (mv_kernel.cu:36-91) for one pixel of one box.
+__device__ __forceinline__ float mv_render(const float4 box, const float* __restrict__ mask,
+                                           int mask_size, int h, int w) {
+  const float box_x1 = box.x, box_y1 = box.y, box_x2 = box.z, box_y2 = box.w;
+  if (w < box_x1 || w > box_x2 || h < box_y1 || h > box_y2) return 0.0f;
+  const float box_width = box_x2 - box_x1 + 1.0;
+  const float box_height = box_y2 - box_y1 + 1.0;
+  const float ratio_w = (float)mask_size / box_width;
+  const float ratio_h = (float)mask_size / box_height;
+  const float inverse_x = ((float)w - box_x1) * ratio_w;
+  const float inverse_y = ((float)h - box_y1) * ratio_h;
+  int start_x = floor(inverse_x);
+  int start_y = floor(inverse_y);
+  if (start_x == mask_size - 1 && start_y == mask_size - 1) {
+    return __ldg(mask + mask_size * mask_size - 1);
+  } else if (start_x == mask_size - 1 || start_y == mask_size - 1) {
+    return __ldg(mask + start_y * mask_size + start_x);
+  } else {
+    int top_left_ind = start_y * mask_size + start_x;
+    int top_right_ind = top_left_ind + 1;
+    int bot_left_ind = top_left_ind + mask_size;
+    int bot_right_ind = bot_left_ind + 1;
+    float top_left_weight = (1 - (inverse_x - start_x)) * (1 - (inverse_y - start_y));
+    float top_right_weight = (inverse_x - start_x) * (1 - (inverse_y - start_y));
+    float bot_left_weight = (1 - (inverse_x - start_x)) * (inverse_y - start_y);
+    float bot_right_weight = (inverse_x - start_x) * (inverse_y - start_y);
+    float val = top_left_weight * __ldg(mask + top_left_ind) +
+                top_right_weight * __ldg(mask + top_right_ind) +
+                bot_left_weight * __ldg(mask + bot_left_ind) +
+                bot_right_weight * __ldg(mask + bot_right_ind);
+    return val;
+  }
+}
+
+struct CandList {
+  float4* box;   // shared
+  float* wgt;    // shared
+  int* ind;      // shared
+  int n;
+};
+
+// mask_aggregate (mv_kernel.cu:93-112) at one pixel: sum in candidate-list order.
+__device__ __forceinline__ float agg_at(const CandList& cl, const float* __restrict__ masks,
+                                        int mask_size, int h, int w) {
+  float val = 0.0f;
+  for (int i = 0; i < cl.n; ++i) {
+    const float4 b = cl.box[i];
+    if (w < b.x || w > b.z || h < b.y || h > b.w) continue;  // render == 0: adds nothing
+    val += (mv_render(b, masks + static_cast<long long>(cl.ind[i]) * mask_size * mask_size,
+                      mask_size, h, w) * cl.wgt[i]);
+  }
+  return val;
+}
+
+__device__ __forceinline__ void load_cands(CandList& cl, const float* __restrict__ boxes,
+                                           int box_dim, const int* __restrict__ cand_inds,
+                                           const float* __restrict__ cand_weights, int begin,
+                                           int end) {
+  cl.n = end - begin;
+  for (int i = threadIdx.x; i < cl.n; i += blockDim.x) {
+    const int ind = cand_inds[begin + i];
+    const float* b = boxes + static_cast<long long>(ind) * box_dim;
+    cl.box[i] = make_float4(b[0], b[1], b[2], b[3]);
+    cl.wgt[i] = cand_weights[begin + i];
+    cl.ind[i] = ind;
+  }
+  __syncthreads();
+}
+
+__global__ void mv_init_bbox_kernel(int* __restrict__ bbox, int total) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < total) {
+    bbox[i * 4 + 0] = INT_MAX;
+    bbox[i * 4 + 1] = INT_MAX;
+    bbox[i * 4 + 2] = INT_MIN;
+    bbox[i * 4 + 3] = INT_MIN;
+  }
+}
+
+// grid (chunks, max_results, batch); 256 threads.
+__global__ void __launch_bounds__(256)
+mv_aggregate_kernel(const float* __restrict__ boxes, const float* __restrict__ masks, int nb,
+                    int box_dim, int mask_size, const int* __restrict__ cand_inds,
+                    const float* __restrict__ cand_weights, long long cand_img_stride,
+                    const int* __restrict__ cand_begin, const int* __restrict__ cand_end,
+                    const int* __restrict__ n_res, int max_results, const int* __restrict__ im_hw,
+                    int* __restrict__ bbox) {
+  extern __shared__ unsigned char smraw[];
+  const int img = blockIdx.z, t = blockIdx.y;
+  if (t >= n_res[img]) return;
+  CandList cl;
+  cl.box = reinterpret_cast<float4*>(smraw);
+  cl.wgt = reinterpret_cast<float*>(cl.box + nb);
+  cl.ind = reinterpret_cast<int*>(cl.wgt + nb);
+  const float* pboxes = boxes + static_cast<long long>(img) * nb * box_dim;
+  const float* pmasks = masks + static_cast<long long>(img) * nb * mask_size * mask_size;
+  const int rt = img * max_results + t;
+  load_cands(cl, pboxes, box_dim, cand_inds + img * cand_img_stride,
+             cand_weights + img * cand_img_stride, cand_begin[rt], cand_end[rt]);
+  const int H = im_hw[img * 2 + 0], W = im_hw[img * 2 + 1];
+  // union region of the candidate boxes (a superset of every pixel with a non-zero render)
+  __shared__ int reg[4];
+  if (threadIdx.x == 0) {
+    reg[0] = INT_MAX;
+    reg[1] = INT_MAX;
+    reg[2] = INT_MIN;
+    reg[3] = INT_MIN;
+  }
+  __syncthreads();
+  {
+    int x0 = INT_MAX, y0 = INT_MAX, x1 = INT_MIN, y1 = INT_MIN;
+    for (int i = threadIdx.x; i < cl.n; i += blockDim.x) {
+      const float4 b = cl.box[i];
+      x0 = min(x0, static_cast<int>(floorf(b.x)));
+      y0 = min(y0, static_cast<int>(floorf(b.y)));
+      x1 = max(x1, static_cast<int>(ceilf(b.z)));
+      y1 = max(y1, static_cast<int>(ceilf(b.w)));
+    }
+    if (x0 != INT_MAX) {
+      atomicMin(&reg[0], x0);
+      atomicMin(&reg[1], y0);
+      atomicMax(&reg[2], x1);
+      atomicMax(&reg[3], y1);
+    }
+  }
+  __syncthreads();
+  const int rx0 = max(reg[0], 0), ry0 = max(reg[1], 0);
+  const int rx1 = min(reg[2], W - 1), ry1 = min(reg[3], H - 1);
+  if (cl.n == 0 || rx1 < rx0 || ry1 < ry0) return;
+  const int rw = rx1 - rx0 + 1, rh = ry1 - ry0 + 1;
+  const long long npix = static_cast<long long>(rw) * rh;
+  int bx0 = INT_MAX, by0 = INT_MAX, bx1 = INT_MIN, by1 = INT_MIN;
+  for (long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; p < npix;
+       p += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int h = ry0 + static_cast<int>(p / rw);
+    const int w = rx0 + static_cast<int>(p % rw);
+    const float v = agg_at(cl, pmasks, mask_size, h, w);
+    if (v > kBinarizeThresh) {  // reduce_mask_col/row, mv_kernel.cu:114-142 (strict >)
+      bx0 = min(bx0, w);
+      bx1 = max(bx1, w);
+      by0 = min(by0, h);
+      by1 = max(by1, h);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    bx0 = min(bx0, __shfl_xor_sync(0xffffffffu, bx0, o));
+    by0 = min(by0, __shfl_xor_sync(0xffffffffu, by0, o));
+    bx1 = max(bx1, __shfl_xor_sync(0xffffffffu, bx1, o));
+    by1 = max(by1, __shfl_xor_sync(0xffffffffu, by1, o));
+  }
+  if ((threadIdx.x & 31) == 0 && bx0 != INT_MAX) {
+    atomicMin(&bbox[rt * 4 + 0], bx0);
+    atomicMin(&bbox[rt * 4 + 1], by0);
+    atomicMax(&bbox[rt * 4 + 2], bx1);
+    atomicMax(&bbox[rt * 4 + 3], by1);
+  }
+}
+
+// grid (max_results, batch); 256 threads.  reduce_bounding_x/y defaults (mv_kernel.cu:144-190)
+// and mask_resize (:193-240).
+__global__ void __launch_bounds__(256)
+mv_finalize_kernel(const float* __restrict__ boxes, const float* __restrict__ masks, int nb,
+                   int box_dim, int mask_size, const int* __restrict__ cand_inds,
+                   const float* __restrict__ cand_weights, long long cand_img_stride,
+                   const int* __restrict__ cand_begin, const int* __restrict__ cand_end,
+                   const int* __restrict__ n_res, int max_results, const int* __restrict__ im_hw,
+                   const int* __restrict__ bbox, float* __restrict__ out_mask,
+                   int* __restrict__ out_box) {
+  extern __shared__ unsigned char smraw[];
+  const int img = blockIdx.y, t = blockIdx.x;
+  if (t >= n_res[img]) return;
+  CandList cl;
+  cl.box = reinterpret_cast<float4*>(smraw);
+  cl.wgt = reinterpret_cast<float*>(cl.box + nb);
+  cl.ind = reinterpret_cast<int*>(cl.wgt + nb);
+  const float* pboxes = boxes + static_cast<long long>(img) * nb * box_dim;
+  const float* pmasks = masks + static_cast<long long>(img) * nb * mask_size * mask_size;
+  const int rt = img * max_results + t;
+  load_cands(cl, pboxes, box_dim, cand_inds + img * cand_img_stride,
+             cand_weights + img * cand_img_stride, cand_begin[rt], cand_end[rt]);
+  const int image_height = im_hw[img * 2 + 0], image_width = im_hw[img * 2 + 1];
+  int bbox_x1 = bbox[rt * 4 + 0], bbox_y1 = bbox[rt * 4 + 1];
+  int bbox_x2 = bbox[rt * 4 + 2], bbox_y2 = bbox[rt * 4 + 3];
+  if (bbox_x1 == INT_MAX) {  // nothing above the threshold: both axes take their defaults
+    bbox_x1 = bbox_x2 = image_width / 2;
+    bbox_y1 = bbox_y2 = image_height / 2;
+  }
+  if (threadIdx.x == 0) {
+    out_box[rt * 4 + 0] = bbox_x1;
+    out_box[rt * 4 + 1] = bbox_y1;
+    out_box[rt * 4 + 2] = bbox_x2;
+    out_box[rt * 4 + 3] = bbox_y2;
+  }
+  for (int index = threadIdx.x; index < mask_size * mask_size; index += blockDim.x) {
+    int w = index % mask_size;
+    int h = index / mask_size;
+    float bbox_width = bbox_x2 - bbox_x1 + 1.0;
+    float bbox_height = bbox_y2 - bbox_y1 + 1.0;
+    float ratio_w = bbox_width / static_cast<float>(mask_size);
+    float ratio_h = bbox_height / static_cast<float>(mask_size);
+    float inverse_x = bbox_x1 + static_cast<float>(w) * ratio_w;
+    float inverse_y = bbox_y1 + static_cast<float>(h) * ratio_h;
+    int start_x = floor(inverse_x);
+    int start_y = floor(inverse_y);
+    float val;
+    if (start_x == image_width - 1 && start_y == image_height - 1) {
+      val = agg_at(cl, pmasks, mask_size, image_height - 1, image_width - 1);
+    } else if (start_x == image_width - 1 || start_y == image_height - 1) {
+      val = agg_at(cl, pmasks, mask_size, start_y, start_x);
+    } else {
+      float top_left_weight = (1 - (inverse_x - start_x)) * (1 - (inverse_y - start_y));
+      float top_right_weight = (inverse_x - start_x) * (1 - (inverse_y - start_y));
+      float bot_left_weight = (1 - (inverse_x - start_x)) * (inverse_y - start_y);
+      float bot_right_weight = (inverse_x - start_x) * (inverse_y - start_y);
+      val = top_left_weight * agg_at(cl, pmasks, mask_size, start_y, start_x) +
+            top_right_weight * agg_at(cl, pmasks, mask_size, start_y, start_x + 1) +
+            bot_left_weight * agg_at(cl, pmasks, mask_size, start_y + 1, start_x) +
+            bot_right_weight * agg_at(cl, pmasks, mask_size, start_y + 1, start_x + 1);
+    }
+    out_mask[static_cast<long long>(rt) * mask_size * mask_size + index] = val;
+  }
+}
+
+// ------------------------------------------------------------------ candidate-list construction
+// One CTA per image.  From the per-class NMS keep lists pick the global score threshold
+// (mask_transform.py:242-244) and enumerate result instances in (class, score-rank) order
+// (:253-270).  kept entry e = (class c, k): original box index = order[c][keep[c][k]].
+__global__ void __launch_bounds__(1024)
+vote_select_kernel(const float* __restrict__ scores, int nb, int ncls,
+                   const int* __restrict__ order, const int* __restrict__ keep, int keep_stride,
+                   const int* __restrict__ num_keep, int max_per_image, int max_results,
+                   int* __restrict__ res_box_idx, int* __restrict__ res_class,
+                   float* __restrict__ res_score, int* __restrict__ n_res,
+                   int* __restrict__ class_bar, int* __restrict__ overflow) {
+  extern __shared__ unsigned char smraw[];
+  const int img = blockIdx.x;
+  const int nprob = ncls - 1;
+  const int cap = nprob * max_per_image;
+  float* s_score = reinterpret_cast<float*>(smraw);      // cap
+  int* s_orig = reinterpret_cast<int*>(s_score + cap);    // cap
+  int* s_flag = s_orig + cap;                             // cap
+  int* s_off = s_flag + cap;                              // nprob + 1
+  __shared__ float s_thresh;
+  __shared__ int s_total;
+  const float* pscores = scores + static_cast<long long>(img) * nb * ncls;
+  if (threadIdx.x == 0) {
+    int off = 0;
+    for (int p = 0; p < nprob; ++p) {
+      s_off[p] = off;
+      off += min(num_keep[img * nprob + p], max_per_image);
+    }
+    s_off[nprob] = off;
+    s_total = off;
+  }
+  __syncthreads();
+  const int total = s_total;
+  for (int p = 0; p < nprob; ++p) {
+    const int prob = img * nprob + p;
+    const int cnt = s_off[p + 1] - s_off[p];
+    for (int k = threadIdx.x; k < cnt; k += blockDim.x) {
+      const int pos = keep[static_cast<long long>(prob) * keep_stride + k];
+      const int orig = order[static_cast<long long>(prob) * nb + pos];
+      s_orig[s_off[p] + k] = orig;
+      s_score[s_off[p] + k] = pscores[static_cast<long long>(orig) * ncls + (p + 1)];
+    }
+  }
+  __syncthreads();
+  if (total == 0) {
+    if (threadIdx.x == 0) {
+      n_res[img] = 0;
+      for (int p = 0; p < nprob; ++p) class_bar[img * nprob + p] = 0;
+    }
+    return;
+  }
+  // thresh = sorted_desc[min(total, max_per_image) - 1]
+  const int want = min(total, max_per_image) - 1;
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    const float se = s_score[e];
+    int rank = 0;
+    for (int j = 0; j < total; ++j) {
+      const float sj = s_score[j];
+      rank += (sj > se || (sj == se && j < e)) ? 1 : 0;
+    }
+    if (rank == want) s_thresh = se;
+  }
+  __syncthreads();
+  const float thresh = s_thresh;
+  for (int e = threadIdx.x; e < total; e += blockDim.x) s_flag[e] = (s_score[e] >= thresh) ? 1 : 0;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0, p = 0;
+    int ovf = 0;
+    for (int e = 0; e < total; ++e) {
+      while (e >= s_off[p + 1]) {
+        class_bar[img * nprob + p] = t;
+        ++p;
+      }
+      if (s_flag[e]) {
+        if (t < max_results) {
+          res_box_idx[img * max_results + t] = s_orig[e];
+          res_class[img * max_results + t] = p + 1;
+          res_score[img * max_results + t] = s_score[e];
+          ++t;
+        } else {
+          ovf = 1;
+        }
+      }
+    }
+    for (; p < nprob; ++p) class_bar[img * nprob + p] = t;
+    n_res[img] = t;
+    if (ovf) atomicExch(overflow, 1);
+  }
+}
+
+// grid (max_results, batch), kMaxBoxes threads.  For result t with query box q = boxes[res_box_idx]:
+// candidates = {i : IoU64(boxes[i], q) >= iou_thresh} in index order (bbox.pyx:38-54,
+// mask_transform.py:262-263); weights = scores[i, c] / fp32(sum_fp64(scores[cands, c])) (:265-267,
+// numpy-1.x semantics, see oracle/oracle.py).
+__global__ void __launch_bounds__(kMaxBoxes)
+vote_candidates_kernel(const float* __restrict__ boxes, const float* __restrict__ scores,
+                       const unsigned char* __restrict__ box_valid, int nb,
+                       int ncls, const int* __restrict__ res_box_idx,
+                       const int* __restrict__ res_class, const int* __restrict__ n_res,
+                       int max_results, double iou_thresh, int* __restrict__ cand_inds,
+                       float* __restrict__ cand_weights, int* __restrict__ cand_begin,
+                       int* __restrict__ cand_end) {
+  const int img = blockIdx.y, t = blockIdx.x;
+  const int rt = img * max_results + t;
+  if (t >= n_res[img]) {
+    if (threadIdx.x == 0) {
+      cand_begin[rt] = t * nb;
+      cand_end[rt] = t * nb;
+    }
+    return;
+  }
+  __shared__ int s_warp[kMaxBoxes / 32];
+  __shared__ int s_list[kMaxBoxes];
+  __shared__ float s_sum;
+  __shared__ int s_cnt;
+  const float* pboxes = boxes + static_cast<long long>(img) * nb * 4;
+  const float* pscores = scores + static_cast<long long>(img) * nb * ncls;
+  const int qi = res_box_idx[rt];
+  const int c = res_class[rt];
+  const double q0 = pboxes[qi * 4 + 0], q1 = pboxes[qi * 4 + 1], q2 = pboxes[qi * 4 + 2],
+               q3 = pboxes[qi * 4 + 3];
+  const double box_area = __dmul_rn(q2 - q0 + 1, q3 - q1 + 1);
+  const int i = threadIdx.x;
+  int flag = 0;
+  if (i < nb) {
+    const double b0 = pboxes[i * 4 + 0], b1 = pboxes[i * 4 + 1], b2 = pboxes[i * 4 + 2],
+                 b3 = pboxes[i * 4 + 3];
+    double ov = 0.0;
+    const double iw = fmin(b2, q2) - fmax(b0, q0) + 1;
+    if (iw > 0) {
+      const double ih = fmin(b3, q3) - fmax(b1, q1) + 1;
+      if (ih > 0) {
+        const double ua = __dsub_rn(__dadd_rn(__dmul_rn(b2 - b0 + 1, b3 - b1 + 1), box_area),
+                                    __dmul_rn(iw, ih));
+        ov = __ddiv_rn(__dmul_rn(iw, ih), ua);
+      }
+    }
+    flag = (ov >= iou_thresh) ? 1 : 0;
+    if (box_valid && !box_valid[static_cast<long long>(img) * nb + i]) flag = 0;  // padding rows
+  }
+  // block-wide exclusive scan of flags (index order)
+  const unsigned bal = __ballot_sync(0xffffffffu, flag);
+  const int lane = i & 31, wid = i >> 5;
+  if (lane == 0) s_warp[wid] = __popc(bal);
+  __syncthreads();
+  if (i == 0) {
+    int run = 0;
+    for (int w2 = 0; w2 < kMaxBoxes / 32; ++w2) {
+      const int v = s_warp[w2];
+      s_warp[w2] = run;
+      run += v;
+    }
+    s_cnt = run;
+  }
+  __syncthreads();
+  const int pos = s_warp[wid] + __popc(bal & ((1u << lane) - 1u));
+  if (flag) s_list[pos] = i;
+  __syncthreads();
+  const int cnt = s_cnt;
+  if (i == 0) {
+    double total = 0.0;
+    for (int k = 0; k < cnt; ++k)
+      total = __dadd_rn(total, static_cast<double>(pscores[static_cast<long long>(s_list[k]) * ncls + c]));
+    s_sum = static_cast<float>(total);
+    cand_begin[rt] = t * nb;
+    cand_end[rt] = t * nb + cnt;
+  }
+  __syncthreads();
+  const float denom = s_sum;
+  int* ci = cand_inds + static_cast<long long>(img) * max_results * nb + static_cast<long long>(t) * nb;
+  float* cw = cand_weights + static_cast<long long>(img) * max_results * nb + static_cast<long long>(t) * nb;
+  if (i < cnt) {
+    const int ind = s_list[i];
+    ci[i] = ind;
+    cw[i] = __fdiv_rn(pscores[static_cast<long long>(ind) * ncls + c], denom);
+  }
+}
+
+static inline int check_launch() { return cudaGetLastError() == cudaSuccess ? MNC_OK : MNC_ERR_CUDA; }
+
+}  // namespace mnc
+
+using namespace mnc;
+
+extern "C" int mnc_mv_device(const float* boxes, const float* masks, int nb, int box_dim,
+                             int mask_size, const int* cand_inds, const float* cand_weights,
+                             long long cand_img_stride, const int* cand_begin, const int* cand_end,
+                             const int* n_res, int max_results, int batch, const int* im_hw,
+                             int* bbox_ws, float* out_mask, int* out_box, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (nb <= 0 || max_results <= 0 || batch <= 0) return MNC_ERR_ARG;
+  const int smem = nb * (16 + 4 + 4);
+  if (smem > 200 * 1024) return MNC_ERR_ARG;
+  static int attr_smem = 48 * 1024;
+  if (smem > attr_smem) {
+    if (cudaFuncSetAttribute(mv_aggregate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             smem) != cudaSuccess ||
+        cudaFuncSetAttribute(mv_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             smem) != cudaSuccess)
+      return MNC_ERR_CUDA;
+    attr_smem = smem;
+  }
+  const int total = batch * max_results;
+  mv_init_bbox_kernel<<<(total + 255) / 256, 256, 0, stream>>>(bbox_ws, total);
+  const int chunks = 24;
+  mv_aggregate_kernel<<<dim3(chunks, max_results, batch), 256, smem, stream>>>(
+      boxes, masks, nb, box_dim, mask_size, cand_inds, cand_weights, cand_img_stride, cand_begin,
+      cand_end, n_res, max_results, im_hw, bbox_ws);
+  mv_finalize_kernel<<<dim3(max_results, batch), 256, smem, stream>>>(
+      boxes, masks, nb, box_dim, mask_size, cand_inds, cand_weights, cand_img_stride, cand_begin,
+      cand_end, n_res, max_results, im_hw, bbox_ws, out_mask, out_box);
+  return check_launch();
+}
+
+extern "C" int mnc_vote_select(const float* scores, int nb, int ncls, const int* order,
+                               const int* keep, int keep_stride, const int* num_keep,
+                               int max_per_image, int max_results, int batch, int* res_box_idx,
+                               int* res_class, float* res_score, int* n_res, int* class_bar,
+                               int* overflow, void* stream_) {
+  const int cap = (ncls - 1) * max_per_image;
+  const int smem = cap * 12 + (ncls + 1) * 4;
+  if (smem > 48 * 1024) return MNC_ERR_ARG;
+  vote_select_kernel<<<batch, 1024, smem, static_cast<cudaStream_t>(stream_)>>>(
+      scores, nb, ncls, order, keep, keep_stride, num_keep, max_per_image, max_results,
+      res_box_idx, res_class, res_score, n_res, class_bar, overflow);
+  return check_launch();
+}
+
+extern "C" int mnc_vote_candidates(const float* boxes, const float* scores,
+                                   const unsigned char* box_valid, int nb, int ncls,
+                                   const int* res_box_idx, const int* res_class, const int* n_res,
+                                   int max_results, int batch, double iou_thresh, int* cand_inds,
+                                   float* cand_weights, int* cand_begin, int* cand_end,
+                                   void* stream_) {
+  if (nb > kMaxBoxes) return MNC_ERR_ARG;
+  vote_candidates_kernel<<<dim3(max_results, batch), kMaxBoxes, 0,
+                           static_cast<cudaStream_t>(stream_)>>>(
+      boxes, scores, box_valid, nb, ncls, res_box_idx, res_class, n_res, max_results, iou_thresh,
+      cand_inds, cand_weights, cand_begin, cand_end);
+  return check_launch();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Reference-compatible host entry point: same arguments and meaning as
+//   void _mv(const float* all_boxes, const float* all_masks, int all_boxes_num,
+//            const int* candidate_inds, const int* candidate_start,
+//            const float* candidate_weights, int candidate_num, int image_height,
+//            int image_width, int box_dim, int mask_size, int result_num,
+//            float* finalize_output_mask, int* finalize_output_box, int device_id)
+//   (lib/nms/gpu_mv.hpp:1-4; candidate_start holds END offsets, mv_kernel.cu:101-102)
+// plus an int status.  Unlike the reference, device_id is honoured.
+extern "C" int mnc_mv_host(const float* all_boxes, const float* all_masks, int all_boxes_num,
+                           const int* candidate_inds, const int* candidate_start,
+                           const float* candidate_weights, int candidate_num, int image_height,
+                           int image_width, int box_dim, int mask_size, int result_num,
+                           float* finalize_output_mask, int* finalize_output_box, int device_id) {
+  if (result_num == 0) return MNC_OK;
+  if (all_boxes_num <= 0 || box_dim < 4 || mask_size <= 0 || result_num < 0 || candidate_num < 0)
+    return MNC_ERR_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return MNC_ERR_NOGPU;
+  int cur = 0;
+  cudaGetDevice(&cur);
+  if (cur != device_id && cudaSetDevice(device_id) != cudaSuccess) return MNC_ERR_CUDA;
+  const size_t nb = all_boxes_num, mm = static_cast<size_t>(mask_size) * mask_size;
+  auto al = [](size_t b) { return (b + 255) & ~static_cast<size_t>(255); };
+  const size_t o_boxes = 0;
+  const size_t o_masks = o_boxes + al(nb * box_dim * 4);
+  const size_t o_inds = o_masks + al(nb * mm * 4);
+  const size_t o_wgt = o_inds + al(static_cast<size_t>(candidate_num) * 4 + 4);
+  const size_t o_begin = o_wgt + al(static_cast<size_t>(candidate_num) * 4 + 4);
+  const size_t o_end = o_begin + al(static_cast<size_t>(result_num) * 4);
+  const size_t o_nres = o_end + al(static_cast<size_t>(result_num) * 4);
+  const size_t o_hw = o_nres + 256;
+  const size_t o_bbox = o_hw + 256;
+  const size_t o_omask = o_bbox + al(static_cast<size_t>(result_num) * 16);
+  const size_t o_obox = o_omask + al(static_cast<size_t>(result_num) * mm * 4);
+  const size_t total = o_obox + al(static_cast<size_t>(result_num) * 16);
+  char* base = nullptr;
+  if (cudaMalloc(&base, total) != cudaSuccess) return MNC_ERR_CUDA;
+  int rc = MNC_OK;
+  int* h_begin = new int[result_num];
+  for (int n = 0; n < result_num; ++n) h_begin[n] = (n == 0) ? 0 : candidate_start[n - 1];
+  const int h_hw[2] = {image_height, image_width};
+  bool ok = true;
+  ok &= cudaMemcpy(base + o_boxes, all_boxes, nb * box_dim * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+  ok &= cudaMemcpy(base + o_masks, all_masks, nb * mm * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+  if (candidate_num > 0) {
+    ok &= cudaMemcpy(base + o_inds, candidate_inds, static_cast<size_t>(candidate_num) * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+    ok &= cudaMemcpy(base + o_wgt, candidate_weights, static_cast<size_t>(candidate_num) * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+  }
+  ok &= cudaMemcpy(base + o_begin, h_begin, static_cast<size_t>(result_num) * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+  ok &= cudaMemcpy(base + o_end, candidate_start, static_cast<size_t>(result_num) * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+  ok &= cudaMemcpy(base + o_nres, &result_num, 4, cudaMemcpyHostToDevice) == cudaSuccess;
+  ok &= cudaMemcpy(base + o_hw, h_hw, 8, cudaMemcpyHostToDevice) == cudaSuccess;
+  delete[] h_begin;
+  if (ok) {
+    rc = mnc_mv_device(reinterpret_cast<float*>(base + o_boxes),
+                       reinterpret_cast<float*>(base + o_masks), all_boxes_num, box_dim, mask_size,
+                       reinterpret_cast<int*>(base + o_inds),
+                       reinterpret_cast<float*>(base + o_wgt), 0,
+                       reinterpret_cast<int*>(base + o_begin), reinterpret_cast<int*>(base + o_end),
+                       reinterpret_cast<int*>(base + o_nres), result_num, 1,
+                       reinterpret_cast<int*>(base + o_hw), reinterpret_cast<int*>(base + o_bbox),
+                       reinterpret_cast<float*>(base + o_omask),
+                       reinterpret_cast<int*>(base + o_obox), nullptr);
+    if (rc == MNC_OK) {
+      ok &= cudaMemcpy(finalize_output_mask, base + o_omask, static_cast<size_t>(result_num) * mm * 4, cudaMemcpyDeviceToHost) == cudaSuccess;
+      ok &= cudaMemcpy(finalize_output_box, base + o_obox, static_cast<size_t>(result_num) * 16, cudaMemcpyDeviceToHost) == cudaSuccess;
+    }
+  }
+  cudaFree(base);
+  if (!ok) return MNC_ERR_CUDA;
+  return rc;
+}
+
+// utils.cython_bbox.bbox_overlaps (lib/utils/bbox.pyx:15-55): float64 IoU matrix, host buffers.
+namespace mnc {
+__global__ void bbox_overlaps_kernel(const double* __restrict__ boxes, int N,
+                                     const double* __restrict__ query, int K,
+                                     double* __restrict__ out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(N) * K) return;
+  const int n = static_cast<int>(i / K), k = static_cast<int>(i % K);
+  const double* b = boxes + 4 * n;
+  const double* q = query + 4 * k;
+  const double box_area = __dmul_rn(q[2] - q[0] + 1, q[3] - q[1] + 1);
+  double ov = 0.0;
+  const double iw = fmin(b[2], q[2]) - fmax(b[0], q[0]) + 1;
+  if (iw > 0) {
+    const double ih = fmin(b[3], q[3]) - fmax(b[1], q[1]) + 1;
+    if (ih > 0) {
+      const double ua = __dsub_rn(__dadd_rn(__dmul_rn(b[2] - b[0] + 1, b[3] - b[1] + 1), box_area),
+                                  __dmul_rn(iw, ih));
+      ov = __ddiv_rn(__dmul_rn(iw, ih), ua);
+    }
+  }
+  out[i] = ov;
+}
+}  // namespace mnc
+
+extern "C" int mnc_bbox_overlaps_host(const double* boxes, int N, const double* query, int K,
+                                      double* out) {
+  if (N <= 0 || K <= 0) return MNC_OK;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return MNC_ERR_NOGPU;
+  double *d_b = nullptr, *d_q = nullptr, *d_o = nullptr;
+  bool ok = cudaMalloc(&d_b, sizeof(double) * 4 * N) == cudaSuccess &&
+            cudaMalloc(&d_q, sizeof(double) * 4 * K) == cudaSuccess &&
+            cudaMalloc(&d_o, sizeof(double) * static_cast<size_t>(N) * K) == cudaSuccess;
+  if (ok) {
+    ok &= cudaMemcpy(d_b, boxes, sizeof(double) * 4 * N, cudaMemcpyHostToDevice) == cudaSuccess;
+    ok &= cudaMemcpy(d_q, query, sizeof(double) * 4 * K, cudaMemcpyHostToDevice) == cudaSuccess;
+    const long long total = static_cast<long long>(N) * K;
+    mnc::bbox_overlaps_kernel<<<static_cast<unsigned>((total + 255) / 256), 256>>>(d_b, N, d_q, K, d_o);
+    ok &= cudaGetLastError() == cudaSuccess;
+    ok &= cudaMemcpy(out, d_o, sizeof(double) * static_cast<size_t>(N) * K, cudaMemcpyDeviceToHost) == cudaSuccess;
+  }
+  cudaFree(d_b);
+  cudaFree(d_q);
+  cudaFree(d_o);
+  return ok ? MNC_OK : MNC_ERR_CUDA;
+}

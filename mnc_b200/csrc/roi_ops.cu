@@ -1,0 +1,455 @@
+// RoI warping, mask resize and mask pooling.
+//
+// Replaces the three MNC Caffe layers' Forward_gpu:
+//   ROIWarping   caffe-mnc/src/caffe/layers/roi_warping_layer.cu:67-107 (+ bilinear :18-64)
+//   MaskResize   caffe-mnc/src/caffe/layers/mask_resize_layer.cu:57-73  (+ bilinear :13-54)
+//   MaskPooling  caffe-mnc/src/caffe/layers/mask_pooling_layer.cu:13-26
+// in two forms:
+//   *_nchw  : the layer contract itself (fp32 NCHW blobs in and out) -- what the ROIWarpingLayer /
+//             MaskResizeLayer / MaskPoolingLayer host mirrors call and what the HBM microbench
+//             (BASELINE.json config 4) times.  One CTA per (RoI, channel slab): the RoI's window of
+//             the feature map is staged in shared memory once, interpolation tables are built once
+//             per RoI, and every output element is written exactly once with coalesced 16 B stores
+//             (the reference writes 3x the bytes: top + argmax_h + argmax_w).
+//   *_split : the fused forms the batched engine uses on split-bf16 NHWC activations: warp (+ the
+//             2x2 max pool of test.prototxt:494-505) straight to the 14x14 grid and the 7x7 box
+//             pool in one pass, never materialising the (R,512,28,28) tensor; mask pooling fused
+//             with its 2x2 pool.
+// The bilinear arithmetic uses explicit round-to-nearest mul/add in the reference's operation order
+// (weights first, then a left-to-right sum), so fp32 results equal the C oracle's bit for bit.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "mnc_b200.h"
+
+namespace mnc {
+
+struct AxisTap {
+  int lo, hi;   // indices (relative to the staged window for the nchw kernel)
+  float l, h;   // l = frac, h = 1 - frac
+  int ok;       // 0: sample out of range -> output 0
+};
+
+// roi_warping_layer.cu:18-47 for one axis.
+__device__ __forceinline__ AxisTap axis_tap(float x, int dim) {
+  AxisTap t;
+  t.ok = !(x < -0.5 || x > dim - 0.5);
+  if (x <= 0) x = 0;
+  int lo = static_cast<int>(x), hi;
+  if (lo >= dim - 1) {
+    hi = lo = dim - 1;
+    x = static_cast<float>(lo);
+  } else {
+    hi = lo + 1;
+  }
+  t.lo = lo;
+  t.hi = hi;
+  t.l = __fsub_rn(x, static_cast<float>(lo));
+  t.h = __fsub_rn(1.f, t.l);
+  return t;
+}
+
+__device__ __forceinline__ float bilerp(const AxisTap& th, const AxisTap& tw, float v1, float v2,
+                                        float v3, float v4) {
+  const float w1 = __fmul_rn(th.h, tw.h), w2 = __fmul_rn(th.h, tw.l);
+  const float w3 = __fmul_rn(th.l, tw.h), w4 = __fmul_rn(th.l, tw.l);
+  float val = __fmul_rn(w1, v1);
+  val = __fadd_rn(val, __fmul_rn(w2, v2));
+  val = __fadd_rn(val, __fmul_rn(w3, v3));
+  val = __fadd_rn(val, __fmul_rn(w4, v4));
+  return val;
+}
+
+struct RoiGeom {
+  int level;
+  float start_h, start_w, bin_h, bin_w;
+};
+
+// roi_warping_layer.cu:78-90
+__device__ __forceinline__ RoiGeom roi_geom(const float* roi, float spatial_scale, int ph_n,
+                                            int pw_n) {
+  RoiGeom g;
+  g.level = static_cast<int>(roi[0]);
+  const float sw = roundf(__fmul_rn(roi[1], spatial_scale));
+  const float sh = roundf(__fmul_rn(roi[2], spatial_scale));
+  const float ew = roundf(__fmul_rn(roi[3], spatial_scale));
+  const float eh = roundf(__fmul_rn(roi[4], spatial_scale));
+  const float rw = fmaxf(__fsub_rn(ew, sw), 0.f);
+  const float rh = fmaxf(__fsub_rn(eh, sh), 0.f);
+  g.start_h = sh;
+  g.start_w = sw;
+  g.bin_h = __fdiv_rn(rh, static_cast<float>(ph_n));
+  g.bin_w = __fdiv_rn(rw, static_cast<float>(pw_n));
+  return g;
+}
+
+// ------------------------------------------------------------------------ ROIWarping, NCHW fp32
+constexpr int kWarpSlab = 8;     // channels per CTA
+constexpr int kMaxPooled = 32;   // pooled_h, pooled_w <= 32
+
+__global__ void __launch_bounds__(256)
+roi_warp_nchw_kernel(const float* __restrict__ feat, int C, int H, int W,
+                     const float* __restrict__ rois, int ph_n, int pw_n, float spatial_scale,
+                     float* __restrict__ out) {
+  extern __shared__ float win[];  // [kWarpSlab][wh][ww]
+  __shared__ AxisTap tap_h[kMaxPooled], tap_w[kMaxPooled];
+  __shared__ int s_hmin, s_wmin, s_wh, s_ww;
+  const int r = blockIdx.x;
+  const int c0 = blockIdx.y * kWarpSlab;
+  const int tid = threadIdx.x;
+  const RoiGeom g = roi_geom(rois + static_cast<long long>(r) * 5, spatial_scale, ph_n, pw_n);
+  if (tid < ph_n) tap_h[tid] = axis_tap(__fadd_rn(g.start_h, __fmul_rn(static_cast<float>(tid), g.bin_h)), H);
+  if (tid >= 32 && tid < 32 + pw_n)
+    tap_w[tid - 32] = axis_tap(__fadd_rn(g.start_w, __fmul_rn(static_cast<float>(tid - 32), g.bin_w)), W);
+  __syncthreads();
+  if (tid == 0) {
+    int hmin = H, hmax = -1, wmin = W, wmax = -1;
+    for (int i = 0; i < ph_n; ++i)
+      if (tap_h[i].ok) {
+        hmin = min(hmin, tap_h[i].lo);
+        hmax = max(hmax, tap_h[i].hi);
+      }
+    for (int i = 0; i < pw_n; ++i)
+      if (tap_w[i].ok) {
+        wmin = min(wmin, tap_w[i].lo);
+        wmax = max(wmax, tap_w[i].hi);
+      }
+    if (hmax < 0 || wmax < 0) {
+      hmin = wmin = 0;
+      hmax = wmax = -1;
+    }
+    s_hmin = hmin;
+    s_wmin = wmin;
+    s_wh = hmax - hmin + 1;
+    s_ww = wmax - wmin + 1;
+  }
+  __syncthreads();
+  const int hmin = s_hmin, wmin = s_wmin, wh = s_wh, ww = s_ww;
+  const int nch = min(kWarpSlab, C - c0);
+  const float* fbase = feat + (static_cast<long long>(g.level) * C + c0) * H * W;
+  const int wsz = wh * ww;
+  for (int i = tid; i < nch * wsz; i += 256) {
+    const int c = i / wsz, rem = i % wsz;
+    const int y = rem / ww, x = rem % ww;
+    win[i] = __ldg(fbase + static_cast<long long>(c) * H * W + (hmin + y) * W + wmin + x);
+  }
+  __syncthreads();
+  const int pp = ph_n * pw_n;
+  const int total = nch * pp;
+  float* obase = out + (static_cast<long long>(r) * C + c0) * pp;
+  const bool vec = (pp % 4 == 0) && ((reinterpret_cast<uintptr_t>(obase) & 15) == 0);
+  for (int i4 = tid * 4; i4 < total; i4 += 256 * 4) {
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int i = i4 + e;
+      float val = 0.f;
+      if (i < total) {
+        const int c = i / pp, rem = i % pp;
+        const int ph = rem / pw_n, pw = rem % pw_n;
+        const AxisTap th = tap_h[ph], tw = tap_w[pw];
+        if (th.ok && tw.ok) {
+          const float* wp = win + c * wsz;
+          const int y0 = (th.lo - hmin) * ww, y1 = (th.hi - hmin) * ww;
+          const int x0 = tw.lo - wmin, x1 = tw.hi - wmin;
+          val = bilerp(th, tw, wp[y0 + x0], wp[y0 + x1], wp[y1 + x0], wp[y1 + x1]);
+        }
+      }
+      v[e] = val;
+    }
+    if (vec && i4 + 3 < total) {
+      __stcs(reinterpret_cast<float4*>(obase + i4), make_float4(v[0], v[1], v[2], v[3]));
+    } else {
+      for (int e = 0; e < 4 && i4 + e < total; ++e) obase[i4 + e] = v[e];
+    }
+  }
+}
+
+// -------------------------------------------------------------- MaskResize / MaskPooling, NCHW
+__global__ void mask_resize_nchw_kernel(const float* __restrict__ in, int planes, int ih_n,
+                                        int iw_n, int oh_n, int ow_n, float* __restrict__ out) {
+  const long long total = static_cast<long long>(planes) * oh_n * ow_n;
+  const float ratio_h = __fdiv_rn(static_cast<float>(ih_n), static_cast<float>(oh_n));
+  const float ratio_w = __fdiv_rn(static_cast<float>(iw_n), static_cast<float>(ow_n));
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int w = static_cast<int>(i % ow_n);
+    const int h = static_cast<int>((i / ow_n) % oh_n);
+    const long long p = i / (static_cast<long long>(ow_n) * oh_n);
+    const AxisTap th = axis_tap(__fmul_rn(static_cast<float>(h), ratio_h), ih_n);
+    const AxisTap tw = axis_tap(__fmul_rn(static_cast<float>(w), ratio_w), iw_n);
+    float val = 0.f;
+    if (th.ok && tw.ok) {
+      const float* b = in + p * ih_n * iw_n;
+      val = bilerp(th, tw, b[th.lo * iw_n + tw.lo], b[th.lo * iw_n + tw.hi],
+                   b[th.hi * iw_n + tw.lo], b[th.hi * iw_n + tw.hi]);
+    }
+    out[i] = val;
+  }
+}
+
+// top[n,c,h,w] = feat[n,c,h,w] * mask[n,0,h,w]; 16-byte streaming loads/stores when hw % 4 == 0.
+__global__ void mask_pool_nchw_kernel(const float* __restrict__ feat,
+                                      const float* __restrict__ mask, int N, int C, int hw,
+                                      float* __restrict__ out) {
+  const long long total4 = static_cast<long long>(N) * C * hw / 4;
+  const int hw4 = hw / 4;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int q = static_cast<int>(i % hw4);
+    const long long n = i / (static_cast<long long>(hw4) * C);
+    const float4 f = __ldcs(reinterpret_cast<const float4*>(feat) + i);
+    const float4 m = __ldg(reinterpret_cast<const float4*>(mask) + n * hw4 + q);
+    __stcs(reinterpret_cast<float4*>(out) + i,
+           make_float4(__fmul_rn(f.x, m.x), __fmul_rn(f.y, m.y), __fmul_rn(f.z, m.z),
+                       __fmul_rn(f.w, m.w)));
+  }
+}
+__global__ void mask_pool_nchw_scalar_kernel(const float* __restrict__ feat,
+                                             const float* __restrict__ mask, int N, int C, int hw,
+                                             float* __restrict__ out) {
+  const long long total = static_cast<long long>(N) * C * hw;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int q = static_cast<int>(i % hw);
+    const long long n = i / (static_cast<long long>(hw) * C);
+    out[i] = __fmul_rn(feat[i], mask[n * hw + q]);
+  }
+}
+
+// ------------------------------------------------------------ fused forms on split-bf16 NHWC
+__device__ __forceinline__ float2 ld_split2(const __nv_bfloat16* hi, const __nv_bfloat16* lo,
+                                            long long off) {
+  const uint32_t h = __ldg(reinterpret_cast<const uint32_t*>(hi + off));
+  const uint32_t l = __ldg(reinterpret_cast<const uint32_t*>(lo + off));
+  float2 r;
+  r.x = __uint_as_float(h << 16) + __uint_as_float(l << 16);
+  r.y = __uint_as_float(h & 0xffff0000u) + __uint_as_float(l & 0xffff0000u);
+  return r;
+}
+__device__ __forceinline__ void st_split2(__nv_bfloat16* hi, __nv_bfloat16* lo, long long off,
+                                          float a, float b) {
+  const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
+  const __nv_bfloat16 la = __float2bfloat16_rn(a - __bfloat162float(ha));
+  const __nv_bfloat16 lb = __float2bfloat16_rn(b - __bfloat162float(hb));
+  *reinterpret_cast<uint32_t*>(hi + off) =
+      static_cast<uint32_t>(__bfloat16_as_ushort(ha)) | (static_cast<uint32_t>(__bfloat16_as_ushort(hb)) << 16);
+  *reinterpret_cast<uint32_t*>(lo + off) =
+      static_cast<uint32_t>(__bfloat16_as_ushort(la)) | (static_cast<uint32_t>(__bfloat16_as_ushort(lb)) << 16);
+}
+
+// One CTA per (RoI, pair of 14x14 output rows).  SUB = 2: warp to 28x28 and take the 2x2 max
+// (stage 1, test.prototxt:479-505); SUB = 1: warp straight to 14x14 (stage 2, :809-820).
+// Also emits the 7x7 box-branch pool (test.prototxt:571-582).  Threads run over channel pairs.
+template <int SUB>
+__global__ void __launch_bounds__(256)
+roi_warp_split_kernel(const __nv_bfloat16* __restrict__ f_hi, const __nv_bfloat16* __restrict__ f_lo,
+                      int C, int H, int W, const float* __restrict__ rois, float spatial_scale,
+                      __nv_bfloat16* __restrict__ o14_hi, __nv_bfloat16* __restrict__ o14_lo,
+                      __nv_bfloat16* __restrict__ o7_hi, __nv_bfloat16* __restrict__ o7_lo) {
+  constexpr int P = 14 * SUB;
+  const int r = blockIdx.x;
+  const int t = blockIdx.y;  // rows 2t, 2t+1 of the 14x14 grid
+  const RoiGeom g = roi_geom(rois + static_cast<long long>(r) * 5, spatial_scale, P, P);
+  const long long img_off = static_cast<long long>(g.level) * H * W * C;
+  for (int c = threadIdx.x * 2; c < C; c += blockDim.x * 2) {
+    for (int jp = 0; jp < 7; ++jp) {
+      float2 best7 = make_float2(-3.402823466e+38f, -3.402823466e+38f);
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy) {
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const int i = 2 * t + dy, j = 2 * jp + dx;
+          float2 cell = make_float2(-3.402823466e+38f, -3.402823466e+38f);
+#pragma unroll
+          for (int sy = 0; sy < SUB; ++sy) {
+            const int ph = i * SUB + sy;
+            const AxisTap th = axis_tap(__fadd_rn(g.start_h, __fmul_rn(static_cast<float>(ph), g.bin_h)), H);
+#pragma unroll
+            for (int sx = 0; sx < SUB; ++sx) {
+              const int pw = j * SUB + sx;
+              const AxisTap tw = axis_tap(__fadd_rn(g.start_w, __fmul_rn(static_cast<float>(pw), g.bin_w)), W);
+              float2 v = make_float2(0.f, 0.f);
+              if (th.ok && tw.ok) {
+                const long long b = img_off + c;
+                const float2 v1 = ld_split2(f_hi, f_lo, b + (static_cast<long long>(th.lo) * W + tw.lo) * C);
+                const float2 v2 = ld_split2(f_hi, f_lo, b + (static_cast<long long>(th.lo) * W + tw.hi) * C);
+                const float2 v3 = ld_split2(f_hi, f_lo, b + (static_cast<long long>(th.hi) * W + tw.lo) * C);
+                const float2 v4 = ld_split2(f_hi, f_lo, b + (static_cast<long long>(th.hi) * W + tw.hi) * C);
+                v.x = bilerp(th, tw, v1.x, v2.x, v3.x, v4.x);
+                v.y = bilerp(th, tw, v1.y, v2.y, v3.y, v4.y);
+              }
+              cell.x = fmaxf(cell.x, v.x);
+              cell.y = fmaxf(cell.y, v.y);
+            }
+          }
+          st_split2(o14_hi, o14_lo, ((static_cast<long long>(r) * 14 + i) * 14 + j) * C + c, cell.x, cell.y);
+          best7.x = fmaxf(best7.x, cell.x);
+          best7.y = fmaxf(best7.y, cell.y);
+        }
+      }
+      st_split2(o7_hi, o7_lo, ((static_cast<long long>(r) * 7 + t) * 7 + jp) * C + c, best7.x, best7.y);
+    }
+  }
+}
+
+// sigmoid (sigmoid_layer.cu:10-14) -> mask_proposal (R,1,M,M) -> MaskResize to (R,1,14,14).
+// One CTA per RoI; logits row stride given.
+__global__ void __launch_bounds__(256)
+sigmoid_resize_kernel(const float* __restrict__ logits, int stride, int M, int O,
+                      float* __restrict__ mask_proposal, float* __restrict__ mask_resized) {
+  extern __shared__ float sm[];  // M*M
+  const int r = blockIdx.x;
+  const float* x = logits + static_cast<long long>(r) * stride;
+  for (int i = threadIdx.x; i < M * M; i += blockDim.x) {
+    const float s = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-x[i])));
+    sm[i] = s;
+    mask_proposal[static_cast<long long>(r) * M * M + i] = s;
+  }
+  __syncthreads();
+  const float ratio = __fdiv_rn(static_cast<float>(M), static_cast<float>(O));
+  for (int i = threadIdx.x; i < O * O; i += blockDim.x) {
+    const int h = i / O, w = i % O;
+    const AxisTap th = axis_tap(__fmul_rn(static_cast<float>(h), ratio), M);
+    const AxisTap tw = axis_tap(__fmul_rn(static_cast<float>(w), ratio), M);
+    float val = 0.f;
+    if (th.ok && tw.ok)
+      val = bilerp(th, tw, sm[th.lo * M + tw.lo], sm[th.lo * M + tw.hi], sm[th.hi * M + tw.lo],
+                   sm[th.hi * M + tw.hi]);
+    mask_resized[static_cast<long long>(r) * O * O + i] = val;
+  }
+}
+
+// MaskPooling + 2x2 max pool on split NHWC: out7[r][t][j][c] = max_{dy,dx} feat14*mask14.
+__global__ void __launch_bounds__(256)
+mask_pool_split_kernel(const __nv_bfloat16* __restrict__ f_hi, const __nv_bfloat16* __restrict__ f_lo,
+                       const float* __restrict__ mask14, int C, __nv_bfloat16* __restrict__ o_hi,
+                       __nv_bfloat16* __restrict__ o_lo) {
+  const int r = blockIdx.x, t = blockIdx.y;
+  __shared__ float m[2][14];
+  if (threadIdx.x < 28)
+    m[threadIdx.x / 14][threadIdx.x % 14] =
+        mask14[static_cast<long long>(r) * 196 + (2 * t + threadIdx.x / 14) * 14 + threadIdx.x % 14];
+  __syncthreads();
+  for (int c = threadIdx.x * 2; c < C; c += blockDim.x * 2) {
+    for (int jp = 0; jp < 7; ++jp) {
+      float2 best = make_float2(-3.402823466e+38f, -3.402823466e+38f);
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const int i = 2 * t + dy, j = 2 * jp + dx;
+          const float2 f = ld_split2(f_hi, f_lo, ((static_cast<long long>(r) * 14 + i) * 14 + j) * C + c);
+          const float mk = m[dy][j];
+          best.x = fmaxf(best.x, __fmul_rn(f.x, mk));
+          best.y = fmaxf(best.y, __fmul_rn(f.y, mk));
+        }
+      st_split2(o_hi, o_lo, ((static_cast<long long>(r) * 7 + t) * 7 + jp) * C + c, best.x, best.y);
+    }
+  }
+}
+
+static inline int check_launch() { return cudaGetLastError() == cudaSuccess ? MNC_OK : MNC_ERR_CUDA; }
+static inline int grid_for(long long n, int block, int cap) {
+  long long g = (n + block - 1) / block;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+}  // namespace mnc
+
+using namespace mnc;
+
+extern "C" int mnc_roi_warp_nchw(const float* feat, int C, int H, int W, const float* rois, int R,
+                                 int pooled_h, int pooled_w, float spatial_scale, float* out,
+                                 void* stream) {
+  if (R <= 0) return MNC_OK;
+  if (pooled_h > kMaxPooled || pooled_w > kMaxPooled || pooled_h <= 0 || pooled_w <= 0)
+    return MNC_ERR_ARG;
+  const int smem = kWarpSlab * H * W * static_cast<int>(sizeof(float));
+  if (smem > 200 * 1024) return MNC_ERR_ARG;
+  static int attr_smem = 0;
+  if (smem > attr_smem) {
+    if (cudaFuncSetAttribute(roi_warp_nchw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             smem) != cudaSuccess)
+      return MNC_ERR_CUDA;
+    attr_smem = smem;
+  }
+  dim3 grid(R, (C + kWarpSlab - 1) / kWarpSlab);
+  roi_warp_nchw_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      feat, C, H, W, rois, pooled_h, pooled_w, spatial_scale, out);
+  return check_launch();
+}
+
+extern "C" int mnc_mask_resize_nchw(const float* in, int N, int C, int in_h, int in_w, int out_h,
+                                    int out_w, float* out, void* stream) {
+  const long long total = static_cast<long long>(N) * C * out_h * out_w;
+  if (total <= 0) return MNC_OK;
+  mask_resize_nchw_kernel<<<grid_for(total, 256, 148 * 8), 256, 0,
+                            static_cast<cudaStream_t>(stream)>>>(in, N * C, in_h, in_w, out_h,
+                                                                 out_w, out);
+  return check_launch();
+}
+
+extern "C" int mnc_mask_pool_nchw(const float* feat, const float* mask, int N, int C, int H, int W,
+                                  float* out, void* stream) {
+  const long long total = static_cast<long long>(N) * C * H * W;
+  if (total <= 0) return MNC_OK;
+  const int hw = H * W;
+  const bool vec = (hw % 4 == 0) && ((reinterpret_cast<uintptr_t>(feat) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(mask) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  if (vec)
+    mask_pool_nchw_kernel<<<grid_for(total / 4, 256, 148 * 16), 256, 0,
+                            static_cast<cudaStream_t>(stream)>>>(feat, mask, N, C, hw, out);
+  else
+    mask_pool_nchw_scalar_kernel<<<grid_for(total, 256, 148 * 16), 256, 0,
+                                   static_cast<cudaStream_t>(stream)>>>(feat, mask, N, C, hw, out);
+  return check_launch();
+}
+
+extern "C" int mnc_roi_warp_split(const void* f_hi, const void* f_lo, int C, int H, int W,
+                                  const float* rois, int R, int sub, float spatial_scale,
+                                  void* o14_hi, void* o14_lo, void* o7_hi, void* o7_lo,
+                                  void* stream) {
+  if (R <= 0) return MNC_OK;
+  if (C % 2 != 0 || (sub != 1 && sub != 2)) return MNC_ERR_ARG;
+  dim3 grid(R, 7);
+  auto s = static_cast<cudaStream_t>(stream);
+  if (sub == 2)
+    roi_warp_split_kernel<2><<<grid, 256, 0, s>>>(
+        static_cast<const __nv_bfloat16*>(f_hi), static_cast<const __nv_bfloat16*>(f_lo), C, H, W,
+        rois, spatial_scale, static_cast<__nv_bfloat16*>(o14_hi),
+        static_cast<__nv_bfloat16*>(o14_lo), static_cast<__nv_bfloat16*>(o7_hi),
+        static_cast<__nv_bfloat16*>(o7_lo));
+  else
+    roi_warp_split_kernel<1><<<grid, 256, 0, s>>>(
+        static_cast<const __nv_bfloat16*>(f_hi), static_cast<const __nv_bfloat16*>(f_lo), C, H, W,
+        rois, spatial_scale, static_cast<__nv_bfloat16*>(o14_hi),
+        static_cast<__nv_bfloat16*>(o14_lo), static_cast<__nv_bfloat16*>(o7_hi),
+        static_cast<__nv_bfloat16*>(o7_lo));
+  return check_launch();
+}
+
+extern "C" int mnc_sigmoid_mask_resize(const float* logits, int stride, int R, int mask_size,
+                                       int out_size, float* mask_proposal, float* mask_resized,
+                                       void* stream) {
+  if (R <= 0) return MNC_OK;
+  sigmoid_resize_kernel<<<R, 256, mask_size * mask_size * sizeof(float),
+                          static_cast<cudaStream_t>(stream)>>>(logits, stride, mask_size, out_size,
+                                                               mask_proposal, mask_resized);
+  return check_launch();
+}
+
+extern "C" int mnc_mask_pool_split(const void* f_hi, const void* f_lo, const float* mask14, int R,
+                                   int C, void* o_hi, void* o_lo, void* stream) {
+  if (R <= 0) return MNC_OK;
+  if (C % 2 != 0) return MNC_ERR_ARG;
+  dim3 grid(R, 7);
+  mask_pool_split_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(f_hi), static_cast<const __nv_bfloat16*>(f_lo), mask14, C,
+      static_cast<__nv_bfloat16*>(o_hi), static_cast<__nv_bfloat16*>(o_lo));
+  return check_launch();
+}

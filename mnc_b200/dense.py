@@ -36,6 +36,22 @@ def fc_weight_to_split(w, chw=None):
     return split(w)
 
 
+class KernelTimer:
+    """Optional per-launch CUDA-event timing of the implicit-GEMM kernel (bench.py's roofline):
+    events are recorded on the launching stream around every igemm launch, together with the
+    launch's algorithmic FLOPs (2*M*N*K on the real, unpadded dims)."""
+
+    def __init__(self):
+        self.records = []   # (start_event, end_event, flops, tag)
+
+    def totals(self):
+        ms = sum(s.elapsed_time(e) for s, e, _, _ in self.records)
+        return ms, sum(f for _, _, f, _ in self.records), len(self.records)
+
+
+timer = None  # set to a KernelTimer to enable
+
+
 def igemm(a, batch, H, W, cin, w, cout, taps, bias=None, relu=False, out=None, out_f32=None,
           out_pix_stride=None, out_ch_offset=0, split_k=1, split_stride=0, bn=0, max_ctas=0,
           impl="tc"):
@@ -48,6 +64,10 @@ def igemm(a, batch, H, W, cin, w, cout, taps, bias=None, relu=False, out=None, o
     else:
         mode, o0, o1 = 0, out[0], out[1]
         stride = out_pix_stride if out_pix_stride is not None else cout
+    if timer is not None and impl == "tc":
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ev1 = torch.cuda.Event(enable_timing=True)
+        ev0.record()
     if impl == "tc":
         rc = lib.mnc_igemm_tc(ptr(a[0]), ptr(a[1]), c_int(batch), c_int(H), c_int(W), c_int(cin),
                               ptr(w[0]), ptr(w[1]), c_int(cout), c_int(taps), ptr(bias),
@@ -55,6 +75,10 @@ def igemm(a, batch, H, W, cin, w, cout, taps, bias=None, relu=False, out=None, o
                               c_int(out_ch_offset), c_int(split_k), c_ll(split_stride), c_int(bn),
                               c_int(max_ctas), cur_stream())
         check(rc, "mnc_igemm_tc")
+        if timer is not None:
+            ev1.record()
+            timer.records.append((ev0, ev1, 2.0 * batch * H * W * cout * taps * cin,
+                                  "%dx%dx%d" % (batch * H * W, cout, taps * cin)))
     else:
         assert split_k == 1
         rc = lib.mnc_igemm_simt(ptr(a[0]), ptr(a[1]), c_int(batch), c_int(H), c_int(W),

@@ -1,0 +1,14 @@
+"""nms.nms_wrapper -- reference lib/nms/nms_wrapper.py:13-21."""
+from mnc_config import cfg
+from nms.gpu_nms import gpu_nms
+
+
+def nms(dets, thresh):
+    """Dispatch to the GPU NMS (cfg.USE_GPU_NMS, lib/mnc_config.py:16).  The reference's CPU
+    variant uses a different comparison (IoU >= thresh, lib/nms/cpu_nms.pyx:65), is not on the
+    path, and is deliberately not provided: there is no CPU fallback."""
+    if dets.shape[0] == 0:
+        return []
+    if cfg.USE_GPU_NMS:
+        return gpu_nms(dets, thresh, device_id=cfg.GPU_ID)
+    raise NotImplementedError("cpu_nms is out of scope (different semantics, no CPU fallback)")

@@ -1,0 +1,275 @@
+"""Device-tensor wrappers over the non-dense C-ABI entry points (include/mnc_b200.h).
+
+All arguments are CUDA torch tensors; everything is launched on torch's current stream.  PyTorch is
+only the allocator / stream provider here: every computation happens in libmnc_b200.so.
+"""
+import ctypes
+
+import torch
+
+from ._lib import lib, ptr, cur_stream, check, c_int, c_ll, c_float
+
+c_double = ctypes.c_double
+lib.mnc_nms_workspace_bytes.restype = ctypes.c_longlong
+
+
+def _i32(*shape, device):
+    return torch.empty(shape, dtype=torch.int32, device=device)
+
+
+# ----------------------------------------------------------------------------- sort / NMS
+def rank_sort_desc(keys, n, problems, outer_stride, inner_stride=0, inner=1, key_stride=1,
+                   valid=None):
+    """-> (order int32 [problems, n], n_valid int32 [problems])."""
+    dev = keys.device
+    order = _i32(problems, n, device=dev)
+    n_valid = _i32(problems, device=dev)
+    check(lib.mnc_rank_sort_desc(ptr(keys), c_ll(outer_stride), c_ll(inner_stride), c_int(inner),
+                                 c_int(key_stride), ptr(valid), c_int(n), c_int(problems),
+                                 ptr(order), ptr(n_valid), cur_stream()), "mnc_rank_sort_desc")
+    return order, n_valid
+
+
+def gather_boxes(src, src_stride, src_outer_stride, inner, order, counts, n_out, problems):
+    """-> (sorted boxes fp32 [problems, n_out, 4], counts int32 [problems])."""
+    dev = src.device
+    dst = torch.zeros((problems, n_out, 4), dtype=torch.float32, device=dev)
+    out_counts = _i32(problems, device=dev)
+    check(lib.mnc_gather_boxes(ptr(src), c_int(src_stride), c_ll(src_outer_stride), c_int(inner),
+                               ptr(order), c_int(order.shape[1]), ptr(counts), c_int(n_out),
+                               c_int(problems), ptr(dst), ptr(out_counts), cur_stream()),
+          "mnc_gather_boxes")
+    return dst, out_counts
+
+
+_nms_ws = {}
+
+
+def nms_sorted(boxes, counts, thresh, max_keep):
+    """boxes fp32 [problems, n_max, 4] score-sorted; counts int32 [problems] or None.
+    -> (keep int32 [problems, max_keep], num int32 [problems])."""
+    problems, n_max, stride = boxes.shape
+    dev = boxes.device
+    nbytes = lib.mnc_nms_workspace_bytes(c_int(n_max), c_int(problems))
+    key = (dev, nbytes)
+    ws = _nms_ws.get(key)
+    if ws is None:
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _nms_ws.clear()
+        _nms_ws[key] = ws
+    mk = max_keep if max_keep > 0 else n_max
+    keep = _i32(problems, mk, device=dev)
+    num = _i32(problems, device=dev)
+    check(lib.mnc_nms_sorted(ptr(boxes), c_int(stride), c_ll(n_max * stride), ptr(counts),
+                             c_int(n_max), c_int(problems), c_float(thresh), c_int(mk), ptr(ws),
+                             ptr(keep), c_int(mk), ptr(num), cur_stream()), "mnc_nms_sorted")
+    return keep, num
+
+
+# ----------------------------------------------------------------------------- proposal pieces
+def generate_anchors():
+    import numpy as np
+    out = np.zeros((9, 4), dtype=np.float32)
+    check(lib.mnc_generate_anchors(ptr(out)), "mnc_generate_anchors")
+    return out
+
+
+def rpn_decode(cls, bbox, im_info, batch, H, W, layout, apply_softmax, feat_stride=16,
+               min_size=16.0):
+    """layout 'nchw': cls (B,18,H,W), bbox (B,36,H,W); 'nhwc': one buffer (B,H,W,Cpad) where
+    channels [0,18) are cls and [18,54) bbox (then `bbox` is ignored)."""
+    dev = cls.device
+    total = H * W * 9
+    proposals = torch.empty((batch, total, 4), dtype=torch.float32, device=dev)
+    scores = torch.empty((batch, total), dtype=torch.float32, device=dev)
+    valid = torch.empty((batch, total), dtype=torch.uint8, device=dev)
+    if layout == "nchw":
+        ci, cc, cp = 18 * H * W, H * W, 1
+        bi, bc, bp = 36 * H * W, H * W, 1
+        bptr = ptr(bbox)
+    else:
+        cpad = cls.shape[-1]
+        ci, cc, cp = H * W * cpad, 1, cpad
+        bi, bc, bp = ci, cc, cp
+        bptr = ctypes.c_void_p(cls.data_ptr() + 18 * 4)
+    check(lib.mnc_rpn_decode(ptr(cls), c_ll(ci), c_ll(cc), c_ll(cp), bptr, c_ll(bi), c_ll(bc),
+                             c_ll(bp), ptr(im_info), c_int(batch), c_int(H), c_int(W),
+                             c_int(feat_stride), c_float(min_size), c_int(int(apply_softmax)),
+                             ptr(proposals), ptr(scores), ptr(valid), cur_stream()),
+          "mnc_rpn_decode")
+    return proposals, scores, valid
+
+
+def write_rois(sorted_boxes, keep, num_keep, max_rois, batch_index_mode):
+    batch, n_sorted, _ = sorted_boxes.shape
+    dev = sorted_boxes.device
+    rois = torch.empty((batch, max_rois, 5), dtype=torch.float32, device=dev)
+    counts = _i32(batch, device=dev)
+    check(lib.mnc_write_rois(ptr(sorted_boxes), c_int(n_sorted), ptr(keep), c_int(keep.shape[1]),
+                             ptr(num_keep), c_int(max_rois), c_int(batch),
+                             c_int(int(batch_index_mode)), ptr(rois), ptr(counts), cur_stream()),
+          "mnc_write_rois")
+    return rois, counts
+
+
+def proposals_from_rpn(cls, bbox, im_info, batch, H, W, layout, apply_softmax, pre_nms_top_n=6000,
+                       post_nms_top_n=300, nms_thresh=0.7, min_size=16.0, batch_index_mode=True,
+                       return_intermediate=False):
+    """Whole ProposalLayer.forward on device (lib/pylayer/proposal_layer.py:52-175)."""
+    proposals, scores, valid = rpn_decode(cls, bbox, im_info, batch, H, W, layout, apply_softmax,
+                                          min_size=min_size)
+    total = H * W * 9
+    order, n_valid = rank_sort_desc(scores, total, batch, outer_stride=total, valid=valid)
+    n_sorted = min(pre_nms_top_n, total) if pre_nms_top_n > 0 else total
+    sorted_boxes, counts = gather_boxes(proposals, 4, total * 4, 1, order, n_valid, n_sorted, batch)
+    keep, num = nms_sorted(sorted_boxes, counts, nms_thresh, post_nms_top_n)
+    rois, roi_counts = write_rois(sorted_boxes, keep, num, post_nms_top_n, batch_index_mode)
+    if return_intermediate:
+        return rois, roi_counts, dict(proposals=proposals, scores=scores, valid=valid, order=order,
+                                      n_valid=n_valid, sorted_boxes=sorted_boxes, counts=counts,
+                                      keep=keep, num=num)
+    return rois, roi_counts
+
+
+def stage_bridge(rois, bbox_pred, seg_cls_prob, im_info, rois_per_img):
+    """rois [T,5], bbox_pred [T,>=84] (row stride = bbox_pred.stride(0)), seg_cls_prob [T,21]."""
+    total = rois.shape[0]
+    out = torch.empty_like(rois)
+    check(lib.mnc_stage_bridge(ptr(rois), ptr(bbox_pred), c_int(bbox_pred.stride(0)),
+                               ptr(seg_cls_prob), c_int(seg_cls_prob.stride(0)),
+                               c_int(seg_cls_prob.shape[1]), ptr(im_info), c_int(rois_per_img),
+                               c_int(total), ptr(out), cur_stream()), "mnc_stage_bridge")
+    return out
+
+
+def softmax_rows(x, cols=None, out=None):
+    rows = x.shape[0]
+    cols = cols or x.shape[1]
+    if out is None:
+        out = torch.empty((rows, cols), dtype=torch.float32, device=x.device)
+    check(lib.mnc_softmax_rows(ptr(x), c_int(x.stride(0)), c_int(rows), c_int(cols), ptr(out),
+                               c_int(out.stride(0)), cur_stream()), "mnc_softmax_rows")
+    return out
+
+
+def unscale_clip(rois, rois_per_img, im_scale, im_hw):
+    total = rois.shape[0]
+    boxes = torch.empty((total, 4), dtype=torch.float32, device=rois.device)
+    check(lib.mnc_unscale_clip(ptr(rois), c_int(total), c_int(rois_per_img), ptr(im_scale),
+                               ptr(im_hw), ptr(boxes), cur_stream()), "mnc_unscale_clip")
+    return boxes
+
+
+# ----------------------------------------------------------------------------- RoI / mask layers
+def roi_warp_nchw(feat, rois, pooled_h, pooled_w, spatial_scale=0.0625, out=None):
+    B, C, H, W = feat.shape
+    R = rois.shape[0]
+    if out is None:
+        out = torch.empty((R, C, pooled_h, pooled_w), dtype=torch.float32, device=feat.device)
+    check(lib.mnc_roi_warp_nchw(ptr(feat), c_int(C), c_int(H), c_int(W), ptr(rois), c_int(R),
+                                c_int(pooled_h), c_int(pooled_w), c_float(spatial_scale), ptr(out),
+                                cur_stream()), "mnc_roi_warp_nchw")
+    return out
+
+
+def mask_resize_nchw(x, out_h, out_w):
+    N, C, ih, iw = x.shape
+    out = torch.empty((N, C, out_h, out_w), dtype=torch.float32, device=x.device)
+    check(lib.mnc_mask_resize_nchw(ptr(x), c_int(N), c_int(C), c_int(ih), c_int(iw), c_int(out_h),
+                                   c_int(out_w), ptr(out), cur_stream()), "mnc_mask_resize_nchw")
+    return out
+
+
+def mask_pool_nchw(feat, mask, out=None):
+    N, C, H, W = feat.shape
+    if mask.shape != (N, 1, H, W):
+        raise ValueError("MaskPooling: mask must be (N,1,H,W) matching feat "
+                         "(mask_pooling_layer.cpp:20-29)")
+    if out is None:
+        out = torch.empty_like(feat)
+    check(lib.mnc_mask_pool_nchw(ptr(feat), ptr(mask), c_int(N), c_int(C), c_int(H), c_int(W),
+                                 ptr(out), cur_stream()), "mnc_mask_pool_nchw")
+    return out
+
+
+def roi_warp_split(feat, C, H, W, rois, sub, out14, out7, spatial_scale=0.0625):
+    """feat split [2,B,H,W,C]; rois [R,5]; out14 split [2,R,14,14,C]; out7 split [2,R,7,7,C]."""
+    R = rois.shape[0]
+    check(lib.mnc_roi_warp_split(ptr(feat[0]), ptr(feat[1]), c_int(C), c_int(H), c_int(W),
+                                 ptr(rois), c_int(R), c_int(sub), c_float(spatial_scale),
+                                 ptr(out14[0]), ptr(out14[1]), ptr(out7[0]), ptr(out7[1]),
+                                 cur_stream()), "mnc_roi_warp_split")
+
+
+def sigmoid_mask_resize(logits, R, mask_size=21, out_size=14):
+    dev = logits.device
+    mp = torch.empty((R, 1, mask_size, mask_size), dtype=torch.float32, device=dev)
+    mr = torch.empty((R, 1, out_size, out_size), dtype=torch.float32, device=dev)
+    check(lib.mnc_sigmoid_mask_resize(ptr(logits), c_int(logits.stride(0)), c_int(R),
+                                      c_int(mask_size), c_int(out_size), ptr(mp), ptr(mr),
+                                      cur_stream()), "mnc_sigmoid_mask_resize")
+    return mp, mr
+
+
+def mask_pool_split(feat14, mask14, R, C, out7):
+    check(lib.mnc_mask_pool_split(ptr(feat14[0]), ptr(feat14[1]), ptr(mask14), c_int(R), c_int(C),
+                                  ptr(out7[0]), ptr(out7[1]), cur_stream()), "mnc_mask_pool_split")
+
+
+# ----------------------------------------------------------------------------- mask voting
+class VotingOverflow(RuntimeError):
+    pass
+
+
+def mask_voting(boxes, masks, scores, im_hw, max_per_image=100, nms_thresh=0.3, iou_thresh=0.5,
+                max_results=128, box_valid=None):
+    """Batched device pipeline of gpu_mask_voting (lib/transform/mask_transform.py:213-286).
+    boxes [B,nb,4] fp32, masks [B,nb,1,M,M] fp32, scores [B,nb,ncls] fp32, im_hw [B,2] int32.
+    box_valid: optional uint8 [B,nb]; rows with 0 are padding and take no part.
+    Returns dict of device tensors: n_res [B], class_bar [B,ncls-1], res_score [B,max_results],
+    res_class, result_mask [B,max_results,1,M,M], result_box [B,max_results,4] int32, plus the
+    candidate lists."""
+    B, nb, ncls = scores.shape
+    M = masks.shape[-1]
+    dev = boxes.device
+    nprob = B * (ncls - 1)
+    # per-class score sort: problem p = (img, c-1); keys at scores[img, :, c]
+    valid_p = None
+    if box_valid is not None:
+        valid_p = box_valid.view(B, 1, nb).expand(B, ncls - 1, nb).contiguous()
+    order, n_valid = rank_sort_desc(scores[:, :, 1:], nb, nprob, outer_stride=nb * ncls,
+                                    inner_stride=1, inner=ncls - 1, key_stride=ncls, valid=valid_p)
+    sorted_boxes, counts = gather_boxes(boxes, 4, nb * 4, ncls - 1, order, n_valid, nb, nprob)
+    keep, num = nms_sorted(sorted_boxes, counts, nms_thresh, min(max_per_image, nb))
+    res_idx = _i32(B, max_results, device=dev)
+    res_cls = _i32(B, max_results, device=dev)
+    res_score = torch.zeros((B, max_results), dtype=torch.float32, device=dev)
+    n_res = _i32(B, device=dev)
+    class_bar = _i32(B, ncls - 1, device=dev)
+    overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+    check(lib.mnc_vote_select(ptr(scores), c_int(nb), c_int(ncls), ptr(order), ptr(keep),
+                              c_int(keep.shape[1]), ptr(num), c_int(max_per_image),
+                              c_int(max_results), c_int(B), ptr(res_idx), ptr(res_cls),
+                              ptr(res_score), ptr(n_res), ptr(class_bar), ptr(overflow),
+                              cur_stream()), "mnc_vote_select")
+    cand_inds = _i32(B, max_results, nb, device=dev)
+    cand_w = torch.empty((B, max_results, nb), dtype=torch.float32, device=dev)
+    cand_begin = _i32(B, max_results, device=dev)
+    cand_end = _i32(B, max_results, device=dev)
+    check(lib.mnc_vote_candidates(ptr(boxes), ptr(scores), ptr(box_valid), c_int(nb), c_int(ncls),
+                                  ptr(res_idx),
+                                  ptr(res_cls), ptr(n_res), c_int(max_results), c_int(B),
+                                  c_double(iou_thresh), ptr(cand_inds), ptr(cand_w),
+                                  ptr(cand_begin), ptr(cand_end), cur_stream()),
+          "mnc_vote_candidates")
+    bbox_ws = _i32(B, max_results, 4, device=dev)
+    out_mask = torch.zeros((B, max_results, 1, M, M), dtype=torch.float32, device=dev)
+    out_box = torch.zeros((B, max_results, 4), dtype=torch.int32, device=dev)
+    check(lib.mnc_mv_device(ptr(boxes), ptr(masks), c_int(nb), c_int(4), c_int(M), ptr(cand_inds),
+                            ptr(cand_w), c_ll(max_results * nb), ptr(cand_begin), ptr(cand_end),
+                            ptr(n_res), c_int(max_results), c_int(B), ptr(im_hw), ptr(bbox_ws),
+                            ptr(out_mask), ptr(out_box), cur_stream()), "mnc_mv_device")
+    return dict(n_res=n_res, class_bar=class_bar, res_score=res_score, res_class=res_cls,
+                res_box_idx=res_idx, result_mask=out_mask, result_box=out_box,
+                cand_inds=cand_inds, cand_weights=cand_w, cand_begin=cand_begin, cand_end=cand_end,
+                overflow=overflow, order=order, keep=keep, num_keep=num)

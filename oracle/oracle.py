@@ -412,55 +412,11 @@ def gpu_mask_voting(masks, boxes, scores, num_classes, max_per_image, im_width, 
 
 
 # --------------------------------------------------------------------------- network
-FULL_ARCH = dict(trunk=[64, 64, 128, 128, 256, 256, 256, 512, 512, 512, 512, 512, 512],
-                 rpn=512, fc=4096, maskest=256)
-# same graph, narrow layers: lets the CPU oracle run end to end in ~a second for parity tests
-TINY_ARCH = dict(trunk=[64, 64, 64, 64, 64, 64, 64, 64, 64, 64, 64, 64, 64],
-                 rpn=64, fc=256, maskest=64)
 TRUNK_NAMES = ["conv1_1", "conv1_2", "conv2_1", "conv2_2", "conv3_1", "conv3_2", "conv3_3",
                "conv4_1", "conv4_2", "conv4_3", "conv5_1", "conv5_2", "conv5_3"]
 POOL_AFTER = {"conv1_2", "conv2_2", "conv3_3", "conv4_3"}
-
-
-def make_weights(arch=None, seed=2016):
-    """Seeded random-init weights keyed by Caffe layer/param names (test.prototxt has fillers only
-    for the RPN layers, :401-402,422-423,436-437): conv & FC weights
-    N(0, sqrt(2/fan_in)), biases 0; RPN weights N(0, 0.01), biases 0.  `_ext` layers share weights
-    (test.prototxt:829-834 etc.).  Returns {name: (weight fp32 ndarray/torch tensor, bias)}."""
-    import torch
-    arch = arch or FULL_ARCH
-    g = torch.Generator().manual_seed(seed)
-    w = {}
-
-    def he(shape, fan_in):
-        return torch.randn(shape, generator=g) * (2.0 / fan_in) ** 0.5
-
-    cin = 3
-    for name, cout in zip(TRUNK_NAMES, arch["trunk"]):
-        wt = he((cout, cin, 3, 3), cin * 9)
-        if name == "conv1_1":
-            # mean-subtracted pixels are O(70) RMS; bring activations to O(1) like a trained net
-            # so softmax / sigmoid outputs are not saturated (saturation would hide errors)
-            wt = wt / 64.0
-        w[name] = (wt, torch.zeros(cout))
-        cin = cout
-    c5 = cin
-    r = arch["rpn"]
-    w["rpn_conv_3x3"] = (torch.randn((r, c5, 3, 3), generator=g) * 0.01, torch.zeros(r))
-    w["rpn_cls_score"] = (torch.randn((18, r, 1, 1), generator=g) * 0.01, torch.zeros(18))
-    w["rpn_bbox_pred"] = (torch.randn((36, r, 1, 1), generator=g) * 0.01, torch.zeros(36))
-    fc, me = arch["fc"], arch["maskest"]
-    w["fc6_maskest"] = (he((me, c5 * 14 * 14), c5 * 14 * 14), torch.zeros(me))
-    w["mask_pred"] = (he((441, me), me), torch.zeros(441))
-    w["fc6"] = (he((fc, c5 * 7 * 7), c5 * 7 * 7), torch.zeros(fc))
-    w["fc7"] = (he((fc, fc), fc), torch.zeros(fc))
-    w["fc6_mask"] = (he((fc, c5 * 7 * 7), c5 * 7 * 7), torch.zeros(fc))
-    w["fc7_mask"] = (he((fc, fc), fc), torch.zeros(fc))
-    w["cls_score"] = (he((21, 2 * fc), 2 * fc), torch.zeros(21))
-    w["seg_cls_score"] = (he((21, 2 * fc), 2 * fc), torch.zeros(21))
-    # bbox_pred deltas kept small so stage-2 boxes stay near stage-1 boxes (trained nets are too)
-    w["bbox_pred"] = (he((84, 2 * fc), 2 * fc) * 0.1, torch.zeros(84))
-    return w
+# Weights are data handed to the oracle by its caller: {caffe layer name: (weight, bias)} fp32
+# torch CPU tensors in Caffe layouts (conv (Cout,Cin,kh,kw); InnerProduct (N,K), K = (c,h,w)).
 
 
 def synthetic_image(i=0, height=600, width=1000):

@@ -1,0 +1,99 @@
+"""gpu_nms / `_nms` drop-in vs the oracle: keep lists must be bit-exact (BASELINE.json north_star)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _install():
+    import mnc_b200.lib as L
+    L.install()
+
+
+@pytest.mark.parametrize("n,thresh", [(1, 0.7), (63, 0.7), (64, 0.5), (65, 0.3), (600, 0.3),
+                                      (6000, 0.7), (10000, 0.7)])
+def test_nms_host_matches_oracle(n, thresh):
+    from oracle import oracle as O
+    from mnc_b200._lib import lib, check
+    boxes = util.random_boxes(n, seed=10 + n)
+    if n <= 6000:
+        boxes = util.nudge_off_threshold(boxes, thresh)
+    scores = util.tie_free_scores(n, seed=11)
+    dets = np.hstack([boxes, scores[:, None]]).astype(np.float32)
+    order = O.order_desc(scores)
+    sorted_dets = np.ascontiguousarray(dets[order])
+    want = O.nms_sorted(sorted_dets, thresh)
+    keep = np.zeros(n, dtype=np.int32)
+    num = ctypes.c_int(0)
+    check(lib.mnc_nms_host(keep.ctypes.data_as(ctypes.c_void_p), ctypes.byref(num),
+                           sorted_dets.ctypes.data_as(ctypes.c_void_p), n, 5,
+                           ctypes.c_float(thresh), 0), "mnc_nms_host")
+    got = keep[:num.value]
+    assert num.value == len(want)
+    assert np.array_equal(got, want)
+
+
+def test_gpu_nms_wrapper_matches_oracle_and_handles_empty():
+    _install()
+    from nms.nms_wrapper import nms
+    from oracle import oracle as O
+    assert nms(np.zeros((0, 5), dtype=np.float32), 0.7) == []
+    boxes = util.nudge_off_threshold(util.random_boxes(2000, seed=3), 0.7)
+    dets = np.hstack([boxes, util.tie_free_scores(2000, seed=4)[:, None]]).astype(np.float32)
+    got = nms(dets, 0.7)
+    want = O.gpu_nms(dets, 0.7)
+    assert [int(x) for x in got] == [int(x) for x in want]
+    with pytest.raises(ValueError):
+        nms(dets.astype(np.float64), 0.7)
+
+
+def test_nms_score_ties_follow_documented_rule():
+    """equal scores: (score desc, index asc)."""
+    _install()
+    from nms.gpu_nms import gpu_nms
+    from oracle import oracle as O
+    boxes = util.random_boxes(500, seed=5, integer=True)
+    scores = np.repeat(np.linspace(0.9, 0.1, 50), 10).astype(np.float32)
+    dets = np.hstack([boxes, scores[:, None]]).astype(np.float32)
+    assert [int(x) for x in gpu_nms(dets, 0.3)] == [int(x) for x in O.gpu_nms(dets, 0.3)]
+
+
+def test_batched_device_nms_with_counts_and_max_keep():
+    import torch
+    from mnc_b200 import ops
+    from oracle import oracle as O
+    P, n_max = 5, 700
+    counts = [700, 1, 0, 333, 64]
+    boxes = np.zeros((P, n_max, 4), dtype=np.float32)
+    for p in range(P):
+        boxes[p] = util.random_boxes(n_max, seed=100 + p, integer=True)
+    tb = torch.from_numpy(boxes).cuda()
+    tc = torch.tensor(counts, dtype=torch.int32).cuda()
+    keep, num = ops.nms_sorted(tb, tc, 0.3, 100)
+    keep, num = keep.cpu().numpy(), num.cpu().numpy()
+    for p in range(P):
+        want = O.nms_sorted(boxes[p, :counts[p]], 0.3)[:100]
+        assert num[p] == len(want)
+        assert np.array_equal(keep[p, :num[p]], want)
+
+
+def test_rank_sort_matches_tie_rule():
+    import torch
+    from mnc_b200 import ops
+    from oracle import oracle as O
+    rng = np.random.default_rng(0)
+    n = 5000
+    s = rng.integers(0, 300, size=(3, n)).astype(np.float32) / 300.0  # many ties
+    valid = (rng.uniform(size=(3, n)) > 0.2).astype(np.uint8)
+    order, nv = ops.rank_sort_desc(torch.from_numpy(s).cuda(), n, 3, outer_stride=n,
+                                   valid=torch.from_numpy(valid).cuda())
+    order, nv = order.cpu().numpy(), nv.cpu().numpy()
+    for p in range(3):
+        idx = np.where(valid[p])[0]
+        want = idx[O.order_desc(s[p, idx])]
+        assert nv[p] == len(idx)
+        assert np.array_equal(order[p, :nv[p]], want)

