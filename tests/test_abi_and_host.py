@@ -1,0 +1,170 @@
+"""CPU tests: the C-ABI library loads and exports every symbol the header declares (no compute
+calls without a GPU), and the host-side logic (prototxt reader, graph check, cfg, sharding,
+record packing, weight container, host bbox helpers)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "mnc_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = sorted(set(re.findall(r"\b(mnc_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 30
+    so = os.path.join(ROOT, "mnc_b200", "libmnc_b200.so")
+    assert os.path.exists(so), "build the library first: python -c 'import __graft_entry__ as g; g.build()'"
+    lib = ctypes.CDLL(so)
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    assert lib.mnc_abi_version() == 1
+
+
+def test_anchor_generator_in_library_matches_known_answer():
+    """host-only entry point (no kernel launch): lib/transform/anchors.py:15-35 minus one."""
+    lib = ctypes.CDLL(os.path.join(ROOT, "mnc_b200", "libmnc_b200.so"))
+    out = np.zeros((9, 4), dtype=np.float32)
+    assert lib.mnc_generate_anchors(out.ctypes.data_as(ctypes.c_void_p)) == 0
+    assert list(out[0]) == [-84, -40, 99, 55] and list(out[8]) == [-168, -344, 183, 359]
+    from oracle import oracle as O
+    assert np.array_equal(out.astype(np.float64), O.generate_anchors())
+
+
+def test_missing_library_fails_loudly(tmp_path, monkeypatch):
+    import importlib
+    import mnc_b200._lib as L
+    monkeypatch.setattr(L, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(ImportError):
+        L._load()
+    importlib.reload(L)
+
+
+def test_prototxt_reader_and_graph_check(tmp_path):
+    import mnc_b200.lib as lib
+    lib.install()
+    from caffe import mnc_graph
+    g = mnc_graph.build_graph()
+    types = [l["type"] for l in g]
+    # layer census of models/VGG16/mnc_5stage/test.prototxt
+    assert types.count("Convolution") == 16 and types.count("InnerProduct") == 18
+    assert types.count("Pooling") == 9 and types.count("ReLU") == 24 and types.count("Softmax") == 5
+    assert types.count("ROIWarping") == 2 and types.count("MaskResize") == 2
+    assert types.count("MaskPooling") == 2 and types.count("Python") == 4 and types.count("Concat") == 2
+
+    def emit(layers):
+        out = ['name: "VGG16"', 'input: "data"', "input_shape { dim: 1 dim: 3 dim: 224 dim: 224 }"]
+        for l in layers:
+            s = ["layer {", '  name: "%s"' % l["name"], '  type: "%s"' % l["type"]]
+            s += ['  bottom: "%s"' % b for b in l["bottom"]] + ['  top: "%s"' % t for t in l["top"]]
+            for k, v in l.items():
+                if isinstance(v, dict):
+                    s.append("  %s {" % k)
+                    for kk, vv in v.items():
+                        s.append("    %s: %s  # c" % (kk, ('"%s"' % vv) if isinstance(vv, str) and kk != "pool" else vv))
+                    s.append("  }")
+            s.append("}")
+            out.append("\n".join(s))
+        return "\n".join(out)
+    p = tmp_path / "test.prototxt"
+    p.write_text(emit(g))
+    assert len(mnc_graph.check_prototxt(str(p))) == len(g)
+    bad = [dict(l) for l in g]
+    bad[-1] = dict(bad[-1], inner_product_param=dict(num_output=80))
+    p.write_text(emit(bad))
+    with pytest.raises(ValueError):
+        mnc_graph.check_prototxt(str(p))
+    ref = "/root/reference/models/VGG16/mnc_5stage/test.prototxt"
+    if os.path.exists(ref):  # build container only
+        assert len(mnc_graph.check_prototxt(ref)) == 88
+
+
+def test_cfg_constants():
+    import mnc_b200.lib as lib
+    lib.install()
+    from mnc_config import cfg
+    assert cfg.USE_GPU_NMS and cfg.MASK_SIZE == 21 and cfg.BINARIZE_THRESH == 0.4
+    assert cfg.TEST.RPN_PRE_NMS_TOP_N == 6000 and cfg.TEST.RPN_POST_NMS_TOP_N == 300
+    assert cfg.TEST.RPN_NMS_THRESH == 0.7 and cfg.TEST.RPN_MIN_SIZE == 16
+    assert cfg.TEST.MASK_MERGE_IOU_THRESH == 0.5 and cfg.TEST.MASK_MERGE_NMS_THRESH == 0.3
+    assert cfg["TEST"].SCALES == (600,) and cfg.TRAIN.MAX_SIZE == 1000
+
+
+def test_host_bbox_helpers_match_oracle():
+    import mnc_b200.lib as lib
+    lib.install()
+    from transform import bbox_transform as T
+    from oracle import oracle as O
+    rng = np.random.default_rng(0)
+    boxes = (rng.uniform(0, 500, size=(50, 4))).astype(np.float32)
+    boxes[:, 2:] += boxes[:, :2]
+    d = rng.normal(0, 0.3, size=(50, 8)).astype(np.float32)
+    assert np.array_equal(T.bbox_transform_inv(boxes, d), O.bbox_transform_inv(boxes, d))
+    a, ka = T.clip_boxes(boxes * 2 - 100, (600, 1000, 3))
+    b, kb = O.clip_boxes(boxes * 2 - 100, (600, 1000, 3))
+    assert np.array_equal(a, b) and np.array_equal(ka, kb)
+    assert np.array_equal(T.filter_small_boxes(boxes, 40), O.filter_small_boxes(boxes, 40))
+    assert T.bbox_transform_inv(np.zeros((0, 4), np.float32), np.zeros((0, 8), np.float32)).shape == (0, 8)
+
+
+def test_blob_and_layer_protocol():
+    import mnc_b200.lib as lib
+    lib.install()
+    import caffe
+    from pylayer.mask_layer import MaskLayer
+    b = caffe.Blob(2, 3, 4, 5)
+    assert (b.num, b.channels, b.height, b.width, b.count) == (2, 3, 4, 5, 120)
+    b.reshape(7, 441)
+    assert b.shape == (7, 441) and b.data.dtype == np.float32
+    b.data[...] = np.arange(7 * 441).reshape(7, 441)
+    top = [caffe.Blob()]
+    layer = MaskLayer(phase=caffe.TEST)
+    assert str(layer.phase) == "TEST"
+    layer.setup([b], top)
+    layer.forward([b], top)
+    assert top[0].shape == (7, 1, 21, 21) and top[0].data[3, 0, 20, 20] == b.data[3, 440]
+
+
+def test_shard_range_and_records():
+    from mnc_b200 import dist as D
+    for total, world in ((64, 8), (10, 4), (3, 8), (8, 1)):
+        got = [D.shard_range(total, r, world) for r in range(world)]
+        assert got[0][0] == 0 and got[-1][1] == total
+        assert all(got[i][1] == got[i + 1][0] for i in range(world - 1))
+        assert max(e - s for s, e in got) - min(e - s for s, e in got) <= 1
+    B = 3
+    boxes = torch.rand(B, 600, 4)
+    masks = torch.rand(B, 600, 1, 21, 21)
+    scores = torch.rand(B, 600, 21)
+    valid = (torch.rand(B, 600) > 0.3).to(torch.uint8)
+    rec = D.pack_records(boxes, masks, scores, valid)
+    assert rec.shape == (B, D.REC_FLOATS)
+    c, b2, m2, s2 = D.unpack_records(rec)
+    assert torch.equal(b2, boxes) and torch.equal(m2, masks) and torch.equal(s2, scores)
+    assert torch.equal(c, valid.sum(1).to(torch.int64))
+
+
+def test_weight_container():
+    from mnc_b200 import weights as Wt
+    w = Wt.make_weights(Wt.TINY_ARCH)
+    w2 = Wt.make_weights(Wt.TINY_ARCH)
+    assert all(torch.equal(w[k][0], w2[k][0]) for k in w)      # seeded
+    assert Wt.arch_of(w) == Wt.TINY_ARCH
+    assert w["fc6"][0].shape == (256, 64 * 49) and w["fc6_maskest"][0].shape == (64, 64 * 196)
+    assert w["cls_score"][0].shape == (21, 512) and w["bbox_pred"][0].shape == (84, 512)
+    assert w["rpn_cls_score"][0].shape == (18, 64, 1, 1)
+    full = Wt.FULL_ARCH
+    assert full["trunk"][-1] == 512 and full["fc"] == 4096   # Appendix A shapes
+
+
+def test_split_representation():
+    from mnc_b200 import weights  # noqa: F401  (package import must work without a GPU)
+    x = torch.randn(1000) * 10
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.float()).to(torch.bfloat16)
+    err = ((hi.float() + lo.float()) - x).abs() / x.abs().clamp_min(1e-6)
+    assert err.max() < 2 ** -15
