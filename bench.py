@@ -211,6 +211,7 @@ def main():
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
           for _ in range(args.steps)]
     barrier()
+    torch.cuda.nvtx.range_push("timed")
     t_wall0 = time.perf_counter()
     for k in range(args.steps):
         flush.fill_(k & 0xff)          # evict L2 between timed steps (outside the event pair)
@@ -218,6 +219,7 @@ def main():
         step()
         ev[k][1].record()
     barrier()
+    torch.cuda.nvtx.range_pop()
     t_wall = time.perf_counter() - t_wall0
     launches = _lib.launch_count - launches0
     ktimer, dense.timer = dense.timer, None

@@ -81,5 +81,6 @@ def test_mv_three_way():
     # allow no mismatch on this seeded input
     assert np.array_equal(rb_o, rb_ref), "oracle boxes differ from reference _mv"
     assert np.array_equal(rb, rb_ref), "CUDA boxes differ from reference _mv"
-    assert util.rel_err(rm_o, rm_ref) < 1e-5
-    assert util.rel_err(rm, rm_ref) < 1e-5
+    # mask values: the reference binary contracts a*b+c into FMA, the C oracle does not
+    assert util.rel_err(rm_o, rm_ref) < 1e-4
+    assert util.rel_err(rm, rm_ref) < 1e-4
