@@ -135,21 +135,19 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int spli
 }
 
 // -------------------------------------------------------------------- conv1_1
-// One thread per output pixel, all COUT channels in registers; the 27xCOUT weights are
-// broadcast from shared memory.  Input is the fp32 NCHW `data` blob.
-template <int COUT>
+// One thread per output pixel.  The 27x64 weights + 64 biases travel as a __grid_constant__ kernel
+// parameter (7 KB): every FFMA takes its weight straight from the constant bank, so the inner loop
+// is pure FMA issue (no shared-memory operand loads).  Input is the fp32 NCHW `data` blob.
+struct Conv11Weights {
+  float w[27][64];  // [c*9 + ky*3 + kx][cout]
+  float b[64];
+};
+
 __global__ void __launch_bounds__(128)
 conv1_1_kernel(const float* __restrict__ data, int batch, int H, int W,
-               const float* __restrict__ weight, const float* __restrict__ bias,
-               __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
-  __shared__ float ws[27][COUT];
-  __shared__ float bs[COUT];
-  for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) {
-    const int co = i / 27, k = i % 27;  // Caffe weight order [co][c][ky][kx]
-    ws[k][co] = weight[i];
-  }
-  for (int i = threadIdx.x; i < COUT; i += blockDim.x) bs[i] = bias ? bias[i] : 0.f;
-  __syncthreads();
+               const __grid_constant__ Conv11Weights wt, __nv_bfloat16* __restrict__ out_hi,
+               __nv_bfloat16* __restrict__ out_lo) {
+  constexpr int COUT = 64;
   const long long HW = static_cast<long long>(H) * W;
   const long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (pix >= batch * HW) return;
@@ -171,7 +169,7 @@ conv1_1_kernel(const float* __restrict__ data, int batch, int H, int W,
       }
   __nv_bfloat16* ph = out_hi + pix * COUT;
   __nv_bfloat16* pl = out_lo + pix * COUT;
-#pragma unroll 1
+#pragma unroll
   for (int c0 = 0; c0 < COUT; c0 += 8) {
     float acc[8];
 #pragma unroll
@@ -179,12 +177,12 @@ conv1_1_kernel(const float* __restrict__ data, int batch, int H, int W,
 #pragma unroll
     for (int k = 0; k < 27; ++k)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = fmaf(in[k], ws[k][c0 + j], acc[j]);
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(in[k], wt.w[k][c0 + j], acc[j]);
     uint32_t hw[4], lw[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const float x0 = fmaxf(acc[2 * e] + bs[c0 + 2 * e], 0.f);
-      const float x1 = fmaxf(acc[2 * e + 1] + bs[c0 + 2 * e + 1], 0.f);
+      const float x0 = fmaxf(acc[2 * e] + wt.b[c0 + 2 * e], 0.f);
+      const float x1 = fmaxf(acc[2 * e + 1] + wt.b[c0 + 2 * e + 1], 0.f);
       __nv_bfloat16 h0, l0, h1, l1;
       split_f32(x0, h0, l0);
       split_f32(x1, h1, l1);
@@ -374,10 +372,30 @@ extern "C" int mnc_splitk_reduce(const float* partial, int splits, long long spl
 extern "C" int mnc_conv1_1(const float* data_nchw, int batch, int H, int W, const float* weight,
                            const float* bias, int Cout, void* out_hi, void* out_lo, void* stream) {
   if (Cout != 64) return MNC_ERR_ARG;
+  // weights live on the device (Caffe order [co][c][ky][kx]); the kernel wants them as a by-value
+  // parameter, so fetch them to the host once per (weight, bias) pointer pair and cache.
+  static const float* cached_w = nullptr;
+  static const float* cached_b = nullptr;
+  static Conv11Weights host;
+  if (cached_w != weight || cached_b != bias) {
+    float tmp[64 * 27];
+    if (cudaMemcpy(tmp, weight, sizeof(tmp), cudaMemcpyDeviceToHost) != cudaSuccess)
+      return MNC_ERR_CUDA;
+    for (int co = 0; co < 64; ++co)
+      for (int k = 0; k < 27; ++k) host.w[k][co] = tmp[co * 27 + k];
+    if (bias) {
+      if (cudaMemcpy(host.b, bias, sizeof(host.b), cudaMemcpyDeviceToHost) != cudaSuccess)
+        return MNC_ERR_CUDA;
+    } else {
+      for (int co = 0; co < 64; ++co) host.b[co] = 0.f;
+    }
+    cached_w = weight;
+    cached_b = bias;
+  }
   const long long pix = static_cast<long long>(batch) * H * W;
-  conv1_1_kernel<64><<<static_cast<unsigned>((pix + 127) / 128), 128, 0,
-                       static_cast<cudaStream_t>(stream)>>>(
-      data_nchw, batch, H, W, weight, bias, static_cast<__nv_bfloat16*>(out_hi),
+  conv1_1_kernel<<<static_cast<unsigned>((pix + 127) / 128), 128, 0,
+                   static_cast<cudaStream_t>(stream)>>>(
+      data_nchw, batch, H, W, host, static_cast<__nv_bfloat16*>(out_hi),
       static_cast<__nv_bfloat16*>(out_lo));
   return check_launch();
 }

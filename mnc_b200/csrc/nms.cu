@@ -3,8 +3,7 @@
 // Replaces `_nms` (lib/nms/nms_kernel.cu:34-78 kernel, :91-144 host wrapper) and the
 // `scores.argsort()[::-1]` calls in front of it (lib/nms/gpu_nms.pyx:25-26,
 // lib/pylayer/proposal_layer.py:139).  Differences in design, not in result:
-//  * suppression words are built with __ballot_sync (lanes = 32 columns, loop over rows), and
-//    stored column-block-major so both the writes here and the scan's reads are coalesced;
+//  * suppression words are built with __ballot_sync (lanes = 32 columns, loop over rows);
 //  * only the upper triangle is computed;
 //  * the greedy reduce runs on the device (one warp per problem) and stops at `max_keep`, so the
 //    n x n/64 word matrix never crosses PCIe (the reference copies 4.5 MB D->H for n = 6000);
@@ -32,7 +31,8 @@ __device__ __forceinline__ float dev_iou(float const* const a, float const* cons
   return interS / (Sa + Sb - interS);
 }
 
-// mask layout: [problem][col_block][row] (u64), row in [0, n_max).
+// mask layout: [problem][row][col_block] (u64), row in [0, n_max): a kept row's words are
+// contiguous, which is what the scan's critical path reads.
 // grid (col_blocks, row_blocks, problems), 128 threads.
 __global__ void __launch_bounds__(128)
 nms_mask_kernel(const float* __restrict__ boxes, int box_stride, long long problem_stride,
@@ -81,60 +81,126 @@ nms_mask_kernel(const float* __restrict__ boxes, int box_stride, long long probl
           static_cast<unsigned long long>(halves[tid][0]) |
           (static_cast<unsigned long long>(halves[tid][1]) << 32);
       const int col_blocks = (n_max + 63) / 64;
-      mask[(static_cast<long long>(prob) * col_blocks + col_blk) * n_max + r] = word;
+      mask[(static_cast<long long>(prob) * n_max + r) * col_blocks + col_blk] = word;
     }
   }
 }
 
-// One warp per problem.  Walks 64-box blocks: resolves the block's internal dependencies from
-// the diagonal words, then ORs the kept rows into the remaining column words in parallel.
-__global__ void __launch_bounds__(32)
+// One CTA (256 threads) per problem.  Walks 64-box blocks: thread 0 resolves the block's internal
+// dependencies from the 64 diagonal words (staged in shared memory), then every thread ORs the
+// kept rows into its own later column word (row-major words: one coalesced read per kept row).
+__global__ void __launch_bounds__(256)
 nms_scan_kernel(const unsigned long long* __restrict__ mask, const int* __restrict__ counts,
                 int n_max, int max_keep, int* __restrict__ keep_out, int keep_stride,
                 int* __restrict__ num_out) {
   extern __shared__ unsigned long long remv[];  // col_blocks words
+  __shared__ unsigned long long diag[64];
+  __shared__ unsigned long long s_kept;
+  __shared__ int s_num;
   const int prob = blockIdx.x;
-  const int lane = threadIdx.x;
+  const int tid = threadIdx.x;
   const int n = min(counts ? counts[prob] : n_max, n_max);
-  const int col_blocks_max = (n_max + 63) / 64;
+  const int cb_max = (n_max + 63) / 64;
   const int col_blocks = (n + 63) / 64;
-  const unsigned long long* pm = mask + static_cast<long long>(prob) * col_blocks_max * n_max;
+  const unsigned long long* pm = mask + static_cast<long long>(prob) * n_max * cb_max;
   int* keep = keep_out + static_cast<long long>(prob) * keep_stride;
-  for (int c = lane; c < col_blocks; c += 32) remv[c] = 0ull;
-  __syncwarp();
-  int num = 0;
-  for (int blk = 0; blk < col_blocks && num < max_keep; ++blk) {
+  for (int c = tid; c < col_blocks; c += blockDim.x) remv[c] = 0ull;
+  if (tid == 0) s_num = 0;
+  __syncthreads();
+  for (int blk = 0; blk < col_blocks; ++blk) {
     const int r0 = blk * 64;
-    // diagonal words of rows r0+lane and r0+32+lane
-    const unsigned long long d0 = (r0 + lane < n) ? pm[static_cast<long long>(blk) * n_max + r0 + lane] : 0ull;
-    const unsigned long long d1 = (r0 + 32 + lane < n) ? pm[static_cast<long long>(blk) * n_max + r0 + 32 + lane] : 0ull;
-    unsigned long long cur = remv[blk];
-    unsigned long long kept = 0ull;
-    const int rows = min(64, n - r0);
-    for (int i = 0; i < rows && num < max_keep; ++i) {
-      const unsigned long long di = __shfl_sync(0xffffffffu, (i < 32) ? d0 : d1, i & 31);
-      if (!((cur >> i) & 1ull)) {
-        if (lane == 0) keep[num] = r0 + i;
-        ++num;
-        kept |= (1ull << i);
-        cur |= di;
+    if (tid < 64) diag[tid] = (r0 + tid < n) ? pm[static_cast<long long>(r0 + tid) * cb_max + blk] : 0ull;
+    __syncthreads();
+    if (tid == 0) {
+      unsigned long long cur = remv[blk], kept = 0ull;
+      int num = s_num;
+      const int rows = min(64, n - r0);
+#pragma unroll 8
+      for (int i = 0; i < rows; ++i) {
+        if (!((cur >> i) & 1ull) && num < max_keep) {
+          keep[num++] = r0 + i;
+          kept |= (1ull << i);
+          cur |= diag[i];
+        }
       }
+      s_kept = kept;
+      s_num = num;
     }
-    // propagate kept rows to later column blocks
-    for (int c = blk + 1 + lane; c < col_blocks; c += 32) {
+    __syncthreads();
+    if (s_num >= max_keep) break;
+    unsigned long long k = s_kept;
+    for (int c = blk + 1 + tid; c < col_blocks; c += blockDim.x) {
       unsigned long long acc = remv[c];
-      unsigned long long k = kept;
-      const unsigned long long* pc = pm + static_cast<long long>(c) * n_max + r0;
-      while (k) {
-        const int i = __ffsll(static_cast<long long>(k)) - 1;
-        k &= k - 1;
-        acc |= pc[i];
+      unsigned long long kk = k;
+      while (kk) {
+        const int i = __ffsll(static_cast<long long>(kk)) - 1;
+        kk &= kk - 1;
+        acc |= pm[static_cast<long long>(r0 + i) * cb_max + c];
       }
       remv[c] = acc;
     }
-    __syncwarp();
+    __syncthreads();
   }
-  if (lane == 0) num_out[prob] = num;
+  if (tid == 0) num_out[prob] = s_num;
+}
+
+// Bitonic sort in shared memory, one CTA per problem, n <= 32768: (key desc, index asc).
+// Keys are mapped to order-preserving uint32 (0 is reserved for invalid / padding entries).
+__device__ __forceinline__ uint32_t f32_sort_key(float f) {
+  const uint32_t b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__global__ void __launch_bounds__(1024)
+bitonic_sort_desc_kernel(const float* __restrict__ keys, long long outer_stride,
+                         long long inner_stride, int inner, int key_stride,
+                         const unsigned char* __restrict__ valid, int n, int np2,
+                         int* __restrict__ order, int* __restrict__ n_valid) {
+  extern __shared__ uint32_t sk[];                          // np2 keys
+  uint16_t* si = reinterpret_cast<uint16_t*>(sk + np2);     // np2 indices
+  __shared__ int s_cnt;
+  const int prob = blockIdx.x;
+  const int tid = threadIdx.x;
+  const float* pk = keys + (prob / inner) * outer_stride + (prob % inner) * inner_stride;
+  const unsigned char* pv = valid ? valid + static_cast<long long>(prob) * n : nullptr;
+  if (tid == 0) s_cnt = 0;
+  __syncthreads();
+  int local = 0;
+  for (int i = tid; i < np2; i += blockDim.x) {
+    uint32_t k = 0u;
+    uint16_t ix = 0xFFFFu;
+    if (i < n && (pv ? pv[i] != 0 : true)) {
+      k = f32_sort_key(pk[static_cast<long long>(i) * key_stride]);
+      ix = static_cast<uint16_t>(i);
+      ++local;
+    }
+    sk[i] = k;
+    si[i] = ix;
+  }
+  if (local) atomicAdd(&s_cnt, local);
+  __syncthreads();
+  for (int k = 2; k <= np2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = tid; t < (np2 >> 1); t += blockDim.x) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int l = i | j;
+        const uint32_t ka = sk[i], kb = sk[l];
+        const uint16_t ia = si[i], ib = si[l];
+        const bool a_first = (ka > kb) || (ka == kb && ia < ib);
+        const bool b_first = (kb > ka) || (ka == kb && ib < ia);
+        const bool up = (i & k) == 0;
+        if (up ? b_first : a_first) {
+          sk[i] = kb;
+          sk[l] = ka;
+          si[i] = ib;
+          si[l] = ia;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  const int cnt = s_cnt;
+  for (int i = tid; i < cnt; i += blockDim.x) order[static_cast<long long>(prob) * n + i] = si[i];
+  if (tid == 0 && n_valid) n_valid[prob] = cnt;
 }
 
 // Rank sort, descending, ties by ascending index.  order[prob][rank] = index for valid items;
@@ -214,7 +280,7 @@ extern "C" int mnc_nms_sorted(const float* boxes, int box_stride, long long prob
   dim3 grid(col_blocks, col_blocks, problems);
   nms_mask_kernel<<<grid, 128, 0, stream>>>(boxes, box_stride, problem_stride, counts, n_max,
                                             thresh, static_cast<unsigned long long*>(workspace));
-  nms_scan_kernel<<<problems, 32, col_blocks * 8, stream>>>(
+  nms_scan_kernel<<<problems, 256, col_blocks * 8, stream>>>(
       static_cast<const unsigned long long*>(workspace), counts, n_max, max_keep, keep_out,
       keep_stride, num_out);
   return check_launch();
@@ -225,6 +291,22 @@ extern "C" int mnc_rank_sort_desc(const float* keys, long long outer_stride,
                                   const unsigned char* valid, int n, int problems, int* order,
                                   int* n_valid, void* stream_) {
   if (n <= 0 || problems <= 0 || inner <= 0) return MNC_ERR_ARG;
+  if (n > 2048 && n <= 32768) {
+    // large single lists (the 21546 RPN anchors): O(n log^2 n) in shared memory
+    int np2 = 1;
+    while (np2 < n) np2 <<= 1;
+    const int smem = np2 * 6;
+    static int attr_smem = 48 * 1024;
+    if (smem > attr_smem) {
+      if (cudaFuncSetAttribute(bitonic_sort_desc_kernel,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+        return MNC_ERR_CUDA;
+      attr_smem = smem;
+    }
+    bitonic_sort_desc_kernel<<<problems, 1024, smem, static_cast<cudaStream_t>(stream_)>>>(
+        keys, outer_stride, inner_stride, inner, key_stride, valid, n, np2, order, n_valid);
+    return check_launch();
+  }
   dim3 grid((n + 255) / 256, problems);
   rank_sort_desc_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream_)>>>(
       keys, outer_stride, inner_stride, inner, key_stride, valid, n, order, n_valid);

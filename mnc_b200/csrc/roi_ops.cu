@@ -88,13 +88,70 @@ __device__ __forceinline__ RoiGeom roi_geom(const float* roi, float spatial_scal
 constexpr int kWarpSlab = 8;     // channels per CTA
 constexpr int kMaxPooled = 32;   // pooled_h, pooled_w <= 32
 
+// One CTA per (RoI, 8-channel slab).  The per-RoI interpolation tables (row taps, column taps)
+// are built once in shared memory; each thread then produces 4 consecutive outputs of one
+// (channel, ph) row: its two feature rows are read through the read-only L1 path (a RoI's window
+// of one channel is <= 9.6 KB, so the 4-tap gathers hit L1 after first touch) and the result
+// leaves as one 16-byte streaming store -- output bytes are written exactly once, fully
+// coalesced.  PW is the compile-time pooled width so the index math has no runtime division.
+template <int PH, int PW>
 __global__ void __launch_bounds__(256)
 roi_warp_nchw_kernel(const float* __restrict__ feat, int C, int H, int W,
-                     const float* __restrict__ rois, int ph_n, int pw_n, float spatial_scale,
+                     const float* __restrict__ rois, float spatial_scale,
                      float* __restrict__ out) {
-  extern __shared__ float win[];  // [kWarpSlab][wh][ww]
+  __shared__ AxisTap tap_h[PH], tap_w[PW];
+  const int r = blockIdx.x;
+  const int c0 = blockIdx.y * kWarpSlab;
+  const int tid = threadIdx.x;
+  const RoiGeom g = roi_geom(rois + static_cast<long long>(r) * 5, spatial_scale, PH, PW);
+  if (tid < PH) tap_h[tid] = axis_tap(__fadd_rn(g.start_h, __fmul_rn(static_cast<float>(tid), g.bin_h)), H);
+  if (tid >= 32 && tid < 32 + PW)
+    tap_w[tid - 32] = axis_tap(__fadd_rn(g.start_w, __fmul_rn(static_cast<float>(tid - 32), g.bin_w)), W);
+  __syncthreads();
+  constexpr int PP = PH * PW;
+  constexpr bool kVec = (PP % 4 == 0);       // 28x28 and 14x14: whole planes in 16-byte quads
+  constexpr int QP = kVec ? PP / 4 : PP;      // work items per channel plane
+  constexpr int EPT = kVec ? 4 : 1;           // outputs per work item
+  const int nch = min(kWarpSlab, C - c0);
+  const float* fbase = feat + (static_cast<long long>(g.level) * C + c0) * H * W;
+  float* obase = out + (static_cast<long long>(r) * C + c0) * PP;
+  const bool aligned = (reinterpret_cast<uintptr_t>(obase) & 15) == 0;
+  for (int q = tid; q < nch * QP; q += 256) {
+    const int c = q / QP;
+    const int i0 = (q - c * QP) * EPT;
+    const float* plane = fbase + static_cast<long long>(c) * H * W;
+    float v[EPT];
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+      const int i = i0 + e;
+      const int ph = i / PW, pw = i - ph * PW;
+      const AxisTap th = tap_h[ph];
+      const AxisTap tw = tap_w[pw];
+      float val = 0.f;
+      if (th.ok && tw.ok) {
+        const float* row0 = plane + th.lo * W;
+        const float* row1 = plane + th.hi * W;
+        val = bilerp(th, tw, __ldg(row0 + tw.lo), __ldg(row0 + tw.hi), __ldg(row1 + tw.lo),
+                     __ldg(row1 + tw.hi));
+      }
+      v[e] = val;
+    }
+    float* o = obase + c * PP + i0;
+    if (kVec && aligned) {
+      __stcs(reinterpret_cast<float4*>(o), make_float4(v[0], v[EPT > 1 ? 1 : 0], v[EPT > 2 ? 2 : 0], v[EPT > 3 ? 3 : 0]));
+    } else {
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) __stcs(o + e, v[e]);
+    }
+  }
+}
+
+// generic pooled size (runtime), same scheme, scalar stores
+__global__ void __launch_bounds__(256)
+roi_warp_nchw_generic_kernel(const float* __restrict__ feat, int C, int H, int W,
+                             const float* __restrict__ rois, int ph_n, int pw_n,
+                             float spatial_scale, float* __restrict__ out) {
   __shared__ AxisTap tap_h[kMaxPooled], tap_w[kMaxPooled];
-  __shared__ int s_hmin, s_wmin, s_wh, s_ww;
   const int r = blockIdx.x;
   const int c0 = blockIdx.y * kWarpSlab;
   const int tid = threadIdx.x;
@@ -103,66 +160,21 @@ roi_warp_nchw_kernel(const float* __restrict__ feat, int C, int H, int W,
   if (tid >= 32 && tid < 32 + pw_n)
     tap_w[tid - 32] = axis_tap(__fadd_rn(g.start_w, __fmul_rn(static_cast<float>(tid - 32), g.bin_w)), W);
   __syncthreads();
-  if (tid == 0) {
-    int hmin = H, hmax = -1, wmin = W, wmax = -1;
-    for (int i = 0; i < ph_n; ++i)
-      if (tap_h[i].ok) {
-        hmin = min(hmin, tap_h[i].lo);
-        hmax = max(hmax, tap_h[i].hi);
-      }
-    for (int i = 0; i < pw_n; ++i)
-      if (tap_w[i].ok) {
-        wmin = min(wmin, tap_w[i].lo);
-        wmax = max(wmax, tap_w[i].hi);
-      }
-    if (hmax < 0 || wmax < 0) {
-      hmin = wmin = 0;
-      hmax = wmax = -1;
-    }
-    s_hmin = hmin;
-    s_wmin = wmin;
-    s_wh = hmax - hmin + 1;
-    s_ww = wmax - wmin + 1;
-  }
-  __syncthreads();
-  const int hmin = s_hmin, wmin = s_wmin, wh = s_wh, ww = s_ww;
+  const int pp = ph_n * pw_n;
   const int nch = min(kWarpSlab, C - c0);
   const float* fbase = feat + (static_cast<long long>(g.level) * C + c0) * H * W;
-  const int wsz = wh * ww;
-  for (int i = tid; i < nch * wsz; i += 256) {
-    const int c = i / wsz, rem = i % wsz;
-    const int y = rem / ww, x = rem % ww;
-    win[i] = __ldg(fbase + static_cast<long long>(c) * H * W + (hmin + y) * W + wmin + x);
-  }
-  __syncthreads();
-  const int pp = ph_n * pw_n;
-  const int total = nch * pp;
   float* obase = out + (static_cast<long long>(r) * C + c0) * pp;
-  const bool vec = (pp % 4 == 0) && ((reinterpret_cast<uintptr_t>(obase) & 15) == 0);
-  for (int i4 = tid * 4; i4 < total; i4 += 256 * 4) {
-    float v[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int i = i4 + e;
-      float val = 0.f;
-      if (i < total) {
-        const int c = i / pp, rem = i % pp;
-        const int ph = rem / pw_n, pw = rem % pw_n;
-        const AxisTap th = tap_h[ph], tw = tap_w[pw];
-        if (th.ok && tw.ok) {
-          const float* wp = win + c * wsz;
-          const int y0 = (th.lo - hmin) * ww, y1 = (th.hi - hmin) * ww;
-          const int x0 = tw.lo - wmin, x1 = tw.hi - wmin;
-          val = bilerp(th, tw, wp[y0 + x0], wp[y0 + x1], wp[y1 + x0], wp[y1 + x1]);
-        }
-      }
-      v[e] = val;
+  for (int i = tid; i < nch * pp; i += 256) {
+    const int c = i / pp, rem = i % pp;
+    const int ph = rem / pw_n, pw = rem % pw_n;
+    const AxisTap th = tap_h[ph], tw = tap_w[pw];
+    float val = 0.f;
+    if (th.ok && tw.ok) {
+      const float* pl = fbase + static_cast<long long>(c) * H * W;
+      val = bilerp(th, tw, __ldg(pl + th.lo * W + tw.lo), __ldg(pl + th.lo * W + tw.hi),
+                   __ldg(pl + th.hi * W + tw.lo), __ldg(pl + th.hi * W + tw.hi));
     }
-    if (vec && i4 + 3 < total) {
-      __stcs(reinterpret_cast<float4*>(obase + i4), make_float4(v[0], v[1], v[2], v[3]));
-    } else {
-      for (int e = 0; e < 4 && i4 + e < total; ++e) obase[i4 + e] = v[e];
-    }
+    obase[i] = val;
   }
 }
 
@@ -241,7 +253,50 @@ __device__ __forceinline__ void st_split2(__nv_bfloat16* hi, __nv_bfloat16* lo, 
 
 // One CTA per (RoI, pair of 14x14 output rows).  SUB = 2: warp to 28x28 and take the 2x2 max
 // (stage 1, test.prototxt:479-505); SUB = 1: warp straight to 14x14 (stage 2, :809-820).
-// Also emits the 7x7 box-branch pool (test.prototxt:571-582).  Threads run over channel pairs.
+// Also emits the 7x7 box-branch pool (test.prototxt:571-582).
+// The interpolation taps depend only on (RoI, sample row/col): they are computed once per CTA
+// into shared memory (2*SUB row taps, 14*SUB column taps).  Threads then run over
+// (cell column, 4-channel group): 8-byte loads from each bf16 plane, coalesced along channels.
+struct __align__(8) bf4 { uint32_t a, b; };
+__device__ __forceinline__ float4 ld_split4(const __nv_bfloat16* hi, const __nv_bfloat16* lo,
+                                            long long off) {
+  const uint2 h = __ldg(reinterpret_cast<const uint2*>(hi + off));
+  const uint2 l = __ldg(reinterpret_cast<const uint2*>(lo + off));
+  float4 r;
+  r.x = __uint_as_float(h.x << 16) + __uint_as_float(l.x << 16);
+  r.y = __uint_as_float(h.x & 0xffff0000u) + __uint_as_float(l.x & 0xffff0000u);
+  r.z = __uint_as_float(h.y << 16) + __uint_as_float(l.y << 16);
+  r.w = __uint_as_float(h.y & 0xffff0000u) + __uint_as_float(l.y & 0xffff0000u);
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_bf2(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return static_cast<uint32_t>(__bfloat16_as_ushort(a)) | (static_cast<uint32_t>(__bfloat16_as_ushort(b)) << 16);
+}
+__device__ __forceinline__ void st_split4(__nv_bfloat16* hi, __nv_bfloat16* lo, long long off,
+                                          const float4 v) {
+  const __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y);
+  const __nv_bfloat16 h2 = __float2bfloat16_rn(v.z), h3 = __float2bfloat16_rn(v.w);
+  const __nv_bfloat16 l0 = __float2bfloat16_rn(v.x - __bfloat162float(h0));
+  const __nv_bfloat16 l1 = __float2bfloat16_rn(v.y - __bfloat162float(h1));
+  const __nv_bfloat16 l2 = __float2bfloat16_rn(v.z - __bfloat162float(h2));
+  const __nv_bfloat16 l3 = __float2bfloat16_rn(v.w - __bfloat162float(h3));
+  *reinterpret_cast<uint2*>(hi + off) = make_uint2(pack_bf2(h0, h1), pack_bf2(h2, h3));
+  *reinterpret_cast<uint2*>(lo + off) = make_uint2(pack_bf2(l0, l1), pack_bf2(l2, l3));
+}
+__device__ __forceinline__ float4 bilerp4(const float w1, const float w2, const float w3,
+                                          const float w4, const float4 v1, const float4 v2,
+                                          const float4 v3, const float4 v4) {
+  float4 r;
+  r.x = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w1, v1.x), __fmul_rn(w2, v2.x)), __fmul_rn(w3, v3.x)), __fmul_rn(w4, v4.x));
+  r.y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w1, v1.y), __fmul_rn(w2, v2.y)), __fmul_rn(w3, v3.y)), __fmul_rn(w4, v4.y));
+  r.z = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w1, v1.z), __fmul_rn(w2, v2.z)), __fmul_rn(w3, v3.z)), __fmul_rn(w4, v4.z));
+  r.w = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w1, v1.w), __fmul_rn(w2, v2.w)), __fmul_rn(w3, v3.w)), __fmul_rn(w4, v4.w));
+  return r;
+}
+__device__ __forceinline__ float4 max4(const float4 a, const float4 b) {
+  return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
+}
+
 template <int SUB>
 __global__ void __launch_bounds__(256)
 roi_warp_split_kernel(const __nv_bfloat16* __restrict__ f_hi, const __nv_bfloat16* __restrict__ f_lo,
@@ -249,48 +304,57 @@ roi_warp_split_kernel(const __nv_bfloat16* __restrict__ f_hi, const __nv_bfloat1
                       __nv_bfloat16* __restrict__ o14_hi, __nv_bfloat16* __restrict__ o14_lo,
                       __nv_bfloat16* __restrict__ o7_hi, __nv_bfloat16* __restrict__ o7_lo) {
   constexpr int P = 14 * SUB;
+  __shared__ AxisTap tap_h[2 * SUB], tap_w[P];
   const int r = blockIdx.x;
   const int t = blockIdx.y;  // rows 2t, 2t+1 of the 14x14 grid
   const RoiGeom g = roi_geom(rois + static_cast<long long>(r) * 5, spatial_scale, P, P);
+  if (threadIdx.x < 2 * SUB) {
+    const int ph = 2 * t * SUB + threadIdx.x;
+    tap_h[threadIdx.x] = axis_tap(__fadd_rn(g.start_h, __fmul_rn(static_cast<float>(ph), g.bin_h)), H);
+  }
+  if (threadIdx.x >= 32 && threadIdx.x < 32 + P) {
+    const int pw = threadIdx.x - 32;
+    tap_w[pw] = axis_tap(__fadd_rn(g.start_w, __fmul_rn(static_cast<float>(pw), g.bin_w)), W);
+  }
+  __syncthreads();
   const long long img_off = static_cast<long long>(g.level) * H * W * C;
-  for (int c = threadIdx.x * 2; c < C; c += blockDim.x * 2) {
-    for (int jp = 0; jp < 7; ++jp) {
-      float2 best7 = make_float2(-3.402823466e+38f, -3.402823466e+38f);
+  const int c4n = C / 4;
+  const float kNeg = -3.402823466e+38f;
+  // work item = (pooled column jp in 0..6, channel quad)
+  for (int item = threadIdx.x; item < 7 * c4n; item += blockDim.x) {
+    const int jp = item / c4n;
+    const int c = (item - jp * c4n) * 4;
+    float4 best7 = make_float4(kNeg, kNeg, kNeg, kNeg);
 #pragma unroll
-      for (int dy = 0; dy < 2; ++dy) {
+    for (int dy = 0; dy < 2; ++dy) {
 #pragma unroll
-        for (int dx = 0; dx < 2; ++dx) {
-          const int i = 2 * t + dy, j = 2 * jp + dx;
-          float2 cell = make_float2(-3.402823466e+38f, -3.402823466e+38f);
+      for (int dx = 0; dx < 2; ++dx) {
+        const int j = 2 * jp + dx;
+        float4 cell = make_float4(kNeg, kNeg, kNeg, kNeg);
 #pragma unroll
-          for (int sy = 0; sy < SUB; ++sy) {
-            const int ph = i * SUB + sy;
-            const AxisTap th = axis_tap(__fadd_rn(g.start_h, __fmul_rn(static_cast<float>(ph), g.bin_h)), H);
+        for (int sy = 0; sy < SUB; ++sy) {
+          const AxisTap th = tap_h[dy * SUB + sy];
 #pragma unroll
-            for (int sx = 0; sx < SUB; ++sx) {
-              const int pw = j * SUB + sx;
-              const AxisTap tw = axis_tap(__fadd_rn(g.start_w, __fmul_rn(static_cast<float>(pw), g.bin_w)), W);
-              float2 v = make_float2(0.f, 0.f);
-              if (th.ok && tw.ok) {
-                const long long b = img_off + c;
-                const float2 v1 = ld_split2(f_hi, f_lo, b + (static_cast<long long>(th.lo) * W + tw.lo) * C);
-                const float2 v2 = ld_split2(f_hi, f_lo, b + (static_cast<long long>(th.lo) * W + tw.hi) * C);
-                const float2 v3 = ld_split2(f_hi, f_lo, b + (static_cast<long long>(th.hi) * W + tw.lo) * C);
-                const float2 v4 = ld_split2(f_hi, f_lo, b + (static_cast<long long>(th.hi) * W + tw.hi) * C);
-                v.x = bilerp(th, tw, v1.x, v2.x, v3.x, v4.x);
-                v.y = bilerp(th, tw, v1.y, v2.y, v3.y, v4.y);
-              }
-              cell.x = fmaxf(cell.x, v.x);
-              cell.y = fmaxf(cell.y, v.y);
+          for (int sx = 0; sx < SUB; ++sx) {
+            const AxisTap tw = tap_w[j * SUB + sx];
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (th.ok && tw.ok) {
+              const long long b = img_off + c;
+              const float4 v1 = ld_split4(f_hi, f_lo, b + (static_cast<long long>(th.lo) * W + tw.lo) * C);
+              const float4 v2 = ld_split4(f_hi, f_lo, b + (static_cast<long long>(th.lo) * W + tw.hi) * C);
+              const float4 v3 = ld_split4(f_hi, f_lo, b + (static_cast<long long>(th.hi) * W + tw.lo) * C);
+              const float4 v4 = ld_split4(f_hi, f_lo, b + (static_cast<long long>(th.hi) * W + tw.hi) * C);
+              v = bilerp4(__fmul_rn(th.h, tw.h), __fmul_rn(th.h, tw.l), __fmul_rn(th.l, tw.h),
+                          __fmul_rn(th.l, tw.l), v1, v2, v3, v4);
             }
+            cell = max4(cell, v);
           }
-          st_split2(o14_hi, o14_lo, ((static_cast<long long>(r) * 14 + i) * 14 + j) * C + c, cell.x, cell.y);
-          best7.x = fmaxf(best7.x, cell.x);
-          best7.y = fmaxf(best7.y, cell.y);
         }
+        st_split4(o14_hi, o14_lo, ((static_cast<long long>(r) * 14 + (2 * t + dy)) * 14 + j) * C + c, cell);
+        best7 = max4(best7, cell);
       }
-      st_split2(o7_hi, o7_lo, ((static_cast<long long>(r) * 7 + t) * 7 + jp) * C + c, best7.x, best7.y);
     }
+    st_split4(o7_hi, o7_lo, ((static_cast<long long>(r) * 7 + t) * 7 + jp) * C + c, best7);
   }
 }
 
@@ -368,18 +432,17 @@ extern "C" int mnc_roi_warp_nchw(const float* feat, int C, int H, int W, const f
   if (R <= 0) return MNC_OK;
   if (pooled_h > kMaxPooled || pooled_w > kMaxPooled || pooled_h <= 0 || pooled_w <= 0)
     return MNC_ERR_ARG;
-  const int smem = kWarpSlab * H * W * static_cast<int>(sizeof(float));
-  if (smem > 200 * 1024) return MNC_ERR_ARG;
-  static int attr_smem = 0;
-  if (smem > attr_smem) {
-    if (cudaFuncSetAttribute(roi_warp_nchw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             smem) != cudaSuccess)
-      return MNC_ERR_CUDA;
-    attr_smem = smem;
-  }
   dim3 grid(R, (C + kWarpSlab - 1) / kWarpSlab);
-  roi_warp_nchw_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
-      feat, C, H, W, rois, pooled_h, pooled_w, spatial_scale, out);
+  auto s = static_cast<cudaStream_t>(stream);
+  if (pooled_h == 28 && pooled_w == 28)
+    roi_warp_nchw_kernel<28, 28><<<grid, 256, 0, s>>>(feat, C, H, W, rois, spatial_scale, out);
+  else if (pooled_h == 14 && pooled_w == 14)
+    roi_warp_nchw_kernel<14, 14><<<grid, 256, 0, s>>>(feat, C, H, W, rois, spatial_scale, out);
+  else if (pooled_h == 7 && pooled_w == 7)
+    roi_warp_nchw_kernel<7, 7><<<grid, 256, 0, s>>>(feat, C, H, W, rois, spatial_scale, out);
+  else
+    roi_warp_nchw_generic_kernel<<<grid, 256, 0, s>>>(feat, C, H, W, rois, pooled_h, pooled_w,
+                                                      spatial_scale, out);
   return check_launch();
 }
 
@@ -415,7 +478,7 @@ extern "C" int mnc_roi_warp_split(const void* f_hi, const void* f_lo, int C, int
                                   void* o14_hi, void* o14_lo, void* o7_hi, void* o7_lo,
                                   void* stream) {
   if (R <= 0) return MNC_OK;
-  if (C % 2 != 0 || (sub != 1 && sub != 2)) return MNC_ERR_ARG;
+  if (C % 4 != 0 || (sub != 1 && sub != 2)) return MNC_ERR_ARG;
   dim3 grid(R, 7);
   auto s = static_cast<cudaStream_t>(stream);
   if (sub == 2)
