@@ -42,7 +42,10 @@ int mnc_device_count(void);
  * and InnerProduct (caffe-mnc/src/caffe/layers/inner_product_layer.cu:21-27) Forward_gpu.
  *   a_hi/a_lo : bf16 [batch][H][W][Cin] planes (inner product: batch=1, H=1, W=rows, Cin=K)
  *   w_hi/w_lo : bf16 [Cout][taps*Cin] planes, K index = tap*Cin + c, tap = ky*3+kx
- *   out_mode 0: out0/out1 = bf16 hi/lo planes; 1: out0 = fp32 (out1 ignored)
+ *   out_mode 0: out0/out1 = bf16 hi/lo planes; 1: out0 = fp32 (out1 ignored);
+ *            2: (conv only) hi/lo planes of the 2x2/2 ceil-mode max-pooled output
+ *               [batch][ceil(H/2)][ceil(W/2)][..] -- Pooling fused into the epilogue
+ *               (pooling_layer.cu:11-47, pooling_layer.cpp:90-93)
  *   output element (pixel p, channel c) at p*out_pix_stride + out_ch_offset + c
  *   split_k > 1 (fp32 mode only): partial sums go to plane s at s*split_stride; finish with
  *   mnc_splitk_reduce.  bn: Cout tile (0 = auto, 64/128/256).  max_ctas: 0 = one CTA per SM.

@@ -41,9 +41,13 @@ class Detector:
         info_h = torch.as_tensor(np.asarray(im_info, dtype=np.float32))
         scale_h = info_h[:, 2].contiguous() if im_scales is None else torch.as_tensor(np.asarray(im_scales, np.float32))
         hw_h = info_h[:, :2].contiguous() if im_shapes is None else torch.as_tensor(np.asarray(im_shapes, np.float32))
-        self._h_in[:B].copy_(blob)                       # user memory -> pinned staging
+        if blob.is_pinned():
+            src = blob                                   # caller already handed page-locked memory
+        else:
+            self._h_in[:B].copy_(blob)                   # user memory -> pinned staging
+            src = self._h_in[:B]
         with torch.cuda.device(dev):
-            self._d_in[:B].copy_(self._h_in[:B], non_blocking=True)
+            self._d_in[:B].copy_(src, non_blocking=True)
             info = info_h.to(dev, non_blocking=True)
             boxes, masks, scores, valid, _ = self.engine.detect(
                 self._d_in[:B], info, hw_h.to(dev), scale_h.to(dev))

@@ -135,64 +135,87 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int spli
 }
 
 // -------------------------------------------------------------------- conv1_1
-// One thread per output pixel.  The 27x64 weights + 64 biases travel as a __grid_constant__ kernel
-// parameter (7 KB): every FFMA takes its weight straight from the constant bank, so the inner loop
-// is pure FMA issue (no shared-memory operand loads).  Input is the fp32 NCHW `data` blob.
-struct Conv11Weights {
-  float w[27][64];  // [c*9 + ky*3 + kx][cout]
-  float b[64];
-};
+// Each thread computes 4 horizontally adjacent pixels x all 64 output channels.  The 3x6x3 input
+// window lives in registers; weights sit in shared memory as [27][64] and are fetched with
+// broadcast 128-bit loads, each feeding 16 FMAs (4 pixels x 4 channels), so the kernel is bound by
+// FMA issue rather than by shared-memory operand traffic.  Input is the fp32 NCHW `data` blob.
+constexpr int kC11Pix = 4;
 
 __global__ void __launch_bounds__(128)
 conv1_1_kernel(const float* __restrict__ data, int batch, int H, int W,
-               const __grid_constant__ Conv11Weights wt, __nv_bfloat16* __restrict__ out_hi,
-               __nv_bfloat16* __restrict__ out_lo) {
+               const float* __restrict__ weight, const float* __restrict__ bias,
+               __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
   constexpr int COUT = 64;
+  __shared__ __align__(16) float ws[27][COUT];
+  __shared__ float bs[COUT];
+  for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) {
+    const int co = i / 27, k = i % 27;  // Caffe weight order [co][c][ky][kx]
+    ws[k][co] = weight[i];
+  }
+  for (int i = threadIdx.x; i < COUT; i += blockDim.x) bs[i] = bias ? bias[i] : 0.f;
+  __syncthreads();
+  const int Wq = (W + kC11Pix - 1) / kC11Pix;
   const long long HW = static_cast<long long>(H) * W;
-  const long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (pix >= batch * HW) return;
-  const int img = static_cast<int>(pix / HW);
-  const int r = static_cast<int>(pix % HW);
-  const int h = r / W, w = r % W;
-  float in[27];
+  const long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= static_cast<long long>(batch) * H * Wq) return;
+  const int img = static_cast<int>(q / (static_cast<long long>(H) * Wq));
+  const int r = static_cast<int>(q % (static_cast<long long>(H) * Wq));
+  const int h = r / Wq, w0 = (r % Wq) * kC11Pix;
+  float in[3][3][kC11Pix + 2];
 #pragma unroll
   for (int c = 0; c < 3; ++c)
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int hs = h + ky - 1, wsx = w + kx - 1;
+      for (int x = 0; x < kC11Pix + 2; ++x) {
+        const int hs = h + ky - 1, wsx = w0 + x - 1;
         float v = 0.f;
         if (hs >= 0 && hs < H && wsx >= 0 && wsx < W)
           v = __ldg(data + (static_cast<long long>(img) * 3 + c) * HW + static_cast<long long>(hs) * W + wsx);
-        in[c * 9 + ky * 3 + kx] = v;
+        in[c][ky][x] = v;
       }
-  __nv_bfloat16* ph = out_hi + pix * COUT;
-  __nv_bfloat16* pl = out_lo + pix * COUT;
-#pragma unroll
+#pragma unroll 1
   for (int c0 = 0; c0 < COUT; c0 += 8) {
-    float acc[8];
+    float acc[kC11Pix][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int p = 0; p < kC11Pix; ++p)
 #pragma unroll
-    for (int k = 0; k < 27; ++k)
+      for (int j = 0; j < 8; ++j) acc[p][j] = 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = fmaf(in[k], wt.w[k][c0 + j], acc[j]);
-    uint32_t hw[4], lw[4];
+    for (int c = 0; c < 3; ++c)
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float x0 = fmaxf(acc[2 * e] + wt.b[c0 + 2 * e], 0.f);
-      const float x1 = fmaxf(acc[2 * e + 1] + wt.b[c0 + 2 * e + 1], 0.f);
-      __nv_bfloat16 h0, l0, h1, l1;
-      split_f32(x0, h0, l0);
-      split_f32(x1, h1, l1);
-      hw[e] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) |
-              (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
-      lw[e] = static_cast<uint32_t>(__bfloat16_as_ushort(l0)) |
-              (static_cast<uint32_t>(__bfloat16_as_ushort(l1)) << 16);
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int k = c * 9 + ky * 3 + kx;
+          const float4 wa = *reinterpret_cast<const float4*>(&ws[k][c0]);
+          const float4 wb = *reinterpret_cast<const float4*>(&ws[k][c0 + 4]);
+          const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+          for (int p = 0; p < kC11Pix; ++p)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[p][j] = fmaf(in[c][ky][p + kx], wv[j], acc[p][j]);
+        }
+#pragma unroll
+    for (int p = 0; p < kC11Pix; ++p) {
+      if (w0 + p >= W) continue;
+      const long long pix = (static_cast<long long>(img) * H + h) * W + w0 + p;
+      uint32_t hw[4], lw[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float x0 = fmaxf(acc[p][2 * e] + bs[c0 + 2 * e], 0.f);
+        const float x1 = fmaxf(acc[p][2 * e + 1] + bs[c0 + 2 * e + 1], 0.f);
+        __nv_bfloat16 h0, l0, h1, l1;
+        split_f32(x0, h0, l0);
+        split_f32(x1, h1, l1);
+        hw[e] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) |
+                (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
+        lw[e] = static_cast<uint32_t>(__bfloat16_as_ushort(l0)) |
+                (static_cast<uint32_t>(__bfloat16_as_ushort(l1)) << 16);
+      }
+      *reinterpret_cast<uint4*>(out_hi + pix * COUT + c0) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+      *reinterpret_cast<uint4*>(out_lo + pix * COUT + c0) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
     }
-    *reinterpret_cast<uint4*>(ph + c0) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-    *reinterpret_cast<uint4*>(pl + c0) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
   }
 }
 
@@ -372,30 +395,10 @@ extern "C" int mnc_splitk_reduce(const float* partial, int splits, long long spl
 extern "C" int mnc_conv1_1(const float* data_nchw, int batch, int H, int W, const float* weight,
                            const float* bias, int Cout, void* out_hi, void* out_lo, void* stream) {
   if (Cout != 64) return MNC_ERR_ARG;
-  // weights live on the device (Caffe order [co][c][ky][kx]); the kernel wants them as a by-value
-  // parameter, so fetch them to the host once per (weight, bias) pointer pair and cache.
-  static const float* cached_w = nullptr;
-  static const float* cached_b = nullptr;
-  static Conv11Weights host;
-  if (cached_w != weight || cached_b != bias) {
-    float tmp[64 * 27];
-    if (cudaMemcpy(tmp, weight, sizeof(tmp), cudaMemcpyDeviceToHost) != cudaSuccess)
-      return MNC_ERR_CUDA;
-    for (int co = 0; co < 64; ++co)
-      for (int k = 0; k < 27; ++k) host.w[k][co] = tmp[co * 27 + k];
-    if (bias) {
-      if (cudaMemcpy(host.b, bias, sizeof(host.b), cudaMemcpyDeviceToHost) != cudaSuccess)
-        return MNC_ERR_CUDA;
-    } else {
-      for (int co = 0; co < 64; ++co) host.b[co] = 0.f;
-    }
-    cached_w = weight;
-    cached_b = bias;
-  }
-  const long long pix = static_cast<long long>(batch) * H * W;
-  conv1_1_kernel<<<static_cast<unsigned>((pix + 127) / 128), 128, 0,
+  const long long quads = static_cast<long long>(batch) * H * ((W + kC11Pix - 1) / kC11Pix);
+  conv1_1_kernel<<<static_cast<unsigned>((quads + 127) / 128), 128, 0,
                    static_cast<cudaStream_t>(stream)>>>(
-      data_nchw, batch, H, W, host, static_cast<__nv_bfloat16*>(out_hi),
+      data_nchw, batch, H, W, weight, bias, static_cast<__nv_bfloat16*>(out_hi),
       static_cast<__nv_bfloat16*>(out_lo));
   return check_launch();
 }

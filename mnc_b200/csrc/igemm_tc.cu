@@ -36,7 +36,7 @@ struct IgemmArgs {
   int k_steps;  // taps * Cin / 64
   int split_k;
   int relu;
-  int out_mode;  // 0: split bf16 (hi, lo); 1: fp32
+  int out_mode;  // 0: split bf16 (hi, lo); 1: fp32; 2: split bf16 after a fused 2x2/2 ceil-mode max pool
   const float* bias;
   __nv_bfloat16* out_hi;
   __nv_bfloat16* out_lo;
@@ -225,7 +225,48 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         ptx::tmem_ld_32x32b_x32(taddr, r);
         ptx::tmem_ld_wait();
         const int ch0 = n0 + c0;
-        if (valid && ch0 < p.Cout) {
+        if (p.out_mode == 2) {
+          // Fused 2x2 stride-2 ceil-mode max pool (pooling_layer.cu:11-47).  With the 8x16 pixel
+          // tile a warp holds two image rows: lanes 0-15 row 2q, lanes 16-31 row 2q+1, so the pool
+          // window of an even column is lanes {l, l^1, l^16, l^17}: two shuffles per channel.
+          // Each of the 4 lanes of a window then stores 8 of the chunk's 32 channels.
+          const int part = (lane & 1) | ((lane >> 4) << 1);
+          float m[8];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = __uint_as_float(r[j]);
+            if (p.bias != nullptr && ch0 + j < p.Cout) x += __ldg(p.bias + ch0 + j);
+            if (p.relu) x = fmaxf(x, 0.f);
+            if (!valid) x = -3.402823466e+38f;
+            x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 1));
+            x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 16));
+            if ((j >> 3) == part) m[j & 7] = x;
+          }
+          const int hp = (h0 + 2 * q) >> 1;
+          const int wp = (w0 + (lane & 14)) >> 1;
+          const int Ho = (p.H + 1) >> 1, Wo = (p.W + 1) >> 1;
+          const int chp = ch0 + part * 8;
+          if (hp < Ho && wp < Wo && (h0 + 2 * q) < p.H && (w0 + (lane & 14)) < p.W && chp < p.Cout) {
+            const long long ppix = (static_cast<long long>(img) * Ho + hp) * Wo + wp;
+            __nv_bfloat16* ph = p.out_hi + ppix * p.out_pix_stride + p.out_ch_offset + chp;
+            __nv_bfloat16* pl = p.out_lo + ppix * p.out_pix_stride + p.out_ch_offset + chp;
+            uint32_t hw[4], lw[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float x0 = m[2 * e], x1 = m[2 * e + 1];
+              const __nv_bfloat16 h0b = __float2bfloat16_rn(x0);
+              const __nv_bfloat16 h1b = __float2bfloat16_rn(x1);
+              const __nv_bfloat16 l0b = __float2bfloat16_rn(x0 - __bfloat162float(h0b));
+              const __nv_bfloat16 l1b = __float2bfloat16_rn(x1 - __bfloat162float(h1b));
+              hw[e] = static_cast<uint32_t>(__bfloat16_as_ushort(h0b)) |
+                      (static_cast<uint32_t>(__bfloat16_as_ushort(h1b)) << 16);
+              lw[e] = static_cast<uint32_t>(__bfloat16_as_ushort(l0b)) |
+                      (static_cast<uint32_t>(__bfloat16_as_ushort(l1b)) << 16);
+            }
+            *reinterpret_cast<uint4*>(ph) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            *reinterpret_cast<uint4*>(pl) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          }
+        } else if (valid && ch0 < p.Cout) {
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -386,6 +427,9 @@ extern "C" int mnc_igemm_tc(const void* a_hi, const void* a_lo, int batch, int H
     return MNC_ERR_ARG;
   if (split_k < 1) split_k = 1;
   if (split_k > 1 && out_mode != 1) return MNC_ERR_ARG;
+  if (out_mode == 2 && (taps != 9 || Cout % 8 != 0 || out_pix_stride % 8 != 0 ||
+                        out_ch_offset % 8 != 0))
+    return MNC_ERR_ARG;
   const bool conv = (taps == 9);
   const int TH = conv ? 8 : 1, TW = conv ? 16 : 128;
   if (bn == 0) bn = (Cout <= 64) ? 64 : (Cout <= 128 ? 128 : 256);
@@ -413,7 +457,7 @@ extern "C" int mnc_igemm_tc(const void* a_hi, const void* a_lo, int batch, int H
   a.out_pix_stride = out_pix_stride;
   a.out_ch_offset = out_ch_offset;
   a.split_stride = split_stride;
-  const int vec = (out_mode == 0) ? 8 : 4;
+  const int vec = (out_mode == 1) ? 4 : 8;
   a.vec_ok = (out_pix_stride % vec == 0) && (out_ch_offset % vec == 0) &&
              (reinterpret_cast<uintptr_t>(out0) % 16 == 0) &&
              (out_mode == 1 || reinterpret_cast<uintptr_t>(out1) % 16 == 0) &&

@@ -298,7 +298,7 @@ __device__ __forceinline__ float4 max4(const float4 a, const float4 b) {
 }
 
 template <int SUB>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 roi_warp_split_kernel(const __nv_bfloat16* __restrict__ f_hi, const __nv_bfloat16* __restrict__ f_lo,
                       int C, int H, int W, const float* __restrict__ rois, float spatial_scale,
                       __nv_bfloat16* __restrict__ o14_hi, __nv_bfloat16* __restrict__ o14_lo,

@@ -54,7 +54,7 @@ timer = None  # set to a KernelTimer to enable
 
 def igemm(a, batch, H, W, cin, w, cout, taps, bias=None, relu=False, out=None, out_f32=None,
           out_pix_stride=None, out_ch_offset=0, split_k=1, split_stride=0, bn=0, max_ctas=0,
-          impl="tc"):
+          impl="tc", pool=False):
     """a: split [2, batch, H, W, cin]; w: split [2, cout, taps*cin].
     Writes split `out` ([2, ..., stride]) or fp32 `out_f32`."""
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
@@ -62,7 +62,7 @@ def igemm(a, batch, H, W, cin, w, cout, taps, bias=None, relu=False, out=None, o
         mode, o0, o1 = 1, out_f32, None
         stride = out_pix_stride if out_pix_stride is not None else cout
     else:
-        mode, o0, o1 = 0, out[0], out[1]
+        mode, o0, o1 = (2 if pool else 0), out[0], out[1]
         stride = out_pix_stride if out_pix_stride is not None else cout
     if timer is not None and impl == "tc":
         ev0 = torch.cuda.Event(enable_timing=True)

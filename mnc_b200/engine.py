@@ -34,6 +34,7 @@ class MNCEngine:
         """weights: {caffe name: (weight, bias)} fp32 tensors in Caffe layouts (see weights.py)."""
         self.device = torch.device(device)
         self.impl = impl
+        self.fuse_pool = True
         self.arch = arch_of(weights)
         self.sms = sm_count or torch.cuda.get_device_properties(self.device).multi_processor_count
         dev = self.device
@@ -125,6 +126,14 @@ class MNCEngine:
                 y = self._split_buf("conv5_3", B, H, W, cout)
             else:
                 y = bufs[nxt].view(-1)[:2 * B * H * W * cout].view(2, B, H, W, cout)
+            fuse = (name in POOL_AFTER) and self.impl == "tc" and self.fuse_pool
+            if fuse:
+                # Pooling fused into the conv epilogue: the full-resolution map is never written
+                Ho, Wo = _ceil_half(H), _ceil_half(W)
+                y = bufs[nxt].view(-1)[:2 * B * Ho * Wo * cout].view(2, B, Ho, Wo, cout)
+                dense.igemm(x, B, H, W, cin, wgt, cout, 9, bias=bias, relu=True, out=y, pool=True)
+                x, cur, cin, H, W = y, nxt, cout, Ho, Wo
+                continue
             dense.igemm(x, B, H, W, cin, wgt, cout, 9, bias=bias, relu=True, out=y, impl=self.impl)
             x, cur, cin = y, nxt, cout
             if name in POOL_AFTER:

@@ -91,3 +91,25 @@ def test_conv1_1_and_pool_and_layout():
     back = torch.zeros_like(pooled)
     dense.nchw_to_split(nchw, back)
     assert torch.equal(dense.merge(back), dense.merge(pooled))
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,bn", [(1, 75, 125, 64, 128, 128), (2, 37, 53, 64, 64, 64),
+                                               (1, 16, 32, 128, 256, 256), (1, 9, 17, 64, 72, 128)])
+def test_conv3x3_with_fused_ceil_mode_pool(B, H, W, Cin, Cout, bn):
+    """conv + bias + ReLU + 2x2/2 ceil-mode max pool in one epilogue == conv then Caffe pooling
+    (pooling_layer.cpp:90-93), including odd H/W (partial windows) and ragged tiles."""
+    import torch.nn.functional as F
+    from mnc_b200 import dense
+    torch.manual_seed(H + W)
+    x = torch.randn(B, Cin, H, W, device="cuda")
+    w = torch.randn(Cout, Cin, 3, 3, device="cuda") / (9 * Cin) ** 0.5
+    b = torch.randn(Cout, device="cuda")
+    xs = dense.split(x.permute(0, 2, 3, 1).contiguous())
+    ws = dense.conv_weight_to_split(w)
+    full = torch.zeros(2, B, H, W, Cout, device="cuda", dtype=torch.bfloat16)
+    dense.igemm(xs, B, H, W, Cin, ws, Cout, 9, bias=b, relu=True, out=full, bn=bn)
+    Ho, Wo = (H + 1) // 2, (W + 1) // 2
+    pooled = torch.zeros(2, B, Ho, Wo, Cout, device="cuda", dtype=torch.bfloat16)
+    dense.igemm(xs, B, H, W, Cin, ws, Cout, 9, bias=b, relu=True, out=pooled, bn=bn, pool=True)
+    want = F.max_pool2d(dense.merge(full).permute(0, 3, 1, 2), 2, 2, ceil_mode=True).permute(0, 2, 3, 1)
+    assert torch.equal(dense.merge(pooled), want)
