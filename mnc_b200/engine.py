@@ -92,9 +92,7 @@ class MNCEngine:
         bn = 64 if N <= 64 else (128 if (N <= 128 or N >= 1024) else 256)
         tiles = math.ceil(M / 128) * math.ceil(N / bn)
         k_steps = K // 64
-        split = 1
-        if self.impl == "tc" and tiles < self.sms * 0.7 and k_steps >= 16:
-            split = max(1, min(math.ceil(self.sms / tiles), k_steps // 8, 32))
+        split = self._pick_split(tiles, k_steps) if self.impl == "tc" else 1
         a4 = a.view(2, 1, 1, M, K)
         if split == 1:
             dense.igemm(a4, 1, 1, M, K, wgt, N, 1, bias=bias, relu=relu, out=out, out_f32=out_f32,
@@ -105,6 +103,33 @@ class MNCEngine:
         dense.igemm(a4, 1, 1, M, K, wgt, N, 1, out_f32=part, split_k=split, split_stride=M * N, bn=bn)
         dense.splitk_reduce(part, split, M * N, M, N, bias=bias, relu=relu, out=out,
                             out_f32=out_f32, out_row_stride=out_stride, out_ch_offset=out_ch_offset)
+
+    def _pick_split(self, tiles, k_steps, max_split=32):
+        """Split-K factor that minimises the wave count of a persistent launch: equal-size tiles
+        over `sms` CTAs cost ceil(tiles*s/sms)/s tile-times (e.g. fc6 at batch 8: 608 tiles on
+        148 SMs = 4.1 waves -> 5; with s = 3, 13/3 = 4.33).  Each extra split adds a little
+        fp32 partial traffic, modelled as 2 % per split."""
+        best, best_cost = 1, None
+        for s in range(1, max_split + 1):
+            if s > 1 and k_steps // s < 8:
+                break
+            cost = math.ceil(tiles * s / self.sms) / s * (1.0 + 0.02 * (s - 1))
+            if best_cost is None or cost < best_cost - 1e-9:
+                best, best_cost = s, cost
+        return best
+
+    def _conv(self, x, B, H, W, cin, wgt, cout, bias, out, key):
+        """3x3 conv + bias + ReLU -> split NHWC, split-K when whole waves would idle."""
+        bn = 64 if cout <= 64 else (128 if cout <= 128 else 256)
+        tiles = B * math.ceil(H / 8) * math.ceil(W / 16) * math.ceil(cout / bn)
+        split = self._pick_split(tiles, 9 * cin // 64, max_split=4) if self.impl == "tc" else 1
+        if split == 1:
+            dense.igemm(x, B, H, W, cin, wgt, cout, 9, bias=bias, relu=True, out=out, impl=self.impl)
+            return
+        M = B * H * W
+        part = self._f32_buf("splitk_" + key, split, M, cout)
+        dense.igemm(x, B, H, W, cin, wgt, cout, 9, out_f32=part, split_k=split, split_stride=M * cout)
+        dense.splitk_reduce(part, split, M * cout, M, cout, bias=bias, relu=True, out=out)
 
     # ------------------------------------------------------------------ trunk
     def trunk(self, data):
@@ -134,7 +159,7 @@ class MNCEngine:
                 dense.igemm(x, B, H, W, cin, wgt, cout, 9, bias=bias, relu=True, out=y, pool=True)
                 x, cur, cin, H, W = y, nxt, cout, Ho, Wo
                 continue
-            dense.igemm(x, B, H, W, cin, wgt, cout, 9, bias=bias, relu=True, out=y, impl=self.impl)
+            self._conv(x, B, H, W, cin, wgt, cout, bias, y, "conv")
             x, cur, cin = y, nxt, cout
             if name in POOL_AFTER:
                 Ho, Wo = _ceil_half(H), _ceil_half(W)
@@ -187,7 +212,7 @@ class MNCEngine:
         c5, r = self.c5, self.arch["rpn"]
         name, wgt, bias = self.convs[-1]
         rpn = self._split_buf("rpn", B, H5, W5, r)
-        dense.igemm(conv5_3, B, H5, W5, c5, wgt, r, 9, bias=bias, relu=True, out=rpn, impl=self.impl)
+        self._conv(conv5_3, B, H5, W5, c5, wgt, r, bias, rpn, "conv")
         rpn_out = self._f32_buf("rpn_out", B, H5, W5, 64)
         self._linear(rpn, B * H5 * W5, r, self.rpn_head[0], 54, self.rpn_head[1], False,
                      out_f32=rpn_out, out_stride=64, key="rpn")

@@ -1,7 +1,7 @@
 /*
  * oracle/mnc_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
  *
- * Plain-C, single-threaded CPU restatement of the CUDA kernels on the MNC inference hot path
+ * Plain-C CPU restatement (OpenMP over independent RoIs where the loop is embarrassingly parallel) of the CUDA kernels on the MNC inference hot path
  * of the reference (daijifeng001/MNC).  Only tests/, __graft_entry__.smoke() and bench.py's
  * cpu_baseline / --impl reference legs may load this library; mnc_b200/ never does.
  *
@@ -107,6 +107,7 @@ static float warp_bilinear(const float* data, int height, int width, float h, fl
  * [batch_idx,x1,y1,x2,y2], out (R,C,ph,pw). */
 void orc_roi_warp(const float* feat, int C, int H, int W, const float* rois, int R, int ph_n,
                   int pw_n, float spatial_scale, float* out) {
+#pragma omp parallel for schedule(dynamic, 4) /* RoIs are independent; per-element math unchanged */
   for (int n = 0; n < R; ++n) {
     const float* roi = rois + 5 * n;
     int roi_level = (int)roi[0];
@@ -138,6 +139,7 @@ void orc_mask_resize(const float* in, int N, int C, int ih_n, int iw_n, int oh_n
                      float* out) {
   float ratio_h = (float)ih_n / (float)oh_n;
   float ratio_w = (float)iw_n / (float)ow_n;
+#pragma omp parallel for
   for (int n = 0; n < N; ++n)
     for (int c = 0; c < C; ++c) {
       const float* plane = in + ((size_t)n * C + c) * ih_n * iw_n;
@@ -154,6 +156,7 @@ void orc_mask_resize(const float* in, int N, int C, int ih_n, int iw_n, int oh_n
 
 /* MaskPooling forward -- caffe-mnc/src/caffe/layers/mask_pooling_layer.cu:13-26. */
 void orc_mask_pool(const float* feat, const float* mask, int N, int C, int H, int W, float* out) {
+#pragma omp parallel for
   for (int n = 0; n < N; ++n)
     for (int c = 0; c < C; ++c)
       for (int i = 0; i < H * W; ++i)

@@ -38,7 +38,7 @@ def build_c():
     src = os.path.join(_HERE, "mnc_oracle.c")
     out = os.path.join(_HERE, "liboracle.so")
     if (not os.path.exists(out)) or os.path.getmtime(out) < os.path.getmtime(src):
-        subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-fno-fast-math", "-shared",
+        subprocess.check_call(["gcc", "-O2", "-fopenmp", "-ffp-contract=off", "-fno-fast-math", "-shared",
                                "-fPIC", "-o", out, src, "-lm"])
     return out
 
