@@ -108,40 +108,72 @@ igemm_simt_kernel(const __nv_bfloat16* __restrict__ a_hi, const __nv_bfloat16* _
 }
 
 // ---------------------------------------------------------------- split-K sum
-__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits,
-                                     long long split_stride, long long rows, int cols,
-                                     const float* __restrict__ bias, int relu, int out_mode,
-                                     void* out0, void* out1, long long out_row_stride,
-                                     int out_ch_offset) {
-  const long long total = rows * cols;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long r = i / cols;
-    const int c = static_cast<int>(i % cols);
-    float v = 0.f;
-    for (int s = 0; s < splits; ++s) v += partial[s * split_stride + i];  // fixed order
-    if (bias) v += bias[c];
-    if (relu) v = fmaxf(v, 0.f);
-    const long long o = r * out_row_stride + out_ch_offset + c;
-    if (out_mode == 0) {
-      __nv_bfloat16 hi, lo;
-      split_f32(v, hi, lo);
-      static_cast<__nv_bfloat16*>(out0)[o] = hi;
-      static_cast<__nv_bfloat16*>(out1)[o] = lo;
+// out = act(sum_s partial[s] + bias).  One thread per 4 consecutive columns (cols % 4 == 0 fast
+// path: 16-byte loads of each partial plane, 8-byte stores to both bf16 planes), rows on grid.y.
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ partial, int splits, long long split_stride,
+                     long long rows, int cols, const float* __restrict__ bias, int relu,
+                     int out_mode, void* out0, void* out1, long long out_row_stride,
+                     int out_ch_offset, int vec) {
+  const int c4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (c4 >= cols) return;
+  for (long long r = blockIdx.y; r < rows; r += gridDim.y) {
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* p = partial + r * cols + c4;
+    if (vec) {
+      for (int s = 0; s < splits; ++s) {  // fixed order: deterministic
+        const float4 x = __ldcs(reinterpret_cast<const float4*>(p + s * split_stride));
+        v[0] += x.x;
+        v[1] += x.y;
+        v[2] += x.z;
+        v[3] += x.w;
+      }
     } else {
-      static_cast<float*>(out0)[o] = v;
+      for (int s = 0; s < splits; ++s)
+        for (int e = 0; e < 4 && c4 + e < cols; ++e) v[e] += p[s * split_stride + e];
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (bias && c4 + e < cols) v[e] += __ldg(bias + c4 + e);
+      if (relu) v[e] = fmaxf(v[e], 0.f);
+    }
+    const long long o = r * out_row_stride + out_ch_offset + c4;
+    if (out_mode == 0) {
+      __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) split_f32(v[e], hi[e], lo[e]);
+      if (vec) {
+        *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(out0) + o) = make_uint2(
+            static_cast<uint32_t>(__bfloat16_as_ushort(hi[0])) | (static_cast<uint32_t>(__bfloat16_as_ushort(hi[1])) << 16),
+            static_cast<uint32_t>(__bfloat16_as_ushort(hi[2])) | (static_cast<uint32_t>(__bfloat16_as_ushort(hi[3])) << 16));
+        *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(out1) + o) = make_uint2(
+            static_cast<uint32_t>(__bfloat16_as_ushort(lo[0])) | (static_cast<uint32_t>(__bfloat16_as_ushort(lo[1])) << 16),
+            static_cast<uint32_t>(__bfloat16_as_ushort(lo[2])) | (static_cast<uint32_t>(__bfloat16_as_ushort(lo[3])) << 16));
+      } else {
+        for (int e = 0; e < 4 && c4 + e < cols; ++e) {
+          static_cast<__nv_bfloat16*>(out0)[o + e] = hi[e];
+          static_cast<__nv_bfloat16*>(out1)[o + e] = lo[e];
+        }
+      }
+    } else {
+      if (vec) {
+        *reinterpret_cast<float4*>(static_cast<float*>(out0) + o) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+        for (int e = 0; e < 4 && c4 + e < cols; ++e) static_cast<float*>(out0)[o + e] = v[e];
+      }
     }
   }
 }
 
 // -------------------------------------------------------------------- conv1_1
-// Each thread computes 4 horizontally adjacent pixels x all 64 output channels.  The 3x6x3 input
-// window lives in registers; weights sit in shared memory as [27][64] and are fetched with
-// broadcast 128-bit loads, each feeding 16 FMAs (4 pixels x 4 channels), so the kernel is bound by
-// FMA issue rather than by shared-memory operand traffic.  Input is the fp32 NCHW `data` blob.
+// Lane = (pixel quad, channel octet): a thread computes 4 horizontally adjacent pixels x 8 output
+// channels; the 8 lanes sharing a pixel quad cover all 64 channels, so every store instruction
+// writes whole 128-byte NHWC pixel rows (no partial-sector writes, which cost read-modify-write
+// traffic in L2).  The 3x6x3 input window sits in registers (loads are shared through L1 by the
+// 8 lanes of a quad); weights come from shared memory with 128-bit loads, 2 per 32 FMAs.
 constexpr int kC11Pix = 4;
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 conv1_1_kernel(const float* __restrict__ data, int batch, int H, int W,
                const float* __restrict__ weight, const float* __restrict__ bias,
                __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
@@ -156,10 +188,11 @@ conv1_1_kernel(const float* __restrict__ data, int batch, int H, int W,
   __syncthreads();
   const int Wq = (W + kC11Pix - 1) / kC11Pix;
   const long long HW = static_cast<long long>(H) * W;
-  const long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (q >= static_cast<long long>(batch) * H * Wq) return;
-  const int img = static_cast<int>(q / (static_cast<long long>(H) * Wq));
-  const int r = static_cast<int>(q % (static_cast<long long>(H) * Wq));
+  const long long gq = static_cast<long long>(blockIdx.x) * (blockDim.x / 8) + threadIdx.x / 8;
+  const int oc = (threadIdx.x & 7) * 8;  // first of this lane's 8 output channels
+  if (gq >= static_cast<long long>(batch) * H * Wq) return;
+  const int img = static_cast<int>(gq / (static_cast<long long>(H) * Wq));
+  const int r = static_cast<int>(gq % (static_cast<long long>(H) * Wq));
   const int h = r / Wq, w0 = (r % Wq) * kC11Pix;
   float in[3][3][kC11Pix + 2];
 #pragma unroll
@@ -174,48 +207,45 @@ conv1_1_kernel(const float* __restrict__ data, int batch, int H, int W,
           v = __ldg(data + (static_cast<long long>(img) * 3 + c) * HW + static_cast<long long>(hs) * W + wsx);
         in[c][ky][x] = v;
       }
-#pragma unroll 1
-  for (int c0 = 0; c0 < COUT; c0 += 8) {
-    float acc[kC11Pix][8];
+  float acc[kC11Pix][8];
 #pragma unroll
-    for (int p = 0; p < kC11Pix; ++p)
+  for (int p = 0; p < kC11Pix; ++p)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[p][j] = 0.f;
+    for (int j = 0; j < 8; ++j) acc[p][j] = 0.f;
 #pragma unroll
-    for (int c = 0; c < 3; ++c)
+  for (int c = 0; c < 3; ++c)
 #pragma unroll
-      for (int ky = 0; ky < 3; ++ky)
+    for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          const int k = c * 9 + ky * 3 + kx;
-          const float4 wa = *reinterpret_cast<const float4*>(&ws[k][c0]);
-          const float4 wb = *reinterpret_cast<const float4*>(&ws[k][c0 + 4]);
-          const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+      for (int kx = 0; kx < 3; ++kx) {
+        const int k = c * 9 + ky * 3 + kx;
+        const float4 wa = *reinterpret_cast<const float4*>(&ws[k][oc]);
+        const float4 wb = *reinterpret_cast<const float4*>(&ws[k][oc + 4]);
+        const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
-          for (int p = 0; p < kC11Pix; ++p)
+        for (int p = 0; p < kC11Pix; ++p)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[p][j] = fmaf(in[c][ky][p + kx], wv[j], acc[p][j]);
-        }
-#pragma unroll
-    for (int p = 0; p < kC11Pix; ++p) {
-      if (w0 + p >= W) continue;
-      const long long pix = (static_cast<long long>(img) * H + h) * W + w0 + p;
-      uint32_t hw[4], lw[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float x0 = fmaxf(acc[p][2 * e] + bs[c0 + 2 * e], 0.f);
-        const float x1 = fmaxf(acc[p][2 * e + 1] + bs[c0 + 2 * e + 1], 0.f);
-        __nv_bfloat16 h0, l0, h1, l1;
-        split_f32(x0, h0, l0);
-        split_f32(x1, h1, l1);
-        hw[e] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) |
-                (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
-        lw[e] = static_cast<uint32_t>(__bfloat16_as_ushort(l0)) |
-                (static_cast<uint32_t>(__bfloat16_as_ushort(l1)) << 16);
+          for (int j = 0; j < 8; ++j) acc[p][j] = fmaf(in[c][ky][p + kx], wv[j], acc[p][j]);
       }
-      *reinterpret_cast<uint4*>(out_hi + pix * COUT + c0) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-      *reinterpret_cast<uint4*>(out_lo + pix * COUT + c0) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+#pragma unroll
+  for (int p = 0; p < kC11Pix; ++p) {
+    if (w0 + p >= W) continue;
+    const long long pix = (static_cast<long long>(img) * H + h) * W + w0 + p;
+    uint32_t hw[4], lw[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float x0 = fmaxf(acc[p][2 * e] + bs[oc + 2 * e], 0.f);
+      const float x1 = fmaxf(acc[p][2 * e + 1] + bs[oc + 2 * e + 1], 0.f);
+      __nv_bfloat16 h0, l0, h1, l1;
+      split_f32(x0, h0, l0);
+      split_f32(x1, h1, l1);
+      hw[e] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) |
+              (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
+      lw[e] = static_cast<uint32_t>(__bfloat16_as_ushort(l0)) |
+              (static_cast<uint32_t>(__bfloat16_as_ushort(l1)) << 16);
     }
+    *reinterpret_cast<uint4*>(out_hi + pix * COUT + oc) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    *reinterpret_cast<uint4*>(out_lo + pix * COUT + oc) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
   }
 }
 
@@ -386,9 +416,17 @@ extern "C" int mnc_splitk_reduce(const float* partial, int splits, long long spl
                                  long long rows, int cols, const float* bias, int relu,
                                  int out_mode, void* out0, void* out1, long long out_row_stride,
                                  int out_ch_offset, void* stream) {
-  splitk_reduce_kernel<<<grid_for(rows * cols, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  if (rows <= 0 || cols <= 0) return MNC_OK;
+  const int vec = (cols % 4 == 0) && (split_stride % 4 == 0) && (out_row_stride % 4 == 0) &&
+                  (out_ch_offset % 4 == 0) && (reinterpret_cast<uintptr_t>(partial) % 16 == 0) &&
+                  (reinterpret_cast<uintptr_t>(out0) % 16 == 0) &&
+                  (out_mode == 1 || reinterpret_cast<uintptr_t>(out1) % 8 == 0);
+  const int tx = (cols + 3) / 4;
+  const int block = tx >= 256 ? 256 : (tx >= 128 ? 128 : (tx >= 64 ? 64 : 32));
+  dim3 grid((tx + block - 1) / block, static_cast<unsigned>(rows < 32768 ? rows : 32768));
+  splitk_reduce_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
       partial, splits, split_stride, rows, cols, bias, relu, out_mode, out0, out1, out_row_stride,
-      out_ch_offset);
+      out_ch_offset, vec);
   return check_launch();
 }
 
@@ -396,7 +434,7 @@ extern "C" int mnc_conv1_1(const float* data_nchw, int batch, int H, int W, cons
                            const float* bias, int Cout, void* out_hi, void* out_lo, void* stream) {
   if (Cout != 64) return MNC_ERR_ARG;
   const long long quads = static_cast<long long>(batch) * H * ((W + kC11Pix - 1) / kC11Pix);
-  conv1_1_kernel<<<static_cast<unsigned>((quads + 127) / 128), 128, 0,
+  conv1_1_kernel<<<static_cast<unsigned>((quads + 31) / 32), 256, 0,
                    static_cast<cudaStream_t>(stream)>>>(
       data_nchw, batch, H, W, weight, bias, static_cast<__nv_bfloat16*>(out_hi),
       static_cast<__nv_bfloat16*>(out_lo));

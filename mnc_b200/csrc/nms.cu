@@ -69,7 +69,14 @@ nms_mask_kernel(const float* __restrict__ boxes, int box_stride, long long probl
     // reference: row box is `cur_box` (a), column box is block_boxes (b); within the diagonal
     // tile only columns j > i are tested (nms_kernel.cu:66-69)
     bool sup = false;
-    if (col_ok && r < n && col > r) sup = dev_iou(row_boxes[rl], cb) > thresh;
+    if (col_ok && r < n && col > r) {
+      // disjoint boxes: interS == 0 exactly, and 0 / x > thresh is false for every x (NaN
+      // included), so the IEEE division of devIoU can be skipped without changing the result
+      const float* a = row_boxes[rl];
+      const bool disjoint = (min(a[2], cb[2]) - max(a[0], cb[0]) + 1 <= 0.f) ||
+                            (min(a[3], cb[3]) - max(a[1], cb[1]) + 1 <= 0.f);
+      if (!disjoint || thresh < 0.f) sup = dev_iou(a, cb) > thresh;
+    }
     const uint32_t bits = __ballot_sync(0xffffffffu, sup);
     if (lane == 0) halves[rl][half] = bits;
   }

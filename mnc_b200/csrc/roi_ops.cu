@@ -283,22 +283,29 @@ __device__ __forceinline__ void st_split4(__nv_bfloat16* hi, __nv_bfloat16* lo, 
   *reinterpret_cast<uint2*>(hi + off) = make_uint2(pack_bf2(h0, h1), pack_bf2(h2, h3));
   *reinterpret_cast<uint2*>(lo + off) = make_uint2(pack_bf2(l0, l1), pack_bf2(l2, l3));
 }
+// fused-path bilinear: same weights-first formula, evaluated with FMAs (the fused outputs are
+// re-quantised to split-bf16 and compared at tolerance; the bit-exact form lives in bilerp()).
 __device__ __forceinline__ float4 bilerp4(const float w1, const float w2, const float w3,
                                           const float w4, const float4 v1, const float4 v2,
                                           const float4 v3, const float4 v4) {
   float4 r;
-  r.x = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w1, v1.x), __fmul_rn(w2, v2.x)), __fmul_rn(w3, v3.x)), __fmul_rn(w4, v4.x));
-  r.y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w1, v1.y), __fmul_rn(w2, v2.y)), __fmul_rn(w3, v3.y)), __fmul_rn(w4, v4.y));
-  r.z = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w1, v1.z), __fmul_rn(w2, v2.z)), __fmul_rn(w3, v3.z)), __fmul_rn(w4, v4.z));
-  r.w = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w1, v1.w), __fmul_rn(w2, v2.w)), __fmul_rn(w3, v3.w)), __fmul_rn(w4, v4.w));
+  r.x = fmaf(w4, v4.x, fmaf(w3, v3.x, fmaf(w2, v2.x, w1 * v1.x)));
+  r.y = fmaf(w4, v4.y, fmaf(w3, v3.y, fmaf(w2, v2.y, w1 * v1.y)));
+  r.z = fmaf(w4, v4.z, fmaf(w3, v3.z, fmaf(w2, v2.z, w1 * v1.z)));
+  r.w = fmaf(w4, v4.w, fmaf(w3, v3.w, fmaf(w2, v2.w, w1 * v1.w)));
   return r;
 }
 __device__ __forceinline__ float4 max4(const float4 a, const float4 b) {
   return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
 }
 
+// Sliding-window form: a thread owns 4 channels and walks the P sample columns of one sample
+// row left to right, keeping the four bilinear corner values in registers.  Sample columns are
+// monotone in w, so a feature column is (re)loaded only when the sample moves onto it: about
+// 2*(roi_w + 2) loads per sample row instead of 4*P.  Cell maxima (SUB x SUB samples -> one 14x14
+// cell) and the 7x7 pool accumulate in registers; the arithmetic per sample is unchanged.
 template <int SUB>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(128)
 roi_warp_split_kernel(const __nv_bfloat16* __restrict__ f_hi, const __nv_bfloat16* __restrict__ f_lo,
                       int C, int H, int W, const float* __restrict__ rois, float spatial_scale,
                       __nv_bfloat16* __restrict__ o14_hi, __nv_bfloat16* __restrict__ o14_lo,
@@ -318,43 +325,64 @@ roi_warp_split_kernel(const __nv_bfloat16* __restrict__ f_hi, const __nv_bfloat1
   }
   __syncthreads();
   const long long img_off = static_cast<long long>(g.level) * H * W * C;
-  const int c4n = C / 4;
   const float kNeg = -3.402823466e+38f;
-  // work item = (pooled column jp in 0..6, channel quad)
-  for (int item = threadIdx.x; item < 7 * c4n; item += blockDim.x) {
-    const int jp = item / c4n;
-    const int c = (item - jp * c4n) * 4;
-    float4 best7 = make_float4(kNeg, kNeg, kNeg, kNeg);
+  for (int c = threadIdx.x * 4; c < C; c += blockDim.x * 4) {
+    float4 best7[7];
 #pragma unroll
+    for (int j = 0; j < 7; ++j) best7[j] = make_float4(kNeg, kNeg, kNeg, kNeg);
+#pragma unroll 1
     for (int dy = 0; dy < 2; ++dy) {
+      float4 cell[14];
 #pragma unroll
-      for (int dx = 0; dx < 2; ++dx) {
-        const int j = 2 * jp + dx;
-        float4 cell = make_float4(kNeg, kNeg, kNeg, kNeg);
+      for (int j = 0; j < 14; ++j) cell[j] = make_float4(kNeg, kNeg, kNeg, kNeg);
+#pragma unroll 1
+      for (int sy = 0; sy < SUB; ++sy) {
+        const AxisTap th = tap_h[dy * SUB + sy];
+        const long long row_lo = img_off + static_cast<long long>(th.lo) * W * C + c;
+        const long long row_hi = img_off + static_cast<long long>(th.hi) * W * C + c;
+        int cur_lo = -1, cur_hi = -1;
+        float4 a_lo = make_float4(0.f, 0.f, 0.f, 0.f), a_hi = a_lo, b_lo = a_lo, b_hi = a_lo;
 #pragma unroll
-        for (int sy = 0; sy < SUB; ++sy) {
-          const AxisTap th = tap_h[dy * SUB + sy];
-#pragma unroll
-          for (int sx = 0; sx < SUB; ++sx) {
-            const AxisTap tw = tap_w[j * SUB + sx];
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (th.ok && tw.ok) {
-              const long long b = img_off + c;
-              const float4 v1 = ld_split4(f_hi, f_lo, b + (static_cast<long long>(th.lo) * W + tw.lo) * C);
-              const float4 v2 = ld_split4(f_hi, f_lo, b + (static_cast<long long>(th.lo) * W + tw.hi) * C);
-              const float4 v3 = ld_split4(f_hi, f_lo, b + (static_cast<long long>(th.hi) * W + tw.lo) * C);
-              const float4 v4 = ld_split4(f_hi, f_lo, b + (static_cast<long long>(th.hi) * W + tw.hi) * C);
-              v = bilerp4(__fmul_rn(th.h, tw.h), __fmul_rn(th.h, tw.l), __fmul_rn(th.l, tw.h),
-                          __fmul_rn(th.l, tw.l), v1, v2, v3, v4);
+        for (int pw = 0; pw < P; ++pw) {
+          const AxisTap tw = tap_w[pw];
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (th.ok && tw.ok) {
+            if (tw.lo != cur_lo) {
+              if (tw.lo == cur_hi) {
+                a_lo = a_hi;
+                b_lo = b_hi;
+              } else {
+                a_lo = ld_split4(f_hi, f_lo, row_lo + static_cast<long long>(tw.lo) * C);
+                b_lo = ld_split4(f_hi, f_lo, row_hi + static_cast<long long>(tw.lo) * C);
+              }
+              cur_lo = tw.lo;
             }
-            cell = max4(cell, v);
+            if (tw.hi != cur_hi) {
+              if (tw.hi == cur_lo) {
+                a_hi = a_lo;
+                b_hi = b_lo;
+              } else {
+                a_hi = ld_split4(f_hi, f_lo, row_lo + static_cast<long long>(tw.hi) * C);
+                b_hi = ld_split4(f_hi, f_lo, row_hi + static_cast<long long>(tw.hi) * C);
+              }
+              cur_hi = tw.hi;
+            }
+            v = bilerp4(__fmul_rn(th.h, tw.h), __fmul_rn(th.h, tw.l), __fmul_rn(th.l, tw.h),
+                        __fmul_rn(th.l, tw.l), a_lo, a_hi, b_lo, b_hi);
           }
+          cell[pw / SUB] = max4(cell[pw / SUB], v);
         }
-        st_split4(o14_hi, o14_lo, ((static_cast<long long>(r) * 14 + (2 * t + dy)) * 14 + j) * C + c, cell);
-        best7 = max4(best7, cell);
+      }
+      const long long obase = ((static_cast<long long>(r) * 14 + (2 * t + dy)) * 14) * C + c;
+#pragma unroll
+      for (int j = 0; j < 14; ++j) {
+        st_split4(o14_hi, o14_lo, obase + static_cast<long long>(j) * C, cell[j]);
+        best7[j >> 1] = max4(best7[j >> 1], cell[j]);
       }
     }
-    st_split4(o7_hi, o7_lo, ((static_cast<long long>(r) * 7 + t) * 7 + jp) * C + c, best7);
+    const long long pbase = ((static_cast<long long>(r) * 7 + t) * 7) * C + c;
+#pragma unroll
+    for (int j = 0; j < 7; ++j) st_split4(o7_hi, o7_lo, pbase + static_cast<long long>(j) * C, best7[j]);
   }
 }
 
@@ -482,13 +510,13 @@ extern "C" int mnc_roi_warp_split(const void* f_hi, const void* f_lo, int C, int
   dim3 grid(R, 7);
   auto s = static_cast<cudaStream_t>(stream);
   if (sub == 2)
-    roi_warp_split_kernel<2><<<grid, 256, 0, s>>>(
+    roi_warp_split_kernel<2><<<grid, 128, 0, s>>>(
         static_cast<const __nv_bfloat16*>(f_hi), static_cast<const __nv_bfloat16*>(f_lo), C, H, W,
         rois, spatial_scale, static_cast<__nv_bfloat16*>(o14_hi),
         static_cast<__nv_bfloat16*>(o14_lo), static_cast<__nv_bfloat16*>(o7_hi),
         static_cast<__nv_bfloat16*>(o7_lo));
   else
-    roi_warp_split_kernel<1><<<grid, 256, 0, s>>>(
+    roi_warp_split_kernel<1><<<grid, 128, 0, s>>>(
         static_cast<const __nv_bfloat16*>(f_hi), static_cast<const __nv_bfloat16*>(f_lo), C, H, W,
         rois, spatial_scale, static_cast<__nv_bfloat16*>(o14_hi),
         static_cast<__nv_bfloat16*>(o14_lo), static_cast<__nv_bfloat16*>(o7_hi),
