@@ -56,6 +56,10 @@ int mnc_igemm_tc(const void* a_hi, const void* a_lo, int batch, int H, int W, in
                  int out_ch_offset, int split_k, long long split_stride, int bn, int max_ctas,
                  void* stream);
 
+/* Thread-block-cluster size of mnc_igemm_tc launches: 2 (default) = CTA pairs share each weight
+ * tile via TMA multicast; 1 = no clusters. */
+int mnc_igemm_set_cluster(int cluster_size);
+
 /* Same contract as mnc_igemm_tc on the fp32 SIMT pipes (exact fp32 FMA on hi+lo operands).
  * Not on the product path: it is the on-device cross-check for the tensor-core kernel. */
 int mnc_igemm_simt(const void* a_hi, const void* a_lo, int batch, int H, int W, int Cin,
@@ -159,9 +163,9 @@ int mnc_mask_pool_nchw(const float* feat, const float* mask, int N, int C, int H
                        float* out, void* stream);
 /* Fused engine forms on split NHWC: RoI warp (+2x2 max when sub == 2) to [R][14][14][C] plus the
  * 7x7 box pool [R][7][7][C]; sigmoid + 21->14 mask resize; mask pooling + 2x2 max. */
-int mnc_roi_warp_split(const void* f_hi, const void* f_lo, int C, int H, int W, const float* rois,
-                       int R, int sub, float spatial_scale, void* o14_hi, void* o14_lo, void* o7_hi,
-                       void* o7_lo, void* stream);
+int mnc_roi_warp_split(const float* feat_nhwc /* fp32 [B][H][W][C] */, int C, int H, int W,
+                       const float* rois, int R, int sub, float spatial_scale, void* o14_hi,
+                       void* o14_lo, void* o7_hi, void* o7_lo, void* stream);
 int mnc_sigmoid_mask_resize(const float* logits, int stride, int R, int mask_size, int out_size,
                             float* mask_proposal, float* mask_resized, void* stream);
 int mnc_mask_pool_split(const void* f_hi, const void* f_lo, const float* mask14, int R, int C,

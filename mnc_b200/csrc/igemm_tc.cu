@@ -60,25 +60,44 @@ struct IgemmCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-__device__ __forceinline__ void decode_tile(const IgemmArgs& p, int t, int& img, int& h0, int& w0,
-                                            int& n0, int& k_begin, int& k_end, int TH, int TW,
+struct Tile {
+  int img, h0, w0, n0, kb, ke, ks;
+  bool dummy;
+};
+
+// Work item `t` of CTA `rank` in a cluster of CL CTAs.  A cluster processes CL consecutive
+// spatial tiles that share one Cout tile (so the weight tile can be multicast); when the spatial
+// tile count is not a multiple of CL the last item carries a dummy tile (all-zero A, no stores).
+template <int CL>
+__device__ __forceinline__ Tile decode_tile(const IgemmArgs& p, int t, int rank, int TH, int TW,
                                             int BN) {
   const int per_img = p.tiles_h * p.tiles_w;
   const int spatial = p.batch * per_img;
-  const int sp = t % spatial;
-  const int rest = t / spatial;
+  const int groups = (spatial + CL - 1) / CL;
+  const int g = t % groups;
+  const int rest = t / groups;
   const int nt = rest % p.tiles_n;
-  const int ks = rest / p.tiles_n;
-  img = sp / per_img;
-  const int r = sp % per_img;
-  h0 = (r / p.tiles_w) * TH;
-  w0 = (r % p.tiles_w) * TW;
-  n0 = nt * BN;
-  k_begin = static_cast<int>(static_cast<long long>(p.k_steps) * ks / p.split_k);
-  k_end = static_cast<int>(static_cast<long long>(p.k_steps) * (ks + 1) / p.split_k);
+  Tile tl;
+  tl.ks = rest / p.tiles_n;
+  const int sp = g * CL + rank;
+  tl.dummy = sp >= spatial;
+  if (tl.dummy) {
+    tl.img = p.batch;  // out of bounds in the batch dimension: TMA zero-fills the A tile
+    tl.h0 = 0;
+    tl.w0 = 0;
+  } else {
+    tl.img = sp / per_img;
+    const int r = sp % per_img;
+    tl.h0 = (r / p.tiles_w) * TH;
+    tl.w0 = (r % p.tiles_w) * TW;
+  }
+  tl.n0 = nt * BN;
+  tl.kb = static_cast<int>(static_cast<long long>(p.k_steps) * tl.ks / p.split_k);
+  tl.ke = static_cast<int>(static_cast<long long>(p.k_steps) * (tl.ks + 1) / p.split_k);
+  return tl;
 }
 
-template <int TH, int TW, int BN>
+template <int TH, int TW, int BN, int CL>
 __global__ void __launch_bounds__(256, 1)
 igemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                 const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
@@ -98,8 +117,13 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = p.split_k * p.tiles_n * p.batch * p.tiles_h * p.tiles_w;
+  const int spatial_tiles = p.batch * p.tiles_h * p.tiles_w;
+  const int total_tiles = p.split_k * p.tiles_n * ((spatial_tiles + CL - 1) / CL);
   const int kchunks = p.Cin / kBlockK;
+  const int rank = (CL > 1) ? static_cast<int>(ptx::cluster_ctarank()) : 0;
+  const int first = blockIdx.x / CL;      // work items are owned by clusters
+  const int stride = gridDim.x / CL;
+  constexpr uint16_t kMask = static_cast<uint16_t>((1u << CL) - 1u);
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm_a_hi);
@@ -110,7 +134,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
-      ptx::mbar_init(&empty_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], CL);  // every CTA of the cluster must release the stage
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tfull_bar[a], 1);
@@ -123,6 +147,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (CL > 1) ptx::cluster_sync_all();  // peers' barriers are initialised before any remote arrive
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -131,10 +156,9 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        int img, h0, w0, n0, kb, ke;
-        decode_tile(p, t, img, h0, w0, n0, kb, ke, TH, TW, BN);
-        for (int k = kb; k < ke; ++k) {
+      for (int t = first; t < total_tiles; t += stride) {
+        const Tile tl = decode_tile<CL>(p, t, rank, TH, TW, BN);
+        for (int k = tl.kb; k < tl.ke; ++k) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + stage * Cfg::kStageBytes;
           ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
@@ -145,13 +169,24 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
             dy = tap / 3 - 1;
             dx = tap % 3 - 1;
           }
-          ptx::tma_load_4d(st, &tm_a_hi, &full_bar[stage], kc * kBlockK, w0 + dx, h0 + dy, img);
-          ptx::tma_load_4d(st + kABytes, &tm_a_lo, &full_bar[stage], kc * kBlockK, w0 + dx,
-                           h0 + dy, img);
-          ptx::tma_load_2d(st + 2 * kABytes, &tm_b_hi, &full_bar[stage],
-                           tap * p.Cin + kc * kBlockK, n0);
-          ptx::tma_load_2d(st + 2 * kABytes + Cfg::kBBytes, &tm_b_lo, &full_bar[stage],
-                           tap * p.Cin + kc * kBlockK, n0);
+          ptx::tma_load_4d(st, &tm_a_hi, &full_bar[stage], kc * kBlockK, tl.w0 + dx, tl.h0 + dy,
+                           tl.img);
+          ptx::tma_load_4d(st + kABytes, &tm_a_lo, &full_bar[stage], kc * kBlockK, tl.w0 + dx,
+                           tl.h0 + dy, tl.img);
+          if (CL == 1) {
+            ptx::tma_load_2d(st + 2 * kABytes, &tm_b_hi, &full_bar[stage],
+                             tap * p.Cin + kc * kBlockK, tl.n0);
+            ptx::tma_load_2d(st + 2 * kABytes + Cfg::kBBytes, &tm_b_lo, &full_bar[stage],
+                             tap * p.Cin + kc * kBlockK, tl.n0);
+          } else {
+            // each CTA fetches 1/CL of the weight tile and multicasts it to the whole cluster
+            constexpr int kSlice = Cfg::kBBytes / CL;
+            const int nrow = tl.n0 + rank * (BN / CL);
+            ptx::tma_load_2d_mcast(st + 2 * kABytes + rank * kSlice, &tm_b_hi, &full_bar[stage],
+                                   tap * p.Cin + kc * kBlockK, nrow, kMask);
+            ptx::tma_load_2d_mcast(st + 2 * kABytes + Cfg::kBBytes + rank * kSlice, &tm_b_lo,
+                                   &full_bar[stage], tap * p.Cin + kc * kBlockK, nrow, kMask);
+          }
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -166,9 +201,9 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
-        int img, h0, w0, n0, kb, ke;
-        decode_tile(p, t, img, h0, w0, n0, kb, ke, TH, TW, BN);
+      for (int t = first; t < total_tiles; t += stride, ++local) {
+        const Tile tl = decode_tile<CL>(p, t, rank, TH, TW, BN);
+        const int kb = tl.kb, ke = tl.ke;
         const int acc = local & 1;
         const uint32_t acc_phase = (local >> 1) & 1;
         ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -192,7 +227,10 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
             ptx::umma_bf16_ss(tmem_d, da_hi, db_lo, idesc, 1u);
             ptx::umma_bf16_ss(tmem_d, da_hi, db_hi, idesc, 1u);
           }
-          ptx::umma_commit(&empty_bar[stage]);
+          if (CL == 1)
+            ptx::umma_commit(&empty_bar[stage]);
+          else
+            ptx::umma_commit_mcast(&empty_bar[stage], kMask);  // frees the stage in every CTA
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -206,15 +244,14 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     const int q = warp - 4;  // TMEM lane quarter == warp_id % 4
     const int row = q * 32 + lane;
     int local = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
-      int img, h0, w0, n0, kb, ke;
-      decode_tile(p, t, img, h0, w0, n0, kb, ke, TH, TW, BN);
-      const int ks = (t / (p.batch * p.tiles_h * p.tiles_w)) / p.tiles_n;
+    for (int t = first; t < total_tiles; t += stride, ++local) {
+      const Tile tl = decode_tile<CL>(p, t, rank, TH, TW, BN);
+      const int img = tl.img, h0 = tl.h0, w0 = tl.w0, n0 = tl.n0, ks = tl.ks;
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
       const int h = h0 + row / TW;
       const int w = w0 + row % TW;
-      const bool valid = (h < p.H) && (w < p.W);
+      const bool valid = !tl.dummy && (h < p.H) && (w < p.W);
       const long long pix = (static_cast<long long>(img) * p.H + h) * p.W + w;
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
       ptx::tc_fence_after();
@@ -246,7 +283,8 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
           const int wp = (w0 + (lane & 14)) >> 1;
           const int Ho = (p.H + 1) >> 1, Wo = (p.W + 1) >> 1;
           const int chp = ch0 + part * 8;
-          if (hp < Ho && wp < Wo && (h0 + 2 * q) < p.H && (w0 + (lane & 14)) < p.W && chp < p.Cout) {
+          if (!tl.dummy && hp < Ho && wp < Wo && (h0 + 2 * q) < p.H && (w0 + (lane & 14)) < p.W &&
+              chp < p.Cout) {
             const long long ppix = (static_cast<long long>(img) * Ho + hp) * Wo + wp;
             __nv_bfloat16* ph = p.out_hi + ppix * p.out_pix_stride + p.out_ch_offset + chp;
             __nv_bfloat16* pl = p.out_lo + ppix * p.out_pix_stride + p.out_ch_offset + chp;
@@ -326,6 +364,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (CL > 1) ptx::cluster_sync_all();  // no CTA leaves while a peer may still signal its barriers
   if (warp == 2) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
@@ -369,12 +408,12 @@ static int make_act_map(CUtensorMap* m, const void* base, int N, int H, int W, i
 }
 
 // bf16 [Cout][Ktot] weight plane, box [BN][64].
-static int make_wgt_map(CUtensorMap* m, const void* base, int Cout, long long Ktot, int BN) {
+static int make_wgt_map(CUtensorMap* m, const void* base, int Cout, long long Ktot, int box_rows) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return MNC_ERR_DRIVER;
   cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)Cout};
   cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
-  cuuint32_t box[2] = {64, (cuuint32_t)BN};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -392,12 +431,12 @@ static int sm_count() {
   return n;
 }
 
-template <int TH, int TW, int BN>
+template <int TH, int TW, int BN, int CL>
 static int launch_igemm(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo,
                         const CUtensorMap& tb_hi, const CUtensorMap& tb_lo, const IgemmArgs& a,
                         int max_ctas, cudaStream_t stream) {
   using Cfg = IgemmCfg<BN>;
-  auto kern = igemm_tc_kernel<TH, TW, BN>;
+  auto kern = igemm_tc_kernel<TH, TW, BN, CL>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e =
@@ -405,17 +444,41 @@ static int launch_igemm(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo,
     if (e != cudaSuccess) return MNC_ERR_CUDA;
     attr_set = true;
   }
-  const int total = a.split_k * a.tiles_n * a.batch * a.tiles_h * a.tiles_w;
+  const int spatial = a.batch * a.tiles_h * a.tiles_w;
+  const int total = a.split_k * a.tiles_n * ((spatial + CL - 1) / CL);
   int grid = sm_count();
   if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
-  if (total < grid) grid = total;
-  kern<<<grid, 256, Cfg::kSmemBytes, stream>>>(ta_hi, ta_lo, tb_hi, tb_lo, a);
-  return cudaGetLastError() == cudaSuccess ? MNC_OK : MNC_ERR_CUDA;
+  if (total * CL < grid) grid = total * CL;
+  grid = (grid / CL) * CL;
+  if (grid < CL) grid = CL;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta_hi, ta_lo, tb_hi, tb_lo, a);
+  return e == cudaSuccess ? MNC_OK : MNC_ERR_CUDA;
 }
 
 }  // namespace mnc
 
 using namespace mnc;
+
+// Cluster size used by mnc_igemm_tc launches (1 or 2).  2 = pairs of CTAs along the pixel/row
+// dimension share each weight tile through TMA multicast (halves weight traffic from L2).
+static int g_igemm_cluster = 2;
+extern "C" int mnc_igemm_set_cluster(int cl) {
+  if (cl != 1 && cl != 2) return MNC_ERR_ARG;
+  g_igemm_cluster = cl;
+  return MNC_OK;
+}
 
 extern "C" int mnc_igemm_tc(const void* a_hi, const void* a_lo, int batch, int H, int W, int Cin,
                             const void* w_hi, const void* w_lo, int Cout, int taps,
@@ -468,11 +531,14 @@ extern "C" int mnc_igemm_tc(const void* a_hi, const void* a_lo, int batch, int H
   if ((rc = make_act_map(&ta_hi, a_hi, batch, H, W, Cin, TH, TW)) != MNC_OK) return rc;
   if ((rc = make_act_map(&ta_lo, a_lo, batch, H, W, Cin, TH, TW)) != MNC_OK) return rc;
   const long long ktot = static_cast<long long>(taps) * Cin;
-  if ((rc = make_wgt_map(&tb_hi, w_hi, Cout, ktot, bn)) != MNC_OK) return rc;
-  if ((rc = make_wgt_map(&tb_lo, w_lo, Cout, ktot, bn)) != MNC_OK) return rc;
+  const int cl = g_igemm_cluster;
+  if ((rc = make_wgt_map(&tb_hi, w_hi, Cout, ktot, bn / cl)) != MNC_OK) return rc;
+  if ((rc = make_wgt_map(&tb_lo, w_lo, Cout, ktot, bn / cl)) != MNC_OK) return rc;
 
-#define MNC_LAUNCH(TH_, TW_, BN_) \
-  return launch_igemm<TH_, TW_, BN_>(ta_hi, ta_lo, tb_hi, tb_lo, a, max_ctas, stream)
+#define MNC_LAUNCH(TH_, TW_, BN_)                                                              \
+  return (cl == 2)                                                                           \
+             ? launch_igemm<TH_, TW_, BN_, 2>(ta_hi, ta_lo, tb_hi, tb_lo, a, max_ctas, stream) \
+             : launch_igemm<TH_, TW_, BN_, 1>(ta_hi, ta_lo, tb_hi, tb_lo, a, max_ctas, stream)
   if (conv) {
     if (bn == 64) MNC_LAUNCH(8, 16, 64);
     if (bn == 128) MNC_LAUNCH(8, 16, 128);

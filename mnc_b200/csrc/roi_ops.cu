@@ -299,15 +299,13 @@ __device__ __forceinline__ float4 max4(const float4 a, const float4 b) {
   return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
 }
 
-// Sliding-window form: a thread owns 4 channels and walks the P sample columns of one sample
-// row left to right, keeping the four bilinear corner values in registers.  Sample columns are
-// monotone in w, so a feature column is (re)loaded only when the sample moves onto it: about
-// 2*(roi_w + 2) loads per sample row instead of 4*P.  Cell maxima (SUB x SUB samples -> one 14x14
-// cell) and the 7x7 pool accumulate in registers; the arithmetic per sample is unchanged.
+// Work item = (pooled column jp, channel quad); taps come from the per-CTA tables.  The feature
+// map is read as fp32 NHWC (the engine keeps an fp32 copy of conv5_3 = hi + lo, 39 MB per batch of
+// 8, so the gathers need no bf16 unpacking): one 16-byte load per tap and channel quad.
 template <int SUB>
-__global__ void __launch_bounds__(128)
-roi_warp_split_kernel(const __nv_bfloat16* __restrict__ f_hi, const __nv_bfloat16* __restrict__ f_lo,
-                      int C, int H, int W, const float* __restrict__ rois, float spatial_scale,
+__global__ void __launch_bounds__(256, 3)
+roi_warp_split_kernel(const float* __restrict__ feat, int C, int H, int W,
+                      const float* __restrict__ rois, float spatial_scale,
                       __nv_bfloat16* __restrict__ o14_hi, __nv_bfloat16* __restrict__ o14_lo,
                       __nv_bfloat16* __restrict__ o7_hi, __nv_bfloat16* __restrict__ o7_lo) {
   constexpr int P = 14 * SUB;
@@ -324,65 +322,44 @@ roi_warp_split_kernel(const __nv_bfloat16* __restrict__ f_hi, const __nv_bfloat1
     tap_w[pw] = axis_tap(__fadd_rn(g.start_w, __fmul_rn(static_cast<float>(pw), g.bin_w)), W);
   }
   __syncthreads();
-  const long long img_off = static_cast<long long>(g.level) * H * W * C;
+  const float* fimg = feat + static_cast<long long>(g.level) * H * W * C;
+  const int c4n = C / 4;
   const float kNeg = -3.402823466e+38f;
-  for (int c = threadIdx.x * 4; c < C; c += blockDim.x * 4) {
-    float4 best7[7];
+  for (int item = threadIdx.x; item < 7 * c4n; item += blockDim.x) {
+    const int jp = item / c4n;
+    const int c = (item - jp * c4n) * 4;
+    float4 best7 = make_float4(kNeg, kNeg, kNeg, kNeg);
 #pragma unroll
-    for (int j = 0; j < 7; ++j) best7[j] = make_float4(kNeg, kNeg, kNeg, kNeg);
-#pragma unroll 1
     for (int dy = 0; dy < 2; ++dy) {
-      float4 cell[14];
 #pragma unroll
-      for (int j = 0; j < 14; ++j) cell[j] = make_float4(kNeg, kNeg, kNeg, kNeg);
-#pragma unroll 1
-      for (int sy = 0; sy < SUB; ++sy) {
-        const AxisTap th = tap_h[dy * SUB + sy];
-        const long long row_lo = img_off + static_cast<long long>(th.lo) * W * C + c;
-        const long long row_hi = img_off + static_cast<long long>(th.hi) * W * C + c;
-        int cur_lo = -1, cur_hi = -1;
-        float4 a_lo = make_float4(0.f, 0.f, 0.f, 0.f), a_hi = a_lo, b_lo = a_lo, b_hi = a_lo;
+      for (int dx = 0; dx < 2; ++dx) {
+        const int j = 2 * jp + dx;
+        float4 cell = make_float4(kNeg, kNeg, kNeg, kNeg);
 #pragma unroll
-        for (int pw = 0; pw < P; ++pw) {
-          const AxisTap tw = tap_w[pw];
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (th.ok && tw.ok) {
-            if (tw.lo != cur_lo) {
-              if (tw.lo == cur_hi) {
-                a_lo = a_hi;
-                b_lo = b_hi;
-              } else {
-                a_lo = ld_split4(f_hi, f_lo, row_lo + static_cast<long long>(tw.lo) * C);
-                b_lo = ld_split4(f_hi, f_lo, row_hi + static_cast<long long>(tw.lo) * C);
-              }
-              cur_lo = tw.lo;
+        for (int sy = 0; sy < SUB; ++sy) {
+          const AxisTap th = tap_h[dy * SUB + sy];
+          const float* r0 = fimg + static_cast<long long>(th.lo) * W * C + c;
+          const float* r1 = fimg + static_cast<long long>(th.hi) * W * C + c;
+#pragma unroll
+          for (int sx = 0; sx < SUB; ++sx) {
+            const AxisTap tw = tap_w[j * SUB + sx];
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (th.ok && tw.ok) {
+              const float4 v1 = __ldg(reinterpret_cast<const float4*>(r0 + tw.lo * C));
+              const float4 v2 = __ldg(reinterpret_cast<const float4*>(r0 + tw.hi * C));
+              const float4 v3 = __ldg(reinterpret_cast<const float4*>(r1 + tw.lo * C));
+              const float4 v4 = __ldg(reinterpret_cast<const float4*>(r1 + tw.hi * C));
+              v = bilerp4(__fmul_rn(th.h, tw.h), __fmul_rn(th.h, tw.l), __fmul_rn(th.l, tw.h),
+                          __fmul_rn(th.l, tw.l), v1, v2, v3, v4);
             }
-            if (tw.hi != cur_hi) {
-              if (tw.hi == cur_lo) {
-                a_hi = a_lo;
-                b_hi = b_lo;
-              } else {
-                a_hi = ld_split4(f_hi, f_lo, row_lo + static_cast<long long>(tw.hi) * C);
-                b_hi = ld_split4(f_hi, f_lo, row_hi + static_cast<long long>(tw.hi) * C);
-              }
-              cur_hi = tw.hi;
-            }
-            v = bilerp4(__fmul_rn(th.h, tw.h), __fmul_rn(th.h, tw.l), __fmul_rn(th.l, tw.h),
-                        __fmul_rn(th.l, tw.l), a_lo, a_hi, b_lo, b_hi);
+            cell = max4(cell, v);
           }
-          cell[pw / SUB] = max4(cell[pw / SUB], v);
         }
-      }
-      const long long obase = ((static_cast<long long>(r) * 14 + (2 * t + dy)) * 14) * C + c;
-#pragma unroll
-      for (int j = 0; j < 14; ++j) {
-        st_split4(o14_hi, o14_lo, obase + static_cast<long long>(j) * C, cell[j]);
-        best7[j >> 1] = max4(best7[j >> 1], cell[j]);
+        st_split4(o14_hi, o14_lo, ((static_cast<long long>(r) * 14 + (2 * t + dy)) * 14 + j) * C + c, cell);
+        best7 = max4(best7, cell);
       }
     }
-    const long long pbase = ((static_cast<long long>(r) * 7 + t) * 7) * C + c;
-#pragma unroll
-    for (int j = 0; j < 7; ++j) st_split4(o7_hi, o7_lo, pbase + static_cast<long long>(j) * C, best7[j]);
+    st_split4(o7_hi, o7_lo, ((static_cast<long long>(r) * 7 + t) * 7 + jp) * C + c, best7);
   }
 }
 
@@ -501,24 +478,22 @@ extern "C" int mnc_mask_pool_nchw(const float* feat, const float* mask, int N, i
   return check_launch();
 }
 
-extern "C" int mnc_roi_warp_split(const void* f_hi, const void* f_lo, int C, int H, int W,
-                                  const float* rois, int R, int sub, float spatial_scale,
-                                  void* o14_hi, void* o14_lo, void* o7_hi, void* o7_lo,
-                                  void* stream) {
+extern "C" int mnc_roi_warp_split(const float* feat_nhwc, int C, int H, int W, const float* rois,
+                                  int R, int sub, float spatial_scale, void* o14_hi, void* o14_lo,
+                                  void* o7_hi, void* o7_lo, void* stream) {
   if (R <= 0) return MNC_OK;
-  if (C % 4 != 0 || (sub != 1 && sub != 2)) return MNC_ERR_ARG;
+  if (C % 4 != 0 || (sub != 1 && sub != 2) || (reinterpret_cast<uintptr_t>(feat_nhwc) & 15))
+    return MNC_ERR_ARG;
   dim3 grid(R, 7);
   auto s = static_cast<cudaStream_t>(stream);
   if (sub == 2)
-    roi_warp_split_kernel<2><<<grid, 128, 0, s>>>(
-        static_cast<const __nv_bfloat16*>(f_hi), static_cast<const __nv_bfloat16*>(f_lo), C, H, W,
-        rois, spatial_scale, static_cast<__nv_bfloat16*>(o14_hi),
+    roi_warp_split_kernel<2><<<grid, 256, 0, s>>>(
+        feat_nhwc, C, H, W, rois, spatial_scale, static_cast<__nv_bfloat16*>(o14_hi),
         static_cast<__nv_bfloat16*>(o14_lo), static_cast<__nv_bfloat16*>(o7_hi),
         static_cast<__nv_bfloat16*>(o7_lo));
   else
-    roi_warp_split_kernel<1><<<grid, 128, 0, s>>>(
-        static_cast<const __nv_bfloat16*>(f_hi), static_cast<const __nv_bfloat16*>(f_lo), C, H, W,
-        rois, spatial_scale, static_cast<__nv_bfloat16*>(o14_hi),
+    roi_warp_split_kernel<1><<<grid, 256, 0, s>>>(
+        feat_nhwc, C, H, W, rois, spatial_scale, static_cast<__nv_bfloat16*>(o14_hi),
         static_cast<__nv_bfloat16*>(o14_lo), static_cast<__nv_bfloat16*>(o7_hi),
         static_cast<__nv_bfloat16*>(o7_lo));
   return check_launch();

@@ -36,6 +36,13 @@ def fc_weight_to_split(w, chw=None):
     return split(w)
 
 
+import os as _os
+
+if _os.environ.get("MNC_IGEMM_CLUSTER"):
+    check(lib.mnc_igemm_set_cluster(c_int(int(_os.environ["MNC_IGEMM_CLUSTER"]))),
+          "mnc_igemm_set_cluster")
+
+
 class KernelTimer:
     """Optional per-launch CUDA-event timing of the implicit-GEMM kernel (bench.py's roofline):
     events are recorded on the launching stream around every igemm launch, together with the
@@ -88,6 +95,11 @@ def igemm(a, batch, H, W, cin, w, cout, taps, bias=None, relu=False, out=None, o
         check(rc, "mnc_igemm_simt")
 
 
+def set_cluster(cl):
+    """Thread-block-cluster size of the tensor-core launches (1 or 2, default 2)."""
+    check(lib.mnc_igemm_set_cluster(c_int(cl)), "mnc_igemm_set_cluster")
+
+
 def splitk_reduce(partial, splits, split_stride, rows, cols, bias=None, relu=False, out=None,
                   out_f32=None, out_row_stride=None, out_ch_offset=0):
     if out_f32 is not None:
@@ -126,3 +138,10 @@ def nchw_to_split(x, out):
     rc = lib.mnc_nchw_to_split(ptr(x), c_int(b), c_int(C), c_int(H), c_int(W), ptr(out[0]),
                                ptr(out[1]), cur_stream())
     check(rc, "mnc_nchw_to_split")
+
+
+def split_to_f32(a, out):
+    """out (fp32, same element order) = hi + lo."""
+    n = out.numel()
+    rc = lib.mnc_split_to_f32(ptr(a[0]), ptr(a[1]), c_ll(n), ptr(out), cur_stream())
+    check(rc, "mnc_split_to_f32")

@@ -105,18 +105,13 @@ class MNCEngine:
                             out_f32=out_f32, out_row_stride=out_stride, out_ch_offset=out_ch_offset)
 
     def _pick_split(self, tiles, k_steps, max_split=32):
-        """Split-K factor that minimises the wave count of a persistent launch: equal-size tiles
-        over `sms` CTAs cost ceil(tiles*s/sms)/s tile-times (e.g. fc6 at batch 8: 608 tiles on
-        148 SMs = 4.1 waves -> 5; with s = 3, 13/3 = 4.33).  Each extra split adds a little
-        fp32 partial traffic, modelled as 2 % per split."""
-        best, best_cost = 1, None
-        for s in range(1, max_split + 1):
-            if s > 1 and k_steps // s < 8:
-                break
-            cost = math.ceil(tiles * s / self.sms) / s * (1.0 + 0.02 * (s - 1))
-            if best_cost is None or cost < best_cost - 1e-9:
-                best, best_cost = s, cost
-        return best
+        """Split-K only when the launch cannot fill the GPU (e.g. fc6_maskest: 19 row tiles,
+        K = 100352).  A wave-quantisation-driven split (608 tiles -> 4.1 waves) was measured and
+        rejected: the extra fp32 partial reduce costs what the shorter tail saves
+        (profiles/r01_notes.md)."""
+        if tiles >= self.sms * 0.7 or k_steps < 16:
+            return 1
+        return max(1, min(math.ceil(self.sms / tiles), k_steps // 8, max_split))
 
     def _conv(self, x, B, H, W, cin, wgt, cout, bias, out, key):
         """3x3 conv + bias + ReLU -> split NHWC, split-K when whole waves would idle."""
@@ -227,7 +222,10 @@ class MNCEngine:
         out["roi_counts"] = roi_counts
         feat14 = self._split_buf("feat14", R, 14, 14, c5)
         box7 = self._split_buf("box7", R, 7, 7, c5)
-        ops.roi_warp_split(conv5_3, c5, H5, W5, rois, 2, feat14, box7)
+        # fp32 copy of conv5_3 (= hi + lo, exact) for the RoI gathers: 39 MB per batch of 8
+        c5f = self._f32_buf("conv5_f32", B, H5, W5, c5)
+        dense.split_to_f32(conv5_3, c5f)
+        ops.roi_warp_split(c5f, c5, H5, W5, rois, 2, feat14, box7)
         s1 = self.head(feat14, box7, R, "s1")
         rois_ext = ops.stage_bridge(rois, s1["bbox_pred"], s1["seg_cls_prob"], im_info,
                                     ROIS_PER_IMAGE)
@@ -243,7 +241,7 @@ class MNCEngine:
             out["_mask_logits"] = s1["mask_logits"].clone()
             out["_mask_resize"] = s1["mask_resize"]
             out["_join"] = s1["join"].clone()
-        ops.roi_warp_split(conv5_3, c5, H5, W5, rois_ext, 1, feat14, box7)
+        ops.roi_warp_split(c5f, c5, H5, W5, rois_ext, 1, feat14, box7)
         s2 = self.head(feat14, box7, R, "s2")
         for k in ("mask_proposal", "seg_cls_prob", "cls_prob", "bbox_pred"):
             out[k + "_ext"] = s2[k]

@@ -193,9 +193,10 @@ def mask_pool_nchw(feat, mask, out=None):
 
 
 def roi_warp_split(feat, C, H, W, rois, sub, out14, out7, spatial_scale=0.0625):
-    """feat split [2,B,H,W,C]; rois [R,5]; out14 split [2,R,14,14,C]; out7 split [2,R,7,7,C]."""
+    """feat fp32 NHWC [B,H,W,C]; rois [R,5]; out14 split [2,R,14,14,C]; out7 split [2,R,7,7,C]."""
     R = rois.shape[0]
-    check(lib.mnc_roi_warp_split(ptr(feat[0]), ptr(feat[1]), c_int(C), c_int(H), c_int(W),
+    assert feat.dtype == torch.float32
+    check(lib.mnc_roi_warp_split(ptr(feat), c_int(C), c_int(H), c_int(W),
                                  ptr(rois), c_int(R), c_int(sub), c_float(spatial_scale),
                                  ptr(out14[0]), ptr(out14[1]), ptr(out7[0]), ptr(out7[1]),
                                  cur_stream()), "mnc_roi_warp_split")

@@ -101,7 +101,7 @@ def test_fused_roi_warp_split(sub):
     R = rois.shape[0]
     o14 = torch.zeros(2, R, 14, 14, C, dtype=torch.bfloat16, device="cuda")
     o7 = torch.zeros(2, R, 7, 7, C, dtype=torch.bfloat16, device="cuda")
-    ops.roi_warp_split(fs, C, H, W, torch.from_numpy(rois).cuda(), sub, o14, o7)
+    ops.roi_warp_split(dense.merge(fs).contiguous(), C, H, W, torch.from_numpy(rois).cuda(), sub, o14, o7)
     want28 = torch.from_numpy(O.roi_warp(feat_q, rois, 14 * sub, 14 * sub))
     want14 = F.max_pool2d(want28, 2, 2) if sub == 2 else want28
     want7 = F.max_pool2d(want14, 2, 2)
