@@ -166,86 +166,86 @@ splitk_reduce_kernel(const float* __restrict__ partial, int splits, long long sp
 }
 
 // -------------------------------------------------------------------- conv1_1
-// Lane = (pixel quad, channel octet): a thread computes 4 horizontally adjacent pixels x 8 output
-// channels; the 8 lanes sharing a pixel quad cover all 64 channels, so every store instruction
-// writes whole 128-byte NHWC pixel rows (no partial-sector writes, which cost read-modify-write
-// traffic in L2).  The 3x6x3 input window sits in registers (loads are shared through L1 by the
-// 8 lanes of a quad); weights come from shared memory with 128-bit loads, 2 per 32 FMAs.
-constexpr int kC11Pix = 4;
+// Weight-stationary SIMT kernel.  Lane l of every warp owns output channels 2l and 2l+1 and keeps
+// their 2x27 weights in registers for the whole CTA; the CTA stages a (8+2) x (64+2) x 3 input
+// tile in shared memory and each warp walks one 64-pixel row, 4 pixels per step.  All lanes read
+// the same input words (broadcast 128/64-bit shared loads, ~4.5 wavefronts per pixel) against
+// 54 FMAs per lane per pixel, so the kernel is FMA-issue bound; a warp's store for one pixel is
+// one contiguous 128-byte NHWC row per bf16 plane.  Input is the fp32 NCHW `data` blob.
+constexpr int kC11TH = 8, kC11TW = 64;
 
 __global__ void __launch_bounds__(256)
 conv1_1_kernel(const float* __restrict__ data, int batch, int H, int W,
                const float* __restrict__ weight, const float* __restrict__ bias,
                __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
   constexpr int COUT = 64;
-  __shared__ __align__(16) float ws[27][COUT];
-  __shared__ float bs[COUT];
-  for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) {
-    const int co = i / 27, k = i % 27;  // Caffe weight order [co][c][ky][kx]
-    ws[k][co] = weight[i];
-  }
-  for (int i = threadIdx.x; i < COUT; i += blockDim.x) bs[i] = bias ? bias[i] : 0.f;
-  __syncthreads();
-  const int Wq = (W + kC11Pix - 1) / kC11Pix;
+  constexpr int SW = kC11TW + 4;  // row pitch: 66 used, padded to 68 so rows stay 16B-aligned
+  __shared__ __align__(16) float tile[3][kC11TH + 2][SW];
+  const int tiles_w = (W + kC11TW - 1) / kC11TW;
+  const int tiles_h = (H + kC11TH - 1) / kC11TH;
+  const int img = blockIdx.x / (tiles_h * tiles_w);
+  const int tr = blockIdx.x % (tiles_h * tiles_w);
+  const int h0 = (tr / tiles_w) * kC11TH, w0 = (tr % tiles_w) * kC11TW;
   const long long HW = static_cast<long long>(H) * W;
-  const long long gq = static_cast<long long>(blockIdx.x) * (blockDim.x / 8) + threadIdx.x / 8;
-  const int oc = (threadIdx.x & 7) * 8;  // first of this lane's 8 output channels
-  if (gq >= static_cast<long long>(batch) * H * Wq) return;
-  const int img = static_cast<int>(gq / (static_cast<long long>(H) * Wq));
-  const int r = static_cast<int>(gq % (static_cast<long long>(H) * Wq));
-  const int h = r / Wq, w0 = (r % Wq) * kC11Pix;
-  float in[3][3][kC11Pix + 2];
+  for (int i = threadIdx.x; i < 3 * (kC11TH + 2) * (kC11TW + 2); i += blockDim.x) {
+    const int c = i / ((kC11TH + 2) * (kC11TW + 2));
+    const int rem = i % ((kC11TH + 2) * (kC11TW + 2));
+    const int y = rem / (kC11TW + 2), x = rem % (kC11TW + 2);
+    const int hs = h0 + y - 1, wsx = w0 + x - 1;
+    float v = 0.f;
+    if (hs >= 0 && hs < H && wsx >= 0 && wsx < W)
+      v = __ldg(data + (static_cast<long long>(img) * 3 + c) * HW + static_cast<long long>(hs) * W + wsx);
+    tile[c][y][x] = v;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float w0r[27], w1r[27];  // Caffe weight order [co][c][ky][kx]
 #pragma unroll
-  for (int c = 0; c < 3; ++c)
+  for (int k = 0; k < 27; ++k) {
+    w0r[k] = __ldg(weight + (2 * lane) * 27 + k);
+    w1r[k] = __ldg(weight + (2 * lane + 1) * 27 + k);
+  }
+  const float b0 = bias ? __ldg(bias + 2 * lane) : 0.f;
+  const float b1 = bias ? __ldg(bias + 2 * lane + 1) : 0.f;
+  __syncthreads();
+  const int y = warp;  // 8 warps <-> 8 tile rows
+  const int h = h0 + y;
+  if (h >= H) return;
+#pragma unroll 1
+  for (int x0 = 0; x0 < kC11TW; x0 += 4) {
+    if (w0 + x0 >= W) break;
+    float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky)
+    for (int c = 0; c < 3; ++c)
 #pragma unroll
-      for (int x = 0; x < kC11Pix + 2; ++x) {
-        const int hs = h + ky - 1, wsx = w0 + x - 1;
-        float v = 0.f;
-        if (hs >= 0 && hs < H && wsx >= 0 && wsx < W)
-          v = __ldg(data + (static_cast<long long>(img) * 3 + c) * HW + static_cast<long long>(hs) * W + wsx);
-        in[c][ky][x] = v;
+      for (int ky = 0; ky < 3; ++ky) {
+        // 6 consecutive inputs x0 .. x0+5 of row y+ky (tile column x0 is image column w0+x0-1)
+        const float4 v4 = *reinterpret_cast<const float4*>(&tile[c][y + ky][x0]);
+        const float2 v2 = *reinterpret_cast<const float2*>(&tile[c][y + ky][x0 + 4]);
+        const float in[6] = {v4.x, v4.y, v4.z, v4.w, v2.x, v2.y};
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int k = c * 9 + ky * 3 + kx;
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            a0[p] = fmaf(in[p + kx], w0r[k], a0[p]);
+            a1[p] = fmaf(in[p + kx], w1r[k], a1[p]);
+          }
+        }
       }
-  float acc[kC11Pix][8];
 #pragma unroll
-  for (int p = 0; p < kC11Pix; ++p)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[p][j] = 0.f;
-#pragma unroll
-  for (int c = 0; c < 3; ++c)
-#pragma unroll
-    for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int k = c * 9 + ky * 3 + kx;
-        const float4 wa = *reinterpret_cast<const float4*>(&ws[k][oc]);
-        const float4 wb = *reinterpret_cast<const float4*>(&ws[k][oc + 4]);
-        const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-#pragma unroll
-        for (int p = 0; p < kC11Pix; ++p)
-#pragma unroll
-          for (int j = 0; j < 8; ++j) acc[p][j] = fmaf(in[c][ky][p + kx], wv[j], acc[p][j]);
-      }
-#pragma unroll
-  for (int p = 0; p < kC11Pix; ++p) {
-    if (w0 + p >= W) continue;
-    const long long pix = (static_cast<long long>(img) * H + h) * W + w0 + p;
-    uint32_t hw[4], lw[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float x0 = fmaxf(acc[p][2 * e] + bs[oc + 2 * e], 0.f);
-      const float x1 = fmaxf(acc[p][2 * e + 1] + bs[oc + 2 * e + 1], 0.f);
-      __nv_bfloat16 h0, l0, h1, l1;
-      split_f32(x0, h0, l0);
-      split_f32(x1, h1, l1);
-      hw[e] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) |
-              (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
-      lw[e] = static_cast<uint32_t>(__bfloat16_as_ushort(l0)) |
-              (static_cast<uint32_t>(__bfloat16_as_ushort(l1)) << 16);
+    for (int p = 0; p < 4; ++p) {
+      const int w = w0 + x0 + p;
+      if (w >= W) break;
+      const long long pix = (static_cast<long long>(img) * H + h) * W + w;
+      const float x0v = fmaxf(a0[p] + b0, 0.f), x1v = fmaxf(a1[p] + b1, 0.f);
+      __nv_bfloat16 hh0, ll0, hh1, ll1;
+      split_f32(x0v, hh0, ll0);
+      split_f32(x1v, hh1, ll1);
+      *reinterpret_cast<uint32_t*>(out_hi + pix * COUT + 2 * lane) =
+          static_cast<uint32_t>(__bfloat16_as_ushort(hh0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(hh1)) << 16);
+      *reinterpret_cast<uint32_t*>(out_lo + pix * COUT + 2 * lane) =
+          static_cast<uint32_t>(__bfloat16_as_ushort(ll0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(ll1)) << 16);
     }
-    *reinterpret_cast<uint4*>(out_hi + pix * COUT + oc) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-    *reinterpret_cast<uint4*>(out_lo + pix * COUT + oc) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
   }
 }
 
@@ -433,9 +433,8 @@ extern "C" int mnc_splitk_reduce(const float* partial, int splits, long long spl
 extern "C" int mnc_conv1_1(const float* data_nchw, int batch, int H, int W, const float* weight,
                            const float* bias, int Cout, void* out_hi, void* out_lo, void* stream) {
   if (Cout != 64) return MNC_ERR_ARG;
-  const long long quads = static_cast<long long>(batch) * H * ((W + kC11Pix - 1) / kC11Pix);
-  conv1_1_kernel<<<static_cast<unsigned>((quads + 31) / 32), 256, 0,
-                   static_cast<cudaStream_t>(stream)>>>(
+  const int tiles = batch * ((H + kC11TH - 1) / kC11TH) * ((W + kC11TW - 1) / kC11TW);
+  conv1_1_kernel<<<tiles, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       data_nchw, batch, H, W, weight, bias, static_cast<__nv_bfloat16*>(out_hi),
       static_cast<__nv_bfloat16*>(out_lo));
   return check_launch();
