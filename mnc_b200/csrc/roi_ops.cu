@@ -89,16 +89,20 @@ constexpr int kWarpSlab = 8;     // channels per CTA
 constexpr int kMaxPooled = 32;   // pooled_h, pooled_w <= 32
 
 // One CTA per (RoI, 8-channel slab).  The per-RoI interpolation tables (row taps, column taps)
-// are built once in shared memory; each thread then produces 4 consecutive outputs of one
-// (channel, ph) row: its two feature rows are read through the read-only L1 path (a RoI's window
-// of one channel is <= 9.6 KB, so the 4-tap gathers hit L1 after first touch) and the result
-// leaves as one 16-byte streaming store -- output bytes are written exactly once, fully
-// coalesced.  PW is the compile-time pooled width so the index math has no runtime division.
-template <int PH, int PW>
+// are built once in shared memory.  A thread owns EPT consecutive output columns for the whole
+// CTA (their column taps live in registers) and walks (channel, ph) rows: per output it issues
+// 4 read-only gathers (a RoI's window of one channel is <= 9.6 KB, L1-resident after first
+// touch), 7 un-fused fp32 ops, and a share of one vector streaming store.  Output bytes are
+// written exactly once, coalesced (the reference writes 3x as much: top + argmax_h + argmax_w).
+template <int PH, int PW, int EPT>
 __global__ void __launch_bounds__(256)
 roi_warp_nchw_kernel(const float* __restrict__ feat, int C, int H, int W,
                      const float* __restrict__ rois, float spatial_scale,
                      float* __restrict__ out) {
+  static_assert(PW % EPT == 0, "row must split into whole vectors");
+  constexpr int QW = PW / EPT;          // threads per output row
+  constexpr int RL = 256 / QW;          // row lanes per CTA
+  constexpr int PP = PH * PW;
   __shared__ AxisTap tap_h[PH], tap_w[PW];
   const int r = blockIdx.x;
   const int c0 = blockIdx.y * kWarpSlab;
@@ -108,37 +112,34 @@ roi_warp_nchw_kernel(const float* __restrict__ feat, int C, int H, int W,
   if (tid >= 32 && tid < 32 + PW)
     tap_w[tid - 32] = axis_tap(__fadd_rn(g.start_w, __fmul_rn(static_cast<float>(tid - 32), g.bin_w)), W);
   __syncthreads();
-  constexpr int PP = PH * PW;
-  constexpr bool kVec = (PP % 4 == 0);       // 28x28 and 14x14: whole planes in 16-byte quads
-  constexpr int QP = kVec ? PP / 4 : PP;      // work items per channel plane
-  constexpr int EPT = kVec ? 4 : 1;           // outputs per work item
+  const int q = tid % QW, rl = tid / QW;
+  if (rl >= RL) return;
+  AxisTap tw[EPT];
+#pragma unroll
+  for (int e = 0; e < EPT; ++e) tw[e] = tap_w[q * EPT + e];
   const int nch = min(kWarpSlab, C - c0);
   const float* fbase = feat + (static_cast<long long>(g.level) * C + c0) * H * W;
-  float* obase = out + (static_cast<long long>(r) * C + c0) * PP;
-  const bool aligned = (reinterpret_cast<uintptr_t>(obase) & 15) == 0;
-  for (int q = tid; q < nch * QP; q += 256) {
-    const int c = q / QP;
-    const int i0 = (q - c * QP) * EPT;
-    const float* plane = fbase + static_cast<long long>(c) * H * W;
+  float* obase = out + (static_cast<long long>(r) * C + c0) * PP + q * EPT;
+  const bool aligned = (reinterpret_cast<uintptr_t>(obase) & (EPT * 4 - 1)) == 0;
+  for (int row = rl; row < nch * PH; row += RL) {
+    const int c = row / PH, ph = row - c * PH;
+    const AxisTap th = tap_h[ph];
+    const float* row0 = fbase + static_cast<long long>(c) * H * W + th.lo * W;
+    const float* row1 = fbase + static_cast<long long>(c) * H * W + th.hi * W;
     float v[EPT];
 #pragma unroll
     for (int e = 0; e < EPT; ++e) {
-      const int i = i0 + e;
-      const int ph = i / PW, pw = i - ph * PW;
-      const AxisTap th = tap_h[ph];
-      const AxisTap tw = tap_w[pw];
       float val = 0.f;
-      if (th.ok && tw.ok) {
-        const float* row0 = plane + th.lo * W;
-        const float* row1 = plane + th.hi * W;
-        val = bilerp(th, tw, __ldg(row0 + tw.lo), __ldg(row0 + tw.hi), __ldg(row1 + tw.lo),
-                     __ldg(row1 + tw.hi));
-      }
+      if (th.ok && tw[e].ok)
+        val = bilerp(th, tw[e], __ldg(row0 + tw[e].lo), __ldg(row0 + tw[e].hi),
+                     __ldg(row1 + tw[e].lo), __ldg(row1 + tw[e].hi));
       v[e] = val;
     }
-    float* o = obase + c * PP + i0;
-    if (kVec && aligned) {
+    float* o = obase + row * PW;  // (c*PH + ph)*PW
+    if (EPT == 4 && aligned) {
       __stcs(reinterpret_cast<float4*>(o), make_float4(v[0], v[EPT > 1 ? 1 : 0], v[EPT > 2 ? 2 : 0], v[EPT > 3 ? 3 : 0]));
+    } else if (EPT == 2 && aligned) {
+      __stcs(reinterpret_cast<float2*>(o), make_float2(v[0], v[EPT > 1 ? 1 : 0]));
     } else {
 #pragma unroll
       for (int e = 0; e < EPT; ++e) __stcs(o + e, v[e]);
@@ -440,11 +441,11 @@ extern "C" int mnc_roi_warp_nchw(const float* feat, int C, int H, int W, const f
   dim3 grid(R, (C + kWarpSlab - 1) / kWarpSlab);
   auto s = static_cast<cudaStream_t>(stream);
   if (pooled_h == 28 && pooled_w == 28)
-    roi_warp_nchw_kernel<28, 28><<<grid, 256, 0, s>>>(feat, C, H, W, rois, spatial_scale, out);
+    roi_warp_nchw_kernel<28, 28, 4><<<grid, 256, 0, s>>>(feat, C, H, W, rois, spatial_scale, out);
   else if (pooled_h == 14 && pooled_w == 14)
-    roi_warp_nchw_kernel<14, 14><<<grid, 256, 0, s>>>(feat, C, H, W, rois, spatial_scale, out);
+    roi_warp_nchw_kernel<14, 14, 2><<<grid, 256, 0, s>>>(feat, C, H, W, rois, spatial_scale, out);
   else if (pooled_h == 7 && pooled_w == 7)
-    roi_warp_nchw_kernel<7, 7><<<grid, 256, 0, s>>>(feat, C, H, W, rois, spatial_scale, out);
+    roi_warp_nchw_kernel<7, 7, 1><<<grid, 256, 0, s>>>(feat, C, H, W, rois, spatial_scale, out);
   else
     roi_warp_nchw_generic_kernel<<<grid, 256, 0, s>>>(feat, C, H, W, rois, pooled_h, pooled_w,
                                                       spatial_scale, out);
