@@ -255,11 +255,20 @@ def main():
     peaks, peak_src = _peaks()
     peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
     ach = k_flops / (k_ms / 1000.0) / 1e12 if k_ms > 0 else 0.0
+    traffic, traffic_note = None, None
+    summ = os.path.join(ROOT, "profiles", "r01_ncu_igemm_summary.json")
+    if os.path.exists(summ):
+        with open(summ) as f:
+            sj = json.load(f)
+        traffic = sj["mean_traffic_bytes_per_launch"]
+        traffic_note = ("dram__bytes_read.sum + dram__bytes_write.sum, mean over the 6 conv launches "
+                        "of the committed ncu --set full capture (profiles/r01_ncu_igemm_summary.json); "
+                        "algorithmic bytes of the same launches: %.3e" % sj["mean_algorithmic_bytes_per_launch"])
     roofline = {
         "kernel": "igemm_tc_kernel (tcgen05 implicit GEMM: 13 conv3x3 + 11 inner-product launch "
                   "sites per step)",
         "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
-        "frac": ach / peak_tf, "traffic": None,
+        "frac": ach / peak_tf, "traffic": traffic, "traffic_note": traffic_note,
         "peak_source": peak_src + ", bf16 dense sustained (kernel timed inside a long step)",
         "launches_timed": k_n, "share_of_step": k_ms / total_ms,
         "algorithmic_flops_per_step": k_flops / args.steps,

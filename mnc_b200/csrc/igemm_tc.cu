@@ -262,6 +262,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         ptx::tmem_ld_32x32b_x32(taddr, r);
         ptx::tmem_ld_wait();
         const int ch0 = n0 + c0;
+        if (p.out_mode == 3) continue;  // diagnostic: accumulators are drained and discarded
         if (p.out_mode == 2) {
           // Fused 2x2 stride-2 ceil-mode max pool (pooling_layer.cu:11-47).  With the 8x16 pixel
           // tile a warp holds two image rows: lanes 0-15 row 2q, lanes 16-31 row 2q+1, so the pool
