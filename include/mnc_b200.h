@@ -59,6 +59,9 @@ int mnc_igemm_tc(const void* a_hi, const void* a_lo, int batch, int H, int W, in
 /* Thread-block-cluster size of mnc_igemm_tc launches: 2 (default) = CTA pairs share each weight
  * tile via TMA multicast; 1 = no clusters. */
 int mnc_igemm_set_cluster(int cluster_size);
+/* K elements per pipeline stage: 64 (SWIZZLE_128B), 32 (SWIZZLE_64B, twice the stages) or
+ * 0 = default (32 for 192/256-wide Cout tiles, 64 otherwise).  bn also accepts 192. */
+int mnc_igemm_set_block_k(int bk);
 
 /* Same contract as mnc_igemm_tc on the fp32 SIMT pipes (exact fp32 FMA on hi+lo operands).
  * Not on the product path: it is the on-device cross-check for the tensor-core kernel. */

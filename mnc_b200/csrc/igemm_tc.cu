@@ -48,14 +48,16 @@ struct IgemmArgs {
 };
 
 constexpr int kBlockM = 128;
-constexpr int kBlockK = 64;
-constexpr int kABytes = kBlockM * kBlockK * 2;  // one bf16 plane of the A tile
 
-template <int BN>
+// BK = K elements per pipeline stage: 64 (128-byte rows, SWIZZLE_128B) or 32 (64-byte rows,
+// SWIZZLE_64B: half-size stages, i.e. twice the pipeline depth in the same shared memory).
+template <int BN, int BK>
 struct IgemmCfg {
-  static constexpr int kBBytes = BN * kBlockK * 2;
+  static constexpr int kABytes = kBlockM * BK * 2;  // one bf16 plane of the A tile
+  static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
-  static constexpr int kStages = (BN == 64) ? 4 : (BN == 128 ? 3 : 2);
+  static constexpr int kStagesRaw = (200 * 1024) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
@@ -97,14 +99,16 @@ __device__ __forceinline__ Tile decode_tile(const IgemmArgs& p, int t, int rank,
   return tl;
 }
 
-template <int TH, int TW, int BN, int CL>
+template <int TH, int TW, int BN, int CL, int BK>
 __global__ void __launch_bounds__(256, 1)
 igemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                 const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                 const IgemmArgs p) {
   static_assert(TH * TW == kBlockM, "pixel tile must have 128 rows");
-  using Cfg = IgemmCfg<BN>;
+  using Cfg = IgemmCfg<BN, BK>;
   constexpr int kStages = Cfg::kStages;
+  constexpr int kABytes = Cfg::kABytes;
+  constexpr int kBlockK = BK;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -218,10 +222,10 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
           const uint32_t b_lo = b_hi + Cfg::kBBytes;
 #pragma unroll
           for (int kk = 0; kk < kBlockK / 16; ++kk) {
-            const uint64_t da_hi = ptx::umma_desc_sw128(a_hi + kk * 32);
-            const uint64_t da_lo = ptx::umma_desc_sw128(a_lo + kk * 32);
-            const uint64_t db_hi = ptx::umma_desc_sw128(b_hi + kk * 32);
-            const uint64_t db_lo = ptx::umma_desc_sw128(b_lo + kk * 32);
+            const uint64_t da_hi = (BK == 64) ? ptx::umma_desc_sw128(a_hi + kk * 32) : ptx::umma_desc_sw64(a_hi + kk * 32);
+            const uint64_t da_lo = (BK == 64) ? ptx::umma_desc_sw128(a_lo + kk * 32) : ptx::umma_desc_sw64(a_lo + kk * 32);
+            const uint64_t db_hi = (BK == 64) ? ptx::umma_desc_sw128(b_hi + kk * 32) : ptx::umma_desc_sw64(b_hi + kk * 32);
+            const uint64_t db_lo = (BK == 64) ? ptx::umma_desc_sw128(b_lo + kk * 32) : ptx::umma_desc_sw64(b_lo + kk * 32);
             // small cross terms first, then the dominant product
             ptx::umma_bf16_ss(tmem_d, da_lo, db_hi, idesc, (k > kb || kk > 0) ? 1u : 0u);
             ptx::umma_bf16_ss(tmem_d, da_hi, db_lo, idesc, 1u);
@@ -395,29 +399,32 @@ static EncodeTiledFn get_encode_fn() {
 
 // bf16 [N][H][W][C] activation plane, box [1][TH][TW][64], 128B swizzle, zero OOB fill.
 static int make_act_map(CUtensorMap* m, const void* base, int N, int H, int W, int C, int TH,
-                        int TW) {
+                        int TW, int bk) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return MNC_ERR_DRIVER;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {64, (cuuint32_t)TW, (cuuint32_t)TH, 1};
+  cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)TW, (cuuint32_t)TH, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides,
-                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? MNC_OK : MNC_ERR_DRIVER;
 }
 
 // bf16 [Cout][Ktot] weight plane, box [BN][64].
-static int make_wgt_map(CUtensorMap* m, const void* base, int Cout, long long Ktot, int box_rows) {
+static int make_wgt_map(CUtensorMap* m, const void* base, int Cout, long long Ktot, int box_rows,
+                        int bk) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return MNC_ERR_DRIVER;
   cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)Cout};
   cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
-  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
-                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? MNC_OK : MNC_ERR_DRIVER;
 }
@@ -432,12 +439,12 @@ static int sm_count() {
   return n;
 }
 
-template <int TH, int TW, int BN, int CL>
+template <int TH, int TW, int BN, int CL, int BK>
 static int launch_igemm(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo,
                         const CUtensorMap& tb_hi, const CUtensorMap& tb_lo, const IgemmArgs& a,
                         int max_ctas, cudaStream_t stream) {
-  using Cfg = IgemmCfg<BN>;
-  auto kern = igemm_tc_kernel<TH, TW, BN, CL>;
+  using Cfg = IgemmCfg<BN, BK>;
+  auto kern = igemm_tc_kernel<TH, TW, BN, CL, BK>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e =
@@ -475,9 +482,18 @@ using namespace mnc;
 // Cluster size used by mnc_igemm_tc launches (1 or 2).  2 = pairs of CTAs along the pixel/row
 // dimension share each weight tile through TMA multicast (halves weight traffic from L2).
 static int g_igemm_cluster = 2;
+static int g_igemm_bk = 0;  // 0 = per-shape default
 extern "C" int mnc_igemm_set_cluster(int cl) {
   if (cl != 1 && cl != 2) return MNC_ERR_ARG;
   g_igemm_cluster = cl;
+  return MNC_OK;
+}
+
+// K elements per pipeline stage for mnc_igemm_tc launches: 64, 32, or 0 = default
+// (32 for Cout tiles of 192/256, where 64 leaves only two stages in shared memory).
+extern "C" int mnc_igemm_set_block_k(int bk) {
+  if (bk != 0 && bk != 32 && bk != 64) return MNC_ERR_ARG;
+  g_igemm_bk = bk;
   return MNC_OK;
 }
 
@@ -489,6 +505,7 @@ extern "C" int mnc_igemm_tc(const void* a_hi, const void* a_lo, int batch, int H
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (Cin % 64 != 0 || (taps != 1 && taps != 9) || batch <= 0 || H <= 0 || W <= 0 || Cout <= 0)
     return MNC_ERR_ARG;
+  int bk = g_igemm_bk;
   if (split_k < 1) split_k = 1;
   if (split_k > 1 && out_mode != 1) return MNC_ERR_ARG;
   if (out_mode == 2 && (taps != 9 || Cout % 8 != 0 || out_pix_stride % 8 != 0 ||
@@ -497,7 +514,10 @@ extern "C" int mnc_igemm_tc(const void* a_hi, const void* a_lo, int batch, int H
   const bool conv = (taps == 9);
   const int TH = conv ? 8 : 1, TW = conv ? 16 : 128;
   if (bn == 0) bn = (Cout <= 64) ? 64 : (Cout <= 128 ? 128 : 256);
-  if (bn != 64 && bn != 128 && bn != 256) return MNC_ERR_ARG;
+  if (bn != 64 && bn != 128 && bn != 192 && bn != 256) return MNC_ERR_ARG;
+  if (bk == 0) bk = (bn >= 192) ? 32 : 64;
+  if (bn == 192) bk = 32;            // instantiated combinations: (64|128|256, 64), (192|256, 32)
+  if (bn < 192) bk = 64;
 
   IgemmArgs a;
   a.batch = batch;
@@ -509,7 +529,7 @@ extern "C" int mnc_igemm_tc(const void* a_hi, const void* a_lo, int batch, int H
   a.tiles_h = (H + TH - 1) / TH;
   a.tiles_w = (W + TW - 1) / TW;
   a.tiles_n = (Cout + bn - 1) / bn;
-  a.k_steps = taps * (Cin / 64);
+  a.k_steps = taps * (Cin / bk);
   if (split_k > a.k_steps) split_k = a.k_steps;
   a.split_k = split_k;
   a.relu = relu;
@@ -529,25 +549,29 @@ extern "C" int mnc_igemm_tc(const void* a_hi, const void* a_lo, int batch, int H
 
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   int rc;
-  if ((rc = make_act_map(&ta_hi, a_hi, batch, H, W, Cin, TH, TW)) != MNC_OK) return rc;
-  if ((rc = make_act_map(&ta_lo, a_lo, batch, H, W, Cin, TH, TW)) != MNC_OK) return rc;
+  if ((rc = make_act_map(&ta_hi, a_hi, batch, H, W, Cin, TH, TW, bk)) != MNC_OK) return rc;
+  if ((rc = make_act_map(&ta_lo, a_lo, batch, H, W, Cin, TH, TW, bk)) != MNC_OK) return rc;
   const long long ktot = static_cast<long long>(taps) * Cin;
   const int cl = g_igemm_cluster;
-  if ((rc = make_wgt_map(&tb_hi, w_hi, Cout, ktot, bn / cl)) != MNC_OK) return rc;
-  if ((rc = make_wgt_map(&tb_lo, w_lo, Cout, ktot, bn / cl)) != MNC_OK) return rc;
+  if ((rc = make_wgt_map(&tb_hi, w_hi, Cout, ktot, bn / cl, bk)) != MNC_OK) return rc;
+  if ((rc = make_wgt_map(&tb_lo, w_lo, Cout, ktot, bn / cl, bk)) != MNC_OK) return rc;
 
-#define MNC_LAUNCH(TH_, TW_, BN_)                                                              \
-  return (cl == 2)                                                                           \
-             ? launch_igemm<TH_, TW_, BN_, 2>(ta_hi, ta_lo, tb_hi, tb_lo, a, max_ctas, stream) \
-             : launch_igemm<TH_, TW_, BN_, 1>(ta_hi, ta_lo, tb_hi, tb_lo, a, max_ctas, stream)
+#define MNC_LAUNCH(TH_, TW_, BN_, BK_)                                                              \
+  return (cl == 2)                                                                                \
+             ? launch_igemm<TH_, TW_, BN_, 2, BK_>(ta_hi, ta_lo, tb_hi, tb_lo, a, max_ctas, stream) \
+             : launch_igemm<TH_, TW_, BN_, 1, BK_>(ta_hi, ta_lo, tb_hi, tb_lo, a, max_ctas, stream)
   if (conv) {
-    if (bn == 64) MNC_LAUNCH(8, 16, 64);
-    if (bn == 128) MNC_LAUNCH(8, 16, 128);
-    MNC_LAUNCH(8, 16, 256);
+    if (bn == 64) MNC_LAUNCH(8, 16, 64, 64);
+    if (bn == 128) MNC_LAUNCH(8, 16, 128, 64);
+    if (bn == 192) MNC_LAUNCH(8, 16, 192, 32);
+    if (bk == 32) MNC_LAUNCH(8, 16, 256, 32);
+    MNC_LAUNCH(8, 16, 256, 64);
   } else {
-    if (bn == 64) MNC_LAUNCH(1, 128, 64);
-    if (bn == 128) MNC_LAUNCH(1, 128, 128);
-    MNC_LAUNCH(1, 128, 256);
+    if (bn == 64) MNC_LAUNCH(1, 128, 64, 64);
+    if (bn == 128) MNC_LAUNCH(1, 128, 128, 64);
+    if (bn == 192) MNC_LAUNCH(1, 128, 192, 32);
+    if (bk == 32) MNC_LAUNCH(1, 128, 256, 32);
+    MNC_LAUNCH(1, 128, 256, 64);
   }
 #undef MNC_LAUNCH
 }

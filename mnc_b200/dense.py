@@ -38,6 +38,8 @@ def fc_weight_to_split(w, chw=None):
 
 import os as _os
 
+if _os.environ.get("MNC_IGEMM_BK"):
+    check(lib.mnc_igemm_set_block_k(c_int(int(_os.environ["MNC_IGEMM_BK"]))), "mnc_igemm_set_block_k")
 if _os.environ.get("MNC_IGEMM_CLUSTER"):
     check(lib.mnc_igemm_set_cluster(c_int(int(_os.environ["MNC_IGEMM_CLUSTER"]))),
           "mnc_igemm_set_cluster")
@@ -98,6 +100,11 @@ def igemm(a, batch, H, W, cin, w, cout, taps, bias=None, relu=False, out=None, o
 def set_cluster(cl):
     """Thread-block-cluster size of the tensor-core launches (1 or 2, default 2)."""
     check(lib.mnc_igemm_set_cluster(c_int(cl)), "mnc_igemm_set_cluster")
+
+
+def set_block_k(bk):
+    """K elements per pipeline stage of the tensor-core launches: 64, 32 or 0 (= per-shape default)."""
+    check(lib.mnc_igemm_set_block_k(c_int(bk)), "mnc_igemm_set_block_k")
 
 
 def splitk_reduce(partial, splits, split_stride, rows, cols, bias=None, relu=False, out=None,
