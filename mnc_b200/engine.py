@@ -89,7 +89,11 @@ class MNCEngine:
                 out_ch_offset=0, key="lin"):
         """y = act(a @ W^T + b) through the implicit-GEMM kernel; split-K when the tile count
         cannot fill the GPU (e.g. fc6_maskest: K = 100352, N = 256)."""
-        bn = 64 if N <= 64 else (128 if (N <= 128 or N >= 1024) else 256)
+        # Cout tile: 192 (BLOCK_K 32, 5 stages) for the wide layers -- at M = 2400, N = 4096 it gives
+        # 19 x 22 = 418 tiles = 2.8 waves of 148 CTAs, against 4.1 (-> 5) waves at 128 and 2.05
+        # (-> 3, at twice the tile cost) at 256; measured 480 vs 404 vs 347 TF/s on the fc6 shape
+        # (profiles/r01_igemm_bk32_bn192.log)
+        bn = 64 if N <= 64 else (128 if N <= 128 else (192 if N >= 1024 else 256))
         tiles = math.ceil(M / 128) * math.ceil(N / bn)
         k_steps = K // 64
         split = self._pick_split(tiles, k_steps) if self.impl == "tc" else 1

@@ -15,7 +15,8 @@ def relerr(a, b):
 @pytest.mark.parametrize("M,K,N,bn,split", [(128, 64, 64, 64, 1), (300, 256, 441, 0, 1),
                                             (2394, 512, 54, 64, 1), (300, 12544, 64, 64, 7),
                                             (600, 8192, 126, 128, 4), (1000, 4096, 4096, 128, 1),
-                                            (257, 3136, 256, 256, 1)])
+                                            (257, 3136, 256, 256, 1), (2400, 1024, 1100, 192, 1),
+                                            (300, 512, 441, 192, 1)])
 def test_inner_product(M, K, N, bn, split):
     from mnc_b200 import dense
     torch.manual_seed(M + N)
