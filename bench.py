@@ -256,12 +256,16 @@ def main():
     n_instances = [int(x) for x in vr["n_res"].cpu().numpy()]
 
     # ------------------------------------------------------------- e2e: host buffers in and out
+    # the reference's callers hand im_detect the raw uint8 image (tools/demo.py:143-146); so does
+    # this: uint8 BGR frames in host memory -> boxes / masks / scores in host memory
+    host_u8 = np.stack([np.random.default_rng(1234 + start + i).integers(
+        0, 256, size=(H, W, 3), dtype=np.uint8) for i in range(B)])
     for _ in range(2):
-        det.im_detect_batch(host_blob)
+        det.im_detect_images(host_u8)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        det.im_detect_batch(host_blob)
+        det.im_detect_images(host_u8)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -316,7 +320,9 @@ def main():
         "data": "synthetic", "config": workload_config(args, world),
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": det.h2d_bytes,
                 "d2h_bytes_per_step": det.d2h_bytes,
-                "api": "mnc_b200.api.Detector.im_detect_batch (pinned host blobs in, host results out)"},
+                "api": "mnc_b200.api.Detector.im_detect_images: uint8 BGR host frames in (pinned "
+                       "staging, H2D), mean/resize/NCHW on device, forward, im_detect tail, "
+                       "boxes+masks+scores D2H to host"},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         "forward_plus_voting": {"value": vote_value, "unit": "images/s",
                                 "instances_per_image": n_instances,

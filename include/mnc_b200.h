@@ -207,6 +207,16 @@ int mnc_mv_device(const float* boxes, const float* masks, int nb, int box_dim, i
                   int batch, const int* im_hw, int* bbox_ws, float* out_mask, int* out_box,
                   void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Input preparation on the device ("next" row 1): prep_im_for_blob +
+ * im_list_to_blob (lib/utils/blob.py:17-50).  img: uint8 BGR [batch][H][W][3] (device);
+ * pixel_means3: HOST doubles (cfg.PIXEL_MEANS, lib/mnc_config.py:20); out: fp32
+ * [batch][3][out_h][out_w] with out = cv2.resize(float32(img) - means, fx=fy=scale, INTER_LINEAR).
+ * out_h/out_w = round(H*scale), round(W*scale) as cv2 computes them. */
+int mnc_prep_images(const unsigned char* img_bgr_hwc, int batch, int H, int W,
+                    const double* pixel_means3, double scale, int out_h, int out_w,
+                    float* out_nchw, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

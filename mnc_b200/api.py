@@ -61,6 +61,41 @@ class Detector:
         return (self._h_boxes[:B].numpy(), self._h_masks[:B].numpy(), self._h_scores[:B].numpy(),
                 self._h_valid[:B].numpy())
 
+    def im_detect_images(self, images_u8):
+        """Batched `im_detect(im, net)` on raw images, as the reference's callers hand them over
+        (tools/demo.py:143-146): uint8 BGR (B,H,W,3) host array, all of one size.  Mean
+        subtraction, the 600/1000 resize rule and HWC->NCHW run on the device (mnc_prep_images),
+        so only B*H*W*3 bytes cross PCIe.  Returns boxes (in original-image coordinates), masks,
+        scores, valid -- host arrays -- and the scale used."""
+        images_u8 = np.ascontiguousarray(images_u8)
+        B, H, W, _ = images_u8.shape
+        scale = ops.im_scale_for((H, W))
+        out_h, out_w = int(np.rint(H * scale)), int(np.rint(W * scale))
+        assert B <= self.max_batch and (out_h, out_w) == tuple(self._d_in.shape[2:])
+        dev = self.device
+        if getattr(self, "_h_u8", None) is None or self._h_u8.shape[1:] != images_u8.shape[1:]:
+            self._h_u8 = torch.empty((self.max_batch, H, W, 3), dtype=torch.uint8).pin_memory()
+            self._d_u8 = torch.empty((self.max_batch, H, W, 3), dtype=torch.uint8, device=dev)
+        self._h_u8[:B].copy_(torch.from_numpy(images_u8))
+        info = torch.tensor([[out_h, out_w, scale]] * B, dtype=torch.float32)
+        hw = torch.tensor([[H, W]] * B, dtype=torch.float32)
+        sc = torch.full((B,), scale, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            self._d_u8[:B].copy_(self._h_u8[:B], non_blocking=True)
+            ops.prep_images(self._d_u8[:B], scale, out=self._d_in[:B])
+            boxes, masks, scores, valid, _ = self.engine.detect(
+                self._d_in[:B], info.to(dev, non_blocking=True), hw.to(dev, non_blocking=True),
+                sc.to(dev, non_blocking=True))
+            self._h_boxes[:B].copy_(boxes, non_blocking=True)
+            self._h_masks[:B].copy_(masks, non_blocking=True)
+            self._h_scores[:B].copy_(scores, non_blocking=True)
+            self._h_valid[:B].copy_(valid, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        self.h2d_bytes = images_u8.nbytes + (info.numel() + hw.numel() + sc.numel()) * 4
+        self.d2h_bytes = (boxes.numel() + masks.numel() + scores.numel()) * 4 + valid.numel()
+        return (self._h_boxes[:B].numpy(), self._h_masks[:B].numpy(), self._h_scores[:B].numpy(),
+                self._h_valid[:B].numpy(), scale)
+
     def mask_voting(self, boxes, masks, scores, valid, im_hw, max_per_image=100):
         """Device-resident batched gpu_mask_voting on `engine.detect` outputs (device tensors)."""
         hw = torch.as_tensor(np.asarray(im_hw, dtype=np.int32)).to(self.device)

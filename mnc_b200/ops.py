@@ -274,3 +274,32 @@ def mask_voting(boxes, masks, scores, im_hw, max_per_image=100, nms_thresh=0.3, 
                 res_box_idx=res_idx, result_mask=out_mask, result_box=out_box,
                 cand_inds=cand_inds, cand_weights=cand_w, cand_begin=cand_begin, cand_end=cand_end,
                 overflow=overflow, order=order, keep=keep, num_keep=num)
+
+
+# ----------------------------------------------------------------------------- input preparation
+PIXEL_MEANS = (102.9801, 115.9465, 122.7717)   # cfg.PIXEL_MEANS, lib/mnc_config.py:20
+
+
+def im_scale_for(shape, target_size=600, max_size=1000):
+    """Scale rule of prep_im_for_blob (lib/utils/blob.py:41-46)."""
+    import numpy as np
+    im_size_min = min(shape[0], shape[1])
+    im_size_max = max(shape[0], shape[1])
+    im_scale = float(target_size) / float(im_size_min)
+    if np.round(im_scale * im_size_max) > max_size:
+        im_scale = float(max_size) / float(im_size_max)
+    return im_scale
+
+
+def prep_images(images_u8, scale, out=None, pixel_means=PIXEL_MEANS):
+    """images_u8: uint8 CUDA tensor [B,H,W,3] (BGR).  -> fp32 [B,3,round(H*s),round(W*s)]."""
+    import numpy as np
+    B, H, W, _ = images_u8.shape
+    out_h, out_w = int(np.rint(H * scale)), int(np.rint(W * scale))
+    if out is None:
+        out = torch.empty((B, 3, out_h, out_w), dtype=torch.float32, device=images_u8.device)
+    means = (ctypes.c_double * 3)(*pixel_means)
+    check(lib.mnc_prep_images(ptr(images_u8), c_int(B), c_int(H), c_int(W), means,
+                              ctypes.c_double(scale), c_int(out_h), c_int(out_w), ptr(out),
+                              cur_stream()), "mnc_prep_images")
+    return out

@@ -436,6 +436,22 @@ def prep_blob(im):
     return np.ascontiguousarray(blob), im_info
 
 
+def prep_im_for_blob(im, target_size=600, max_size=1000):
+    """lib/utils/blob.py:36-50 verbatim (cv2 is the reference's own dependency): returns the
+    mean-subtracted, resized float32 HWC image and the scale."""
+    import cv2
+    im = im.astype(np.float32, copy=True)
+    im -= CFG.PIXEL_MEANS
+    im_shape = im.shape
+    im_size_min = np.min(im_shape[0:2])
+    im_size_max = np.max(im_shape[0:2])
+    im_scale = float(target_size) / float(im_size_min)
+    if np.round(im_scale * im_size_max) > max_size:
+        im_scale = float(max_size) / float(im_size_max)
+    im = cv2.resize(im, None, None, fx=im_scale, fy=im_scale, interpolation=cv2.INTER_LINEAR)
+    return im, im_scale
+
+
 def _t(x):
     import torch
     return x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))

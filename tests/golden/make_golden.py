@@ -79,6 +79,16 @@ def main():
     si = np.array([[224, 320, 1.0]], dtype=np.float32)
     np.savez_compressed(os.path.join(OUT, "stage_bridge.npz"), rois=sr.astype(np.float32), deltas=sd,
                         prob=sp, im_info=si, rois_ext=O.stage_bridge_forward(sr.astype(np.float32), sd, sp, si))
+    # ---- input preparation: cv2.resize(INTER_LINEAR) of the mean-subtracted float image
+    # (blob.py:36-50); up-scaling 1.6x, the cap branch (max side), and down-scaling
+    cases = {}
+    for name, (h, w, tgt, mx) in {"up": (30, 50, 48, 100), "cap": (20, 70, 48, 100), "down": (90, 120, 48, 100)}.items():
+        im = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+        out, sc = O.prep_im_for_blob(im, tgt, mx)
+        cases["im_" + name] = im
+        cases["out_" + name] = out
+        cases["scale_" + name] = np.array([sc, tgt, mx], dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, "prep.npz"), **cases)
     print("golden fixtures written to", OUT)
 
 
