@@ -62,6 +62,9 @@ int mnc_igemm_set_cluster(int cluster_size);
 /* K elements per pipeline stage: 64 (SWIZZLE_128B), 32 (SWIZZLE_64B, twice the stages) or
  * 0 = default (32 for 192/256-wide Cout tiles, 64 otherwise).  bn also accepts 192. */
 int mnc_igemm_set_block_k(int bk);
+/* out_mode 0 epilogue: 1 (default) = stage tiles in shared memory and write them with TMA bulk
+ * tensor stores; 0 = per-thread 16-byte global stores. */
+int mnc_igemm_set_tma_store(int on);
 
 /* Same contract as mnc_igemm_tc on the fp32 SIMT pipes (exact fp32 FMA on hi+lo operands).
  * Not on the product path: it is the on-device cross-check for the tensor-core kernel. */

@@ -45,6 +45,7 @@ struct IgemmArgs {
   int out_ch_offset;
   long long split_stride;  // elements between split-K partial planes (fp32 mode)
   int vec_ok;              // 16-byte vector stores are aligned
+  int tma_store;           // out_mode 0 only: epilogue stages tiles in smem and TMA-stores them
 };
 
 constexpr int kBlockM = 128;
@@ -56,10 +57,14 @@ struct IgemmCfg {
   static constexpr int kABytes = kBlockM * BK * 2;  // one bf16 plane of the A tile
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
-  static constexpr int kStagesRaw = (200 * 1024) / kStageBytes;
+  static constexpr int kStagesRaw = (192 * 1024) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  // epilogue staging: 2 buffers x (hi, lo) x 128 rows x 32 channels x 2 B
+  static constexpr int kStagingBytes = 2 * 2 * 128 * 64;
+  static constexpr int kBarrierBytes = 1024;
+  static constexpr int kSmemBytes =
+      kStages * kStageBytes + 1024 /*align*/ + kBarrierBytes + kStagingBytes;
 };
 
 struct Tile {
@@ -103,6 +108,7 @@ template <int TH, int TW, int BN, int CL, int BK>
 __global__ void __launch_bounds__(256, 1)
 igemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                 const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                const __grid_constant__ CUtensorMap tm_o_hi, const __grid_constant__ CUtensorMap tm_o_lo,
                 const IgemmArgs p) {
   static_assert(TH * TW == kBlockM, "pixel tile must have 128 rows");
   using Cfg = IgemmCfg<BN, BK>;
@@ -118,6 +124,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
   uint64_t* tfull_bar = empty_bar + kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint8_t* staging = smem + kStages * Cfg::kStageBytes + Cfg::kBarrierBytes;  // 1024-aligned
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -248,6 +255,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     const int q = warp - 4;  // TMEM lane quarter == warp_id % 4
     const int row = q * 32 + lane;
     int local = 0;
+    int chunk_ctr = 0;
     for (int t = first; t < total_tiles; t += stride, ++local) {
       const Tile tl = decode_tile<CL>(p, t, rank, TH, TW, BN);
       const int img = tl.img, h0 = tl.h0, w0 = tl.w0, n0 = tl.n0, ks = tl.ks;
@@ -309,6 +317,54 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
             *reinterpret_cast<uint4*>(ph) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
             *reinterpret_cast<uint4*>(pl) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
           }
+        } else if (p.tma_store) {
+          // ---- out_mode 0 via shared-memory staging + TMA store: each thread owns one pixel row
+          // of the 128 x 32-channel chunk (64 B per bf16 plane, written with the 64B-swizzle
+          // pattern so the 16-byte stores are bank-conflict free); one elected thread then issues
+          // two bulk tensor stores (hi, lo).  TMA clips ragged tiles, channel tails and the
+          // cluster's dummy tile, and the global writes are whole 64-byte rows.
+          const int buf = chunk_ctr & 1;
+          uint8_t* sb = staging + buf * (2 * 128 * 64);
+          if (threadIdx.x == 128) ptx::tma_store_wait_read<1>();  // this buffer's previous store
+          ptx::named_bar_sync(1, 128);
+          if (ch0 < p.Cout) {
+            float bv[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              bv[j] = (p.bias != nullptr && ch0 + j < p.Cout) ? __ldg(p.bias + ch0 + j) : 0.f;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint32_t hw[4], lw[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float x0 = __uint_as_float(r[g * 8 + 2 * e]) + bv[g * 8 + 2 * e];
+                float x1 = __uint_as_float(r[g * 8 + 2 * e + 1]) + bv[g * 8 + 2 * e + 1];
+                if (p.relu) {
+                  x0 = fmaxf(x0, 0.f);
+                  x1 = fmaxf(x1, 0.f);
+                }
+                const __nv_bfloat16 h0b = __float2bfloat16_rn(x0);
+                const __nv_bfloat16 h1b = __float2bfloat16_rn(x1);
+                const __nv_bfloat16 l0b = __float2bfloat16_rn(x0 - __bfloat162float(h0b));
+                const __nv_bfloat16 l1b = __float2bfloat16_rn(x1 - __bfloat162float(h1b));
+                hw[e] = static_cast<uint32_t>(__bfloat16_as_ushort(h0b)) |
+                        (static_cast<uint32_t>(__bfloat16_as_ushort(h1b)) << 16);
+                lw[e] = static_cast<uint32_t>(__bfloat16_as_ushort(l0b)) |
+                        (static_cast<uint32_t>(__bfloat16_as_ushort(l1b)) << 16);
+              }
+              const int off = row * 64 + ((g ^ ((row >> 1) & 3)) << 4);
+              *reinterpret_cast<uint4*>(sb + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+              *reinterpret_cast<uint4*>(sb + 128 * 64 + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            }
+          }
+          ptx::fence_proxy_async();
+          ptx::named_bar_sync(1, 128);
+          if (threadIdx.x == 128 && ch0 < p.Cout) {
+            ptx::tma_store_4d(&tm_o_hi, sb, ch0, w0, h0, img);
+            ptx::tma_store_4d(&tm_o_lo, sb + 128 * 64, ch0, w0, h0, img);
+            ptx::tma_store_commit();
+          }
+          ++chunk_ctr;
         } else if (valid && ch0 < p.Cout) {
           float v[32];
 #pragma unroll
@@ -365,6 +421,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
       ptx::tc_fence_before();
       ptx::mbar_arrive(&tempty_bar[acc]);
     }
+    if (threadIdx.x == 128) ptx::tma_store_wait_read<0>();  // smem must outlive the bulk stores
   }
 
   ptx::tc_fence_before();
@@ -429,6 +486,23 @@ static int make_wgt_map(CUtensorMap* m, const void* base, int Cout, long long Kt
   return r == CUDA_SUCCESS ? MNC_OK : MNC_ERR_DRIVER;
 }
 
+// bf16 output plane seen as [N][H][W][Cout] with pixel stride `pix_stride` elements; box
+// [1][TH][TW][32], 64-byte swizzle (matches the epilogue's staging layout).
+static int make_out_map(CUtensorMap* m, const void* base, int N, int H, int W, int Cout,
+                        long long pix_stride, int TH, int TW) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return MNC_ERR_DRIVER;
+  cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)pix_stride * 2, (cuuint64_t)W * pix_stride * 2,
+                           (cuuint64_t)H * W * pix_stride * 2};
+  cuuint32_t box[4] = {32, (cuuint32_t)TW, (cuuint32_t)TH, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MNC_OK : MNC_ERR_DRIVER;
+}
+
 static int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -441,7 +515,8 @@ static int sm_count() {
 
 template <int TH, int TW, int BN, int CL, int BK>
 static int launch_igemm(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo,
-                        const CUtensorMap& tb_hi, const CUtensorMap& tb_lo, const IgemmArgs& a,
+                        const CUtensorMap& tb_hi, const CUtensorMap& tb_lo,
+                        const CUtensorMap& to_hi, const CUtensorMap& to_lo, const IgemmArgs& a,
                         int max_ctas, cudaStream_t stream) {
   using Cfg = IgemmCfg<BN, BK>;
   auto kern = igemm_tc_kernel<TH, TW, BN, CL, BK>;
@@ -471,7 +546,7 @@ static int launch_igemm(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo,
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta_hi, ta_lo, tb_hi, tb_lo, a);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta_hi, ta_lo, tb_hi, tb_lo, to_hi, to_lo, a);
   return e == cudaSuccess ? MNC_OK : MNC_ERR_CUDA;
 }
 
@@ -483,6 +558,11 @@ using namespace mnc;
 // dimension share each weight tile through TMA multicast (halves weight traffic from L2).
 static int g_igemm_cluster = 2;
 static int g_igemm_bk = 0;  // 0 = per-shape default
+static int g_igemm_tma_store = 1;
+extern "C" int mnc_igemm_set_tma_store(int on) {
+  g_igemm_tma_store = on ? 1 : 0;
+  return MNC_OK;
+}
 extern "C" int mnc_igemm_set_cluster(int cl) {
   if (cl != 1 && cl != 2) return MNC_ERR_ARG;
   g_igemm_cluster = cl;
@@ -552,14 +632,26 @@ extern "C" int mnc_igemm_tc(const void* a_hi, const void* a_lo, int batch, int H
   if ((rc = make_act_map(&ta_hi, a_hi, batch, H, W, Cin, TH, TW, bk)) != MNC_OK) return rc;
   if ((rc = make_act_map(&ta_lo, a_lo, batch, H, W, Cin, TH, TW, bk)) != MNC_OK) return rc;
   const long long ktot = static_cast<long long>(taps) * Cin;
+  // epilogue through shared memory + TMA store when the output planes allow a tensor map
+  CUtensorMap to_hi = ta_hi, to_lo = ta_lo;  // placeholders when unused
+  a.tma_store = 0;
+  if (out_mode == 0 && g_igemm_tma_store && out_pix_stride % 8 == 0 && out_ch_offset % 8 == 0 &&
+      reinterpret_cast<uintptr_t>(out0) % 16 == 0 && reinterpret_cast<uintptr_t>(out1) % 16 == 0) {
+    const __nv_bfloat16* bh = static_cast<const __nv_bfloat16*>(out0) + out_ch_offset;
+    const __nv_bfloat16* bl = static_cast<const __nv_bfloat16*>(out1) + out_ch_offset;
+    if (make_out_map(&to_hi, bh, batch, H, W, Cout, out_pix_stride, TH, TW) == MNC_OK &&
+        make_out_map(&to_lo, bl, batch, H, W, Cout, out_pix_stride, TH, TW) == MNC_OK)
+      a.tma_store = 1;
+  }
   const int cl = g_igemm_cluster;
   if ((rc = make_wgt_map(&tb_hi, w_hi, Cout, ktot, bn / cl, bk)) != MNC_OK) return rc;
   if ((rc = make_wgt_map(&tb_lo, w_lo, Cout, ktot, bn / cl, bk)) != MNC_OK) return rc;
 
-#define MNC_LAUNCH(TH_, TW_, BN_, BK_)                                                              \
-  return (cl == 2)                                                                                \
-             ? launch_igemm<TH_, TW_, BN_, 2, BK_>(ta_hi, ta_lo, tb_hi, tb_lo, a, max_ctas, stream) \
-             : launch_igemm<TH_, TW_, BN_, 1, BK_>(ta_hi, ta_lo, tb_hi, tb_lo, a, max_ctas, stream)
+#define MNC_LAUNCH(TH_, TW_, BN_, BK_)                                                            \
+  return (cl == 2) ? launch_igemm<TH_, TW_, BN_, 2, BK_>(ta_hi, ta_lo, tb_hi, tb_lo, to_hi, to_lo, \
+                                                         a, max_ctas, stream)                     \
+                   : launch_igemm<TH_, TW_, BN_, 1, BK_>(ta_hi, ta_lo, tb_hi, tb_lo, to_hi, to_lo, \
+                                                         a, max_ctas, stream)
   if (conv) {
     if (bn == 64) MNC_LAUNCH(8, 16, 64, 64);
     if (bn == 128) MNC_LAUNCH(8, 16, 128, 64);

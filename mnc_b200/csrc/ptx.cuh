@@ -81,6 +81,25 @@ __device__ __forceinline__ void tma_load_2d_mcast(void* smem_dst, const void* tm
       : "memory");
 }
 
+// TMA store (shared -> global), bulk-group completion.
+__device__ __forceinline__ void tma_store_4d(const void* tmap, const void* smem_src, int c0, int c1,
+                                             int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+      ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int kPending>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // ------------------------------------------------------------------ clusters
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
