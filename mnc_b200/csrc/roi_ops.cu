@@ -88,21 +88,23 @@ __device__ __forceinline__ RoiGeom roi_geom(const float* roi, float spatial_scal
 constexpr int kWarpSlab = 16;    // channels per CTA
 constexpr int kMaxPooled = 32;   // pooled_h, pooled_w <= 32
 
-// One CTA per (RoI, 8-channel slab).  The per-RoI interpolation tables (row taps, column taps)
-// are built once in shared memory.  A thread owns EPT consecutive output columns for the whole
-// CTA (their column taps live in registers) and walks (channel, ph) rows: per output it issues
-// 4 read-only gathers (a RoI's window of one channel is <= 9.6 KB, L1-resident after first
-// touch), 7 un-fused fp32 ops, and a share of one vector streaming store.  Output bytes are
-// written exactly once, coalesced (the reference writes 3x as much: top + argmax_h + argmax_w).
+// One CTA per (RoI, 16-channel slab).  The per-RoI interpolation tables (row taps, column taps)
+// are built once in shared memory; each thread then fixes EPT consecutive outputs of the P x P
+// plane and keeps, in registers, their four gather offsets and four bilinear weights (weights
+// formed first, as roi_warping_layer.cu:56 does).  The channel loop is then 4 read-only gathers
+// (a RoI's window of one channel is <= 9.6 KB, L1-resident after first touch) + 7 un-fused fp32
+// ops per output and one vector streaming store per EPT outputs: ~13 instructions per output
+// instead of ~50 when offsets and weights are recomputed per element (profiles/README.md).
+// Output bytes are written exactly once, coalesced (the reference also writes argmax_h/argmax_w).
 template <int PH, int PW, int EPT>
 __global__ void __launch_bounds__(256)
 roi_warp_nchw_kernel(const float* __restrict__ feat, int C, int H, int W,
                      const float* __restrict__ rois, float spatial_scale,
                      float* __restrict__ out) {
-  static_assert(PW % EPT == 0, "row must split into whole vectors");
-  constexpr int QW = PW / EPT;          // threads per output row
-  constexpr int RL = 256 / QW;          // row lanes per CTA
   constexpr int PP = PH * PW;
+  static_assert(PP % EPT == 0, "plane must split into whole vectors");
+  constexpr int TPC = PP / EPT;         // threads per channel plane
+  constexpr int CLN = 256 / TPC > 0 ? 256 / TPC : 1;  // channel lanes per CTA
   __shared__ AxisTap tap_h[PH], tap_w[PW];
   const int r = blockIdx.x;
   const int c0 = blockIdx.y * kWarpSlab;
@@ -112,48 +114,53 @@ roi_warp_nchw_kernel(const float* __restrict__ feat, int C, int H, int W,
   if (tid >= 32 && tid < 32 + PW)
     tap_w[tid - 32] = axis_tap(__fadd_rn(g.start_w, __fmul_rn(static_cast<float>(tid - 32), g.bin_w)), W);
   __syncthreads();
-  const int q = tid % QW, rl = tid / QW;
-  if (rl >= RL) return;
-  AxisTap tw[EPT];
+  const int q = tid % TPC, cl = tid / TPC;
+  if (cl >= CLN) return;
+  int off[EPT][4];
+  float wgt[EPT][4];
+  bool ok[EPT];
 #pragma unroll
-  for (int e = 0; e < EPT; ++e) tw[e] = tap_w[q * EPT + e];
+  for (int e = 0; e < EPT; ++e) {
+    const int i = q * EPT + e;
+    const int ph = i / PW, pw = i - ph * PW;
+    const AxisTap th = tap_h[ph], tw = tap_w[pw];
+    ok[e] = th.ok && tw.ok;
+    off[e][0] = ok[e] ? th.lo * W + tw.lo : 0;
+    off[e][1] = ok[e] ? th.lo * W + tw.hi : 0;
+    off[e][2] = ok[e] ? th.hi * W + tw.lo : 0;
+    off[e][3] = ok[e] ? th.hi * W + tw.hi : 0;
+    wgt[e][0] = __fmul_rn(th.h, tw.h);
+    wgt[e][1] = __fmul_rn(th.h, tw.l);
+    wgt[e][2] = __fmul_rn(th.l, tw.h);
+    wgt[e][3] = __fmul_rn(th.l, tw.l);
+  }
   const int nch = min(kWarpSlab, C - c0);
-  const float* fbase = feat + (static_cast<long long>(g.level) * C + c0) * H * W;
+  const int HW = H * W;
+  const float* fbase = feat + (static_cast<long long>(g.level) * C + c0) * HW;
   float* obase = out + (static_cast<long long>(r) * C + c0) * PP + q * EPT;
-  const bool aligned = (reinterpret_cast<uintptr_t>(obase) & (EPT * 4 - 1)) == 0;
-  // two rows per iteration: 8*EPT independent gathers in flight per thread
-  for (int row = rl; row < nch * PH; row += 2 * RL) {
-    float v[2][EPT];
+  const bool aligned = (reinterpret_cast<uintptr_t>(obase) & (EPT * 4 - 1)) == 0 && (PP % EPT == 0);
+#pragma unroll 2
+  for (int c = cl; c < nch; c += CLN) {
+    const float* plane = fbase + static_cast<long long>(c) * HW;
+    float v[EPT];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int rw = row + u * RL;
-      const bool live = rw < nch * PH;
-      const int c = live ? rw / PH : 0, ph = live ? rw - (rw / PH) * PH : 0;
-      const AxisTap th = tap_h[ph];
-      const float* row0 = fbase + static_cast<long long>(c) * H * W + th.lo * W;
-      const float* row1 = fbase + static_cast<long long>(c) * H * W + th.hi * W;
-#pragma unroll
-      for (int e = 0; e < EPT; ++e) {
-        float val = 0.f;
-        if (live && th.ok && tw[e].ok)
-          val = bilerp(th, tw[e], __ldg(row0 + tw[e].lo), __ldg(row0 + tw[e].hi),
-                       __ldg(row1 + tw[e].lo), __ldg(row1 + tw[e].hi));
-        v[u][e] = val;
-      }
+    for (int e = 0; e < EPT; ++e) {
+      const float v1 = __ldg(plane + off[e][0]), v2 = __ldg(plane + off[e][1]);
+      const float v3 = __ldg(plane + off[e][2]), v4 = __ldg(plane + off[e][3]);
+      float val = __fmul_rn(wgt[e][0], v1);
+      val = __fadd_rn(val, __fmul_rn(wgt[e][1], v2));
+      val = __fadd_rn(val, __fmul_rn(wgt[e][2], v3));
+      val = __fadd_rn(val, __fmul_rn(wgt[e][3], v4));
+      v[e] = ok[e] ? val : 0.f;
     }
+    float* o = obase + c * PP;
+    if (EPT == 4 && aligned) {
+      __stcs(reinterpret_cast<float4*>(o), make_float4(v[0], v[EPT > 1 ? 1 : 0], v[EPT > 2 ? 2 : 0], v[EPT > 3 ? 3 : 0]));
+    } else if (EPT == 2 && aligned) {
+      __stcs(reinterpret_cast<float2*>(o), make_float2(v[0], v[EPT > 1 ? 1 : 0]));
+    } else {
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int rw = row + u * RL;
-      if (rw >= nch * PH) break;
-      float* o = obase + rw * PW;  // (c*PH + ph)*PW
-      if (EPT == 4 && aligned) {
-        __stcs(reinterpret_cast<float4*>(o), make_float4(v[u][0], v[u][EPT > 1 ? 1 : 0], v[u][EPT > 2 ? 2 : 0], v[u][EPT > 3 ? 3 : 0]));
-      } else if (EPT == 2 && aligned) {
-        __stcs(reinterpret_cast<float2*>(o), make_float2(v[u][0], v[u][EPT > 1 ? 1 : 0]));
-      } else {
-#pragma unroll
-        for (int e = 0; e < EPT; ++e) __stcs(o + e, v[u][e]);
-      }
+      for (int e = 0; e < EPT; ++e) __stcs(o + e, v[e]);
     }
   }
 }
@@ -454,7 +461,7 @@ extern "C" int mnc_roi_warp_nchw(const float* feat, int C, int H, int W, const f
   if (pooled_h == 28 && pooled_w == 28)
     roi_warp_nchw_kernel<28, 28, 4><<<grid, 256, 0, s>>>(feat, C, H, W, rois, spatial_scale, out);
   else if (pooled_h == 14 && pooled_w == 14)
-    roi_warp_nchw_kernel<14, 14, 2><<<grid, 256, 0, s>>>(feat, C, H, W, rois, spatial_scale, out);
+    roi_warp_nchw_kernel<14, 14, 4><<<grid, 256, 0, s>>>(feat, C, H, W, rois, spatial_scale, out);
   else if (pooled_h == 7 && pooled_w == 7)
     roi_warp_nchw_kernel<7, 7, 1><<<grid, 256, 0, s>>>(feat, C, H, W, rois, spatial_scale, out);
   else
