@@ -60,11 +60,15 @@ int mnc_igemm_tc(const void* a_hi, const void* a_lo, int batch, int H, int W, in
  * tile via TMA multicast; 1 = no clusters. */
 int mnc_igemm_set_cluster(int cluster_size);
 /* K elements per pipeline stage: 64 (SWIZZLE_128B), 32 (SWIZZLE_64B, twice the stages) or
- * 0 = default (32 for 192/256-wide Cout tiles, 64 otherwise).  bn also accepts 192. */
+ * 0 = default (64; the 192-wide Cout tile always uses 32).  bn also accepts 192. */
 int mnc_igemm_set_block_k(int bk);
 /* out_mode 0 epilogue: 1 (default) = stage tiles in shared memory and write them with TMA bulk
  * tensor stores; 0 = per-thread 16-byte global stores. */
 int mnc_igemm_set_tma_store(int on);
+/* 3x3 convolutions with Cout tiles <= 128: 1 (default) = halo kernel (one TMA box of the pixel
+ * tile + border feeds all 9 filter taps through shifted shared-memory descriptors);
+ * 0 = per-tap activation loads. */
+int mnc_igemm_set_halo(int on);
 
 /* Same contract as mnc_igemm_tc on the fp32 SIMT pipes (exact fp32 FMA on hi+lo operands).
  * Not on the product path: it is the on-device cross-check for the tensor-core kernel. */

@@ -104,6 +104,191 @@ __device__ __forceinline__ Tile decode_tile(const IgemmArgs& p, int t, int rank,
   return tl;
 }
 
+// ---------------------------------------------------------------------------------- epilogue
+// Shared by the per-tap kernel and the halo kernel: warps 4..7 drain the TMEM accumulators of
+// every tile this CTA owns (bias, ReLU, optional 2x2 ceil-mode max pool, re-split, store).
+template <int TH, int TW, int BN, int CL>
+__device__ __forceinline__ void run_epilogue(const IgemmArgs& p, const CUtensorMap* tm_o_hi_p,
+                                             const CUtensorMap* tm_o_lo_p, uint8_t* staging,
+                                             uint64_t* tfull_bar, uint64_t* tempty_bar,
+                                             uint32_t tmem_base, int rank, int first, int stride,
+                                             int total_tiles) {
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q = warp - 4;  // TMEM lane quarter == warp_id % 4
+  const int row = q * 32 + lane;
+  int local = 0;
+  int chunk_ctr = 0;
+  for (int t = first; t < total_tiles; t += stride, ++local) {
+    const Tile tl = decode_tile<CL>(p, t, rank, TH, TW, BN);
+    const int img = tl.img, h0 = tl.h0, w0 = tl.w0, n0 = tl.n0, ks = tl.ks;
+    const int acc = local & 1;
+    const uint32_t acc_phase = (local >> 1) & 1;
+    const int h = h0 + row / TW;
+    const int w = w0 + row % TW;
+    const bool valid = !tl.dummy && (h < p.H) && (w < p.W);
+    const long long pix = (static_cast<long long>(img) * p.H + h) * p.W + w;
+    ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+    ptx::tc_fence_after();
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c0;
+      ptx::tmem_ld_32x32b_x32(taddr, r);
+      ptx::tmem_ld_wait();
+      const int ch0 = n0 + c0;
+      if (p.out_mode == 3) continue;  // diagnostic: accumulators are drained and discarded
+      if (p.out_mode == 2) {
+        // Fused 2x2 stride-2 ceil-mode max pool (pooling_layer.cu:11-47).  A warp holds 32/TW
+        // whole image rows of the pixel tile (TW = 16: two rows, TW = 8: four), so the pool window
+        // of an even (row, column) is lanes {l, l^1, l^TW, l^(TW+1)}: two shuffles per channel.
+        // Each of the 4 lanes of a window then stores 8 of the chunk's 32 channels.
+        const int part = (lane & 1) | (((lane / TW) & 1) << 1);
+        const int hl = (row / TW) & ~1;   // tile-local top row / left column of this lane's window
+        const int wl = (row % TW) & ~1;
+        float m[8];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = __uint_as_float(r[j]);
+          if (p.bias != nullptr && ch0 + j < p.Cout) x += __ldg(p.bias + ch0 + j);
+          if (p.relu) x = fmaxf(x, 0.f);
+          if (!valid) x = -3.402823466e+38f;
+          x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 1));
+          x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, TW));
+          if ((j >> 3) == part) m[j & 7] = x;
+        }
+        const int hp = (h0 + hl) >> 1;
+        const int wp = (w0 + wl) >> 1;
+        const int Ho = (p.H + 1) >> 1, Wo = (p.W + 1) >> 1;
+        const int chp = ch0 + part * 8;
+        if (!tl.dummy && hp < Ho && wp < Wo && (h0 + hl) < p.H && (w0 + wl) < p.W &&
+            chp < p.Cout) {
+          const long long ppix = (static_cast<long long>(img) * Ho + hp) * Wo + wp;
+          __nv_bfloat16* ph = p.out_hi + ppix * p.out_pix_stride + p.out_ch_offset + chp;
+          __nv_bfloat16* pl = p.out_lo + ppix * p.out_pix_stride + p.out_ch_offset + chp;
+          uint32_t hw[4], lw[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float x0 = m[2 * e], x1 = m[2 * e + 1];
+            const __nv_bfloat16 h0b = __float2bfloat16_rn(x0);
+            const __nv_bfloat16 h1b = __float2bfloat16_rn(x1);
+            const __nv_bfloat16 l0b = __float2bfloat16_rn(x0 - __bfloat162float(h0b));
+            const __nv_bfloat16 l1b = __float2bfloat16_rn(x1 - __bfloat162float(h1b));
+            hw[e] = static_cast<uint32_t>(__bfloat16_as_ushort(h0b)) |
+                    (static_cast<uint32_t>(__bfloat16_as_ushort(h1b)) << 16);
+            lw[e] = static_cast<uint32_t>(__bfloat16_as_ushort(l0b)) |
+                    (static_cast<uint32_t>(__bfloat16_as_ushort(l1b)) << 16);
+          }
+          *reinterpret_cast<uint4*>(ph) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          *reinterpret_cast<uint4*>(pl) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        }
+      } else if (p.tma_store) {
+        // ---- out_mode 0 via shared-memory staging + TMA store: each thread owns one pixel row
+        // of the 128 x 32-channel chunk (64 B per bf16 plane, written with the 64B-swizzle
+        // pattern so the 16-byte stores are bank-conflict free); one elected thread then issues
+        // two bulk tensor stores (hi, lo).  TMA clips ragged tiles, channel tails and the
+        // cluster's dummy tile, and the global writes are whole 64-byte rows.
+        const int buf = chunk_ctr & 1;
+        uint8_t* sb = staging + buf * (2 * 128 * 64);
+        if (threadIdx.x == 128) ptx::tma_store_wait_read<1>();  // this buffer's previous store
+        ptx::named_bar_sync(1, 128);
+        if (ch0 < p.Cout) {
+          float bv[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            bv[j] = (p.bias != nullptr && ch0 + j < p.Cout) ? __ldg(p.bias + ch0 + j) : 0.f;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint32_t hw[4], lw[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float x0 = __uint_as_float(r[g * 8 + 2 * e]) + bv[g * 8 + 2 * e];
+              float x1 = __uint_as_float(r[g * 8 + 2 * e + 1]) + bv[g * 8 + 2 * e + 1];
+              if (p.relu) {
+                x0 = fmaxf(x0, 0.f);
+                x1 = fmaxf(x1, 0.f);
+              }
+              const __nv_bfloat16 h0b = __float2bfloat16_rn(x0);
+              const __nv_bfloat16 h1b = __float2bfloat16_rn(x1);
+              const __nv_bfloat16 l0b = __float2bfloat16_rn(x0 - __bfloat162float(h0b));
+              const __nv_bfloat16 l1b = __float2bfloat16_rn(x1 - __bfloat162float(h1b));
+              hw[e] = static_cast<uint32_t>(__bfloat16_as_ushort(h0b)) |
+                      (static_cast<uint32_t>(__bfloat16_as_ushort(h1b)) << 16);
+              lw[e] = static_cast<uint32_t>(__bfloat16_as_ushort(l0b)) |
+                      (static_cast<uint32_t>(__bfloat16_as_ushort(l1b)) << 16);
+            }
+            const int off = row * 64 + ((g ^ ((row >> 1) & 3)) << 4);
+            *reinterpret_cast<uint4*>(sb + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            *reinterpret_cast<uint4*>(sb + 128 * 64 + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          }
+        }
+        ptx::fence_proxy_async();
+        ptx::named_bar_sync(1, 128);
+        if (threadIdx.x == 128 && ch0 < p.Cout) {
+          ptx::tma_store_4d(tm_o_hi_p, sb, ch0, w0, h0, img);
+          ptx::tma_store_4d(tm_o_lo_p, sb + 128 * 64, ch0, w0, h0, img);
+          ptx::tma_store_commit();
+        }
+        ++chunk_ctr;
+      } else if (valid && ch0 < p.Cout) {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = __uint_as_float(r[j]);
+          if (p.bias != nullptr && ch0 + j < p.Cout) x += __ldg(p.bias + ch0 + j);
+          if (p.relu) x = fmaxf(x, 0.f);
+          v[j] = x;
+        }
+        const bool fullchunk = (ch0 + 32 <= p.Cout) && p.vec_ok;
+        if (p.out_mode == 0) {
+          __nv_bfloat16* ph = p.out_hi + pix * p.out_pix_stride + p.out_ch_offset + ch0;
+          __nv_bfloat16* pl = p.out_lo + pix * p.out_pix_stride + p.out_ch_offset + ch0;
+          if (fullchunk) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint32_t hw[4], lw[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float x0 = v[g * 8 + 2 * e], x1 = v[g * 8 + 2 * e + 1];
+                const __nv_bfloat16 h0b = __float2bfloat16_rn(x0);
+                const __nv_bfloat16 h1b = __float2bfloat16_rn(x1);
+                const __nv_bfloat16 l0b = __float2bfloat16_rn(x0 - __bfloat162float(h0b));
+                const __nv_bfloat16 l1b = __float2bfloat16_rn(x1 - __bfloat162float(h1b));
+                hw[e] = static_cast<uint32_t>(__bfloat16_as_ushort(h0b)) |
+                        (static_cast<uint32_t>(__bfloat16_as_ushort(h1b)) << 16);
+                lw[e] = static_cast<uint32_t>(__bfloat16_as_ushort(l0b)) |
+                        (static_cast<uint32_t>(__bfloat16_as_ushort(l1b)) << 16);
+              }
+              *reinterpret_cast<uint4*>(ph + g * 8) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+              *reinterpret_cast<uint4*>(pl + g * 8) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            }
+          } else {
+            for (int j = 0; j < 32 && ch0 + j < p.Cout; ++j) {
+              const __nv_bfloat16 hb = __float2bfloat16_rn(v[j]);
+              ph[j] = hb;
+              pl[j] = __float2bfloat16_rn(v[j] - __bfloat162float(hb));
+            }
+          }
+        } else {
+          float* po = p.out_f32 + ks * p.split_stride + pix * p.out_pix_stride +
+                      p.out_ch_offset + ch0;
+          if (fullchunk) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              *reinterpret_cast<float4*>(po + g * 4) =
+                  make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+          } else {
+            for (int j = 0; j < 32 && ch0 + j < p.Cout; ++j) po[j] = v[j];
+          }
+        }
+      }
+    }
+    ptx::tc_fence_before();
+    ptx::mbar_arrive(&tempty_bar[acc]);
+  }
+  if (threadIdx.x == 128) ptx::tma_store_wait_read<0>();  // smem must outlive the bulk stores
+}
+
 template <int TH, int TW, int BN, int CL, int BK>
 __global__ void __launch_bounds__(256, 1)
 igemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
@@ -252,181 +437,202 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     }
   } else if (warp >= 4) {
     // ---------------------------------------------------------------- epilogue
-    const int q = warp - 4;  // TMEM lane quarter == warp_id % 4
-    const int row = q * 32 + lane;
-    int local = 0;
-    int chunk_ctr = 0;
-    for (int t = first; t < total_tiles; t += stride, ++local) {
-      const Tile tl = decode_tile<CL>(p, t, rank, TH, TW, BN);
-      const int img = tl.img, h0 = tl.h0, w0 = tl.w0, n0 = tl.n0, ks = tl.ks;
-      const int acc = local & 1;
-      const uint32_t acc_phase = (local >> 1) & 1;
-      const int h = h0 + row / TW;
-      const int w = w0 + row % TW;
-      const bool valid = !tl.dummy && (h < p.H) && (w < p.W);
-      const long long pix = (static_cast<long long>(img) * p.H + h) * p.W + w;
-      ptx::mbar_wait(&tfull_bar[acc], acc_phase);
-      ptx::tc_fence_after();
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c0;
-        ptx::tmem_ld_32x32b_x32(taddr, r);
-        ptx::tmem_ld_wait();
-        const int ch0 = n0 + c0;
-        if (p.out_mode == 3) continue;  // diagnostic: accumulators are drained and discarded
-        if (p.out_mode == 2) {
-          // Fused 2x2 stride-2 ceil-mode max pool (pooling_layer.cu:11-47).  With the 8x16 pixel
-          // tile a warp holds two image rows: lanes 0-15 row 2q, lanes 16-31 row 2q+1, so the pool
-          // window of an even column is lanes {l, l^1, l^16, l^17}: two shuffles per channel.
-          // Each of the 4 lanes of a window then stores 8 of the chunk's 32 channels.
-          const int part = (lane & 1) | ((lane >> 4) << 1);
-          float m[8];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float x = __uint_as_float(r[j]);
-            if (p.bias != nullptr && ch0 + j < p.Cout) x += __ldg(p.bias + ch0 + j);
-            if (p.relu) x = fmaxf(x, 0.f);
-            if (!valid) x = -3.402823466e+38f;
-            x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 1));
-            x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 16));
-            if ((j >> 3) == part) m[j & 7] = x;
-          }
-          const int hp = (h0 + 2 * q) >> 1;
-          const int wp = (w0 + (lane & 14)) >> 1;
-          const int Ho = (p.H + 1) >> 1, Wo = (p.W + 1) >> 1;
-          const int chp = ch0 + part * 8;
-          if (!tl.dummy && hp < Ho && wp < Wo && (h0 + 2 * q) < p.H && (w0 + (lane & 14)) < p.W &&
-              chp < p.Cout) {
-            const long long ppix = (static_cast<long long>(img) * Ho + hp) * Wo + wp;
-            __nv_bfloat16* ph = p.out_hi + ppix * p.out_pix_stride + p.out_ch_offset + chp;
-            __nv_bfloat16* pl = p.out_lo + ppix * p.out_pix_stride + p.out_ch_offset + chp;
-            uint32_t hw[4], lw[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float x0 = m[2 * e], x1 = m[2 * e + 1];
-              const __nv_bfloat16 h0b = __float2bfloat16_rn(x0);
-              const __nv_bfloat16 h1b = __float2bfloat16_rn(x1);
-              const __nv_bfloat16 l0b = __float2bfloat16_rn(x0 - __bfloat162float(h0b));
-              const __nv_bfloat16 l1b = __float2bfloat16_rn(x1 - __bfloat162float(h1b));
-              hw[e] = static_cast<uint32_t>(__bfloat16_as_ushort(h0b)) |
-                      (static_cast<uint32_t>(__bfloat16_as_ushort(h1b)) << 16);
-              lw[e] = static_cast<uint32_t>(__bfloat16_as_ushort(l0b)) |
-                      (static_cast<uint32_t>(__bfloat16_as_ushort(l1b)) << 16);
-            }
-            *reinterpret_cast<uint4*>(ph) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-            *reinterpret_cast<uint4*>(pl) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-          }
-        } else if (p.tma_store) {
-          // ---- out_mode 0 via shared-memory staging + TMA store: each thread owns one pixel row
-          // of the 128 x 32-channel chunk (64 B per bf16 plane, written with the 64B-swizzle
-          // pattern so the 16-byte stores are bank-conflict free); one elected thread then issues
-          // two bulk tensor stores (hi, lo).  TMA clips ragged tiles, channel tails and the
-          // cluster's dummy tile, and the global writes are whole 64-byte rows.
-          const int buf = chunk_ctr & 1;
-          uint8_t* sb = staging + buf * (2 * 128 * 64);
-          if (threadIdx.x == 128) ptx::tma_store_wait_read<1>();  // this buffer's previous store
-          ptx::named_bar_sync(1, 128);
-          if (ch0 < p.Cout) {
-            float bv[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              bv[j] = (p.bias != nullptr && ch0 + j < p.Cout) ? __ldg(p.bias + ch0 + j) : 0.f;
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              uint32_t hw[4], lw[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float x0 = __uint_as_float(r[g * 8 + 2 * e]) + bv[g * 8 + 2 * e];
-                float x1 = __uint_as_float(r[g * 8 + 2 * e + 1]) + bv[g * 8 + 2 * e + 1];
-                if (p.relu) {
-                  x0 = fmaxf(x0, 0.f);
-                  x1 = fmaxf(x1, 0.f);
-                }
-                const __nv_bfloat16 h0b = __float2bfloat16_rn(x0);
-                const __nv_bfloat16 h1b = __float2bfloat16_rn(x1);
-                const __nv_bfloat16 l0b = __float2bfloat16_rn(x0 - __bfloat162float(h0b));
-                const __nv_bfloat16 l1b = __float2bfloat16_rn(x1 - __bfloat162float(h1b));
-                hw[e] = static_cast<uint32_t>(__bfloat16_as_ushort(h0b)) |
-                        (static_cast<uint32_t>(__bfloat16_as_ushort(h1b)) << 16);
-                lw[e] = static_cast<uint32_t>(__bfloat16_as_ushort(l0b)) |
-                        (static_cast<uint32_t>(__bfloat16_as_ushort(l1b)) << 16);
-              }
-              const int off = row * 64 + ((g ^ ((row >> 1) & 3)) << 4);
-              *reinterpret_cast<uint4*>(sb + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-              *reinterpret_cast<uint4*>(sb + 128 * 64 + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-            }
-          }
-          ptx::fence_proxy_async();
-          ptx::named_bar_sync(1, 128);
-          if (threadIdx.x == 128 && ch0 < p.Cout) {
-            ptx::tma_store_4d(&tm_o_hi, sb, ch0, w0, h0, img);
-            ptx::tma_store_4d(&tm_o_lo, sb + 128 * 64, ch0, w0, h0, img);
-            ptx::tma_store_commit();
-          }
-          ++chunk_ctr;
-        } else if (valid && ch0 < p.Cout) {
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float x = __uint_as_float(r[j]);
-            if (p.bias != nullptr && ch0 + j < p.Cout) x += __ldg(p.bias + ch0 + j);
-            if (p.relu) x = fmaxf(x, 0.f);
-            v[j] = x;
-          }
-          const bool fullchunk = (ch0 + 32 <= p.Cout) && p.vec_ok;
-          if (p.out_mode == 0) {
-            __nv_bfloat16* ph = p.out_hi + pix * p.out_pix_stride + p.out_ch_offset + ch0;
-            __nv_bfloat16* pl = p.out_lo + pix * p.out_pix_stride + p.out_ch_offset + ch0;
-            if (fullchunk) {
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                uint32_t hw[4], lw[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float x0 = v[g * 8 + 2 * e], x1 = v[g * 8 + 2 * e + 1];
-                  const __nv_bfloat16 h0b = __float2bfloat16_rn(x0);
-                  const __nv_bfloat16 h1b = __float2bfloat16_rn(x1);
-                  const __nv_bfloat16 l0b = __float2bfloat16_rn(x0 - __bfloat162float(h0b));
-                  const __nv_bfloat16 l1b = __float2bfloat16_rn(x1 - __bfloat162float(h1b));
-                  hw[e] = static_cast<uint32_t>(__bfloat16_as_ushort(h0b)) |
-                          (static_cast<uint32_t>(__bfloat16_as_ushort(h1b)) << 16);
-                  lw[e] = static_cast<uint32_t>(__bfloat16_as_ushort(l0b)) |
-                          (static_cast<uint32_t>(__bfloat16_as_ushort(l1b)) << 16);
-                }
-                *reinterpret_cast<uint4*>(ph + g * 8) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                *reinterpret_cast<uint4*>(pl + g * 8) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-              }
-            } else {
-              for (int j = 0; j < 32 && ch0 + j < p.Cout; ++j) {
-                const __nv_bfloat16 hb = __float2bfloat16_rn(v[j]);
-                ph[j] = hb;
-                pl[j] = __float2bfloat16_rn(v[j] - __bfloat162float(hb));
-              }
-            }
-          } else {
-            float* po = p.out_f32 + ks * p.split_stride + pix * p.out_pix_stride +
-                        p.out_ch_offset + ch0;
-            if (fullchunk) {
-#pragma unroll
-              for (int g = 0; g < 8; ++g)
-                *reinterpret_cast<float4*>(po + g * 4) =
-                    make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
-            } else {
-              for (int j = 0; j < 32 && ch0 + j < p.Cout; ++j) po[j] = v[j];
-            }
-          }
-        }
-      }
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(&tempty_bar[acc]);
-    }
-    if (threadIdx.x == 128) ptx::tma_store_wait_read<0>();  // smem must outlive the bulk stores
+    run_epilogue<TH, TW, BN, CL>(p, &tm_o_hi, &tm_o_lo, staging, tfull_bar, tempty_bar, tmem_base,
+                                 rank, first, stride, total_tiles);
   }
 
   ptx::tc_fence_before();
   __syncthreads();
   if (CL > 1) ptx::cluster_sync_all();  // no CTA leaves while a peer may still signal its barriers
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------ halo kernel
+// 3x3 convolution for the low-Cin layers (conv1_2, conv2_x), where the per-tap kernel is bound by
+// the rate at which activation tiles arrive in shared memory (each pixel is fetched 9 times, once
+// per filter tap).  Here the pixel tile is 16 rows x 8 columns and ONE TMA box [18][10][64ch]
+// brings in the tile plus its halo; every filter tap is then a *shifted window* of that box:
+// the tcgen05 shared-memory descriptor takes start = halo + ((ky*10 + kx) * 128 B) and a stride
+// between 8-row groups of 1280 B (one halo row) instead of the canonical 1024 B.  This is legal
+// because the 128B swizzle is a pure function of the shared-memory address (verified on B200 by
+// scripts/exp/umma_offset_test.cu: all 9 windows read back exactly).  Activation traffic into the
+// SM drops from 9 x 32 KB to 46 KB per (tile, 64-channel chunk); weights stream per tap through
+// their own ring of stages.
+constexpr int kHaloTH = 16, kHaloTW = 8;
+constexpr int kHaloRows = (kHaloTH + 2) * (kHaloTW + 2);          // 180 pixels
+constexpr int kHaloPlaneBytes = kHaloRows * 128;                   // 23040
+constexpr int kHaloPlanePad = (kHaloPlaneBytes + 1023) / 1024 * 1024;  // 23552
+constexpr int kHaloABytes = 2 * kHaloPlanePad;                     // hi + lo
+constexpr int kHaloNA = 2;
+
+template <int BN>
+struct HaloCfg {
+  static constexpr int kBBytes = BN * 128;                        // one plane of one tap's weights
+  static constexpr int kBStage = 2 * kBBytes;
+  static constexpr int kNB = (192 * 1024 - kHaloNA * kHaloABytes) / kBStage;
+  static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
+  static constexpr int kStagingBytes = 2 * 2 * 128 * 64;
+  static constexpr int kBarrierBytes = 1024;
+  static constexpr int kRingBytes = kHaloNA * kHaloABytes + kNB * kBStage;
+  static constexpr int kSmemBytes = kRingBytes + 1024 + kBarrierBytes + kStagingBytes;
+};
+
+__device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(256, 1)
+conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                    const __grid_constant__ CUtensorMap tm_o_hi, const __grid_constant__ CUtensorMap tm_o_lo,
+                    const IgemmArgs p) {
+  using Cfg = HaloCfg<BN>;
+  constexpr int TH = kHaloTH, TW = kHaloTW, NB = Cfg::kNB;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* a_ring = smem;
+  uint8_t* b_ring = smem + kHaloNA * kHaloABytes;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + Cfg::kRingBytes);
+  uint64_t* a_empty = a_full + kHaloNA;
+  uint64_t* b_full = a_empty + kHaloNA;
+  uint64_t* b_empty = b_full + NB;
+  uint64_t* tfull_bar = b_empty + NB;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint8_t* staging = smem + Cfg::kRingBytes + Cfg::kBarrierBytes;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.tiles_n * p.batch * p.tiles_h * p.tiles_w;
+  const int kchunks = p.Cin / 64;
+  const int first = blockIdx.x, stride = gridDim.x;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tm_a_hi);
+    ptx::prefetch_tmap(&tm_a_lo);
+    ptx::prefetch_tmap(&tm_b_hi);
+    ptx::prefetch_tmap(&tm_b_lo);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kHaloNA; ++s) {
+      ptx::mbar_init(&a_full[s], 1);
+      ptx::mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < NB; ++s) {
+      ptx::mbar_init(&b_full[s], 1);
+      ptx::mbar_init(&b_empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tfull_bar[a], 1);
+      ptx::mbar_init(&tempty_bar[a], 128);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) ptx::tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      for (int t = first; t < total_tiles; t += stride) {
+        const Tile tl = decode_tile<1>(p, t, 0, TH, TW, BN);
+        for (int kc = 0; kc < kchunks; ++kc) {
+          ptx::mbar_wait(&a_empty[as], aph ^ 1);
+          uint8_t* sa = a_ring + as * kHaloABytes;
+          ptx::mbar_arrive_expect_tx(&a_full[as], 2 * kHaloPlaneBytes);
+          ptx::tma_load_4d(sa, &tm_a_hi, &a_full[as], kc * 64, tl.w0 - 1, tl.h0 - 1, tl.img);
+          ptx::tma_load_4d(sa + kHaloPlanePad, &tm_a_lo, &a_full[as], kc * 64, tl.w0 - 1,
+                           tl.h0 - 1, tl.img);
+          if (++as == kHaloNA) {
+            as = 0;
+            aph ^= 1;
+          }
+          for (int tap = 0; tap < 9; ++tap) {
+            ptx::mbar_wait(&b_empty[bs], bph ^ 1);
+            uint8_t* sb = b_ring + bs * Cfg::kBStage;
+            ptx::mbar_arrive_expect_tx(&b_full[bs], Cfg::kBStage);
+            ptx::tma_load_2d(sb, &tm_b_hi, &b_full[bs], tap * p.Cin + kc * 64, tl.n0);
+            ptx::tma_load_2d(sb + Cfg::kBBytes, &tm_b_lo, &b_full[bs], tap * p.Cin + kc * 64,
+                             tl.n0);
+            if (++bs == NB) {
+              bs = 0;
+              bph ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // -------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16_m128(BN);
+      constexpr uint32_t kSbo = (TW + 2) * 128;  // one halo row
+      int as = 0, bs = 0, local = 0;
+      uint32_t aph = 0, bph = 0;
+      for (int t = first; t < total_tiles; t += stride, ++local) {
+        const int acc = local & 1;
+        const uint32_t acc_phase = (local >> 1) & 1;
+        ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kc = 0; kc < kchunks; ++kc) {
+          ptx::mbar_wait(&a_full[as], aph);
+          ptx::tc_fence_after();
+          const uint32_t a_hi0 = ptx::smem_u32(a_ring + as * kHaloABytes);
+          const uint32_t a_lo0 = a_hi0 + kHaloPlanePad;
+          for (int tap = 0; tap < 9; ++tap) {
+            ptx::mbar_wait(&b_full[bs], bph);
+            ptx::tc_fence_after();
+            const uint32_t woff = ((tap / 3) * (TW + 2) + (tap % 3)) * 128;  // shifted window
+            const uint32_t b_hi = ptx::smem_u32(b_ring + bs * Cfg::kBStage);
+            const uint32_t b_lo = b_hi + Cfg::kBBytes;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint64_t da_hi = umma_desc_sw128_sbo(a_hi0 + woff + kk * 32, kSbo);
+              const uint64_t da_lo = umma_desc_sw128_sbo(a_lo0 + woff + kk * 32, kSbo);
+              const uint64_t db_hi = ptx::umma_desc_sw128(b_hi + kk * 32);
+              const uint64_t db_lo = ptx::umma_desc_sw128(b_lo + kk * 32);
+              ptx::umma_bf16_ss(tmem_d, da_lo, db_hi, idesc, (kc > 0 || tap > 0 || kk > 0) ? 1u : 0u);
+              ptx::umma_bf16_ss(tmem_d, da_hi, db_lo, idesc, 1u);
+              ptx::umma_bf16_ss(tmem_d, da_hi, db_hi, idesc, 1u);
+            }
+            ptx::umma_commit(&b_empty[bs]);
+            if (++bs == NB) {
+              bs = 0;
+              bph ^= 1;
+            }
+          }
+          ptx::umma_commit(&a_empty[as]);
+          if (++as == kHaloNA) {
+            as = 0;
+            aph ^= 1;
+          }
+        }
+        ptx::umma_commit(&tfull_bar[acc]);
+      }
+    }
+  } else if (warp >= 4) {
+    run_epilogue<TH, TW, BN, 1>(p, &tm_o_hi, &tm_o_lo, staging, tfull_bar, tempty_bar, tmem_base, 0,
+                                first, stride, total_tiles);
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
   if (warp == 2) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
@@ -550,6 +756,27 @@ static int launch_igemm(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo,
   return e == cudaSuccess ? MNC_OK : MNC_ERR_CUDA;
 }
 
+template <int BN>
+static int launch_halo(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CUtensorMap& tb_hi,
+                       const CUtensorMap& tb_lo, const CUtensorMap& to_hi, const CUtensorMap& to_lo,
+                       const IgemmArgs& a, int max_ctas, cudaStream_t stream) {
+  using Cfg = HaloCfg<BN>;
+  auto kern = conv_halo_tc_kernel<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) !=
+        cudaSuccess)
+      return MNC_ERR_CUDA;
+    attr_set = true;
+  }
+  const int total = a.tiles_n * a.batch * a.tiles_h * a.tiles_w;
+  int grid = sm_count();
+  if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
+  if (total < grid) grid = total;
+  kern<<<grid, 256, Cfg::kSmemBytes, stream>>>(ta_hi, ta_lo, tb_hi, tb_lo, to_hi, to_lo, a);
+  return cudaGetLastError() == cudaSuccess ? MNC_OK : MNC_ERR_CUDA;
+}
+
 }  // namespace mnc
 
 using namespace mnc;
@@ -558,6 +785,11 @@ using namespace mnc;
 // dimension share each weight tile through TMA multicast (halves weight traffic from L2).
 static int g_igemm_cluster = 2;
 static int g_igemm_bk = 0;  // 0 = per-shape default
+static int g_igemm_halo = 1;  // halo-reuse kernel for 3x3 convs with Cout tiles <= 128
+extern "C" int mnc_igemm_set_halo(int on) {
+  g_igemm_halo = on ? 1 : 0;
+  return MNC_OK;
+}
 static int g_igemm_tma_store = 1;
 extern "C" int mnc_igemm_set_tma_store(int on) {
   g_igemm_tma_store = on ? 1 : 0;
@@ -569,8 +801,8 @@ extern "C" int mnc_igemm_set_cluster(int cl) {
   return MNC_OK;
 }
 
-// K elements per pipeline stage for mnc_igemm_tc launches: 64, 32, or 0 = default
-// (32 for Cout tiles of 192/256, where 64 leaves only two stages in shared memory).
+// K elements per pipeline stage for mnc_igemm_tc launches: 64, 32, or 0 = default (64; the
+// 192-wide Cout tile exists only with 32).
 extern "C" int mnc_igemm_set_block_k(int bk) {
   if (bk != 0 && bk != 32 && bk != 64) return MNC_ERR_ARG;
   g_igemm_bk = bk;
@@ -592,10 +824,11 @@ extern "C" int mnc_igemm_tc(const void* a_hi, const void* a_lo, int batch, int H
                         out_ch_offset % 8 != 0))
     return MNC_ERR_ARG;
   const bool conv = (taps == 9);
-  const int TH = conv ? 8 : 1, TW = conv ? 16 : 128;
   if (bn == 0) bn = (Cout <= 64) ? 64 : (Cout <= 128 ? 128 : 256);
+  const bool halo = conv && g_igemm_halo && (bn == 64 || bn == 128) && split_k == 1;
+  const int TH = conv ? (halo ? kHaloTH : 8) : 1, TW = conv ? (halo ? kHaloTW : 16) : 128;
   if (bn != 64 && bn != 128 && bn != 192 && bn != 256) return MNC_ERR_ARG;
-  if (bk == 0) bk = (bn >= 192) ? 32 : 64;
+  if (bk == 0) bk = 64;              // measured: BLOCK_K 64 wins at BN 256 (profiles/r01_igemm_bk32_bn192.log)
   if (bn == 192) bk = 32;            // instantiated combinations: (64|128|256, 64), (192|256, 32)
   if (bn < 192) bk = 64;
 
@@ -629,8 +862,11 @@ extern "C" int mnc_igemm_tc(const void* a_hi, const void* a_lo, int batch, int H
 
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   int rc;
-  if ((rc = make_act_map(&ta_hi, a_hi, batch, H, W, Cin, TH, TW, bk)) != MNC_OK) return rc;
-  if ((rc = make_act_map(&ta_lo, a_lo, batch, H, W, Cin, TH, TW, bk)) != MNC_OK) return rc;
+  if (halo) bk = 64;
+  // halo kernel: the activation box is the pixel tile plus a one-pixel border
+  const int box_h = halo ? TH + 2 : TH, box_w = halo ? TW + 2 : TW;
+  if ((rc = make_act_map(&ta_hi, a_hi, batch, H, W, Cin, box_h, box_w, bk)) != MNC_OK) return rc;
+  if ((rc = make_act_map(&ta_lo, a_lo, batch, H, W, Cin, box_h, box_w, bk)) != MNC_OK) return rc;
   const long long ktot = static_cast<long long>(taps) * Cin;
   // epilogue through shared memory + TMA store when the output planes allow a tensor map
   CUtensorMap to_hi = ta_hi, to_lo = ta_lo;  // placeholders when unused
@@ -643,9 +879,14 @@ extern "C" int mnc_igemm_tc(const void* a_hi, const void* a_lo, int batch, int H
         make_out_map(&to_lo, bl, batch, H, W, Cout, out_pix_stride, TH, TW) == MNC_OK)
       a.tma_store = 1;
   }
-  const int cl = g_igemm_cluster;
+  const int cl = halo ? 1 : g_igemm_cluster;
   if ((rc = make_wgt_map(&tb_hi, w_hi, Cout, ktot, bn / cl, bk)) != MNC_OK) return rc;
   if ((rc = make_wgt_map(&tb_lo, w_lo, Cout, ktot, bn / cl, bk)) != MNC_OK) return rc;
+  if (halo) {
+    a.k_steps = 9 * (Cin / 64);
+    if (bn == 64) return launch_halo<64>(ta_hi, ta_lo, tb_hi, tb_lo, to_hi, to_lo, a, max_ctas, stream);
+    return launch_halo<128>(ta_hi, ta_lo, tb_hi, tb_lo, to_hi, to_lo, a, max_ctas, stream);
+  }
 
 #define MNC_LAUNCH(TH_, TW_, BN_, BK_)                                                            \
   return (cl == 2) ? launch_igemm<TH_, TW_, BN_, 2, BK_>(ta_hi, ta_lo, tb_hi, tb_lo, to_hi, to_lo, \

@@ -461,7 +461,7 @@ extern "C" int mnc_roi_warp_nchw(const float* feat, int C, int H, int W, const f
   if (pooled_h == 28 && pooled_w == 28)
     roi_warp_nchw_kernel<28, 28, 4><<<grid, 256, 0, s>>>(feat, C, H, W, rois, spatial_scale, out);
   else if (pooled_h == 14 && pooled_w == 14)
-    roi_warp_nchw_kernel<14, 14, 4><<<grid, 256, 0, s>>>(feat, C, H, W, rois, spatial_scale, out);
+    roi_warp_nchw_kernel<14, 14, 2><<<grid, 256, 0, s>>>(feat, C, H, W, rois, spatial_scale, out);
   else if (pooled_h == 7 && pooled_w == 7)
     roi_warp_nchw_kernel<7, 7, 1><<<grid, 256, 0, s>>>(feat, C, H, W, rois, spatial_scale, out);
   else

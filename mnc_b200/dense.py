@@ -38,6 +38,8 @@ def fc_weight_to_split(w, chw=None):
 
 import os as _os
 
+if _os.environ.get("MNC_IGEMM_HALO"):
+    check(lib.mnc_igemm_set_halo(c_int(int(_os.environ["MNC_IGEMM_HALO"]))), "mnc_igemm_set_halo")
 if _os.environ.get("MNC_IGEMM_BK"):
     check(lib.mnc_igemm_set_block_k(c_int(int(_os.environ["MNC_IGEMM_BK"]))), "mnc_igemm_set_block_k")
 if _os.environ.get("MNC_IGEMM_CLUSTER"):
