@@ -260,6 +260,7 @@ def main():
     # this: uint8 BGR frames in host memory -> boxes / masks / scores in host memory
     host_u8 = np.stack([np.random.default_rng(1234 + start + i).integers(
         0, 256, size=(H, W, 3), dtype=np.uint8) for i in range(B)])
+    host_u8 = torch.from_numpy(host_u8).pin_memory()   # the step's inputs live in pinned host memory
     for _ in range(2):
         det.im_detect_images(host_u8)
     barrier()

@@ -67,6 +67,13 @@ class Detector:
         subtraction, the 600/1000 resize rule and HWC->NCHW run on the device (mnc_prep_images),
         so only B*H*W*3 bytes cross PCIe.  Returns boxes (in original-image coordinates), masks,
         scores, valid -- host arrays -- and the scale used."""
+        pinned_src = None
+        if isinstance(images_u8, torch.Tensor):
+            # a page-locked uint8 tensor goes to the device without the staging copy
+            assert images_u8.dtype == torch.uint8 and images_u8.is_contiguous()
+            if images_u8.is_pinned():
+                pinned_src = images_u8
+            images_u8 = images_u8.numpy()
         images_u8 = np.ascontiguousarray(images_u8)
         B, H, W, _ = images_u8.shape
         scale = ops.im_scale_for((H, W))
@@ -76,12 +83,14 @@ class Detector:
         if getattr(self, "_h_u8", None) is None or self._h_u8.shape[1:] != images_u8.shape[1:]:
             self._h_u8 = torch.empty((self.max_batch, H, W, 3), dtype=torch.uint8).pin_memory()
             self._d_u8 = torch.empty((self.max_batch, H, W, 3), dtype=torch.uint8, device=dev)
-        self._h_u8[:B].copy_(torch.from_numpy(images_u8))
+        if pinned_src is None:
+            self._h_u8[:B].copy_(torch.from_numpy(images_u8))
+            pinned_src = self._h_u8[:B]
         info = torch.tensor([[out_h, out_w, scale]] * B, dtype=torch.float32)
         hw = torch.tensor([[H, W]] * B, dtype=torch.float32)
         sc = torch.full((B,), scale, dtype=torch.float32)
         with torch.cuda.device(dev):
-            self._d_u8[:B].copy_(self._h_u8[:B], non_blocking=True)
+            self._d_u8[:B].copy_(pinned_src, non_blocking=True)
             ops.prep_images(self._d_u8[:B], scale, out=self._d_in[:B])
             boxes, masks, scores, valid, _ = self.engine.detect(
                 self._d_in[:B], info.to(dev, non_blocking=True), hw.to(dev, non_blocking=True),

@@ -107,7 +107,7 @@ __device__ __forceinline__ Tile decode_tile(const IgemmArgs& p, int t, int rank,
 // ---------------------------------------------------------------------------------- epilogue
 // Shared by the per-tap kernel and the halo kernel: warps 4..7 drain the TMEM accumulators of
 // every tile this CTA owns (bias, ReLU, optional 2x2 ceil-mode max pool, re-split, store).
-template <int TH, int TW, int BN, int CL>
+template <int TH, int TW, int BN, int CL, bool ACC2 = false>
 __device__ __forceinline__ void run_epilogue(const IgemmArgs& p, const CUtensorMap* tm_o_hi_p,
                                              const CUtensorMap* tm_o_lo_p, uint8_t* staging,
                                              uint64_t* tfull_bar, uint64_t* tempty_bar,
@@ -133,9 +133,20 @@ __device__ __forceinline__ void run_epilogue(const IgemmArgs& p, const CUtensorM
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t r[32];
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c0;
+      // ACC2: the tile's sum is split over two column blocks (see conv_halo_tc_kernel)
+      constexpr int kAccCols = ACC2 ? 2 * BN : BN;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccCols + c0;
       ptx::tmem_ld_32x32b_x32(taddr, r);
-      ptx::tmem_ld_wait();
+      if (ACC2) {
+        uint32_t r2[32];
+        ptx::tmem_ld_32x32b_x32(taddr + BN, r2);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+      } else {
+        ptx::tmem_ld_wait();
+      }
       const int ch0 = n0 + c0;
       if (p.out_mode == 3) continue;  // diagnostic: accumulators are drained and discarded
       if (p.out_mode == 2) {
@@ -473,7 +484,8 @@ struct HaloCfg {
   static constexpr int kBBytes = BN * 128;                        // one plane of one tap's weights
   static constexpr int kBStage = 2 * kBBytes;
   static constexpr int kNB = (192 * 1024 - kHaloNA * kHaloABytes) / kBStage;
-  static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
+  // accumulators: two column blocks per tile ([hi*hi + lo*hi | hi*lo]), double-buffered
+  static constexpr int kTmemCols = (4 * BN <= 256) ? 256 : 512;
   static constexpr int kStagingBytes = 2 * 2 * 128 * 64;
   static constexpr int kBarrierBytes = 1024;
   static constexpr int kRingBytes = kHaloNA * kHaloABytes + kNB * kBStage;
@@ -580,7 +592,13 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = ptx::umma_idesc_bf16_m128(BN);
+      // The per-instruction overhead of tcgen05.mma (~40 cycles) matters at these small N, so
+      // the three split-precision products are issued as two instructions: the hi and lo weight
+      // planes sit back to back in the stage, so A_hi x [B_hi | B_lo] is ONE N = 2*BN MMA into
+      // columns [0, 2BN), and A_lo x B_hi accumulates into columns [0, BN).  The epilogue adds
+      // the two column blocks.
+      constexpr uint32_t idesc1 = ptx::umma_idesc_bf16_m128(2 * BN);
+      constexpr uint32_t idesc2 = ptx::umma_idesc_bf16_m128(BN);
       constexpr uint32_t kSbo = (TW + 2) * 128;  // one halo row
       int as = 0, bs = 0, local = 0;
       uint32_t aph = 0, bph = 0;
@@ -589,7 +607,7 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
         const uint32_t acc_phase = (local >> 1) & 1;
         ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * BN;
+        const uint32_t tmem_d = tmem_base + acc * (2 * BN);
         for (int kc = 0; kc < kchunks; ++kc) {
           ptx::mbar_wait(&a_full[as], aph);
           ptx::tc_fence_after();
@@ -599,17 +617,15 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
             ptx::mbar_wait(&b_full[bs], bph);
             ptx::tc_fence_after();
             const uint32_t woff = ((tap / 3) * (TW + 2) + (tap % 3)) * 128;  // shifted window
-            const uint32_t b_hi = ptx::smem_u32(b_ring + bs * Cfg::kBStage);
-            const uint32_t b_lo = b_hi + Cfg::kBBytes;
+            const uint32_t b_hi = ptx::smem_u32(b_ring + bs * Cfg::kBStage);  // [hi rows | lo rows]
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
               const uint64_t da_hi = umma_desc_sw128_sbo(a_hi0 + woff + kk * 32, kSbo);
               const uint64_t da_lo = umma_desc_sw128_sbo(a_lo0 + woff + kk * 32, kSbo);
-              const uint64_t db_hi = ptx::umma_desc_sw128(b_hi + kk * 32);
-              const uint64_t db_lo = ptx::umma_desc_sw128(b_lo + kk * 32);
-              ptx::umma_bf16_ss(tmem_d, da_lo, db_hi, idesc, (kc > 0 || tap > 0 || kk > 0) ? 1u : 0u);
-              ptx::umma_bf16_ss(tmem_d, da_hi, db_lo, idesc, 1u);
-              ptx::umma_bf16_ss(tmem_d, da_hi, db_hi, idesc, 1u);
+              const uint64_t db = ptx::umma_desc_sw128(b_hi + kk * 32);
+              const uint32_t accum = (kc > 0 || tap > 0 || kk > 0) ? 1u : 0u;
+              ptx::umma_bf16_ss(tmem_d, da_hi, db, idesc1, accum);
+              ptx::umma_bf16_ss(tmem_d, da_lo, db, idesc2, 1u);
             }
             ptx::umma_commit(&b_empty[bs]);
             if (++bs == NB) {
@@ -627,8 +643,8 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
       }
     }
   } else if (warp >= 4) {
-    run_epilogue<TH, TW, BN, 1>(p, &tm_o_hi, &tm_o_lo, staging, tfull_bar, tempty_bar, tmem_base, 0,
-                                first, stride, total_tiles);
+    run_epilogue<TH, TW, BN, 1, true>(p, &tm_o_hi, &tm_o_lo, staging, tfull_bar, tempty_bar,
+                                      tmem_base, 0, first, stride, total_tiles);
   }
 
   ptx::tc_fence_before();

@@ -318,9 +318,17 @@ __device__ __forceinline__ float4 max4(const float4 a, const float4 b) {
   return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
 }
 
-// Work item = (pooled column jp, channel quad); taps come from the per-CTA tables.  The feature
-// map is read as fp32 NHWC (the engine keeps an fp32 copy of conv5_3 = hi + lo, 39 MB per batch of
-// 8, so the gathers need no bf16 unpacking): one 16-byte load per tap and channel quad.
+// Work item = (pooled column jp, channel quad).  Everything that depends only on the sample
+// position -- the four gather offsets and the four bilinear weights (weights formed first,
+// roi_warping_layer.cu:56) -- is computed once per CTA into a shared-memory table (2*SUB sample
+// rows x 14*SUB sample columns, 32 B per sample) and read back with two broadcast 128-bit loads.
+// The feature map is read as fp32 NHWC (the engine keeps an fp32 copy of conv5_3 = hi + lo, 39 MB
+// per batch of 8, so the gathers need no bf16 unpacking): one 16-byte load per tap and quad.
+struct __align__(16) SampleTab {
+  int off[4];    // element offsets of the 4 taps within the image (channel 0)
+  float w[4];    // bilinear weights; all four are 0 for an out-of-range sample
+};
+
 template <int SUB>
 __global__ void __launch_bounds__(256, 3)
 roi_warp_split_kernel(const float* __restrict__ feat, int C, int H, int W,
@@ -328,17 +336,27 @@ roi_warp_split_kernel(const float* __restrict__ feat, int C, int H, int W,
                       __nv_bfloat16* __restrict__ o14_hi, __nv_bfloat16* __restrict__ o14_lo,
                       __nv_bfloat16* __restrict__ o7_hi, __nv_bfloat16* __restrict__ o7_lo) {
   constexpr int P = 14 * SUB;
-  __shared__ AxisTap tap_h[2 * SUB], tap_w[P];
+  constexpr int NS = 2 * SUB * P;  // samples handled by this CTA
+  __shared__ SampleTab tab[NS];
   const int r = blockIdx.x;
   const int t = blockIdx.y;  // rows 2t, 2t+1 of the 14x14 grid
   const RoiGeom g = roi_geom(rois + static_cast<long long>(r) * 5, spatial_scale, P, P);
-  if (threadIdx.x < 2 * SUB) {
-    const int ph = 2 * t * SUB + threadIdx.x;
-    tap_h[threadIdx.x] = axis_tap(__fadd_rn(g.start_h, __fmul_rn(static_cast<float>(ph), g.bin_h)), H);
-  }
-  if (threadIdx.x >= 32 && threadIdx.x < 32 + P) {
-    const int pw = threadIdx.x - 32;
-    tap_w[pw] = axis_tap(__fadd_rn(g.start_w, __fmul_rn(static_cast<float>(pw), g.bin_w)), W);
+  for (int i = threadIdx.x; i < NS; i += blockDim.x) {
+    const int sr = i / P, pw = i - sr * P;
+    const int ph = 2 * t * SUB + sr;
+    const AxisTap th = axis_tap(__fadd_rn(g.start_h, __fmul_rn(static_cast<float>(ph), g.bin_h)), H);
+    const AxisTap tw = axis_tap(__fadd_rn(g.start_w, __fmul_rn(static_cast<float>(pw), g.bin_w)), W);
+    const bool ok = th.ok && tw.ok;
+    SampleTab e;
+    e.off[0] = ok ? (th.lo * W + tw.lo) * C : 0;
+    e.off[1] = ok ? (th.lo * W + tw.hi) * C : 0;
+    e.off[2] = ok ? (th.hi * W + tw.lo) * C : 0;
+    e.off[3] = ok ? (th.hi * W + tw.hi) * C : 0;
+    e.w[0] = ok ? __fmul_rn(th.h, tw.h) : 0.f;
+    e.w[1] = ok ? __fmul_rn(th.h, tw.l) : 0.f;
+    e.w[2] = ok ? __fmul_rn(th.l, tw.h) : 0.f;
+    e.w[3] = ok ? __fmul_rn(th.l, tw.l) : 0.f;
+    tab[i] = e;
   }
   __syncthreads();
   const float* fimg = feat + static_cast<long long>(g.level) * H * W * C;
@@ -347,6 +365,7 @@ roi_warp_split_kernel(const float* __restrict__ feat, int C, int H, int W,
   for (int item = threadIdx.x; item < 7 * c4n; item += blockDim.x) {
     const int jp = item / c4n;
     const int c = (item - jp * c4n) * 4;
+    const float* fc = fimg + c;
     float4 best7 = make_float4(kNeg, kNeg, kNeg, kNeg);
 #pragma unroll
     for (int dy = 0; dy < 2; ++dy) {
@@ -356,22 +375,16 @@ roi_warp_split_kernel(const float* __restrict__ feat, int C, int H, int W,
         float4 cell = make_float4(kNeg, kNeg, kNeg, kNeg);
 #pragma unroll
         for (int sy = 0; sy < SUB; ++sy) {
-          const AxisTap th = tap_h[dy * SUB + sy];
-          const float* r0 = fimg + static_cast<long long>(th.lo) * W * C + c;
-          const float* r1 = fimg + static_cast<long long>(th.hi) * W * C + c;
 #pragma unroll
           for (int sx = 0; sx < SUB; ++sx) {
-            const AxisTap tw = tap_w[j * SUB + sx];
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (th.ok && tw.ok) {
-              const float4 v1 = __ldg(reinterpret_cast<const float4*>(r0 + tw.lo * C));
-              const float4 v2 = __ldg(reinterpret_cast<const float4*>(r0 + tw.hi * C));
-              const float4 v3 = __ldg(reinterpret_cast<const float4*>(r1 + tw.lo * C));
-              const float4 v4 = __ldg(reinterpret_cast<const float4*>(r1 + tw.hi * C));
-              v = bilerp4(__fmul_rn(th.h, tw.h), __fmul_rn(th.h, tw.l), __fmul_rn(th.l, tw.h),
-                          __fmul_rn(th.l, tw.l), v1, v2, v3, v4);
-            }
-            cell = max4(cell, v);
+            const SampleTab& e = tab[(dy * SUB + sy) * P + j * SUB + sx];
+            const int4 of = *reinterpret_cast<const int4*>(e.off);
+            const float4 wg = *reinterpret_cast<const float4*>(e.w);
+            const float4 v1 = __ldg(reinterpret_cast<const float4*>(fc + of.x));
+            const float4 v2 = __ldg(reinterpret_cast<const float4*>(fc + of.y));
+            const float4 v3 = __ldg(reinterpret_cast<const float4*>(fc + of.z));
+            const float4 v4 = __ldg(reinterpret_cast<const float4*>(fc + of.w));
+            cell = max4(cell, bilerp4(wg.x, wg.y, wg.z, wg.w, v1, v2, v3, v4));
           }
         }
         st_split4(o14_hi, o14_lo, ((static_cast<long long>(r) * 14 + (2 * t + dy)) * 14 + j) * C + c, cell);
