@@ -9,9 +9,9 @@ class Net(object):
 
     prototxt : path to models/VGG16/mnc_5stage/test.prototxt (checked against the built-in graph)
                or None for the built-in graph.
-    weights  : {caffe layer name: (weight, bias)} dict, a torch-saved file of such a dict, or None
-               for the seeded random initialiser (mnc_b200/weights.py).  Reading .caffemodel(.h5)
-               is a "next" row (no h5py / protobuf schema here).
+    weights  : {caffe layer name: (weight, bias)} dict, a binary `.caffemodel`
+               (mnc_b200/caffemodel.py), a torch-saved file of such a dict, or None for the seeded
+               random initialiser (mnc_b200/weights.py).  `.caffemodel.h5` needs h5py (absent).
     """
 
     def __init__(self, prototxt=None, weights=None, phase=1):
@@ -26,6 +26,9 @@ class Net(object):
         self._graph = mnc_graph.build_graph()
         if weights is None:
             weights = make_weights()
+        elif isinstance(weights, str) and weights.endswith(".caffemodel"):
+            from mnc_b200.caffemodel import weights_from_caffemodel
+            weights = weights_from_caffemodel(weights)      # binary NetParameter, by layer name
         elif isinstance(weights, str):
             weights = torch.load(weights, map_location="cpu")
         self._device = torch.device("cuda", _state["device"])

