@@ -224,6 +224,26 @@ int mnc_prep_images(const unsigned char* img_bgr_hwc, int batch, int H, int W,
                     const double* pixel_means3, double scale, int out_h, int out_w,
                     float* out_nchw, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Result rendering ("next" row 3): _convert_pred_to_image
+ * (lib/utils/vis_seg.py:101-131, called from tools/demo.py:153-158) for a batch of images.
+ * boxes [batch][max_n][box_dim] (x1,y1,x2,y2[,score]; rounded half-to-even and clipped inside),
+ * masks [batch][max_n][M][M], cls [batch][max_n] class ids, counts [batch] valid instances
+ * (painted in list order).  inst_img / cls_img: int32 [batch][H][W] (either may be NULL); bgr:
+ * optional uint8 [batch][H][W][3] = _get_voc_color_map()[cls_img][::-1] (vis_seg.py:133-148,
+ * demo.py:160-164).  All device pointers. */
+int mnc_paste_instances(const float* boxes, int box_dim, const float* masks, const int* cls,
+                        const int* counts, int batch, int max_n, int mask_size, int H, int W,
+                        float thresh, int* inst_img, int* cls_img, unsigned char* bgr,
+                        void* stream);
+
+/* cv2.resize(mask, (bw, bh)) >= thresh for n predictions at once, as the AP^r evaluator does per
+ * prediction (lib/utils/voc_eval.py:249-251).  rboxes int32 [n][4] already rounded; out is one
+ * packed uint8 buffer, prediction i occupying bw_i*bh_i bytes (row-major) at offsets[i];
+ * max_area = max_i bw_i*bh_i.  All device pointers. */
+int mnc_binarize_masks(const int* rboxes, const float* masks, int n, int mask_size, float thresh,
+                       const long long* offsets, int max_area, unsigned char* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,12 +29,21 @@ class Detector:
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
+    def _fit_input(self, H, W):
+        """Input staging follows the blob size (real images scale to 600x800 ... 901x600,
+        lib/utils/blob.py:41-46); the engine's own buffers grow on demand."""
+        if tuple(self._d_in.shape[2:]) != (H, W):
+            B = self.max_batch
+            self._h_in = torch.empty((B, 3, H, W), dtype=torch.float32).pin_memory()
+            self._d_in = torch.empty((B, 3, H, W), dtype=torch.float32, device=self.device)
+
     def im_detect_batch(self, blob, im_info=None, im_scales=None, im_shapes=None):
         """blob: (B,3,H,W) fp32 numpy / CPU tensor (mean-subtracted BGR, as `im_list_to_blob`
         returns).  im_info: (B,3) [H, W, scale] (default: blob size, scale 1).  Synchronous."""
         blob = torch.as_tensor(blob)
         B, _, H, W = blob.shape
-        assert B <= self.max_batch and tuple(self._h_in.shape[2:]) == (H, W)
+        assert B <= self.max_batch
+        self._fit_input(H, W)
         dev = self.device
         if im_info is None:
             im_info = np.tile(np.array([[H, W, 1.0]], dtype=np.float32), (B, 1))
@@ -78,7 +87,8 @@ class Detector:
         B, H, W, _ = images_u8.shape
         scale = ops.im_scale_for((H, W))
         out_h, out_w = int(np.rint(H * scale)), int(np.rint(W * scale))
-        assert B <= self.max_batch and (out_h, out_w) == tuple(self._d_in.shape[2:])
+        assert B <= self.max_batch
+        self._fit_input(out_h, out_w)
         dev = self.device
         if getattr(self, "_h_u8", None) is None or self._h_u8.shape[1:] != images_u8.shape[1:]:
             self._h_u8 = torch.empty((self.max_batch, H, W, 3), dtype=torch.uint8).pin_memory()

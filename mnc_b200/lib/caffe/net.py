@@ -4,6 +4,24 @@ from collections import OrderedDict
 import numpy as np
 
 
+def load_weights(prototxt=None, weights=None):
+    """Resolve the `weights` argument of caffe.Net into the engine's {layer: (weight, bias)} dict
+    (and check the prototxt against the built-in 5-stage graph)."""
+    import torch
+    from mnc_b200.weights import make_weights
+    from . import mnc_graph
+    if prototxt is not None:
+        mnc_graph.check_prototxt(prototxt)
+    if weights is None:
+        return make_weights()
+    if isinstance(weights, str) and weights.endswith(".caffemodel"):
+        from mnc_b200.caffemodel import weights_from_caffemodel
+        return weights_from_caffemodel(weights)      # binary NetParameter, by layer name
+    if isinstance(weights, str):
+        return torch.load(weights, map_location="cpu")
+    return weights
+
+
 class Net(object):
     """Net(prototxt, weights, phase).
 
@@ -17,20 +35,11 @@ class Net(object):
     def __init__(self, prototxt=None, weights=None, phase=1):
         import torch
         from mnc_b200.engine import MNCEngine
-        from mnc_b200.weights import make_weights
         from . import Blob, _state, mnc_graph
         if phase != 1:
             raise NotImplementedError("inference (caffe.TEST) only")
-        if prototxt is not None:
-            mnc_graph.check_prototxt(prototxt)
+        weights = load_weights(prototxt, weights)
         self._graph = mnc_graph.build_graph()
-        if weights is None:
-            weights = make_weights()
-        elif isinstance(weights, str) and weights.endswith(".caffemodel"):
-            from mnc_b200.caffemodel import weights_from_caffemodel
-            weights = weights_from_caffemodel(weights)      # binary NetParameter, by layer name
-        elif isinstance(weights, str):
-            weights = torch.load(weights, map_location="cpu")
         self._device = torch.device("cuda", _state["device"])
         with torch.cuda.device(self._device):
             self._engine = MNCEngine(weights, device=self._device)

@@ -12,3 +12,14 @@ def nms(dets, thresh):
     if cfg.USE_GPU_NMS:
         return gpu_nms(dets, thresh, device_id=cfg.GPU_ID)
     raise NotImplementedError("cpu_nms is out of scope (different semantics, no CPU fallback)")
+
+
+def apply_nms_mask_single(box, mask, thresh):
+    """NMS on one image's (n,5) detections, masks following the kept rows
+    (reference lib/nms/nms_wrapper.py:65-71)."""
+    if len(box) == 0:
+        return box, mask
+    keep = nms(box, thresh)
+    if len(keep) == 0:
+        return box, mask
+    return box[keep, :].copy(), mask[keep, :].copy()

@@ -39,3 +39,11 @@ def gpu_mask_voting(masks, boxes, scores, num_classes, max_per_image, im_width, 
         list_result_box.append(result_box[cls_start:cls_end, :])
         list_result_mask.append(result_mask[cls_start:cls_end, :, :, :])
     return list_result_mask, list_result_box
+
+
+def mask_overlap(box1, box2, mask1, mask2):
+    """Region IoU of two binary masks living in different integer boxes
+    (reference lib/transform/mask_transform.py:16-46)."""
+    from utils.voc_eval import _region_iou
+    return _region_iou(box1, np.asarray(mask1), np.asarray(mask1).sum(),
+                       box2, np.asarray(mask2), np.asarray(mask2).sum())

@@ -303,3 +303,60 @@ def prep_images(images_u8, scale, out=None, pixel_means=PIXEL_MEANS):
                               ctypes.c_double(scale), c_int(out_h), c_int(out_w), ptr(out),
                               cur_stream()), "mnc_prep_images")
     return out
+
+
+# ----------------------------------------------------------------------------- result rendering
+def paste_instances(boxes, masks, cls, counts, H, W, thresh=0.4, want_bgr=False):
+    """Batched `_convert_pred_to_image` (lib/utils/vis_seg.py:101-131).  boxes [B,n,>=4] fp32,
+    masks [B,n,(1,)M,M] fp32, cls [B,n] int32, counts [B] int32 -- device tensors, instances in
+    painting order.  -> inst_img, cls_img int32 [B,H,W] (+ uint8 BGR [B,H,W,3] colour image)."""
+    B, n, box_dim = boxes.shape
+    M = masks.shape[-1]
+    dev = boxes.device
+    boxes = boxes.contiguous().float()
+    masks = masks.contiguous().float()
+    cls = cls.contiguous().to(torch.int32)
+    counts = counts.contiguous().to(torch.int32)
+    inst = torch.empty((B, H, W), dtype=torch.int32, device=dev)
+    clsi = torch.empty((B, H, W), dtype=torch.int32, device=dev)
+    bgr = torch.empty((B, H, W, 3), dtype=torch.uint8, device=dev) if want_bgr else None
+    check(lib.mnc_paste_instances(ptr(boxes), c_int(box_dim), ptr(masks), ptr(cls), ptr(counts),
+                                  c_int(B), c_int(n), c_int(M), c_int(H), c_int(W), c_float(thresh),
+                                  ptr(inst), ptr(clsi), ptr(bgr), cur_stream()),
+          "mnc_paste_instances")
+    return (inst, clsi, bgr) if want_bgr else (inst, clsi)
+
+
+def select_for_display(vote, vis_thresh=0.5):
+    """`get_vis_dict` (tools/demo.py:103-120) on the device: keep voted results with
+    score >= vis_thresh, order preserved (results are class-major, as the reference's loops
+    visit them).  vote: the dict `mask_voting` returns.  -> boxes [B,R,4] fp32, masks, cls, counts."""
+    n_res, score = vote["n_res"], vote["res_score"]
+    B, R = score.shape
+    live = (torch.arange(R, device=score.device)[None, :] < n_res[:, None]) & (score >= vis_thresh)
+    perm = torch.sort((~live).to(torch.int8), dim=1, stable=True).indices
+    boxes = torch.gather(vote["result_box"].float(), 1, perm[:, :, None].expand(B, R, 4))
+    M = vote["result_mask"].shape[-1]
+    masks = torch.gather(vote["result_mask"].view(B, R, M * M), 1, perm[:, :, None].expand(B, R, M * M))
+    cls = torch.gather(vote["res_class"], 1, perm)
+    return boxes, masks.view(B, R, M, M), cls, live.sum(dim=1).to(torch.int32)
+
+
+def binarize_masks(rboxes, masks, thresh=0.4):
+    """cv2.resize(mask, box size) >= thresh for every prediction (lib/utils/voc_eval.py:249-251).
+    rboxes int32 [n,4] (rounded boxes), masks fp32 [n,M,M], both on the device.
+    -> (packed uint8 device tensor, offsets int64 host array of n+1 entries)."""
+    import numpy as np
+    n = rboxes.shape[0]
+    M = masks.shape[-1]
+    rb = rboxes.contiguous().to(torch.int32)
+    hb = rb.cpu().numpy().astype(np.int64)
+    areas = np.maximum(hb[:, 2] - hb[:, 0] + 1, 0) * np.maximum(hb[:, 3] - hb[:, 1] + 1, 0)
+    offsets = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(areas, out=offsets[1:])
+    out = torch.empty((max(int(offsets[-1]), 1),), dtype=torch.uint8, device=rboxes.device)
+    d_off = torch.from_numpy(offsets[:-1].copy()).to(rboxes.device)
+    check(lib.mnc_binarize_masks(ptr(rb), ptr(masks.contiguous().float()), c_int(n), c_int(M),
+                                 c_float(thresh), ptr(d_off), c_int(int(areas.max()) if n else 0),
+                                 ptr(out), cur_stream()), "mnc_binarize_masks")
+    return out, offsets

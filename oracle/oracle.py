@@ -562,3 +562,128 @@ def im_detect(w, im):
     data, im_info = prep_blob(im)
     blobs = net_forward(w, data, im_info)
     return im_detect_tail(blobs, im.shape), blobs
+
+
+# ------------------------------------------------------------------- result rendering / AP^r
+def voc_color_map(n=256):  # vis_seg.py:133-148
+    cmap = np.zeros((n, 3))
+    for i in range(n):
+        r = g = b = 0
+        cid = i
+        for j in range(8):
+            bits = np.unpackbits(np.array([cid], dtype=np.uint8))
+            r |= int(bits[-1]) << (7 - j)
+            g |= int(bits[-2]) << (7 - j)
+            b |= int(bits[-3]) << (7 - j)
+            cid >>= 3
+        cmap[i] = (r, g, b)
+    return cmap
+
+
+def convert_pred_to_image(img_width, img_height, pred_dict, thresh=0.4):  # vis_seg.py:101-131
+    import cv2
+    inst_img = np.zeros((img_height, img_width))
+    cls_img = np.zeros((img_height, img_width))
+    for i in range(len(pred_dict["boxes"])):
+        box = np.round(pred_dict["boxes"][i]).astype(int)
+        box[0] = min(max(box[0], 0), img_width - 1)
+        box[1] = min(max(box[1], 0), img_height - 1)
+        box[2] = min(max(box[2], 0), img_width - 1)
+        box[3] = min(max(box[3], 0), img_height - 1)
+        mask = cv2.resize(pred_dict["masks"][i].astype(np.float32),
+                          (int(box[2] - box[0] + 1), int(box[3] - box[1] + 1)))
+        mask = mask >= thresh
+        ys, xs = slice(box[1], box[3] + 1), slice(box[0], box[2] + 1)
+        inst_img[ys, xs] = np.where(mask, i + 1, inst_img[ys, xs])
+        cls_img[ys, xs] = np.where(mask, pred_dict["cls_name"][i], cls_img[ys, xs])
+        cls_img[box[1]:box[3] + 1, box[0] - 1:box[0] + 1] = 150
+        cls_img[box[1]:box[3] + 1, box[2] - 1:box[2] + 1] = 150
+        cls_img[box[1] - 1:box[1] + 1, box[0]:box[2] + 1] = 150
+        cls_img[box[3] - 1:box[3] + 1, box[0]:box[2] + 1] = 150
+    return inst_img.astype(int), cls_img.astype(int)
+
+
+def voc_ap(rec, prec, use_07_metric=False):  # voc_eval.py:19-55
+    if use_07_metric:
+        ap = 0.0
+        for t in np.arange(0.0, 1.1, 0.1):
+            p = 0 if np.sum(rec >= t) == 0 else np.max(prec[rec >= t])
+            ap += p / 11.0
+        return ap
+    mrec = np.concatenate(([0.0], rec, [1.0]))
+    mpre = np.concatenate(([0.0], prec, [0.0]))
+    for i in range(mpre.size - 1, 0, -1):
+        mpre[i - 1] = np.maximum(mpre[i - 1], mpre[i])
+    i = np.where(mrec[1:] != mrec[:-1])[0]
+    return np.sum((mrec[i + 1] - mrec[i]) * mpre[i + 1])
+
+
+def mask_overlap(box1, box2, mask1, mask2):  # mask_transform.py:16-46
+    x1, y1 = max(box1[0], box2[0]), max(box1[1], box2[1])
+    x2, y2 = min(box1[2], box2[2]), min(box1[3], box2[3])
+    if x1 > x2 or y1 > y2:
+        return 0
+    w, h = x2 - x1 + 1, y2 - y1 + 1
+    a = mask1[y1 - box1[1]: y1 - box1[1] + h, x1 - box1[0]: x1 - box1[0] + w]
+    b = mask2[y1 - box2[1]: y1 - box2[1] + h, x1 - box2[0]: x1 - box2[0] + w]
+    inter = np.logical_and(b, a).sum()
+    union = mask1.sum() + mask2.sum() - inter
+    if union < 1.0:
+        return 0
+    return float(inter) / float(union)
+
+
+def eval_sds(boxes_pkl, masks_pkl, image_names, gt_pkl, ov_thresh=0.5, thresh=0.4, mask_size=21):
+    """voc_eval.py:195-283 steps 3-7 on in-memory structures: boxes_pkl[i] (n_i,5),
+    masks_pkl[i] (n_i,1,M,M) per image; gt_pkl {image: [{'mask_bound', 'mask'}]}."""
+    import cv2
+    import copy
+    gt_pkl = copy.deepcopy(gt_pkl)
+    for lst in gt_pkl.values():
+        for g in lst:
+            g["already_detect"] = 0
+    box_num = sum(len(b) for b in boxes_pkl)
+    new_boxes = np.zeros((box_num, 5))
+    new_masks = np.zeros((box_num, mask_size, mask_size))
+    new_image = []
+    cnt = 0
+    for image_ind in range(len(image_names)):
+        for box_ind in range(len(boxes_pkl[image_ind])):
+            new_boxes[cnt] = boxes_pkl[image_ind][box_ind]
+            new_masks[cnt] = masks_pkl[image_ind][box_ind]
+            new_image.append(image_names[image_ind])
+            cnt += 1
+    keep_inds = np.argsort(-new_boxes[:, -1])
+    new_boxes = new_boxes[keep_inds, :]
+    new_masks = new_masks[keep_inds, :, :]
+    num_pred = new_boxes.shape[0]
+    fp = np.zeros((num_pred, 1))
+    tp = np.zeros((num_pred, 1))
+    for i in range(num_pred):
+        pred_box = np.round(new_boxes[i, :4]).astype(int)
+        pred_mask = cv2.resize(new_masks[i].astype(np.float32),
+                               (int(pred_box[2] - pred_box[0] + 1), int(pred_box[3] - pred_box[1] + 1)))
+        pred_mask = pred_mask >= thresh
+        image_index = new_image[keep_inds[i]]
+        if image_index not in gt_pkl:
+            fp[i] = 1
+            continue
+        cur_overlap, cur_ind = -1000, -1
+        for ind2, gt in enumerate(gt_pkl[image_index]):
+            ov = mask_overlap(np.round(gt["mask_bound"]).astype(int), pred_box, gt["mask"], pred_mask)
+            if ov > cur_overlap:
+                cur_overlap, cur_ind = ov, ind2
+        if cur_overlap >= ov_thresh:
+            if gt_pkl[image_index][cur_ind]["already_detect"]:
+                fp[i] = 1
+            else:
+                tp[i] = 1
+                gt_pkl[image_index][cur_ind]["already_detect"] = 1
+        else:
+            fp[i] = 1
+    num_pos = sum(len(v) for v in gt_pkl.values())
+    fp = np.cumsum(fp)
+    tp = np.cumsum(tp)
+    rec = tp / float(num_pos)
+    prec = tp / np.maximum(fp + tp, np.finfo(np.float64).eps)
+    return voc_ap(rec, prec, True)

@@ -204,3 +204,36 @@ def test_caffemodel_roundtrip_and_protobuf_crosscheck(tmp_path):
     assert np.array_equal(got["ip1"][0].ravel(), np.arange(6, dtype=np.float32))
     with pytest.raises(KeyError):
         CM.weights_from_caffemodel(str(q))
+
+
+def test_eval_host_helpers_match_oracle_and_voc_palette():
+    """voc_ap / mask_overlap / colour map of the evaluator boundary against the
+    oracle restatements and the published PASCAL VOC palette (known answers)."""
+    import mnc_b200.lib as L
+    L.install()
+    from utils.voc_eval import voc_ap
+    from utils.vis_seg import _get_voc_color_map, get_vis_dict
+    from transform.mask_transform import mask_overlap
+    from oracle import oracle as O
+    rng = np.random.default_rng(3)
+    for trial in range(5):
+        hits = rng.integers(0, 2, 80)
+        tp, fp = np.cumsum(hits), np.cumsum(1 - hits)
+        rec, prec = tp / 57.0, tp / np.maximum(tp + fp, np.finfo(np.float64).eps)
+        assert voc_ap(rec, prec, True) == O.voc_ap(rec, prec, True)
+        assert voc_ap(rec, prec, False) == pytest.approx(O.voc_ap(rec, prec, False), abs=1e-15)
+    assert voc_ap(np.zeros(0), np.zeros(0), True) == 0.0
+    for trial in range(20):
+        b1 = rng.integers(0, 40, 2); b1 = np.concatenate([b1, b1 + rng.integers(0, 30, 2)])
+        b2 = rng.integers(0, 40, 2); b2 = np.concatenate([b2, b2 + rng.integers(0, 30, 2)])
+        m1 = rng.uniform(size=(b1[3] - b1[1] + 1, b1[2] - b1[0] + 1)) > 0.5
+        m2 = rng.uniform(size=(b2[3] - b2[1] + 1, b2[2] - b2[0] + 1)) > 0.3
+        assert mask_overlap(b1, b2, m1, m2) == O.mask_overlap(b1, b2, m1, m2)
+    cmap = _get_voc_color_map()
+    assert np.array_equal(cmap, O.voc_color_map())
+    assert cmap[1].tolist() == [128, 0, 0] and cmap[15].tolist() == [192, 128, 128]
+    assert cmap[20].tolist() == [0, 64, 128] and cmap[255].tolist() == [224, 224, 192]
+    dets = [np.array([[1, 2, 3, 4, 0.9], [5, 6, 7, 8, 0.2]], np.float32), np.zeros((0, 5), np.float32)]
+    segs = [np.ones((2, 1, 21, 21), np.float32), np.zeros((0, 1, 21, 21), np.float32)]
+    d = get_vis_dict(dets, segs, "n", ["a", "b"], vis_thresh=0.5)
+    assert d["cls_name"] == [1] and d["boxes"][0][4] == np.float32(0.9) and d["masks"][0].shape == (21, 21)
