@@ -198,7 +198,8 @@ int mnc_bbox_overlaps_host(const double* boxes, int N, const double* query, int 
 /* Device pipeline of gpu_mask_voting (lib/transform/mask_transform.py:213-286), batched:
  * after per-class rank sort + NMS (mnc_rank_sort_desc / mnc_gather_boxes / mnc_nms_sorted with
  * problems = batch*(ncls-1)), vote_select picks the global threshold and enumerates results,
- * vote_candidates builds the (inds, weights) lists, mv_device renders/aggregates/resizes. */
+ * vote_candidates builds the (inds, weights) lists, mv_device renders/aggregates/resizes.
+ * mv_device's bbox_ws: int32 workspace of batch*max_results*4 + batch entries. */
 int mnc_vote_select(const float* scores, int nb, int ncls, const int* order, const int* keep,
                     int keep_stride, const int* num_keep, int max_per_image, int max_results,
                     int batch, int* res_box_idx, int* res_class, float* res_score, int* n_res,
@@ -243,6 +244,28 @@ int mnc_paste_instances(const float* boxes, int box_dim, const float* masks, con
  * max_area = max_i bw_i*bh_i.  All device pointers. */
 int mnc_binarize_masks(const int* rboxes, const float* masks, int n, int mask_size, float thresh,
                        const long long* offsets, int max_area, unsigned char* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Sibling test graphs ("next" row 4).
+ * mnc_roi_pool_nchw: ROIPoolingLayer::Forward_gpu (caffe-mnc/src/caffe/layers/
+ * roi_pooling_layer.cu:17-105): fp32 NCHW feat [B][C][H][W], rois [R][5] -> out
+ * [R][C][pooled_h][pooled_w], argmax (int32, same shape; may be NULL).  Empty bins give 0 / -1.
+ * mnc_roi_pool_split / mnc_roi_sample_split: engine forms on the fp32 NHWC feature copy ->
+ * split-bf16 rows [R][P][P][C] (ROIPooling, and ROIWarping roi_warping_layer.cu:67-107 without a
+ * pool after it, as faster_rcnn_end2end/test.prototxt:479-490 uses it). */
+/* _detection_forward tail (lib/caffeWrapper/TesterWrapper.py:229-234): for every RoI and class,
+ * bbox_transform_inv(rois[:,1:5] / im_scale, bbox_pred[:, 4c:4c+4]) clipped to the image.
+ * out [total][ncls][4]; im_scale [batch]; im_hw [batch][2] (original image size). */
+int mnc_decode_class_boxes(const float* rois, int total, int rois_per_img, const float* bbox_pred,
+                           int bbox_stride, int ncls, const float* im_scale, const float* im_hw,
+                           float* out, void* stream);
+int mnc_roi_pool_nchw(const float* feat, int C, int H, int W, const float* rois, int R,
+                      int pooled_h, int pooled_w, float spatial_scale, float* out, int* argmax,
+                      void* stream);
+int mnc_roi_pool_split(const float* feat_nhwc, int C, int H, int W, const float* rois, int R,
+                       int pooled, float spatial_scale, void* o_hi, void* o_lo, void* stream);
+int mnc_roi_sample_split(const float* feat_nhwc, int C, int H, int W, const float* rois, int R,
+                         int pooled, float spatial_scale, void* o_hi, void* o_lo, void* stream);
 
 #ifdef __cplusplus
 }

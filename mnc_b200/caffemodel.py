@@ -113,18 +113,34 @@ MNC_LAYERS = ["conv1_1", "conv1_2", "conv2_1", "conv2_2", "conv3_1", "conv3_2", 
               "cls_score", "seg_cls_score", "bbox_pred"]
 
 
-def weights_from_caffemodel(path):
-    """The engine's weight dict {name: (weight, bias)} from a caffemodel of the MNC 5-stage net.
-    The `_ext` layers share these parameters (test.prototxt:829-834 ...), so only the owners are
-    read.  (The reference's snapshots already hold un-normalised bbox_pred weights,
-    lib/caffeWrapper/SolverWrapper.py:67-115.)"""
+_RPN = ("rpn_conv_3x3", "rpn_cls_score", "rpn_bbox_pred")
+_MASK = ("fc6_maskest", "mask_pred", "fc6_mask", "fc7_mask", "seg_cls_score")
+GRAPH_LAYERS = {
+    "mnc_5stage": MNC_LAYERS,
+    "faster_rcnn": [n for n in MNC_LAYERS if n not in _MASK],     # faster_rcnn_end2end/test.prototxt
+    "cfm": [n for n in MNC_LAYERS if n not in _RPN],              # cfm/test.prototxt (no RPN)
+}
+# layer names that differ between the graphs' prototxts (faster_rcnn_end2end/test.prototxt:391-405)
+_ALIASES = {"rpn_conv_3x3": ("rpn_conv/3x3",)}
+
+
+def weights_from_caffemodel(path, kind="mnc_5stage"):
+    """The engine's weight dict {name: (weight, bias)} from a caffemodel of one of the supported
+    test graphs.  The `_ext` layers share the owners' parameters (test.prototxt:829-834 ...), so
+    only the owners are read.  (The reference's snapshots already hold un-normalised bbox_pred
+    weights, lib/caffeWrapper/SolverWrapper.py:67-115.)"""
     import torch
     layers = load_caffemodel(path)
-    missing = [n for n in MNC_LAYERS if n not in layers]
+    for name, others in _ALIASES.items():
+        for o in others:
+            if name not in layers and o in layers:
+                layers[name] = layers[o]
+    wanted = GRAPH_LAYERS[kind]
+    missing = [n for n in wanted if n not in layers]
     if missing:
-        raise KeyError("caffemodel lacks MNC layers: %s" % ", ".join(missing))
+        raise KeyError("caffemodel lacks %s layers: %s" % (kind, ", ".join(missing)))
     out = {}
-    for n in MNC_LAYERS:
+    for n in wanted:
         blobs = layers[n]
         w = blobs[0]
         b = blobs[1].reshape(-1) if len(blobs) > 1 else np.zeros(w.shape[0], np.float32)

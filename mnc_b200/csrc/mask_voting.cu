@@ -73,6 +73,7 @@ struct CandList {
   float* wgt;    // shared
   int* ind;      // shared
   float2* ratio; // shared: (mask_size / box_width, mask_size / box_height), mv_kernel.cu:55-58
+  float* suf;    // shared: suf[i] = sum of wgt[i..n)
   int n;
 };
 
@@ -89,6 +90,26 @@ __device__ __forceinline__ float agg_at(const CandList& cl, const float* __restr
   return val;
 }
 
+// The predicate  agg_at(...) > 0.4  without always finishing the sum.  Valid when every mask value
+// of the image lies in [0, 1] and every weight is >= 0 (checked on the device by mv_range_kernel):
+// the terms are then non-negative, so fp32 partial sums never decrease -- once one exceeds the
+// threshold the final sum does too; and the final sum is at most partial + remaining weights
+// (render <= 1), so when even that (with a 1e-4 margin, >> the accumulated rounding) cannot reach
+// the threshold the pixel is off.  Same answer as comparing the full candidate-order sum.
+__device__ __forceinline__ bool agg_exceeds_unit(const CandList& cl, const float* __restrict__ masks,
+                                                 int mask_size, int h, int w) {
+  float val = 0.0f;
+  for (int i = 0; i < cl.n; ++i) {
+    if (val + cl.suf[i] * 1.0001f <= kBinarizeThresh) return false;
+    const float4 b = cl.box[i];
+    if (w < b.x || w > b.z || h < b.y || h > b.w) continue;
+    val += (mv_render(b, cl.ratio[i], masks + static_cast<long long>(cl.ind[i]) * mask_size * mask_size,
+                      mask_size, h, w) * cl.wgt[i]);
+    if (val > kBinarizeThresh) return true;
+  }
+  return val > kBinarizeThresh;
+}
+
 __device__ __forceinline__ void load_cands(CandList& cl, const float* __restrict__ boxes,
                                            int box_dim, const int* __restrict__ cand_inds,
                                            const float* __restrict__ cand_weights, int begin,
@@ -103,10 +124,48 @@ __device__ __forceinline__ void load_cands(CandList& cl, const float* __restrict
     cl.ratio[i] = mv_ratio(cl.box[i], mask_size);
   }
   __syncthreads();
+  if (threadIdx.x == 0) {
+    float acc = 0.f;
+    for (int i = cl.n - 1; i >= 0; --i) {
+      acc += cl.wgt[i];
+      cl.suf[i] = acc;
+    }
+  }
+  __syncthreads();
 }
 
-__global__ void mv_init_bbox_kernel(int* __restrict__ bbox, int total) {
+// unit[img] = 1 iff all mask values of the image are in [0,1] and all candidate weights are >= 0
+// (NaNs fail the test).  grid (32, batch); unit[] preset to 1.
+__global__ void __launch_bounds__(256)
+mv_range_kernel(const float* __restrict__ masks, long long masks_per_img,
+                const float* __restrict__ cand_weights, long long cand_img_stride,
+                const int* __restrict__ cand_begin, const int* __restrict__ cand_end,
+                const int* __restrict__ n_res, int max_results, int* __restrict__ unit) {
+  const int img = blockIdx.y;
+  const float* m = masks + img * masks_per_img;
+  bool ok = true;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < masks_per_img;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float v = m[i];
+    ok &= (v >= 0.f && v <= 1.f);
+  }
+  if (blockIdx.x == 0) {
+    const int nr = min(n_res[img], max_results);
+    int lo = INT_MAX, hi = 0;
+    for (int t = 0; t < nr; ++t) {
+      lo = min(lo, cand_begin[img * max_results + t]);
+      hi = max(hi, cand_end[img * max_results + t]);
+    }
+    for (int i = lo + threadIdx.x; i < hi; i += blockDim.x)
+      ok &= (cand_weights[img * cand_img_stride + i] >= 0.f);
+  }
+  if (!__syncthreads_and(ok) && threadIdx.x == 0) atomicAnd(&unit[img], 0);
+}
+
+__global__ void mv_init_bbox_kernel(int* __restrict__ bbox, int total, int* __restrict__ unit,
+                                    int batch) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < batch) unit[i] = 1;
   if (i < total) {
     bbox[i * 4 + 0] = INT_MAX;
     bbox[i * 4 + 1] = INT_MAX;
@@ -122,7 +181,7 @@ mv_aggregate_kernel(const float* __restrict__ boxes, const float* __restrict__ m
                     const float* __restrict__ cand_weights, long long cand_img_stride,
                     const int* __restrict__ cand_begin, const int* __restrict__ cand_end,
                     const int* __restrict__ n_res, int max_results, const int* __restrict__ im_hw,
-                    int* __restrict__ bbox) {
+                    const int* __restrict__ unit, int* __restrict__ bbox) {
   extern __shared__ unsigned char smraw[];
   const int img = blockIdx.z, t = blockIdx.y;
   if (t >= n_res[img]) return;
@@ -131,6 +190,7 @@ mv_aggregate_kernel(const float* __restrict__ boxes, const float* __restrict__ m
   cl.wgt = reinterpret_cast<float*>(cl.box + nb);
   cl.ind = reinterpret_cast<int*>(cl.wgt + nb);
   cl.ratio = reinterpret_cast<float2*>(cl.ind + nb);
+  cl.suf = reinterpret_cast<float*>(cl.ratio + nb);
   const float* pboxes = boxes + static_cast<long long>(img) * nb * box_dim;
   const float* pmasks = masks + static_cast<long long>(img) * nb * mask_size * mask_size;
   const int rt = img * max_results + t;
@@ -168,13 +228,16 @@ mv_aggregate_kernel(const float* __restrict__ boxes, const float* __restrict__ m
   if (cl.n == 0 || rx1 < rx0 || ry1 < ry0) return;
   const int rw = rx1 - rx0 + 1, rh = ry1 - ry0 + 1;
   const long long npix = static_cast<long long>(rw) * rh;
+  const bool unit_range = unit[img] != 0;
   int bx0 = INT_MAX, by0 = INT_MAX, bx1 = INT_MIN, by1 = INT_MIN;
   for (long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; p < npix;
        p += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int h = ry0 + static_cast<int>(p / rw);
     const int w = rx0 + static_cast<int>(p % rw);
-    const float v = agg_at(cl, pmasks, mask_size, h, w);
-    if (v > kBinarizeThresh) {  // reduce_mask_col/row, mv_kernel.cu:114-142 (strict >)
+    // reduce_mask_col/row, mv_kernel.cu:114-142 (strict >)
+    const bool on = unit_range ? agg_exceeds_unit(cl, pmasks, mask_size, h, w)
+                               : agg_at(cl, pmasks, mask_size, h, w) > kBinarizeThresh;
+    if (on) {
       bx0 = min(bx0, w);
       bx1 = max(bx1, w);
       by0 = min(by0, h);
@@ -214,6 +277,7 @@ mv_finalize_kernel(const float* __restrict__ boxes, const float* __restrict__ ma
   cl.wgt = reinterpret_cast<float*>(cl.box + nb);
   cl.ind = reinterpret_cast<int*>(cl.wgt + nb);
   cl.ratio = reinterpret_cast<float2*>(cl.ind + nb);
+  cl.suf = reinterpret_cast<float*>(cl.ratio + nb);
   const float* pboxes = boxes + static_cast<long long>(img) * nb * box_dim;
   const float* pmasks = masks + static_cast<long long>(img) * nb * mask_size * mask_size;
   const int rt = img * max_results + t;
@@ -454,7 +518,7 @@ extern "C" int mnc_mv_device(const float* boxes, const float* masks, int nb, int
                              int* bbox_ws, float* out_mask, int* out_box, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (nb <= 0 || max_results <= 0 || batch <= 0) return MNC_ERR_ARG;
-  const int smem = nb * (16 + 4 + 4 + 8);
+  const int smem = nb * (16 + 4 + 4 + 8 + 4);
   if (smem > 200 * 1024) return MNC_ERR_ARG;
   static int attr_smem = 48 * 1024;
   if (smem > attr_smem) {
@@ -466,11 +530,15 @@ extern "C" int mnc_mv_device(const float* boxes, const float* masks, int nb, int
     attr_smem = smem;
   }
   const int total = batch * max_results;
-  mv_init_bbox_kernel<<<(total + 255) / 256, 256, 0, stream>>>(bbox_ws, total);
+  int* unit = bbox_ws + static_cast<long long>(total) * 4;   // [batch] flags after the boxes
+  mv_init_bbox_kernel<<<(total + 255) / 256, 256, 0, stream>>>(bbox_ws, total, unit, batch);
+  mv_range_kernel<<<dim3(32, batch), 256, 0, stream>>>(
+      masks, static_cast<long long>(nb) * mask_size * mask_size, cand_weights, cand_img_stride,
+      cand_begin, cand_end, n_res, max_results, unit);
   const int chunks = 24;
   mv_aggregate_kernel<<<dim3(chunks, max_results, batch), 256, smem, stream>>>(
       boxes, masks, nb, box_dim, mask_size, cand_inds, cand_weights, cand_img_stride, cand_begin,
-      cand_end, n_res, max_results, im_hw, bbox_ws);
+      cand_end, n_res, max_results, im_hw, unit, bbox_ws);
   mv_finalize_kernel<<<dim3(max_results, batch), 256, smem, stream>>>(
       boxes, masks, nb, box_dim, mask_size, cand_inds, cand_weights, cand_img_stride, cand_begin,
       cand_end, n_res, max_results, im_hw, bbox_ws, out_mask, out_box);
@@ -538,7 +606,7 @@ extern "C" int mnc_mv_host(const float* all_boxes, const float* all_masks, int a
   const size_t o_nres = o_end + al(static_cast<size_t>(result_num) * 4);
   const size_t o_hw = o_nres + 256;
   const size_t o_bbox = o_hw + 256;
-  const size_t o_omask = o_bbox + al(static_cast<size_t>(result_num) * 16);
+  const size_t o_omask = o_bbox + al(static_cast<size_t>(result_num) * 16 + 4);  // + unit flag
   const size_t o_obox = o_omask + al(static_cast<size_t>(result_num) * mm * 4);
   const size_t total = o_obox + al(static_cast<size_t>(result_num) * 16);
   char* base = nullptr;

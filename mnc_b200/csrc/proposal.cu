@@ -213,6 +213,29 @@ __global__ void unscale_clip_kernel(const float* __restrict__ rois, int total, i
   b[3] = clipf(__fdiv_rn(r[4], s), hmax);
 }
 
+// TesterWrapper._detection_forward tail (lib/caffeWrapper/TesterWrapper.py:229-234): boxes =
+// rois[:,1:5] / im_scale; pred = bbox_transform_inv(boxes, deltas) for every class; clip to the
+// original image.  One thread per (RoI, class).
+__global__ void decode_class_boxes_kernel(const float* __restrict__ rois, int total,
+                                          int rois_per_img, const float* __restrict__ bbox_pred,
+                                          int bbox_stride, int ncls,
+                                          const float* __restrict__ im_scale,
+                                          const float* __restrict__ im_hw,
+                                          float* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total * ncls) return;
+  const int i = t / ncls, c = t - i * ncls;
+  const int img = i / rois_per_img;
+  const float s = im_scale[img];
+  const float* r = rois + static_cast<long long>(i) * 5;
+  const float* d = bbox_pred + static_cast<long long>(i) * bbox_stride + 4 * c;
+  float o[4];
+  decode_clip(__fdiv_rn(r[1], s), __fdiv_rn(r[2], s), __fdiv_rn(r[3], s), __fdiv_rn(r[4], s), d[0],
+              d[1], d[2], d[3], im_hw[img * 2 + 0], im_hw[img * 2 + 1], o);
+  *reinterpret_cast<float4*>(out + (static_cast<long long>(i) * ncls + c) * 4) =
+      make_float4(o[0], o[1], o[2], o[3]);
+}
+
 static inline int check_launch() { return cudaGetLastError() == cudaSuccess ? MNC_OK : MNC_ERR_CUDA; }
 
 }  // namespace mnc
@@ -282,5 +305,17 @@ extern "C" int mnc_unscale_clip(const float* rois, int total, int rois_per_img,
   if (total <= 0) return MNC_OK;
   unscale_clip_kernel<<<(total + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
       rois, total, rois_per_img, im_scale, im_hw, boxes);
+  return check_launch();
+}
+
+extern "C" int mnc_decode_class_boxes(const float* rois, int total, int rois_per_img,
+                                      const float* bbox_pred, int bbox_stride, int ncls,
+                                      const float* im_scale, const float* im_hw, float* out,
+                                      void* stream) {
+  if (total <= 0) return MNC_OK;
+  if (ncls <= 0 || bbox_stride < 4 * ncls) return MNC_ERR_ARG;
+  const int n = total * ncls;
+  decode_class_boxes_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      rois, total, rois_per_img, bbox_pred, bbox_stride, ncls, im_scale, im_hw, out);
   return check_launch();
 }

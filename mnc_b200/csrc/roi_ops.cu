@@ -395,6 +395,144 @@ roi_warp_split_kernel(const float* __restrict__ feat, int C, int H, int W,
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Sibling test graphs.
+//   ROIPooling  caffe-mnc/src/caffe/layers/roi_pooling_layer.cu:17-77 (Fast R-CNN max over integer
+//               bins; CFM test net, models/VGG16/cfm/test.prototxt:399-465)
+//   ROIWarping at 7x7 straight into fc6 (Faster R-CNN test net,
+//               models/VGG16/faster_rcnn_end2end/test.prototxt:479-490)
+struct PoolBin {
+  int h0, h1, w0, w1;
+};
+
+// roi_pooling_layer.cu:29-57 for pooled cell (ph, pw)
+__device__ __forceinline__ PoolBin roi_pool_bin(const float* roi, float spatial_scale, int H, int W,
+                                                int PH, int PW, int ph, int pw) {
+  const int sw = static_cast<int>(roundf(__fmul_rn(roi[1], spatial_scale)));
+  const int sh = static_cast<int>(roundf(__fmul_rn(roi[2], spatial_scale)));
+  const int ew = static_cast<int>(roundf(__fmul_rn(roi[3], spatial_scale)));
+  const int eh = static_cast<int>(roundf(__fmul_rn(roi[4], spatial_scale)));
+  const int rw = max(ew - sw + 1, 1), rh = max(eh - sh + 1, 1);
+  const float bh = __fdiv_rn(static_cast<float>(rh), static_cast<float>(PH));
+  const float bw = __fdiv_rn(static_cast<float>(rw), static_cast<float>(PW));
+  PoolBin b;
+  b.h0 = static_cast<int>(floorf(__fmul_rn(static_cast<float>(ph), bh)));
+  b.w0 = static_cast<int>(floorf(__fmul_rn(static_cast<float>(pw), bw)));
+  b.h1 = static_cast<int>(ceilf(__fmul_rn(static_cast<float>(ph + 1), bh)));
+  b.w1 = static_cast<int>(ceilf(__fmul_rn(static_cast<float>(pw + 1), bw)));
+  b.h0 = min(max(b.h0 + sh, 0), H);
+  b.h1 = min(max(b.h1 + sh, 0), H);
+  b.w0 = min(max(b.w0 + sw, 0), W);
+  b.w1 = min(max(b.w1 + sw, 0), W);
+  return b;
+}
+
+// Layer contract: fp32 NCHW in and out (+ optional argmax, which the reference always writes).
+// grid (R, ceil(C/16)); the RoI's PH*PW bins are computed once per CTA into shared memory.
+__global__ void __launch_bounds__(256)
+roi_pool_nchw_kernel(const float* __restrict__ feat, int C, int H, int W,
+                     const float* __restrict__ rois, float spatial_scale, int PH, int PW,
+                     float* __restrict__ out, int* __restrict__ argmax) {
+  extern __shared__ PoolBin bins[];
+  const int r = blockIdx.x;
+  const int c0 = blockIdx.y * kWarpSlab;
+  const float* roi = rois + static_cast<long long>(r) * 5;
+  const int PP = PH * PW;
+  for (int i = threadIdx.x; i < PP; i += blockDim.x)
+    bins[i] = roi_pool_bin(roi, spatial_scale, H, W, PH, PW, i / PW, i % PW);
+  __syncthreads();
+  const int level = static_cast<int>(roi[0]);
+  const int nc = min(kWarpSlab, C - c0);
+  for (int i = threadIdx.x; i < nc * PP; i += blockDim.x) {
+    const int c = c0 + i / PP, cell = i % PP;
+    const PoolBin b = bins[cell];
+    const float* plane = feat + (static_cast<long long>(level) * C + c) * H * W;
+    const bool empty = (b.h1 <= b.h0) || (b.w1 <= b.w0);
+    float best = empty ? 0.f : -3.402823466e+38f;
+    int arg = -1;
+    for (int h = b.h0; h < b.h1; ++h)
+      for (int w = b.w0; w < b.w1; ++w) {
+        const float v = __ldg(plane + h * W + w);
+        if (v > best) {
+          best = v;
+          arg = h * W + w;
+        }
+      }
+    const long long o = (static_cast<long long>(r) * C + c) * PP + cell;
+    out[o] = best;
+    if (argmax) argmax[o] = arg;
+  }
+}
+
+// Engine form: fp32 NHWC feature copy in, split-bf16 rows [r][ph][pw][c] out (the K order the FC
+// weights are permuted to).  grid (R, P); each thread owns (pw, channel quad) items of row ph.
+__global__ void __launch_bounds__(256)
+roi_pool_split_kernel(const float* __restrict__ feat, int C, int H, int W,
+                      const float* __restrict__ rois, float spatial_scale, int P,
+                      __nv_bfloat16* __restrict__ o_hi, __nv_bfloat16* __restrict__ o_lo) {
+  __shared__ PoolBin bins[kMaxPooled];
+  const int r = blockIdx.x, ph = blockIdx.y;
+  const float* roi = rois + static_cast<long long>(r) * 5;
+  if (threadIdx.x < P) bins[threadIdx.x] = roi_pool_bin(roi, spatial_scale, H, W, P, P, ph, threadIdx.x);
+  __syncthreads();
+  const float* fimg = feat + static_cast<long long>(static_cast<int>(roi[0])) * H * W * C;
+  const int c4n = C / 4;
+  for (int item = threadIdx.x; item < P * c4n; item += blockDim.x) {
+    const int pw = item / c4n, c = (item - pw * c4n) * 4;
+    const PoolBin b = bins[pw];
+    const bool empty = (b.h1 <= b.h0) || (b.w1 <= b.w0);
+    const float init = empty ? 0.f : -3.402823466e+38f;
+    float4 best = make_float4(init, init, init, init);
+    for (int h = b.h0; h < b.h1; ++h)
+      for (int w = b.w0; w < b.w1; ++w)
+        best = max4(best, __ldg(reinterpret_cast<const float4*>(fimg + (static_cast<long long>(h) * W + w) * C + c)));
+    st_split4(o_hi, o_lo, ((static_cast<long long>(r) * P + ph) * P + pw) * C + c, best);
+  }
+}
+
+// ROIWarping at P x P straight to split-bf16 rows [r][ph][pw][c] (no pooling after it).
+__global__ void __launch_bounds__(256)
+roi_sample_split_kernel(const float* __restrict__ feat, int C, int H, int W,
+                        const float* __restrict__ rois, float spatial_scale, int P,
+                        __nv_bfloat16* __restrict__ o_hi, __nv_bfloat16* __restrict__ o_lo) {
+  __shared__ SampleTab tab[kMaxPooled];
+  const int r = blockIdx.x, ph = blockIdx.y;
+  const RoiGeom g = roi_geom(rois + static_cast<long long>(r) * 5, spatial_scale, P, P);
+  if (threadIdx.x < P) {
+    const int pw = threadIdx.x;
+    const AxisTap th = axis_tap(__fadd_rn(g.start_h, __fmul_rn(static_cast<float>(ph), g.bin_h)), H);
+    const AxisTap tw = axis_tap(__fadd_rn(g.start_w, __fmul_rn(static_cast<float>(pw), g.bin_w)), W);
+    const bool ok = th.ok && tw.ok;
+    SampleTab e;
+    e.off[0] = ok ? (th.lo * W + tw.lo) * C : 0;
+    e.off[1] = ok ? (th.lo * W + tw.hi) * C : 0;
+    e.off[2] = ok ? (th.hi * W + tw.lo) * C : 0;
+    e.off[3] = ok ? (th.hi * W + tw.hi) * C : 0;
+    e.w[0] = ok ? __fmul_rn(th.h, tw.h) : 0.f;
+    e.w[1] = ok ? __fmul_rn(th.h, tw.l) : 0.f;
+    e.w[2] = ok ? __fmul_rn(th.l, tw.h) : 0.f;
+    e.w[3] = ok ? __fmul_rn(th.l, tw.l) : 0.f;
+    tab[pw] = e;
+  }
+  __syncthreads();
+  const float* fimg = feat + static_cast<long long>(g.level) * H * W * C;
+  const int c4n = C / 4;
+  for (int item = threadIdx.x; item < P * c4n; item += blockDim.x) {
+    const int pw = item / c4n, c = (item - pw * c4n) * 4;
+    const SampleTab& e = tab[pw];
+    const int4 of = *reinterpret_cast<const int4*>(e.off);
+    const float4 wg = *reinterpret_cast<const float4*>(e.w);
+    const float* fc = fimg + c;
+    const float4 v = bilerp4(wg.x, wg.y, wg.z, wg.w, __ldg(reinterpret_cast<const float4*>(fc + of.x)),
+                             __ldg(reinterpret_cast<const float4*>(fc + of.y)),
+                             __ldg(reinterpret_cast<const float4*>(fc + of.z)),
+                             __ldg(reinterpret_cast<const float4*>(fc + of.w)));
+    st_split4(o_hi, o_lo, ((static_cast<long long>(r) * P + ph) * P + pw) * C + c, v);
+  }
+}
+
+
 // sigmoid (sigmoid_layer.cu:10-14) -> mask_proposal (R,1,M,M) -> MaskResize to (R,1,14,14).
 // One CTA per RoI; logits row stride given.
 __global__ void __launch_bounds__(256)
@@ -528,6 +666,45 @@ extern "C" int mnc_roi_warp_split(const float* feat_nhwc, int C, int H, int W, c
         feat_nhwc, C, H, W, rois, spatial_scale, static_cast<__nv_bfloat16*>(o14_hi),
         static_cast<__nv_bfloat16*>(o14_lo), static_cast<__nv_bfloat16*>(o7_hi),
         static_cast<__nv_bfloat16*>(o7_lo));
+  return check_launch();
+}
+
+extern "C" int mnc_roi_pool_nchw(const float* feat, int C, int H, int W, const float* rois, int R,
+                                 int pooled_h, int pooled_w, float spatial_scale, float* out,
+                                 int* argmax, void* stream) {
+  if (R <= 0) return MNC_OK;
+  if (C <= 0 || pooled_h <= 0 || pooled_w <= 0) return MNC_ERR_ARG;
+  const int smem = pooled_h * pooled_w * static_cast<int>(sizeof(PoolBin));
+  if (smem > 48 * 1024) return MNC_ERR_ARG;
+  dim3 grid(R, (C + kWarpSlab - 1) / kWarpSlab);
+  roi_pool_nchw_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      feat, C, H, W, rois, spatial_scale, pooled_h, pooled_w, out, argmax);
+  return check_launch();
+}
+
+extern "C" int mnc_roi_pool_split(const float* feat_nhwc, int C, int H, int W, const float* rois,
+                                  int R, int pooled, float spatial_scale, void* o_hi, void* o_lo,
+                                  void* stream) {
+  if (R <= 0) return MNC_OK;
+  if (C % 4 != 0 || pooled <= 0 || pooled > kMaxPooled ||
+      (reinterpret_cast<uintptr_t>(feat_nhwc) & 15))
+    return MNC_ERR_ARG;
+  roi_pool_split_kernel<<<dim3(R, pooled), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      feat_nhwc, C, H, W, rois, spatial_scale, pooled, static_cast<__nv_bfloat16*>(o_hi),
+      static_cast<__nv_bfloat16*>(o_lo));
+  return check_launch();
+}
+
+extern "C" int mnc_roi_sample_split(const float* feat_nhwc, int C, int H, int W, const float* rois,
+                                    int R, int pooled, float spatial_scale, void* o_hi, void* o_lo,
+                                    void* stream) {
+  if (R <= 0) return MNC_OK;
+  if (C % 4 != 0 || pooled <= 0 || pooled > kMaxPooled ||
+      (reinterpret_cast<uintptr_t>(feat_nhwc) & 15))
+    return MNC_ERR_ARG;
+  roi_sample_split_kernel<<<dim3(R, pooled), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      feat_nhwc, C, H, W, rois, spatial_scale, pooled, static_cast<__nv_bfloat16*>(o_hi),
+      static_cast<__nv_bfloat16*>(o_lo));
   return check_launch();
 }
 

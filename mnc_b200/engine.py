@@ -47,20 +47,26 @@ class MNCEngine:
         self.conv1_1 = w["conv1_1"]
         self.convs = []
         for name in TRUNK_NAMES[1:] + ["rpn_conv_3x3"]:
-            self.convs.append((name, dense.conv_weight_to_split(w[name][0]), w[name][1]))
-        r = self.arch["rpn"]
-        rpn_w = torch.cat([w["rpn_cls_score"][0].reshape(18, r), w["rpn_bbox_pred"][0].reshape(36, r)])
-        self.rpn_head = (dense.split(rpn_w), torch.cat([w["rpn_cls_score"][1], w["rpn_bbox_pred"][1]]).contiguous())
+            if name in w:   # the CFM test net has no RPN (proposals are an input)
+                self.convs.append((name, dense.conv_weight_to_split(w[name][0]), w[name][1]))
+        self.trunk_convs = [c for c in self.convs if c[0] != "rpn_conv_3x3"]
+        if "rpn_conv_3x3" in w:
+            r = self.arch["rpn"]
+            rpn_w = torch.cat([w["rpn_cls_score"][0].reshape(18, r), w["rpn_bbox_pred"][0].reshape(36, r)])
+            self.rpn_head = (dense.split(rpn_w), torch.cat([w["rpn_cls_score"][1], w["rpn_bbox_pred"][1]]).contiguous())
         c5 = self.c5
-        self.fc6_maskest = (dense.fc_weight_to_split(w["fc6_maskest"][0], (c5, 14, 14)), w["fc6_maskest"][1])
-        self.mask_pred = (dense.split(w["mask_pred"][0]), w["mask_pred"][1])
         self.fc6 = (dense.fc_weight_to_split(w["fc6"][0], (c5, 7, 7)), w["fc6"][1])
         self.fc7 = (dense.split(w["fc7"][0]), w["fc7"][1])
-        self.fc6_mask = (dense.fc_weight_to_split(w["fc6_mask"][0], (c5, 7, 7)), w["fc6_mask"][1])
-        self.fc7_mask = (dense.split(w["fc7_mask"][0]), w["fc7_mask"][1])
-        # cls_score | seg_cls_score | bbox_pred share their input: one 8192 -> 126 inner product
-        cls_w = torch.cat([w["cls_score"][0], w["seg_cls_score"][0], w["bbox_pred"][0]])
-        cls_b = torch.cat([w["cls_score"][1], w["seg_cls_score"][1], w["bbox_pred"][1]])
+        if "fc6_maskest" in w:
+            self.fc6_maskest = (dense.fc_weight_to_split(w["fc6_maskest"][0], (c5, 14, 14)), w["fc6_maskest"][1])
+            self.mask_pred = (dense.split(w["mask_pred"][0]), w["mask_pred"][1])
+            self.fc6_mask = (dense.fc_weight_to_split(w["fc6_mask"][0], (c5, 7, 7)), w["fc6_mask"][1])
+            self.fc7_mask = (dense.split(w["fc7_mask"][0]), w["fc7_mask"][1])
+        # cls_score | seg_cls_score | bbox_pred share their input: one inner product for all of them
+        names = [n for n in ("cls_score", "seg_cls_score", "bbox_pred") if n in w]
+        self.cls_head_names = names
+        cls_w = torch.cat([w[n][0] for n in names])
+        cls_b = torch.cat([w[n][1] for n in names])
         self.cls_heads = (dense.split(cls_w), cls_b.contiguous())
         self._buf = {}
 
@@ -143,7 +149,7 @@ class MNCEngine:
         cin = ch[0]
         if "conv1_1" in POOL_AFTER:
             raise NotImplementedError
-        for (name, wgt, bias) in self.convs[:-1]:
+        for (name, wgt, bias) in self.trunk_convs:
             cout = wgt.shape[1]
             nxt = 1 - cur
             if name == "conv5_3":
@@ -199,14 +205,17 @@ class MNCEngine:
                     cls_prob=cls_prob, seg_cls_prob=seg_cls_prob, bbox_pred=bbox_pred,
                     seg_cls_score=heads[:, 21:42], join=join)
 
-    # ------------------------------------------------------------------ whole forward
-    def forward(self, data, im_info, keep_intermediate=False):
-        """data fp32 (B,3,H,W) device, im_info fp32 (B,3) device [h, w, scale].
-        Returns device tensors named after the blobs callers read (tools/demo.py:84-90):
-        rois (B*300,5), mask_proposal (B*300,1,21,21), seg_cls_prob (B*300,21) and the `_ext`
-        versions, plus roi_counts (B,) = number of real (non-padding) RoIs per image."""
+    # ------------------------------------------------------------------ trunk + RPN + proposals
+    def conv5_f32(self, conv5_3, B, H5, W5):
+        """fp32 copy of conv5_3 (= hi + lo, exact) for the RoI gathers: 39 MB per batch of 8."""
+        c5f = self._f32_buf("conv5_f32", B, H5, W5, self.c5)
+        dense.split_to_f32(conv5_3, c5f)
+        return c5f
+
+    def rpn_rois(self, data, im_info, keep_intermediate=False):
+        """test.prototxt:19-476: trunk, rpn_conv_3x3, rpn_cls_score | rpn_bbox_pred, softmax,
+        ProposalLayer.  -> conv5_3 (split NHWC), H5, W5, fp32 conv5_3, rois (B*300,5), counts."""
         B = data.shape[0]
-        out = {}
         conv5_3, H5, W5 = self.trunk(data)
         c5, r = self.c5, self.arch["rpn"]
         name, wgt, bias = self.convs[-1]
@@ -219,16 +228,24 @@ class MNCEngine:
                                      pre_nms_top_n=PRE_NMS_TOP_N, post_nms_top_n=ROIS_PER_IMAGE,
                                      nms_thresh=RPN_NMS_THRESH, min_size=RPN_MIN_SIZE,
                                      batch_index_mode=True, return_intermediate=keep_intermediate)
-        rois3, roi_counts = res[0], res[1]
+        rois = res[0].view(B * ROIS_PER_IMAGE, 5)
+        return conv5_3, H5, W5, self.conv5_f32(conv5_3, B, H5, W5), rois, res[1], res, rpn_out
+
+    # ------------------------------------------------------------------ whole forward
+    def forward(self, data, im_info, keep_intermediate=False):
+        """data fp32 (B,3,H,W) device, im_info fp32 (B,3) device [h, w, scale].
+        Returns device tensors named after the blobs callers read (tools/demo.py:84-90):
+        rois (B*300,5), mask_proposal (B*300,1,21,21), seg_cls_prob (B*300,21) and the `_ext`
+        versions, plus roi_counts (B,) = number of real (non-padding) RoIs per image."""
+        B = data.shape[0]
+        out = {}
+        conv5_3, H5, W5, c5f, rois, roi_counts, res, rpn_out = self.rpn_rois(data, im_info, keep_intermediate)
+        c5 = self.c5
         R = B * ROIS_PER_IMAGE
-        rois = rois3.view(R, 5)
         out["rois"] = rois
         out["roi_counts"] = roi_counts
         feat14 = self._split_buf("feat14", R, 14, 14, c5)
         box7 = self._split_buf("box7", R, 7, 7, c5)
-        # fp32 copy of conv5_3 (= hi + lo, exact) for the RoI gathers: 39 MB per batch of 8
-        c5f = self._f32_buf("conv5_f32", B, H5, W5, c5)
-        dense.split_to_f32(conv5_3, c5f)
         ops.roi_warp_split(c5f, c5, H5, W5, rois, 2, feat14, box7)
         s1 = self.head(feat14, box7, R, "s1")
         rois_ext = ops.stage_bridge(rois, s1["bbox_pred"], s1["seg_cls_prob"], im_info,

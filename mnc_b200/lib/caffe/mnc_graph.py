@@ -23,6 +23,89 @@ def _ip(name, bottom, top, n):
                 inner_product_param=dict(num_output=n))
 
 
+def _trunk():
+    L = []
+    cfgs = [("1", 2, 64), ("2", 2, 128), ("3", 3, 256), ("4", 3, 512), ("5", 3, 512)]
+    prev = "data"
+    for blk, n, ch in cfgs:
+        for i in range(1, n + 1):
+            nm = "conv%s_%d" % (blk, i)
+            L.append(_conv(nm, prev, nm, ch))
+            L.append(_relu("relu%s_%d" % (blk, i), nm))
+            prev = nm
+        if blk != "5":
+            L.append(_pool("pool" + blk, prev, "pool" + blk))
+            prev = "pool" + blk
+    return L
+
+
+def build_frcnn_graph():
+    """models/VGG16/faster_rcnn_end2end/test.prototxt (the RPN layers are named `rpn_conv/3x3`,
+    `rpn/output` there; Dropout is the identity in TEST phase)."""
+    L = _trunk()
+    L.append(_conv("rpn_conv/3x3", "conv5_3", "rpn/output", 512))
+    L.append(_relu("rpn_relu/3x3", "rpn/output"))
+    L.append(_conv("rpn_cls_score", "rpn/output", "rpn_cls_score", 18, k=1, pad=0))
+    L.append(_conv("rpn_bbox_pred", "rpn/output", "rpn_bbox_pred", 36, k=1, pad=0))
+    L.append(dict(name="rpn_cls_score_reshape", type="Reshape", bottom=["rpn_cls_score"],
+                  top=["rpn_cls_score_reshape"]))
+    L.append(dict(name="rpn_cls_prob", type="Softmax", bottom=["rpn_cls_score_reshape"],
+                  top=["rpn_cls_prob"]))
+    L.append(dict(name="rpn_cls_prob_reshape", type="Reshape", bottom=["rpn_cls_prob"],
+                  top=["rpn_cls_prob_reshape"]))
+    L.append(dict(name="proposal", type="Python",
+                  bottom=["rpn_cls_prob_reshape", "rpn_bbox_pred", "im_info"], top=["rois"],
+                  python_param=dict(module="pylayer.proposal_layer", layer="ProposalLayer")))
+    L.append(dict(name="roi_pool5", type="ROIWarping", bottom=["conv5_3", "rois"], top=["pool5"],
+                  roi_warping_param=dict(pooled_w=7, pooled_h=7, spatial_scale=0.0625)))
+    L.append(_ip("fc6", "pool5", "fc6", 4096))
+    L.append(_relu("relu6", "fc6"))
+    L.append(dict(name="drop6", type="Dropout", bottom=["fc6"], top=["fc6"]))
+    L.append(_ip("fc7", "fc6", "fc7", 4096))
+    L.append(_relu("relu7", "fc7"))
+    L.append(dict(name="drop7", type="Dropout", bottom=["fc7"], top=["fc7"]))
+    L.append(_ip("cls_score", "fc7", "cls_score", 21))
+    L.append(dict(name="cls_prob", type="Softmax", bottom=["cls_score"], top=["cls_prob"]))
+    L.append(_ip("bbox_pred", "fc7", "bbox_pred", 84))
+    return L
+
+
+def build_cfm_graph():
+    """models/VGG16/cfm/test.prototxt: inputs data, rois, masks; no RPN."""
+    L = _trunk()
+    rp = lambda name, top, p: dict(name=name, type="ROIPooling", bottom=["conv5_3", "rois"], top=[top],
+                                   roi_pooling_param=dict(pooled_w=p, pooled_h=p, spatial_scale=0.0625))
+    L.append(rp("roi_pooling_conv5", "roi_pooling_conv5", 7))
+    L.append(_ip("fc6", "roi_pooling_conv5", "fc6", 4096))
+    L.append(_relu("relu6", "fc6"))
+    L.append(_ip("fc7", "fc6", "fc7", 4096))
+    L.append(_relu("relu7", "fc7"))
+    L.append(rp("roi_pooling_conv5_mask", "roi_pooling_conv5_mask", 14))
+    L.append(dict(name="mask_pooling", type="MaskPooling", bottom=["roi_pooling_conv5_mask", "masks"],
+                  top=["roi_mask_conv5"]))
+    L.append(_pool("roi_mask_conv5", "roi_mask_conv5", "roi_mask_conv5_pool"))
+    L.append(_ip("fc6_mask", "roi_mask_conv5_pool", "fc6_mask", 4096))
+    L.append(_relu("relu6_mask", "fc6_mask"))
+    L.append(_ip("fc7_mask", "fc6_mask", "fc7_mask", 4096))
+    L.append(_relu("relu7_mask", "fc7_mask"))
+    L.append(_ip("fc6_maskest", "roi_pooling_conv5_mask", "fc6_maskest", 256))
+    L.append(_relu("relu6_maskest", "fc6_maskest"))
+    L.append(_ip("mask_pred", "fc6_maskest", "mask_pred", 441))
+    L.append(dict(name="mask_prob", type="Sigmoid", bottom=["mask_pred"], top=["mask_prob"]))
+    L.append(dict(name="join_box_mask", type="Concat", bottom=["fc7_mask", "fc7"], top=["join_box_mask"]))
+    L.append(_ip("cls_score", "join_box_mask", "cls_score", 21))
+    L.append(dict(name="cls_prob", type="Softmax", bottom=["cls_score"], top=["cls_prob"]))
+    L.append(_ip("seg_cls_score", "join_box_mask", "seg_cls_score", 21))
+    L.append(dict(name="seg_cls_prob", type="Softmax", bottom=["seg_cls_score"], top=["seg_cls_prob"]))
+    L.append(_ip("bbox_pred", "join_box_mask", "bbox_pred", 84))
+    return L
+
+
+GRAPHS = {"mnc_5stage": lambda: build_graph(), "faster_rcnn": build_frcnn_graph, "cfm": build_cfm_graph}
+GRAPH_INPUTS = {"mnc_5stage": ["data", "im_info"], "faster_rcnn": ["data", "im_info"],
+                "cfm": ["data", "rois", "masks"]}
+
+
 def build_graph():
     L = []
     cfgs = [("1", 2, 64), ("2", 2, 128), ("3", 3, 256), ("4", 3, 512), ("5", 3, 512)]
@@ -163,30 +246,51 @@ def parse_prototxt(text):
     return block(0)[0]
 
 
-def check_prototxt(path):
-    """Raise unless `path` describes the MNC 5-stage test graph (names, types, wiring and the
-    parameters this engine bakes in).  Returns the parsed layer list."""
-    with open(path) as f:
-        net = parse_prototxt(f.read())
-    layers = net.get("layer", [])
-    if not isinstance(layers, list):
-        layers = [layers]
-    ref = build_graph()
+def _as_list(v):
+    return v if isinstance(v, list) else ([] if v is None else [v])
+
+
+def _mismatch(layers, ref):
+    """None if the parsed layer list equals the reference graph, else a description."""
     if len(layers) != len(ref):
-        raise ValueError("unsupported net: %d layers, MNC 5-stage test graph has %d" % (len(layers), len(ref)))
+        return "%d layers where %d expected" % (len(layers), len(ref))
     for got, want in zip(layers, ref):
-        as_list = lambda v: v if isinstance(v, list) else ([] if v is None else [v])
         if got.get("name") != want["name"] or got.get("type") != want["type"]:
-            raise ValueError("unsupported net: layer %r/%r where %r/%r expected" % (
-                got.get("name"), got.get("type"), want["name"], want["type"]))
-        if as_list(got.get("bottom")) != want["bottom"] or as_list(got.get("top")) != want["top"]:
-            raise ValueError("unsupported net: wiring of layer %r differs" % want["name"])
+            return "layer %r/%r where %r/%r expected" % (got.get("name"), got.get("type"),
+                                                        want["name"], want["type"])
+        if _as_list(got.get("bottom")) != want["bottom"] or _as_list(got.get("top")) != want["top"]:
+            return "wiring of layer %r differs" % want["name"]
         for pk in ("convolution_param", "inner_product_param", "roi_warping_param",
-                   "mask_resize_param", "pooling_param"):
+                   "roi_pooling_param", "mask_resize_param", "pooling_param"):
             if pk in want:
                 for k, v in want[pk].items():
                     gv = got.get(pk, {}).get(k)
-                    if gv != v and not (isinstance(v, float) and abs(float(gv) - v) < 1e-9):
-                        raise ValueError("unsupported net: %s.%s.%s = %r, engine implements %r" % (
-                            want["name"], pk, k, gv, v))
+                    if gv != v and not (isinstance(v, float) and gv is not None and abs(float(gv) - v) < 1e-9):
+                        return "%s.%s.%s = %r, engine implements %r" % (want["name"], pk, k, gv, v)
+    return None
+
+
+def identify_prototxt(path):
+    """Which of the supported test graphs `path` describes: "mnc_5stage" (models/VGG16/mnc_5stage/
+    test.prototxt), "faster_rcnn" (faster_rcnn_end2end/test.prototxt) or "cfm" (cfm/test.prototxt);
+    names, types, wiring and the parameters the engines bake in must all match.  -> (kind, layers)."""
+    with open(path) as f:
+        net = parse_prototxt(f.read())
+    layers = _as_list(net.get("layer", []))
+    why = {}
+    for kind, build in GRAPHS.items():
+        why[kind] = _mismatch(layers, build())
+        if why[kind] is None:
+            if _as_list(net.get("input")) != GRAPH_INPUTS[kind]:
+                raise ValueError("unsupported net: inputs %r, %s takes %r" % (
+                    net.get("input"), kind, GRAPH_INPUTS[kind]))
+            return kind, layers
+    raise ValueError("unsupported net: " + "; ".join("not %s (%s)" % kv for kv in why.items()))
+
+
+def check_prototxt(path, kind="mnc_5stage"):
+    """Raise unless `path` describes the given test graph.  Returns the parsed layer list."""
+    got, layers = identify_prototxt(path)
+    if got != kind:
+        raise ValueError("unsupported net: %s is the %s graph, %s expected" % (path, got, kind))
     return layers

@@ -27,3 +27,7 @@ cfg.TEST.MASK_MERGE_IOU_THRESH = 0.5         # :136
 cfg.TEST.MASK_MERGE_NMS_THRESH = 0.3         # :137
 cfg.TEST.USE_MASK_MERGE = True               # :151
 cfg.TEST.USE_GPU_MASK_MERGE = True           # :152
+cfg.TEST.CFM_INPUT_MASK_SIZE = 14            # :138
+cfg.TEST.MAX_ROIS_GPU = [2000]               # :144
+cfg.TEST.GROUP_SCALE = 1                     # :145
+cfg.TEST.USE_TOP_K_MCG = 0                   # :148

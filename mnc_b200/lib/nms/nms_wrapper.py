@@ -23,3 +23,20 @@ def apply_nms_mask_single(box, mask, thresh):
     if len(keep) == 0:
         return box, mask
     return box[keep, :].copy(), mask[keep, :].copy()
+
+
+def apply_nms(all_boxes, thresh):
+    """Per class and image NMS over `all_boxes[cls][image]` (n,5) arrays
+    (reference lib/nms/nms_wrapper.py:24-41)."""
+    num_classes, num_images = len(all_boxes), len(all_boxes[0])
+    out = [[[] for _ in range(num_images)] for _ in range(num_classes)]
+    for c in range(num_classes):
+        for i in range(num_images):
+            dets = all_boxes[c][i]
+            if len(dets) == 0:
+                continue
+            keep = nms(dets, thresh)
+            if len(keep) == 0:
+                continue
+            out[c][i] = dets[keep, :].copy()
+    return out

@@ -160,6 +160,16 @@ def unscale_clip(rois, rois_per_img, im_scale, im_hw):
     return boxes
 
 
+def decode_class_boxes(rois, bbox_pred, rois_per_img, im_scale, im_hw, ncls=21):
+    """-> (R, ncls*4) fp32: per-class decoded boxes in original-image coordinates, clipped."""
+    R = rois.shape[0]
+    out = torch.empty((R, ncls * 4), dtype=torch.float32, device=rois.device)
+    check(lib.mnc_decode_class_boxes(ptr(rois), c_int(R), c_int(rois_per_img), ptr(bbox_pred),
+                                     c_int(bbox_pred.stride(0)), c_int(ncls), ptr(im_scale),
+                                     ptr(im_hw), ptr(out), cur_stream()), "mnc_decode_class_boxes")
+    return out
+
+
 # ----------------------------------------------------------------------------- RoI / mask layers
 def roi_warp_nchw(feat, rois, pooled_h, pooled_w, spatial_scale=0.0625, out=None):
     B, C, H, W = feat.shape
@@ -217,6 +227,32 @@ def mask_pool_split(feat14, mask14, R, C, out7):
                                   ptr(out7[0]), ptr(out7[1]), cur_stream()), "mnc_mask_pool_split")
 
 
+def roi_pool_nchw(feat, rois, pooled_h, pooled_w, spatial_scale=0.0625, out=None, argmax=None):
+    """ROIPoolingLayer forward (roi_pooling_layer.cu:17-105) on fp32 NCHW device tensors."""
+    B, C, H, W = feat.shape
+    R = rois.shape[0]
+    if out is None:
+        out = torch.empty((R, C, pooled_h, pooled_w), dtype=torch.float32, device=feat.device)
+    check(lib.mnc_roi_pool_nchw(ptr(feat), c_int(C), c_int(H), c_int(W), ptr(rois), c_int(R),
+                                c_int(pooled_h), c_int(pooled_w), c_float(spatial_scale), ptr(out),
+                                ptr(argmax), cur_stream()), "mnc_roi_pool_nchw")
+    return out
+
+
+def roi_pool_split(feat, C, H, W, rois, pooled, out, spatial_scale=0.0625):
+    """feat fp32 NHWC [B,H,W,C]; rois [R,5]; out split [2,R,P,P,C] (ROIPooling)."""
+    check(lib.mnc_roi_pool_split(ptr(feat), c_int(C), c_int(H), c_int(W), ptr(rois),
+                                 c_int(rois.shape[0]), c_int(pooled), c_float(spatial_scale),
+                                 ptr(out[0]), ptr(out[1]), cur_stream()), "mnc_roi_pool_split")
+
+
+def roi_sample_split(feat, C, H, W, rois, pooled, out, spatial_scale=0.0625):
+    """feat fp32 NHWC [B,H,W,C]; rois [R,5]; out split [2,R,P,P,C] (ROIWarping, no pool after)."""
+    check(lib.mnc_roi_sample_split(ptr(feat), c_int(C), c_int(H), c_int(W), ptr(rois),
+                                   c_int(rois.shape[0]), c_int(pooled), c_float(spatial_scale),
+                                   ptr(out[0]), ptr(out[1]), cur_stream()), "mnc_roi_sample_split")
+
+
 # ----------------------------------------------------------------------------- mask voting
 class VotingOverflow(RuntimeError):
     pass
@@ -263,7 +299,7 @@ def mask_voting(boxes, masks, scores, im_hw, max_per_image=100, nms_thresh=0.3, 
                                   c_double(iou_thresh), ptr(cand_inds), ptr(cand_w),
                                   ptr(cand_begin), ptr(cand_end), cur_stream()),
           "mnc_vote_candidates")
-    bbox_ws = _i32(B, max_results, 4, device=dev)
+    bbox_ws = _i32(B * max_results * 4 + B, device=dev)   # tight boxes + per-image range flag
     out_mask = torch.zeros((B, max_results, 1, M, M), dtype=torch.float32, device=dev)
     out_box = torch.zeros((B, max_results, 4), dtype=torch.int32, device=dev)
     check(lib.mnc_mv_device(ptr(boxes), ptr(masks), c_int(nb), c_int(4), c_int(M), ptr(cand_inds),

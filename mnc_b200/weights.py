@@ -58,5 +58,28 @@ def make_weights(arch=None, seed=2016):
 def arch_of(weights):
     """Recover the layer widths from a weight dict."""
     return dict(trunk=[weights[n][0].shape[0] for n in TRUNK_NAMES],
-                rpn=weights["rpn_conv_3x3"][0].shape[0], fc=weights["fc7"][0].shape[0],
-                maskest=weights["fc6_maskest"][0].shape[0])
+                rpn=weights["rpn_conv_3x3"][0].shape[0] if "rpn_conv_3x3" in weights else 0,
+                fc=weights["fc7"][0].shape[0],
+                maskest=weights["fc6_maskest"][0].shape[0] if "fc6_maskest" in weights else 0)
+
+
+def make_sibling_weights(graph, arch=None, seed=2016):
+    """Seeded weights for the sibling test graphs (mnc_b200/siblings.py), same initialiser:
+    "faster_rcnn": no mask layers, cls_score (21, fc) / bbox_pred (84, fc) on fc7 alone
+    (faster_rcnn_end2end/test.prototxt:558-616); "cfm": the 5-stage layer set minus the RPN
+    (cfm/test.prototxt has no RPN: proposals are inputs)."""
+    arch = arch or FULL_ARCH
+    w = make_weights(arch, seed)
+    fc = arch["fc"]
+    if graph == "faster_rcnn":
+        g = torch.Generator().manual_seed(seed + 1)
+        for n in ("fc6_maskest", "mask_pred", "fc6_mask", "fc7_mask", "seg_cls_score"):
+            del w[n]
+        w["cls_score"] = (torch.randn((21, fc), generator=g) * (2.0 / fc) ** 0.5, torch.zeros(21))
+        w["bbox_pred"] = (torch.randn((84, fc), generator=g) * (2.0 / fc) ** 0.5 * 0.1, torch.zeros(84))
+    elif graph == "cfm":
+        for n in ("rpn_conv_3x3", "rpn_cls_score", "rpn_bbox_pred"):
+            del w[n]
+    else:
+        raise ValueError(graph)
+    return w

@@ -134,6 +134,52 @@ void orc_roi_warp(const float* feat, int C, int H, int W, const float* rois, int
   }
 }
 
+/* ROIPooling forward -- caffe-mnc/src/caffe/layers/roi_pooling_layer.cu:17-77 (same arithmetic as
+ * the CPU form roi_pooling_layer.cpp:47-127).  feat (B,C,H,W), rois (R,5), out/argmax (R,C,ph,pw);
+ * argmax may be NULL. */
+void orc_roi_pool(const float* feat, int C, int H, int W, const float* rois, int R, int ph_n,
+                  int pw_n, float spatial_scale, float* out, int* argmax) {
+#pragma omp parallel for schedule(dynamic, 4)
+  for (int n = 0; n < R; ++n) {
+    const float* roi = rois + 5 * n;
+    int roi_batch_ind = (int)roi[0];
+    int roi_start_w = (int)roundf(roi[1] * spatial_scale);
+    int roi_start_h = (int)roundf(roi[2] * spatial_scale);
+    int roi_end_w = (int)roundf(roi[3] * spatial_scale);
+    int roi_end_h = (int)roundf(roi[4] * spatial_scale);
+    int roi_width = roi_end_w - roi_start_w + 1 > 1 ? roi_end_w - roi_start_w + 1 : 1;
+    int roi_height = roi_end_h - roi_start_h + 1 > 1 ? roi_end_h - roi_start_h + 1 : 1;
+    float bin_size_h = (float)roi_height / (float)ph_n;
+    float bin_size_w = (float)roi_width / (float)pw_n;
+    for (int c = 0; c < C; ++c) {
+      const float* plane = feat + ((size_t)roi_batch_ind * C + c) * H * W;
+      for (int ph = 0; ph < ph_n; ++ph)
+        for (int pw = 0; pw < pw_n; ++pw) {
+          int hstart = (int)floorf((float)ph * bin_size_h);
+          int wstart = (int)floorf((float)pw * bin_size_w);
+          int hend = (int)ceilf((float)(ph + 1) * bin_size_h);
+          int wend = (int)ceilf((float)(pw + 1) * bin_size_w);
+          hstart = hstart + roi_start_h < 0 ? 0 : (hstart + roi_start_h > H ? H : hstart + roi_start_h);
+          hend = hend + roi_start_h < 0 ? 0 : (hend + roi_start_h > H ? H : hend + roi_start_h);
+          wstart = wstart + roi_start_w < 0 ? 0 : (wstart + roi_start_w > W ? W : wstart + roi_start_w);
+          wend = wend + roi_start_w < 0 ? 0 : (wend + roi_start_w > W ? W : wend + roi_start_w);
+          int is_empty = (hend <= hstart) || (wend <= wstart);
+          float maxval = is_empty ? 0.f : -3.402823466e+38f;
+          int maxidx = -1;
+          for (int h = hstart; h < hend; ++h)
+            for (int w = wstart; w < wend; ++w)
+              if (plane[h * W + w] > maxval) {
+                maxval = plane[h * W + w];
+                maxidx = h * W + w;
+              }
+          size_t o = (((size_t)n * C + c) * ph_n + ph) * pw_n + pw;
+          out[o] = maxval;
+          if (argmax) argmax[o] = maxidx;
+        }
+    }
+  }
+}
+
 /* MaskResize forward -- caffe-mnc/src/caffe/layers/mask_resize_layer.cu:13-73. */
 void orc_mask_resize(const float* in, int N, int C, int ih_n, int iw_n, int oh_n, int ow_n,
                      float* out) {

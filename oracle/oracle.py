@@ -296,6 +296,20 @@ def roi_warp(feat, rois, pooled_h, pooled_w, spatial_scale=0.0625):
     return out
 
 
+def roi_pool(feat, rois, pooled_h, pooled_w, spatial_scale=0.0625, return_argmax=False):
+    """ROIPoolingLayer forward -- roi_pooling_layer.cu:17-77.  feat (B,C,H,W), rois (R,5)."""
+    feat = np.ascontiguousarray(feat, dtype=np.float32)
+    rois = np.ascontiguousarray(rois, dtype=np.float32)
+    B, C, H, W = feat.shape
+    R = rois.shape[0]
+    out = np.zeros((R, C, pooled_h, pooled_w), dtype=np.float32)
+    arg = np.zeros((R, C, pooled_h, pooled_w), dtype=np.int32)
+    _lib().orc_roi_pool(_p(feat), ctypes.c_int(C), ctypes.c_int(H), ctypes.c_int(W), _p(rois),
+                        ctypes.c_int(R), ctypes.c_int(pooled_h), ctypes.c_int(pooled_w),
+                        ctypes.c_float(spatial_scale), _p(out), _p(arg))
+    return (out, arg) if return_argmax else out
+
+
 def mask_resize(masks, out_h, out_w):
     """MaskResizeLayer forward -- mask_resize_layer.cu:57-73."""
     masks = np.ascontiguousarray(masks, dtype=np.float32)
@@ -543,6 +557,110 @@ def net_forward(w, data, im_info):
         for k, v in s2.items():
             blobs[k + "_ext"] = v
     return blobs
+
+
+def frcnn_net_forward(w, data, im_info):
+    """Faster R-CNN test net for one image -- models/VGG16/faster_rcnn_end2end/test.prototxt:
+    trunk, RPN, proposal (:463-476), ROIWarping 7x7 (:479-490), fc6/fc7 (Dropout is the identity
+    in TEST phase, dropout_layer.cpp:41-44), cls_score+Softmax, bbox_pred (:558-616)."""
+    import torch
+    import torch.nn.functional as F
+    with torch.no_grad():
+        blobs = {}
+        conv5_3 = trunk_forward(w, data)
+        blobs["conv5_3"] = conv5_3.numpy()
+        prob, bbox = rpn_forward(w, conv5_3)
+        blobs["rpn_cls_prob_reshape"] = prob.numpy()
+        blobs["rpn_bbox_pred"] = bbox.numpy()
+        rois = proposal_layer_forward(blobs["rpn_cls_prob_reshape"], blobs["rpn_bbox_pred"], im_info)
+        blobs["rois"] = rois
+        pool5 = roi_warp(blobs["conv5_3"], rois, 7, 7)
+        blobs["pool5"] = pool5
+        R = rois.shape[0]
+        fc6 = F.relu(F.linear(_t(pool5).reshape(R, -1), *w["fc6"]))
+        fc7 = F.relu(F.linear(fc6, *w["fc7"]))
+        blobs["fc7"] = fc7.numpy()
+        blobs["cls_prob"] = torch.softmax(F.linear(fc7, *w["cls_score"]), dim=1).numpy()
+        blobs["bbox_pred"] = F.linear(fc7, *w["bbox_pred"]).numpy()
+    return blobs
+
+
+def detection_tail(blobs, im_shape, im_scale=1.0):
+    """TesterWrapper._detection_forward :226-237."""
+    boxes = blobs["rois"][:, 1:5] / im_scale
+    pred_boxes = bbox_transform_inv(boxes, blobs["bbox_pred"])
+    pred_boxes, _ = clip_boxes(pred_boxes, im_shape)
+    return blobs["cls_prob"], pred_boxes
+
+
+def cfm_net_forward(w, data, rois, masks):
+    """CFM test net -- models/VGG16/cfm/test.prototxt: data (S,3,H,W) image pyramid, rois (R,5)
+    [level, x1,y1,x2,y2], masks (R,1,14,14).  ROIPooling 7x7 -> fc6/fc7 (:397-443); ROIPooling
+    14x14 -> MaskPooling with the input masks -> 2x2 max pool -> fc6_mask/fc7_mask (:447-512);
+    fc6_maskest/mask_pred/Sigmoid on the un-masked 14x14 feature (:517-549); Concat, cls_score,
+    seg_cls_score, bbox_pred (:553-620)."""
+    import torch
+    import torch.nn.functional as F
+    with torch.no_grad():
+        blobs = {}
+        conv5_3 = trunk_forward(w, data).numpy()
+        blobs["conv5_3"] = conv5_3
+        R = rois.shape[0]
+        box7 = roi_pool(conv5_3, rois, 7, 7)
+        blobs["roi_pooling_conv5"] = box7
+        fc6 = F.relu(F.linear(_t(box7).reshape(R, -1), *w["fc6"]))
+        fc7 = F.relu(F.linear(fc6, *w["fc7"]))
+        feat14 = roi_pool(conv5_3, rois, 14, 14)
+        blobs["roi_pooling_conv5_mask"] = feat14
+        masked = mask_pool(feat14, masks)
+        m7 = F.max_pool2d(_t(masked), 2, 2)
+        blobs["roi_mask_conv5_pool"] = m7.numpy()
+        fc6m = F.relu(F.linear(m7.reshape(R, -1), *w["fc6_mask"]))
+        fc7m = F.relu(F.linear(fc6m, *w["fc7_mask"]))
+        h = F.relu(F.linear(_t(feat14).reshape(R, -1), *w["fc6_maskest"]))
+        blobs["mask_pred"] = F.linear(h, *w["mask_pred"]).numpy()
+        blobs["mask_prob"] = torch.sigmoid(_t(blobs["mask_pred"])).numpy()
+        join = torch.cat([fc7m, fc7], dim=1)
+        blobs["cls_prob"] = torch.softmax(F.linear(join, *w["cls_score"]), dim=1).numpy()
+        blobs["seg_cls_score"] = F.linear(join, *w["seg_cls_score"]).numpy()
+        blobs["seg_cls_prob"] = torch.softmax(_t(blobs["seg_cls_score"]), dim=1).numpy()
+        blobs["bbox_pred"] = F.linear(join, *w["bbox_pred"]).numpy()
+    return blobs
+
+
+def prep_im_for_blob_cfm(im, input_scales, max_size=1000):
+    """lib/utils/blob.py:53-85: one resized copy per scale, zero-padded into one blob."""
+    import cv2
+    im_orig = im.astype(np.float32, copy=True)
+    im_orig -= CFG.PIXEL_MEANS
+    size_min, size_max = np.min(im_orig.shape[0:2]), np.max(im_orig.shape[0:2])
+    ims, scales = [], []
+    for target_size in input_scales:
+        im_scale = float(target_size) / float(size_min)
+        if np.round(im_scale * size_max) > max_size:
+            im_scale = float(max_size) / float(size_max)
+        ims.append(cv2.resize(im_orig, None, None, fx=im_scale, fy=im_scale, interpolation=cv2.INTER_LINEAR))
+        scales.append(im_scale)
+    max_shape = np.array([i.shape for i in ims]).max(axis=0)
+    blob = np.zeros((len(ims), max_shape[0], max_shape[1], 3), dtype=np.float32)
+    for i, x in enumerate(ims):
+        blob[i, 0:x.shape[0], 0:x.shape[1], :] = x
+    return blob.transpose((0, 3, 1, 2)), np.array(scales)
+
+
+def pred_rois_for_blob(im_rois, im_scales):
+    """lib/utils/blob.py:88-106: level = scale whose scaled area is closest to 224^2."""
+    im_rois = im_rois.astype(np.float64, copy=False)
+    if len(im_scales) > 1:
+        widths = im_rois[:, 2] - im_rois[:, 0] + 1
+        heights = im_rois[:, 3] - im_rois[:, 1] + 1
+        areas = widths * heights
+        scaled_areas = areas[:, np.newaxis] * (im_scales[np.newaxis, :] ** 2)
+        levels = np.abs(scaled_areas - 224 * 224).argmin(axis=1)[:, np.newaxis]
+    else:
+        levels = np.zeros((im_rois.shape[0], 1), dtype=np.int64)
+    im_rois = im_rois * im_scales[levels]
+    return np.hstack((levels.astype(np.float64), im_rois))
 
 
 def im_detect_tail(blobs, im_shape, im_scale=1.0):

@@ -35,3 +35,32 @@ torch.cuda.nvtx.range_pop()
 print("voting batch 8: %.3f ms; results per image %s; candidates per result (img 0): %s" % (
     e0.elapsed_time(e1), r["n_res"].cpu().tolist(),
     (r["cand_end"][0] - r["cand_begin"][0])[:int(r["n_res"][0])].cpu().tolist()[:20]))
+
+# ---- where does forward+voting time go?  (device time vs host launch time)
+import time
+def timed(fn, n=10):
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(True), torch.cuda.Event(True)
+    t0 = time.perf_counter()
+    a.record()
+    for _ in range(n):
+        fn()
+    b.record()
+    t_host = time.perf_counter() - t0
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / n, t_host * 1e3 / n
+
+def fwd():
+    return eng.detect(data, info, hw, sc)
+
+def vote():
+    return ops.mask_voting(boxes, masks, scores, hwi, box_valid=valid)
+
+def both():
+    b_, m_, s_, v_, _ = eng.detect(data, info, hw, sc)
+    return ops.mask_voting(b_, m_, s_, hwi, box_valid=v_)
+
+for name, fn in (("forward", fwd), ("voting x10 back-to-back", vote), ("forward+voting", both)):
+    fn()
+    dev_ms, host_ms = timed(fn)
+    print("%-28s device %.3f ms/iter   host launch %.3f ms/iter" % (name, dev_ms, host_ms))

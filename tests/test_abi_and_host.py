@@ -56,8 +56,10 @@ def test_prototxt_reader_and_graph_check(tmp_path):
     assert types.count("ROIWarping") == 2 and types.count("MaskResize") == 2
     assert types.count("MaskPooling") == 2 and types.count("Python") == 4 and types.count("Concat") == 2
 
-    def emit(layers):
-        out = ['name: "VGG16"', 'input: "data"', "input_shape { dim: 1 dim: 3 dim: 224 dim: 224 }"]
+    def emit(layers, inputs=("data", "im_info")):
+        out = ['name: "VGG16"']
+        for name in inputs:
+            out += ['input: "%s"' % name, "input_shape { dim: 1 dim: 3 }"]
         for l in layers:
             s = ["layer {", '  name: "%s"' % l["name"], '  type: "%s"' % l["type"]]
             s += ['  bottom: "%s"' % b for b in l["bottom"]] + ['  top: "%s"' % t for t in l["top"]]
@@ -78,9 +80,24 @@ def test_prototxt_reader_and_graph_check(tmp_path):
     p.write_text(emit(bad))
     with pytest.raises(ValueError):
         mnc_graph.check_prototxt(str(p))
-    ref = "/root/reference/models/VGG16/mnc_5stage/test.prototxt"
-    if os.path.exists(ref):  # build container only
-        assert len(mnc_graph.check_prototxt(ref)) == 88
+    # the sibling test graphs are told apart by their layers
+    for kind, n_layers in (("faster_rcnn", 48), ("cfm", 52)):
+        gk = mnc_graph.GRAPHS[kind]()
+        assert len(gk) == n_layers
+        p.write_text(emit(gk, mnc_graph.GRAPH_INPUTS[kind]))
+        assert mnc_graph.identify_prototxt(str(p))[0] == kind
+        with pytest.raises(ValueError):
+            mnc_graph.check_prototxt(str(p))          # not the 5-stage graph
+    p.write_text(emit(mnc_graph.GRAPHS["cfm"](), ("data", "im_info")))
+    with pytest.raises(ValueError):
+        mnc_graph.identify_prototxt(str(p))           # CFM layers with the wrong inputs
+    base = "/root/reference/models/VGG16/"
+    if os.path.exists(base):  # build container only
+        assert len(mnc_graph.check_prototxt(base + "mnc_5stage/test.prototxt")) == 88
+        assert mnc_graph.identify_prototxt(base + "faster_rcnn_end2end/test.prototxt")[0] == "faster_rcnn"
+        assert mnc_graph.identify_prototxt(base + "cfm/test.prototxt")[0] == "cfm"
+        with pytest.raises(ValueError):
+            mnc_graph.identify_prototxt(base + "mnc_5stage/train.prototxt")
 
 
 def test_cfg_constants():
@@ -204,6 +221,21 @@ def test_caffemodel_roundtrip_and_protobuf_crosscheck(tmp_path):
     assert np.array_equal(got["ip1"][0].ravel(), np.arange(6, dtype=np.float32))
     with pytest.raises(KeyError):
         CM.weights_from_caffemodel(str(q))
+    # sibling graphs: Faster R-CNN snapshots name the RPN conv `rpn_conv/3x3`
+    # (faster_rcnn_end2end/test.prototxt:391); CFM snapshots have no RPN at all
+    wf = Wt.make_sibling_weights("faster_rcnn", Wt.TINY_ARCH)
+    renamed = {("rpn_conv/3x3" if k == "rpn_conv_3x3" else k): v for k, v in wf.items()}
+    pf = str(tmp_path / "frcnn_tiny.caffemodel")
+    CM.save_caffemodel(renamed, pf)
+    bf = CM.weights_from_caffemodel(pf, "faster_rcnn")
+    assert set(bf) == set(wf) and torch.equal(bf["rpn_conv_3x3"][0], wf["rpn_conv_3x3"][0])
+    assert bf["cls_score"][0].shape == (21, Wt.TINY_ARCH["fc"])
+    with pytest.raises(KeyError):
+        CM.weights_from_caffemodel(pf, "mnc_5stage")
+    wc = Wt.make_sibling_weights("cfm", Wt.TINY_ARCH)
+    pc = str(tmp_path / "cfm_tiny.caffemodel")
+    CM.save_caffemodel(wc, pc)
+    assert set(CM.weights_from_caffemodel(pc, "cfm")) == set(wc)
 
 
 def test_eval_host_helpers_match_oracle_and_voc_palette():
