@@ -127,6 +127,14 @@ int mnc_nms_sorted(const float* boxes, int box_stride, long long problem_stride,
 int mnc_rank_sort_desc(const float* keys, long long outer_stride, long long inner_stride, int inner,
                        int key_stride, const unsigned char* valid, int n, int problems, int* order,
                        int* n_valid, void* stream);
+/* Same ordering, but only the k best entries are produced: order[prob][0..min(n_valid, k)) and
+ * n_out[prob] = min(n_valid, k) -- what `scores.argsort()[::-1][:pre_nms_topN]`
+ * (lib/pylayer/proposal_layer.py:139-142) consumes.  Radix select + sort of the selection in one
+ * CTA per problem; returns MNC_ERR_ARG when n / k exceed its shared-memory budget
+ * (8*pow2(k) + 4*n <= 200 KB), in which case use mnc_rank_sort_desc. */
+int mnc_topk_sort_desc(const float* keys, long long outer_stride, long long inner_stride, int inner,
+                       int key_stride, const unsigned char* valid, int n, int problems, int k,
+                       int* order, int order_stride, int* n_out, void* stream);
 /* dst[p][k][0..3] = src[(p / inner)][order[p*order_stride + k]][0..3], k < min(counts[p], n_out);
  * out_counts[p] = that minimum. */
 int mnc_gather_boxes(const float* src, int src_stride, long long src_outer_stride, int inner,

@@ -520,7 +520,7 @@ extern "C" int mnc_mv_device(const float* boxes, const float* masks, int nb, int
   if (nb <= 0 || max_results <= 0 || batch <= 0) return MNC_ERR_ARG;
   const int smem = nb * (16 + 4 + 4 + 8 + 4);
   if (smem > 200 * 1024) return MNC_ERR_ARG;
-  static int attr_smem = 48 * 1024;
+  static int attr_smem = 40 * 1024;
   if (smem > attr_smem) {
     if (cudaFuncSetAttribute(mv_aggregate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              smem) != cudaSuccess ||

@@ -101,11 +101,12 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const int* __restri
                 int n_max, int max_keep, int* __restrict__ keep_out, int keep_stride,
                 int* __restrict__ num_out) {
   extern __shared__ unsigned long long remv[];  // col_blocks words
-  __shared__ unsigned long long diag[64];
-  __shared__ unsigned long long s_kept;
-  __shared__ int s_num;
+  __shared__ unsigned long long diag[2][64];
+  __shared__ int s_rows[64];
+  __shared__ int s_nk, s_num;
   const int prob = blockIdx.x;
   const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const int n = min(counts ? counts[prob] : n_max, n_max);
   const int cb_max = (n_max + 63) / 64;
   const int col_blocks = (n + 63) / 64;
@@ -113,38 +114,48 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const int* __restri
   int* keep = keep_out + static_cast<long long>(prob) * keep_stride;
   for (int c = tid; c < col_blocks; c += blockDim.x) remv[c] = 0ull;
   if (tid == 0) s_num = 0;
+  if (tid < 64) diag[0][tid] = (tid < n) ? pm[static_cast<long long>(tid) * cb_max] : 0ull;
   __syncthreads();
   for (int blk = 0; blk < col_blocks; ++blk) {
     const int r0 = blk * 64;
-    if (tid < 64) diag[tid] = (r0 + tid < n) ? pm[static_cast<long long>(r0 + tid) * cb_max + blk] : 0ull;
-    __syncthreads();
+    const int buf = blk & 1;
     if (tid == 0) {
-      unsigned long long cur = remv[blk], kept = 0ull;
-      int num = s_num;
+      // greedy pass over the 64 candidates of this block (bit i of diag[i'] = i' suppresses i)
+      unsigned long long cur = remv[blk];
+      int num = s_num, nk = 0;
       const int rows = min(64, n - r0);
 #pragma unroll 8
       for (int i = 0; i < rows; ++i) {
         if (!((cur >> i) & 1ull) && num < max_keep) {
           keep[num++] = r0 + i;
-          kept |= (1ull << i);
-          cur |= diag[i];
+          s_rows[nk++] = r0 + i;
+          cur |= diag[buf][i];
         }
       }
-      s_kept = kept;
+      s_nk = nk;
       s_num = num;
+    } else if (tid >= 64 && tid < 128 && blk + 1 < col_blocks) {
+      // meanwhile: the next block's diagonal words (independent of what is kept here)
+      const int r = r0 + 64 + (tid - 64);
+      diag[buf ^ 1][tid - 64] = (r < n) ? pm[static_cast<long long>(r) * cb_max + blk + 1] : 0ull;
     }
     __syncthreads();
     if (s_num >= max_keep) break;
-    unsigned long long k = s_kept;
-    for (int c = blk + 1 + tid; c < col_blocks; c += blockDim.x) {
-      unsigned long long acc = remv[c];
-      unsigned long long kk = k;
-      while (kk) {
-        const int i = __ffsll(static_cast<long long>(kk)) - 1;
-        kk &= kk - 1;
-        acc |= pm[static_cast<long long>(r0 + i) * cb_max + c];
+    // OR the kept rows into the running suppression words of the later column blocks.  Lanes
+    // run along a row (coalesced 8-byte loads), warps split the kept rows; a warp's <= 8 loads
+    // per column chunk are independent, so the whole phase costs about one memory round trip.
+    const int nk = s_nk;
+    if (nk > 0) {
+      for (int c0 = blk + 1; c0 < col_blocks; c0 += 32) {
+        const int c = c0 + lane;
+        unsigned long long acc = 0ull;
+        if (c < col_blocks) {
+#pragma unroll 8
+          for (int q = warp; q < nk; q += nwarps)
+            acc |= __ldg(pm + static_cast<long long>(s_rows[q]) * cb_max + c);
+          if (acc) atomicOr(&remv[c], acc);
+        }
       }
-      remv[c] = acc;
     }
     __syncthreads();
   }
@@ -208,6 +219,141 @@ bitonic_sort_desc_kernel(const float* __restrict__ keys, long long outer_stride,
   const int cnt = s_cnt;
   for (int i = tid; i < cnt; i += blockDim.x) order[static_cast<long long>(prob) * n + i] = si[i];
   if (tid == 0 && n_valid) n_valid[prob] = cnt;
+}
+
+// Top-k selection + sort, one CTA per problem: order[prob][0..min(n_valid, k)) = indices of the k
+// best entries in (key desc, index asc) order -- all that `scores.argsort()[::-1][:pre_nms_topN]`
+// (proposal_layer.py:139-142) ever uses.  Sorting all 21546 anchors (32768-slot bitonic network,
+// every stage through shared memory) cost 0.38 ms per batch; here
+//   1. keys -> order-preserving u32 in shared memory,
+//   2. 4-pass byte-wise radix select finds T = the k-th largest key,
+//   3. entries above T are compacted (any order), entries equal to T are taken in index order
+//      until k are selected (the tie rule),
+//   4. the <= 8192 selected (key, ~index) pairs are bitonic-sorted as packed u64.
+constexpr int kTopkThreads = 1024;
+
+__global__ void __launch_bounds__(kTopkThreads)
+topk_sort_desc_kernel(const float* __restrict__ keys, long long outer_stride,
+                      long long inner_stride, int inner, int key_stride,
+                      const unsigned char* __restrict__ valid, int n, int k, int np2,
+                      int* __restrict__ order, int order_stride, int* __restrict__ n_out) {
+  extern __shared__ unsigned long long sbuf[];               // np2 packed pairs
+  uint32_t* skey = reinterpret_cast<uint32_t*>(sbuf + np2);  // n keys
+  __shared__ uint32_t hist[256];
+  __shared__ int s_nv, s_pos, s_warp[32], s_run;
+  __shared__ uint32_t s_prefix;
+  __shared__ int s_need, s_eq;
+  const int prob = blockIdx.x, tid = threadIdx.x;
+  const float* pk = keys + (prob / inner) * outer_stride + (prob % inner) * inner_stride;
+  const unsigned char* pv = valid ? valid + static_cast<long long>(prob) * n : nullptr;
+  if (tid == 0) {
+    s_nv = 0;
+    s_pos = 0;
+    s_run = 0;
+  }
+  __syncthreads();
+  int local = 0;
+  for (int i = tid; i < n; i += kTopkThreads) {
+    uint32_t key = 0u;
+    if (pv ? pv[i] != 0 : true) {
+      key = f32_sort_key(pk[static_cast<long long>(i) * key_stride]);
+      ++local;
+    }
+    skey[i] = key;
+  }
+  if (local) atomicAdd(&s_nv, local);
+  __syncthreads();
+  const int K = min(k, s_nv);
+  if (K == 0) {
+    if (tid == 0) n_out[prob] = 0;
+    return;
+  }
+  // ---- radix select: T = K-th largest key
+  if (tid == 0) {
+    s_prefix = 0u;
+    s_need = K;
+  }
+  for (int pass = 3; pass >= 0; --pass) {
+    if (tid < 256) hist[tid] = 0u;
+    __syncthreads();
+    const uint32_t prefix = s_prefix;
+    const int sh = 8 * pass;
+    for (int i = tid; i < n; i += kTopkThreads) {
+      const uint32_t key = skey[i];
+      if (key == 0u) continue;
+      const bool match = (pass == 3) || ((key >> (sh + 8)) == (prefix >> (sh + 8)));
+      if (match) atomicAdd(&hist[(key >> sh) & 255u], 1u);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int need = s_need, cum = 0, b = 255;
+      for (; b > 0; --b) {
+        if (cum + static_cast<int>(hist[b]) >= need) break;
+        cum += hist[b];
+      }
+      s_prefix = prefix | (static_cast<uint32_t>(b) << sh);
+      s_need = need - cum;
+      s_eq = hist[b];
+    }
+    __syncthreads();
+  }
+  const uint32_t T = s_prefix;
+  const int need = s_need;       // how many entries equal to T are taken (>= 1)
+  const int above = K - need;    // entries strictly above T
+  const bool ties_ordered = s_eq != need;
+  for (int i = tid; i < n; i += kTopkThreads) {
+    const uint32_t key = skey[i];
+    if (key > T || (!ties_ordered && key == T)) {
+      const int p = atomicAdd(&s_pos, 1);
+      sbuf[p] = (static_cast<unsigned long long>(key) << 32) | (0xFFFFFFFFu - static_cast<uint32_t>(i));
+    }
+  }
+  if (ties_ordered) {
+    // more entries equal to T than slots: lowest indices win
+    for (int base = 0; base < n; base += kTopkThreads) {
+      const int i = base + tid;
+      const bool flag = i < n && skey[i] == T;
+      const unsigned bal = __ballot_sync(0xffffffffu, flag);
+      if ((tid & 31) == 0) s_warp[tid >> 5] = __popc(bal);
+      __syncthreads();
+      int off = s_run;
+      for (int w = 0; w < (tid >> 5); ++w) off += s_warp[w];
+      off += __popc(bal & ((1u << (tid & 31)) - 1u));
+      if (flag && off < need)
+        sbuf[above + off] = (static_cast<unsigned long long>(T) << 32) |
+                            (0xFFFFFFFFu - static_cast<uint32_t>(i));
+      __syncthreads();
+      if (tid == 0) {
+        int tot = 0;
+        for (int w = 0; w < kTopkThreads / 32; ++w) tot += s_warp[w];
+        s_run += tot;
+      }
+      __syncthreads();
+      if (s_run >= need) break;
+    }
+  }
+  for (int i = K + tid; i < np2; i += kTopkThreads) sbuf[i] = 0ull;
+  __syncthreads();
+  // ---- bitonic sort, descending, on packed (key, ~index)
+  for (int kk = 2; kk <= np2; kk <<= 1) {
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      for (int t = tid; t < (np2 >> 1); t += kTopkThreads) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int l = i | j;
+        const unsigned long long a = sbuf[i], b = sbuf[l];
+        const bool up = (i & kk) == 0;
+        if (up ? (b > a) : (a > b)) {
+          sbuf[i] = b;
+          sbuf[l] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  int* po = order + static_cast<long long>(prob) * order_stride;
+  for (int i = tid; i < K; i += kTopkThreads)
+    po[i] = static_cast<int>(0xFFFFFFFFu - static_cast<uint32_t>(sbuf[i] & 0xFFFFFFFFull));
+  if (tid == 0) n_out[prob] = K;
 }
 
 // Rank sort, descending, ties by ascending index.  order[prob][rank] = index for valid items;
@@ -303,7 +449,7 @@ extern "C" int mnc_rank_sort_desc(const float* keys, long long outer_stride,
     int np2 = 1;
     while (np2 < n) np2 <<= 1;
     const int smem = np2 * 6;
-    static int attr_smem = 48 * 1024;
+    static int attr_smem = 40 * 1024;   // opt in early: static shared memory counts against 48 KB
     if (smem > attr_smem) {
       if (cudaFuncSetAttribute(bitonic_sort_desc_kernel,
                                cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
@@ -317,6 +463,29 @@ extern "C" int mnc_rank_sort_desc(const float* keys, long long outer_stride,
   dim3 grid((n + 255) / 256, problems);
   rank_sort_desc_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream_)>>>(
       keys, outer_stride, inner_stride, inner, key_stride, valid, n, order, n_valid);
+  return check_launch();
+}
+
+extern "C" int mnc_topk_sort_desc(const float* keys, long long outer_stride, long long inner_stride,
+                                  int inner, int key_stride, const unsigned char* valid, int n,
+                                  int problems, int k, int* order, int order_stride, int* n_out,
+                                  void* stream_) {
+  if (n <= 0 || problems <= 0 || inner <= 0 || k <= 0 || order_stride < (k < n ? k : n))
+    return MNC_ERR_ARG;
+  int np2 = 2;
+  while (np2 < (k < n ? k : n)) np2 <<= 1;
+  const size_t smem = static_cast<size_t>(np2) * 8 + static_cast<size_t>(n) * 4;
+  if (smem > 200 * 1024) return MNC_ERR_ARG;   // callers fall back to mnc_rank_sort_desc
+  static int attr_smem = 40 * 1024;     // opt in early: static shared memory counts against 48 KB
+  if (static_cast<int>(smem) > attr_smem) {
+    if (cudaFuncSetAttribute(topk_sort_desc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(smem)) != cudaSuccess)
+      return MNC_ERR_CUDA;
+    attr_smem = static_cast<int>(smem);
+  }
+  topk_sort_desc_kernel<<<problems, kTopkThreads, smem, static_cast<cudaStream_t>(stream_)>>>(
+      keys, outer_stride, inner_stride, inner, key_stride, valid, n, k, np2, order, order_stride,
+      n_out);
   return check_launch();
 }
 

@@ -30,6 +30,21 @@ def rank_sort_desc(keys, n, problems, outer_stride, inner_stride=0, inner=1, key
     return order, n_valid
 
 
+def topk_sort_desc(keys, n, problems, k, outer_stride, inner_stride=0, inner=1, key_stride=1,
+                   valid=None):
+    """The k best entries in (key desc, index asc) order.
+    -> (order int32 [problems, min(k, n)], n_out int32 [problems])."""
+    dev = keys.device
+    kk = min(k, n)
+    order = _i32(problems, kk, device=dev)
+    n_out = _i32(problems, device=dev)
+    check(lib.mnc_topk_sort_desc(ptr(keys), c_ll(outer_stride), c_ll(inner_stride), c_int(inner),
+                                 c_int(key_stride), ptr(valid), c_int(n), c_int(problems), c_int(kk),
+                                 ptr(order), c_int(kk), ptr(n_out), cur_stream()),
+          "mnc_topk_sort_desc")
+    return order, n_out
+
+
 def gather_boxes(src, src_stride, src_outer_stride, inner, order, counts, n_out, problems):
     """-> (sorted boxes fp32 [problems, n_out, 4], counts int32 [problems])."""
     dev = src.device
@@ -119,8 +134,11 @@ def proposals_from_rpn(cls, bbox, im_info, batch, H, W, layout, apply_softmax, p
     proposals, scores, valid = rpn_decode(cls, bbox, im_info, batch, H, W, layout, apply_softmax,
                                           min_size=min_size)
     total = H * W * 9
-    order, n_valid = rank_sort_desc(scores, total, batch, outer_stride=total, valid=valid)
     n_sorted = min(pre_nms_top_n, total) if pre_nms_top_n > 0 else total
+    if 8 * (1 << max(n_sorted - 1, 1).bit_length()) + 4 * total <= 200 * 1024:
+        order, n_valid = topk_sort_desc(scores, total, batch, n_sorted, outer_stride=total, valid=valid)
+    else:   # beyond the select kernel's shared-memory budget: sort everything
+        order, n_valid = rank_sort_desc(scores, total, batch, outer_stride=total, valid=valid)
     sorted_boxes, counts = gather_boxes(proposals, 4, total * 4, 1, order, n_valid, n_sorted, batch)
     keep, num = nms_sorted(sorted_boxes, counts, nms_thresh, post_nms_top_n)
     rois, roi_counts = write_rois(sorted_boxes, keep, num, post_nms_top_n, batch_index_mode)

@@ -97,3 +97,33 @@ def test_rank_sort_matches_tie_rule():
         want = idx[O.order_desc(s[p, idx])]
         assert nv[p] == len(idx)
         assert np.array_equal(order[p, :nv[p]], want)
+
+
+@pytest.mark.parametrize("n,k,tie_levels", [(21546, 6000, 0), (21546, 6000, 300), (5000, 6000, 50),
+                                            (9000, 100, 7), (3000, 1, 0), (12000, 8192, 2)])
+def test_topk_sort_is_prefix_of_full_order(n, k, tie_levels):
+    """mnc_topk_sort_desc == first k entries of the (score desc, index asc) order, including when
+    the k-th score is shared by more entries than there are slots (lowest indices win)."""
+    import torch
+    from mnc_b200 import ops
+    from oracle import oracle as O
+    rng = np.random.default_rng(n + k)
+    P = 3
+    if tie_levels:
+        s = rng.integers(0, tie_levels, size=(P, n)).astype(np.float32) / tie_levels
+    else:
+        s = rng.uniform(-1, 1, size=(P, n)).astype(np.float32)
+    valid = (rng.uniform(size=(P, n)) > 0.15).astype(np.uint8)
+    valid[2, :] = 0
+    valid[2, 17:40] = 1                       # fewer valid entries than k
+    order, cnt = ops.topk_sort_desc(torch.from_numpy(s).cuda(), n, P, k, outer_stride=n,
+                                    valid=torch.from_numpy(valid).cuda())
+    order, cnt = order.cpu().numpy(), cnt.cpu().numpy()
+    for p in range(P):
+        idx = np.where(valid[p])[0]
+        want = idx[O.order_desc(s[p, idx])][:k]
+        assert cnt[p] == len(want)
+        assert np.array_equal(order[p, :cnt[p]], want)
+    # no `valid` array: everything takes part
+    order, cnt = ops.topk_sort_desc(torch.from_numpy(s).cuda(), n, P, k, outer_stride=n)
+    assert np.array_equal(order[0].cpu().numpy()[:min(k, n)], O.order_desc(s[0])[:k])
