@@ -149,6 +149,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--dump-igemm", default=None,
+                    help="write the ordered list of tensor-core launches of the timed region "
+                         "(shape, algorithmic FLOPs / bytes) as JSON, for scripts/ncu_tc_summary.py")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -223,6 +226,9 @@ def main():
     t_wall = time.perf_counter() - t_wall0
     launches = _lib.launch_count - launches0
     ktimer, dense.timer = dense.timer, None
+    if args.dump_igemm and rank == 0:
+        with open(args.dump_igemm, "w") as f:
+            json.dump({"steps": args.steps, "launches": ktimer.manifest}, f)
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     clocks = sampler.finish() if rank == 0 else None
     tms = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
@@ -281,18 +287,25 @@ def main():
 
     # ------------------------------------------------------------- roofline of the dominant kernel
     k_ms, k_flops, k_n = ktimer.totals()
+    # per launch site (order of launch within a step): mean ms over the timed steps
+    per_step = k_n // args.steps if args.steps else 0
+    site_ms = [0.0] * per_step
+    for i, (e0, e1, _, _) in enumerate(ktimer.records):
+        site_ms[i % per_step] += e0.elapsed_time(e1) / args.steps
+    site_tags = [ktimer.records[i][3] for i in range(per_step)]
     peaks, peak_src = _peaks()
     peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
     ach = k_flops / (k_ms / 1000.0) / 1e12 if k_ms > 0 else 0.0
     traffic, traffic_note = None, None
-    summ = os.path.join(ROOT, "profiles", "r01_ncu_igemm_summary.json")
+    summ = os.path.join(ROOT, "profiles", "r01_ncu_tc_summary.json")
     if os.path.exists(summ):
         with open(summ) as f:
             sj = json.load(f)
         traffic = sj["mean_traffic_bytes_per_launch"]
-        traffic_note = ("dram__bytes_read.sum + dram__bytes_write.sum, mean over the 6 conv launches "
-                        "of the committed ncu --set full capture (profiles/r01_ncu_igemm_summary.json); "
-                        "algorithmic bytes of the same launches: %.3e" % sj["mean_algorithmic_bytes_per_launch"])
+        traffic_note = ("dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the %d "
+                        "tensor-core launches of one step in the committed ncu --set full capture "
+                        "(profiles/r01_ncu_tc_summary.json); algorithmic bytes of the same launches: "
+                        "%.3e per launch" % (sj["n_launches"], sj["mean_algorithmic_bytes_per_launch"]))
     roofline = {
         "kernel": "igemm_tc_kernel (tcgen05 implicit GEMM: 13 conv3x3 + 11 inner-product launch "
                   "sites per step)",
@@ -300,6 +313,7 @@ def main():
         "frac": ach / peak_tf, "traffic": traffic, "traffic_note": traffic_note,
         "peak_source": peak_src + ", bf16 dense sustained (kernel timed inside a long step)",
         "launches_timed": k_n, "share_of_step": k_ms / total_ms,
+        "ms_by_launch_site": [[t, round(m, 4)] for t, m in zip(site_tags, site_ms)],
         "algorithmic_flops_per_step": k_flops / args.steps,
         "tensor_work_factor": 3,
         "frac_tensor_pipe": 3 * ach / peak_tf,

@@ -184,6 +184,11 @@ int mnc_mask_pool_nchw(const float* feat, const float* mask, int N, int C, int H
 int mnc_roi_warp_split(const float* feat_nhwc /* fp32 [B][H][W][C] */, int C, int H, int W,
                        const float* rois, int R, int sub, float spatial_scale, void* o14_hi,
                        void* o14_lo, void* o7_hi, void* o7_lo, void* stream);
+/* Kernel choice for mnc_roi_warp_split: 0 (default) = one gather of 4 taps per sample, 1 =
+ * column-walking kernel (separable bilinear, taps cached in registers; 2.4x fewer loads but
+ * measured 1.2-1.5x slower: serial dependence per thread, scripts/gpu_roi_warp_ab.py).  Returns the previous setting.
+ * For A/B measurement (scripts/microbench.py). */
+int mnc_roi_warp_set_walk(int on);
 int mnc_sigmoid_mask_resize(const float* logits, int stride, int R, int mask_size, int out_size,
                             float* mask_proposal, float* mask_resized, void* stream);
 int mnc_mask_pool_split(const void* f_hi, const void* f_lo, const float* mask14, int R, int C,

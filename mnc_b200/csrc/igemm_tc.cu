@@ -360,7 +360,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    {  // whole warp, warp-uniform arguments; one lane is elected inside each issue (ptx.cuh)
       int stage = 0;
       uint32_t phase = 0;
       for (int t = first; t < total_tiles; t += stride) {
@@ -368,7 +368,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         for (int k = tl.kb; k < tl.ke; ++k) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + stage * Cfg::kStageBytes;
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          ptx::mbar_arrive_expect_tx_w(&full_bar[stage], Cfg::kStageBytes);
           const int tap = k / kchunks;
           const int kc = k - tap * kchunks;
           int dy = 0, dx = 0;
@@ -376,22 +376,22 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
             dy = tap / 3 - 1;
             dx = tap % 3 - 1;
           }
-          ptx::tma_load_4d(st, &tm_a_hi, &full_bar[stage], kc * kBlockK, tl.w0 + dx, tl.h0 + dy,
+          ptx::tma_load_4d_w(st, &tm_a_hi, &full_bar[stage], kc * kBlockK, tl.w0 + dx, tl.h0 + dy,
                            tl.img);
-          ptx::tma_load_4d(st + kABytes, &tm_a_lo, &full_bar[stage], kc * kBlockK, tl.w0 + dx,
+          ptx::tma_load_4d_w(st + kABytes, &tm_a_lo, &full_bar[stage], kc * kBlockK, tl.w0 + dx,
                            tl.h0 + dy, tl.img);
           if (CL == 1) {
-            ptx::tma_load_2d(st + 2 * kABytes, &tm_b_hi, &full_bar[stage],
+            ptx::tma_load_2d_w(st + 2 * kABytes, &tm_b_hi, &full_bar[stage],
                              tap * p.Cin + kc * kBlockK, tl.n0);
-            ptx::tma_load_2d(st + 2 * kABytes + Cfg::kBBytes, &tm_b_lo, &full_bar[stage],
+            ptx::tma_load_2d_w(st + 2 * kABytes + Cfg::kBBytes, &tm_b_lo, &full_bar[stage],
                              tap * p.Cin + kc * kBlockK, tl.n0);
           } else {
             // each CTA fetches 1/CL of the weight tile and multicasts it to the whole cluster
             constexpr int kSlice = Cfg::kBBytes / CL;
             const int nrow = tl.n0 + rank * (BN / CL);
-            ptx::tma_load_2d_mcast(st + 2 * kABytes + rank * kSlice, &tm_b_hi, &full_bar[stage],
+            ptx::tma_load_2d_mcast_w(st + 2 * kABytes + rank * kSlice, &tm_b_hi, &full_bar[stage],
                                    tap * p.Cin + kc * kBlockK, nrow, kMask);
-            ptx::tma_load_2d_mcast(st + 2 * kABytes + Cfg::kBBytes + rank * kSlice, &tm_b_lo,
+            ptx::tma_load_2d_mcast_w(st + 2 * kABytes + Cfg::kBBytes + rank * kSlice, &tm_b_lo,
                                    &full_bar[stage], tap * p.Cin + kc * kBlockK, nrow, kMask);
           }
           if (++stage == kStages) {
@@ -403,7 +403,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
+    {  // whole warp, warp-uniform arguments; one lane is elected inside each issue (ptx.cuh)
       constexpr uint32_t idesc = ptx::umma_idesc_bf16_m128(BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -430,20 +430,20 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
             const uint64_t db_hi = (BK == 64) ? ptx::umma_desc_sw128(b_hi + kk * 32) : ptx::umma_desc_sw64(b_hi + kk * 32);
             const uint64_t db_lo = (BK == 64) ? ptx::umma_desc_sw128(b_lo + kk * 32) : ptx::umma_desc_sw64(b_lo + kk * 32);
             // small cross terms first, then the dominant product
-            ptx::umma_bf16_ss(tmem_d, da_lo, db_hi, idesc, (k > kb || kk > 0) ? 1u : 0u);
-            ptx::umma_bf16_ss(tmem_d, da_hi, db_lo, idesc, 1u);
-            ptx::umma_bf16_ss(tmem_d, da_hi, db_hi, idesc, 1u);
+            ptx::umma_bf16_ss_w(tmem_d, da_lo, db_hi, idesc, (k > kb || kk > 0) ? 1u : 0u);
+            ptx::umma_bf16_ss_w(tmem_d, da_hi, db_lo, idesc, 1u);
+            ptx::umma_bf16_ss_w(tmem_d, da_hi, db_hi, idesc, 1u);
           }
           if (CL == 1)
-            ptx::umma_commit(&empty_bar[stage]);
+            ptx::umma_commit_w(&empty_bar[stage]);
           else
-            ptx::umma_commit_mcast(&empty_bar[stage], kMask);  // frees the stage in every CTA
+            ptx::umma_commit_mcast_w(&empty_bar[stage], kMask);  // frees the stage in every CTA
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        ptx::umma_commit(&tfull_bar[acc]);
+        ptx::umma_commit_w(&tfull_bar[acc]);
       }
     }
   } else if (warp >= 4) {
@@ -558,7 +558,7 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    {  // whole warp, warp-uniform arguments; one lane is elected inside each issue (ptx.cuh)
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       for (int t = first; t < total_tiles; t += stride) {
@@ -566,9 +566,9 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
         for (int kc = 0; kc < kchunks; ++kc) {
           ptx::mbar_wait(&a_empty[as], aph ^ 1);
           uint8_t* sa = a_ring + as * kHaloABytes;
-          ptx::mbar_arrive_expect_tx(&a_full[as], 2 * kHaloPlaneBytes);
-          ptx::tma_load_4d(sa, &tm_a_hi, &a_full[as], kc * 64, tl.w0 - 1, tl.h0 - 1, tl.img);
-          ptx::tma_load_4d(sa + kHaloPlanePad, &tm_a_lo, &a_full[as], kc * 64, tl.w0 - 1,
+          ptx::mbar_arrive_expect_tx_w(&a_full[as], 2 * kHaloPlaneBytes);
+          ptx::tma_load_4d_w(sa, &tm_a_hi, &a_full[as], kc * 64, tl.w0 - 1, tl.h0 - 1, tl.img);
+          ptx::tma_load_4d_w(sa + kHaloPlanePad, &tm_a_lo, &a_full[as], kc * 64, tl.w0 - 1,
                            tl.h0 - 1, tl.img);
           if (++as == kHaloNA) {
             as = 0;
@@ -577,9 +577,9 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
           for (int tap = 0; tap < 9; ++tap) {
             ptx::mbar_wait(&b_empty[bs], bph ^ 1);
             uint8_t* sb = b_ring + bs * Cfg::kBStage;
-            ptx::mbar_arrive_expect_tx(&b_full[bs], Cfg::kBStage);
-            ptx::tma_load_2d(sb, &tm_b_hi, &b_full[bs], tap * p.Cin + kc * 64, tl.n0);
-            ptx::tma_load_2d(sb + Cfg::kBBytes, &tm_b_lo, &b_full[bs], tap * p.Cin + kc * 64,
+            ptx::mbar_arrive_expect_tx_w(&b_full[bs], Cfg::kBStage);
+            ptx::tma_load_2d_w(sb, &tm_b_hi, &b_full[bs], tap * p.Cin + kc * 64, tl.n0);
+            ptx::tma_load_2d_w(sb + Cfg::kBBytes, &tm_b_lo, &b_full[bs], tap * p.Cin + kc * 64,
                              tl.n0);
             if (++bs == NB) {
               bs = 0;
@@ -591,7 +591,7 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
+    {  // whole warp, warp-uniform arguments; one lane is elected inside each issue (ptx.cuh)
       // The per-instruction overhead of tcgen05.mma (~40 cycles) matters at these small N, so
       // the three split-precision products are issued as two instructions: the hi and lo weight
       // planes sit back to back in the stage, so A_hi x [B_hi | B_lo] is ONE N = 2*BN MMA into
@@ -617,29 +617,31 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
             ptx::mbar_wait(&b_full[bs], bph);
             ptx::tc_fence_after();
             const uint32_t woff = ((tap / 3) * (TW + 2) + (tap % 3)) * 128;  // shifted window
-            const uint32_t b_hi = ptx::smem_u32(b_ring + bs * Cfg::kBStage);  // [hi rows | lo rows]
+            // descriptor low words (start address >> 4); + 2 per 16-element k slice
+            const uint32_t la_hi = ptx::desc_lo(a_hi0 + woff);
+            const uint32_t la_lo = ptx::desc_lo(a_lo0 + woff);
+            const uint32_t lb = ptx::desc_lo(ptx::smem_u32(b_ring + bs * Cfg::kBStage));  // [hi | lo]
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
-              const uint64_t da_hi = umma_desc_sw128_sbo(a_hi0 + woff + kk * 32, kSbo);
-              const uint64_t da_lo = umma_desc_sw128_sbo(a_lo0 + woff + kk * 32, kSbo);
-              const uint64_t db = ptx::umma_desc_sw128(b_hi + kk * 32);
               const uint32_t accum = (kc > 0 || tap > 0 || kk > 0) ? 1u : 0u;
-              ptx::umma_bf16_ss(tmem_d, da_hi, db, idesc1, accum);
-              ptx::umma_bf16_ss(tmem_d, da_lo, db, idesc2, 1u);
+              ptx::umma_bf16_ss_w32<ptx::desc_hi_sw128_sbo(kSbo), ptx::kDescHiSw128>(
+                  tmem_d, la_hi + 2 * kk, lb + 2 * kk, idesc1, accum);
+              ptx::umma_bf16_ss_w32<ptx::desc_hi_sw128_sbo(kSbo), ptx::kDescHiSw128>(
+                  tmem_d, la_lo + 2 * kk, lb + 2 * kk, idesc2, 1u);
             }
-            ptx::umma_commit(&b_empty[bs]);
+            ptx::umma_commit_w(&b_empty[bs]);
             if (++bs == NB) {
               bs = 0;
               bph ^= 1;
             }
           }
-          ptx::umma_commit(&a_empty[as]);
+          ptx::umma_commit_w(&a_empty[as]);
           if (++as == kHaloNA) {
             as = 0;
             aph ^= 1;
           }
         }
-        ptx::umma_commit(&tfull_bar[acc]);
+        ptx::umma_commit_w(&tfull_bar[acc]);
       }
     }
   } else if (warp >= 4) {

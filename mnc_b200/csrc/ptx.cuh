@@ -172,6 +172,109 @@ __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// ------------------------------------------------------------------ warp-convergent issue
+// tcgen05.mma / tcgen05.commit / cp.async.bulk.tensor take their operands from UNIFORM registers.
+// When the issuing code sits inside `if (lane == 0) { ... }` the compiler treats every value in
+// that region as per-thread and wraps each instruction in an ELECT + 5x R2UR + branch "waterfall"
+// (~40 issue cycles per MMA, measured as the per-instruction overhead of the small-N layers).
+// The `_w` forms below are meant to be executed by ALL 32 lanes of a converged warp with
+// warp-uniform arguments: the election happens inside the asm block, so the operands are computed
+// on the uniform datapath and reach the instruction directly.  elect.sync with a full mask always
+// elects the same lane, so the MMAs and the commits that track them come from one thread.
+__device__ __forceinline__ void umma_bf16_ss_w(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_w(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(
+          smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mcast_w(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+      ::"r"(smem_u32(bar)), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_w(uint64_t* bar, uint32_t bytes) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+      "r"(bytes)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_w(void* smem_dst, const void* tmap, uint64_t* bar,
+                                              int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];\n\t}"
+      ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_w(void* smem_dst, const void* tmap, uint64_t* bar,
+                                              int c0, int c1) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];\n\t}"
+      ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mcast_w(void* smem_dst, const void* tmap, uint64_t* bar,
+                                                    int c0, int c1, uint16_t cta_mask) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      ".multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;\n\t}"
+      ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+
+// Same, with the descriptors passed as their 32-bit low words (14-bit start address field; the
+// caller adds 2 per 32 bytes) and the high words -- stride-byte-offset, version, swizzle mode:
+// compile-time constants -- as template arguments, so only two 32-bit values travel to the
+// uniform registers per instruction.
+template <uint32_t kHiA, uint32_t kHiB>
+__device__ __forceinline__ void umma_bf16_ss_w32(uint32_t tmem_d, uint32_t desc_a_lo,
+                                                 uint32_t desc_b_lo, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %6};\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+      ::"r"(tmem_d),
+      "r"(desc_a_lo), "r"(desc_b_lo), "r"(idesc), "r"(accumulate), "n"(kHiA), "n"(kHiB)
+      : "memory");
+}
+// high words of the two descriptor flavours
+constexpr uint32_t kDescHiSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+constexpr uint32_t kDescHiSw64 = (512u >> 4) | (1u << 14) | (4u << 29);
+constexpr uint32_t desc_hi_sw128_sbo(uint32_t sbo_bytes) { return (sbo_bytes >> 4) | (1u << 14) | (2u << 29); }
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr) { return (smem_addr & 0x3FFFFu) >> 4; }
+
 // K-major, 128-byte-swizzled operand tile (rows of 64 bf16 = 128 B, 8-row atoms of
 // 1024 B).  Field layout follows the sm_100 shared-memory matrix descriptor:
 // [0,14) addr>>4, [16,30) LBO>>4 (unused for swizzled K-major), [32,46) SBO>>4,

@@ -299,8 +299,10 @@ __device__ __forceinline__ void st_split4(__nv_bfloat16* hi, __nv_bfloat16* lo, 
   const __nv_bfloat16 l1 = __float2bfloat16_rn(v.y - __bfloat162float(h1));
   const __nv_bfloat16 l2 = __float2bfloat16_rn(v.z - __bfloat162float(h2));
   const __nv_bfloat16 l3 = __float2bfloat16_rn(v.w - __bfloat162float(h3));
-  *reinterpret_cast<uint2*>(hi + off) = make_uint2(pack_bf2(h0, h1), pack_bf2(h2, h3));
-  *reinterpret_cast<uint2*>(lo + off) = make_uint2(pack_bf2(l0, l1), pack_bf2(l2, l3));
+  // streaming stores: the RoI feature tensors (~1.2 GB per stage) are consumed once by the next
+  // GEMM and must not evict conv5_3 (39 MB, re-read by every RoI) from L2
+  __stcs(reinterpret_cast<uint2*>(hi + off), make_uint2(pack_bf2(h0, h1), pack_bf2(h2, h3)));
+  __stcs(reinterpret_cast<uint2*>(lo + off), make_uint2(pack_bf2(l0, l1), pack_bf2(l2, l3)));
 }
 // fused-path bilinear: same weights-first formula, evaluated with FMAs (the fused outputs are
 // re-quantised to split-bf16 and compared at tolerance; the bit-exact form lives in bilerp()).
@@ -395,6 +397,111 @@ roi_warp_split_kernel(const float* __restrict__ feat, int C, int H, int W,
   }
 }
 
+
+// Same outputs, fewer loads.  The sample grid of a RoI is regular, so bilinear sampling separates:
+// for a sample row s (row taps y_lo, y_hi fixed) the column function
+//     C_s(x) = hy * F[y_lo][x] + ly * F[y_hi][x]
+// is all that sample row ever needs, and sample (s, pw) = hx * C_s(x_lo) + lx * C_s(x_hi).
+// A thread owns one channel quad and one pooled-7 row (2*SUB sample rows) and WALKS the sample
+// columns left to right, keeping C_s(x_lo), C_s(x_hi) of every sample row in registers; when the
+// taps move one feature column to the right the pair shifts and one new column is fetched (two
+// 16-byte loads per sample row).  A RoI that is Wr feature columns wide costs ~2*(Wr+1) loads per
+// sample row instead of 4 per sample (4 * 14 * SUB): 3-4x fewer L1 transactions for typical
+// proposals, and never more.  Control flow depends only on the RoI, so warps never diverge.
+// (Rounding differs from the weights-first form by an ulp; the fused path is tolerance-checked,
+// the bit-exact layer kernel is roi_warp_nchw_kernel.)
+__device__ __forceinline__ float4 col_lerp(const float* __restrict__ plo, const float* __restrict__ phi,
+                                           int xoff, float hy, float ly) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(plo + xoff));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(phi + xoff));
+  return make_float4(fmaf(ly, b.x, hy * a.x), fmaf(ly, b.y, hy * a.y), fmaf(ly, b.z, hy * a.z),
+                     fmaf(ly, b.w, hy * a.w));
+}
+
+template <int SUB>
+__global__ void __launch_bounds__(256)
+roi_warp_walk_kernel(const float* __restrict__ feat, int C, int H, int W,
+                     const float* __restrict__ rois, float spatial_scale,
+                     __nv_bfloat16* __restrict__ o14_hi, __nv_bfloat16* __restrict__ o14_lo,
+                     __nv_bfloat16* __restrict__ o7_hi, __nv_bfloat16* __restrict__ o7_lo) {
+  constexpr int P = 14 * SUB;
+  constexpr int NR = 2 * SUB;  // sample rows feeding one row of the 7x7 grid
+  __shared__ AxisTap colt[P];
+  __shared__ AxisTap rowt[2 * NR];
+  const int r = blockIdx.x;
+  const RoiGeom g = roi_geom(rois + static_cast<long long>(r) * 5, spatial_scale, P, P);
+  if (threadIdx.x < P) {
+    colt[threadIdx.x] =
+        axis_tap(__fadd_rn(g.start_w, __fmul_rn(static_cast<float>(threadIdx.x), g.bin_w)), W);
+  } else if (threadIdx.x < P + 2 * NR) {
+    const int i = threadIdx.x - P;
+    const int ph = blockIdx.y * 2 * NR + i;   // rows of pooled-7 rows 2*blockIdx.y, 2*blockIdx.y+1
+    rowt[i] = axis_tap(__fadd_rn(g.start_h, __fmul_rn(static_cast<float>(ph), g.bin_h)), H);
+  }
+  __syncthreads();
+  const int half = threadIdx.x >> 7;
+  const int t = 2 * blockIdx.y + half;
+  if (t >= 7) return;
+  const float* fimg = feat + static_cast<long long>(g.level) * H * W * C;
+  const float kNeg = -3.402823466e+38f;
+  for (int c = (threadIdx.x & 127) * 4; c < C; c += 512) {
+    const float* plo[NR];
+    const float* phi[NR];
+    float hy[NR], ly[NR];
+    bool rok[NR];
+#pragma unroll
+    for (int s = 0; s < NR; ++s) {
+      const AxisTap th = rowt[half * NR + s];
+      plo[s] = fimg + static_cast<long long>(th.lo) * W * C + c;
+      phi[s] = fimg + static_cast<long long>(th.hi) * W * C + c;
+      hy[s] = th.h;
+      ly[s] = th.l;
+      rok[s] = th.ok != 0;
+    }
+    float4 Clo[NR], Chi[NR];
+#pragma unroll
+    for (int s = 0; s < NR; ++s) Clo[s] = Chi[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int cx_lo = -1, cx_hi = -1;
+    float4 best7 = make_float4(kNeg, kNeg, kNeg, kNeg);
+    for (int j = 0; j < 14; ++j) {
+      float4 cell[2];
+      cell[0] = cell[1] = make_float4(kNeg, kNeg, kNeg, kNeg);
+#pragma unroll
+      for (int sx = 0; sx < SUB; ++sx) {
+        const AxisTap tw = colt[j * SUB + sx];
+        if (tw.ok && (tw.lo != cx_lo || tw.hi != cx_hi)) {
+          const bool shift = tw.lo == cx_hi;
+          const bool keep_lo = tw.lo == cx_lo;
+#pragma unroll
+          for (int s = 0; s < NR; ++s) {
+            if (!rok[s]) continue;
+            if (shift) Clo[s] = Chi[s];
+            else if (!keep_lo) Clo[s] = col_lerp(plo[s], phi[s], tw.lo * C, hy[s], ly[s]);
+            if (tw.hi == tw.lo) Chi[s] = Clo[s];
+            else Chi[s] = col_lerp(plo[s], phi[s], tw.hi * C, hy[s], ly[s]);
+          }
+          cx_lo = tw.lo;
+          cx_hi = tw.hi;
+        }
+#pragma unroll
+        for (int s = 0; s < NR; ++s) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);   // out-of-range sample: 0 (and it pools)
+          if (tw.ok && rok[s])
+            v = make_float4(fmaf(tw.l, Chi[s].x, tw.h * Clo[s].x), fmaf(tw.l, Chi[s].y, tw.h * Clo[s].y),
+                            fmaf(tw.l, Chi[s].z, tw.h * Clo[s].z), fmaf(tw.l, Chi[s].w, tw.h * Clo[s].w));
+          cell[s / SUB] = max4(cell[s / SUB], v);
+        }
+      }
+      st_split4(o14_hi, o14_lo, ((static_cast<long long>(r) * 14 + 2 * t) * 14 + j) * C + c, cell[0]);
+      st_split4(o14_hi, o14_lo, ((static_cast<long long>(r) * 14 + 2 * t + 1) * 14 + j) * C + c, cell[1]);
+      best7 = max4(best7, max4(cell[0], cell[1]));
+      if (j & 1) {
+        st_split4(o7_hi, o7_lo, ((static_cast<long long>(r) * 7 + t) * 7 + (j >> 1)) * C + c, best7);
+        best7 = make_float4(kNeg, kNeg, kNeg, kNeg);
+      }
+    }
+  }
+}
 
 // ------------------------------------------------------------------------------------------------
 // Sibling test graphs.
@@ -648,14 +755,35 @@ extern "C" int mnc_mask_pool_nchw(const float* feat, const float* mask, int N, i
   return check_launch();
 }
 
+static int g_roi_walk = 0;  // measured slower on real proposals (profiles/README.md): latency-bound
+extern "C" int mnc_roi_warp_set_walk(int on) {
+  const int prev = g_roi_walk;
+  g_roi_walk = on ? 1 : 0;
+  return prev;
+}
+
 extern "C" int mnc_roi_warp_split(const float* feat_nhwc, int C, int H, int W, const float* rois,
                                   int R, int sub, float spatial_scale, void* o14_hi, void* o14_lo,
                                   void* o7_hi, void* o7_lo, void* stream) {
   if (R <= 0) return MNC_OK;
   if (C % 4 != 0 || (sub != 1 && sub != 2) || (reinterpret_cast<uintptr_t>(feat_nhwc) & 15))
     return MNC_ERR_ARG;
-  dim3 grid(R, 7);
   auto s = static_cast<cudaStream_t>(stream);
+  if (g_roi_walk) {
+    dim3 wgrid(R, 4);
+    if (sub == 2)
+      roi_warp_walk_kernel<2><<<wgrid, 256, 0, s>>>(
+          feat_nhwc, C, H, W, rois, spatial_scale, static_cast<__nv_bfloat16*>(o14_hi),
+          static_cast<__nv_bfloat16*>(o14_lo), static_cast<__nv_bfloat16*>(o7_hi),
+          static_cast<__nv_bfloat16*>(o7_lo));
+    else
+      roi_warp_walk_kernel<1><<<wgrid, 256, 0, s>>>(
+          feat_nhwc, C, H, W, rois, spatial_scale, static_cast<__nv_bfloat16*>(o14_hi),
+          static_cast<__nv_bfloat16*>(o14_lo), static_cast<__nv_bfloat16*>(o7_hi),
+          static_cast<__nv_bfloat16*>(o7_lo));
+    return check_launch();
+  }
+  dim3 grid(R, 7);
   if (sub == 2)
     roi_warp_split_kernel<2><<<grid, 256, 0, s>>>(
         feat_nhwc, C, H, W, rois, spatial_scale, static_cast<__nv_bfloat16*>(o14_hi),

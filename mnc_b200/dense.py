@@ -54,6 +54,7 @@ class KernelTimer:
 
     def __init__(self):
         self.records = []   # (start_event, end_event, flops, tag)
+        self.manifest = []  # one dict per launch: shape, algorithmic FLOPs and bytes
 
     def totals(self):
         ms = sum(s.elapsed_time(e) for s, e, _, _ in self.records)
@@ -90,6 +91,15 @@ def igemm(a, batch, H, W, cin, w, cout, taps, bias=None, relu=False, out=None, o
             ev1.record()
             timer.records.append((ev0, ev1, 2.0 * batch * H * W * cout * taps * cin,
                                   "%dx%dx%d" % (batch * H * W, cout, taps * cin)))
+            # algorithmic bytes: activations in once (split bf16 = 4 B/elt), weights in once,
+            # result out once (split bf16 or fp32 = 4 B/elt; pooled outputs are a quarter;
+            # split-K partials are counted as written, their reduce is a separate kernel)
+            m_out = batch * ((H + 1) // 2) * ((W + 1) // 2) if pool else batch * H * W
+            timer.manifest.append(dict(
+                M=batch * H * W, N=cout, K=taps * cin, taps=taps, bn=bn, split_k=split_k,
+                pooled=bool(pool), fp32_out=out_f32 is not None,
+                flops=2.0 * batch * H * W * cout * taps * cin,
+                bytes=4.0 * (batch * H * W * cin + cout * taps * cin + m_out * cout * max(split_k, 1))))
     else:
         assert split_k == 1
         rc = lib.mnc_igemm_simt(ptr(a[0]), ptr(a[1]), c_int(batch), c_int(H), c_int(W),

@@ -118,10 +118,17 @@ class MNCEngine:
         """Split-K only when the launch cannot fill the GPU (e.g. fc6_maskest: 19 row tiles,
         K = 100352).  A wave-quantisation-driven split (608 tiles -> 4.1 waves) was measured and
         rejected: the extra fp32 partial reduce costs what the shorter tail saves
-        (profiles/r01_notes.md)."""
+        (profiles/README.md).  When splitting, the factor minimises waves x k-steps-per-CTA:
+        19 tiles x 8 = 152 work items on 148 SMs ran as two waves (0.47 ms); x 7 = 133 is one."""
         if tiles >= self.sms * 0.7 or k_steps < 16:
             return 1
-        return max(1, min(math.ceil(self.sms / tiles), k_steps // 8, max_split))
+        best, best_cost = 1, None
+        for s in range(1, min(max_split, max(1, k_steps // 8)) + 1):
+            waves = math.ceil(tiles * s / self.sms)
+            cost = waves * math.ceil(k_steps / s) + 0.5 * s      # + partial-sum traffic per split
+            if best_cost is None or cost < best_cost:
+                best, best_cost = s, cost
+        return best
 
     def _conv(self, x, B, H, W, cin, wgt, cout, bias, out, key):
         """3x3 conv + bias + ReLU -> split NHWC, split-K when whole waves would idle."""
