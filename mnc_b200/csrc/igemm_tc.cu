@@ -68,7 +68,8 @@ struct IgemmCfg {
 };
 
 struct Tile {
-  int img, h0, w0, n0, kb, ke, ks;
+  int img, h0, w0, n0, ks;
+  int kb, kn, kstride;   // this work item's k-steps: kb, kb + kstride, ... (kn of them)
   bool dummy;
 };
 
@@ -99,8 +100,13 @@ __device__ __forceinline__ Tile decode_tile(const IgemmArgs& p, int t, int rank,
     tl.w0 = (r % p.tiles_w) * TW;
   }
   tl.n0 = nt * BN;
-  tl.kb = static_cast<int>(static_cast<long long>(p.k_steps) * tl.ks / p.split_k);
-  tl.ke = static_cast<int>(static_cast<long long>(p.k_steps) * (tl.ks + 1) / p.split_k);
+  // Split-K work items take INTERLEAVED k-steps (ks, ks + split, ks + 2*split, ...): the CTAs that
+  // share a row tile start together and advance in step, so at any moment they read adjacent
+  // 128-byte segments of the same activation rows -- DRAM sees ~split*128 contiguous bytes per row
+  // instead of isolated 128-byte touches 200 KB apart (fc6_maskest: K = 100352, 963 MB read once).
+  tl.kb = tl.ks;
+  tl.kstride = p.split_k;
+  tl.kn = (p.k_steps - tl.ks + p.split_k - 1) / p.split_k;
   return tl;
 }
 
@@ -365,7 +371,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
       uint32_t phase = 0;
       for (int t = first; t < total_tiles; t += stride) {
         const Tile tl = decode_tile<CL>(p, t, rank, TH, TW, BN);
-        for (int k = tl.kb; k < tl.ke; ++k) {
+        for (int i = 0, k = tl.kb; i < tl.kn; ++i, k += tl.kstride) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + stage * Cfg::kStageBytes;
           ptx::mbar_arrive_expect_tx_w(&full_bar[stage], Cfg::kStageBytes);
@@ -410,13 +416,13 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
       int local = 0;
       for (int t = first; t < total_tiles; t += stride, ++local) {
         const Tile tl = decode_tile<CL>(p, t, rank, TH, TW, BN);
-        const int kb = tl.kb, ke = tl.ke;
+        const int kn = tl.kn;
         const int acc = local & 1;
         const uint32_t acc_phase = (local >> 1) & 1;
         ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
-        for (int k = kb; k < ke; ++k) {
+        for (int i = 0; i < kn; ++i) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
           const uint32_t a_hi = ptx::smem_u32(smem + stage * Cfg::kStageBytes);
@@ -430,7 +436,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
             const uint64_t db_hi = (BK == 64) ? ptx::umma_desc_sw128(b_hi + kk * 32) : ptx::umma_desc_sw64(b_hi + kk * 32);
             const uint64_t db_lo = (BK == 64) ? ptx::umma_desc_sw128(b_lo + kk * 32) : ptx::umma_desc_sw64(b_lo + kk * 32);
             // small cross terms first, then the dominant product
-            ptx::umma_bf16_ss_w(tmem_d, da_lo, db_hi, idesc, (k > kb || kk > 0) ? 1u : 0u);
+            ptx::umma_bf16_ss_w(tmem_d, da_lo, db_hi, idesc, (i > 0 || kk > 0) ? 1u : 0u);
             ptx::umma_bf16_ss_w(tmem_d, da_hi, db_lo, idesc, 1u);
             ptx::umma_bf16_ss_w(tmem_d, da_hi, db_hi, idesc, 1u);
           }

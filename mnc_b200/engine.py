@@ -92,7 +92,7 @@ class MNCEngine:
         return t[:need].view(*shape)
 
     def _linear(self, a, M, K, wgt, N, bias, relu, out=None, out_f32=None, out_stride=None,
-                out_ch_offset=0, key="lin"):
+                out_ch_offset=0, key="lin", block_k=0):
         """y = act(a @ W^T + b) through the implicit-GEMM kernel; split-K when the tile count
         cannot fill the GPU (e.g. fc6_maskest: K = 100352, N = 256)."""
         # Cout tile: 192 (BLOCK_K 32, 5 stages) for the wide layers -- at M = 2400, N = 4096 it gives
@@ -110,7 +110,11 @@ class MNCEngine:
                         impl=self.impl)
             return
         part = self._f32_buf("splitk_" + key, split, M, N)
+        if block_k:
+            dense.set_block_k(block_k)
         dense.igemm(a4, 1, 1, M, K, wgt, N, 1, out_f32=part, split_k=split, split_stride=M * N, bn=bn)
+        if block_k:
+            dense.set_block_k(0)
         dense.splitk_reduce(part, split, M * N, M, N, bias=bias, relu=relu, out=out,
                             out_f32=out_f32, out_row_stride=out_stride, out_ch_offset=out_ch_offset)
 
@@ -186,8 +190,11 @@ class MNCEngine:
         """test.prototxt:509-785 on R RoIs.  feat14 split [2,R,14,14,C5], box7 split [2,R,7,7,C5]."""
         c5, fc, me = self.c5, self.fc, self.me
         h_me = self._split_buf("h_me", R, me)
+        # fc6_maskest streams its 963 MB activation matrix from HBM exactly once (a single Cout
+        # tile: no L2 reuse), so it wants loads in flight rather than big stages: BLOCK_K 32 gives a
+        # 4-deep ring at BN 256 (2-deep at 64 left every k-step waiting ~2 us for DRAM)
         self._linear(feat14, R, 196 * c5, self.fc6_maskest[0], me, self.fc6_maskest[1], True,
-                     out=h_me, key="me")
+                     out=h_me, key="me", block_k=32)
         logits = self._f32_buf("mask_logits_" + tag, R, 448)
         self._linear(h_me, R, me, self.mask_pred[0], 441, self.mask_pred[1], False,
                      out_f32=logits, out_stride=448, key="mp")
