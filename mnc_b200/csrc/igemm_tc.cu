@@ -853,8 +853,8 @@ extern "C" int mnc_igemm_tc(const void* a_hi, const void* a_lo, int batch, int H
   const int TH = conv ? (halo ? kHaloTH : 8) : 1, TW = conv ? (halo ? kHaloTW : 16) : 128;
   if (bn != 64 && bn != 128 && bn != 192 && bn != 256) return MNC_ERR_ARG;
   if (bk == 0) bk = 64;              // measured: BLOCK_K 64 wins at BN 256 (profiles/r01_igemm_bk32_bn192.log)
-  if (bn == 192) bk = 32;            // instantiated combinations: (64|128|256, 64), (192|256, 32)
-  if (bn < 192) bk = 64;
+  if (bn == 192) bk = 32;            // instantiated: (64|128|256, 64), (192|256, 32), FC only (128, 32)
+  if (bn < 128 || (bn == 128 && conv)) bk = 64;
 
   IgemmArgs a;
   a.batch = batch;
@@ -925,6 +925,7 @@ extern "C" int mnc_igemm_tc(const void* a_hi, const void* a_lo, int batch, int H
     MNC_LAUNCH(8, 16, 256, 64);
   } else {
     if (bn == 64) MNC_LAUNCH(1, 128, 64, 64);
+    if (bn == 128 && bk == 32) MNC_LAUNCH(1, 128, 128, 32);
     if (bn == 128) MNC_LAUNCH(1, 128, 128, 64);
     if (bn == 192) MNC_LAUNCH(1, 128, 192, 32);
     if (bk == 32) MNC_LAUNCH(1, 128, 256, 32);

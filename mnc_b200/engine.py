@@ -92,14 +92,14 @@ class MNCEngine:
         return t[:need].view(*shape)
 
     def _linear(self, a, M, K, wgt, N, bias, relu, out=None, out_f32=None, out_stride=None,
-                out_ch_offset=0, key="lin", block_k=0):
+                out_ch_offset=0, key="lin", block_k=0, bn=0):
         """y = act(a @ W^T + b) through the implicit-GEMM kernel; split-K when the tile count
         cannot fill the GPU (e.g. fc6_maskest: K = 100352, N = 256)."""
         # Cout tile: 192 (BLOCK_K 32, 5 stages) for the wide layers -- at M = 2400, N = 4096 it gives
         # 19 x 22 = 418 tiles = 2.8 waves of 148 CTAs, against 4.1 (-> 5) waves at 128 and 2.05
         # (-> 3, at twice the tile cost) at 256; measured 480 vs 404 vs 347 TF/s on the fc6 shape
         # (profiles/r01_igemm_bk32_bn192.log)
-        bn = 64 if N <= 64 else (128 if N <= 128 else (192 if N >= 1024 else 256))
+        bn = bn or (64 if N <= 64 else (128 if N <= 128 else (192 if N >= 1024 else 256)))
         tiles = math.ceil(M / 128) * math.ceil(N / bn)
         k_steps = K // 64
         split = self._pick_split(tiles, k_steps) if self.impl == "tc" else 1
@@ -192,7 +192,9 @@ class MNCEngine:
         h_me = self._split_buf("h_me", R, me)
         # fc6_maskest streams its 963 MB activation matrix from HBM exactly once (a single Cout
         # tile: no L2 reuse), so it wants loads in flight rather than big stages: BLOCK_K 32 gives a
-        # 4-deep ring at BN 256 (2-deep at 64 left every k-step waiting ~2 us for DRAM)
+        # 4-deep ring at BN 256 (2-deep at 64 left every k-step waiting ~2 us for DRAM).  A 6-deep
+        # ring (BN 128) is no faster: what remains (2.7 TB/s) is the DRAM efficiency of 128-byte
+        # row segments 200 KB apart, the price of K-major rows with K = 100352.
         self._linear(feat14, R, 196 * c5, self.fc6_maskest[0], me, self.fc6_maskest[1], True,
                      out=h_me, key="me", block_k=32)
         logits = self._f32_buf("mask_logits_" + tag, R, 448)
