@@ -86,6 +86,11 @@ int mnc_splitk_reduce(const float* partial, int splits, long long split_stride, 
  * (test.prototxt:19-43), written as split NHWC.  weight fp32 [Cout][3][3][3] (Caffe order). */
 int mnc_conv1_1(const float* data_nchw, int batch, int H, int W, const float* weight,
                 const float* bias, int Cout, void* out_hi, void* out_lo, void* stream);
+/* The same layer on the tensor cores (what the engine uses; the fp32 FMA form above stays as the
+ * cross-check).  w_stacked: bf16 [128][32], rows 0..63 / 64..127 = hi / lo plane of
+ * weight.reshape(64, 27) (k = c*9 + ky*3 + kx), columns 27..31 zero.  Cout is 64. */
+int mnc_conv1_1_tc(const float* data_nchw, int batch, int H, int W, const void* w_stacked,
+                   const float* bias, void* out_hi, void* out_lo, void* stream);
 
 /* 2x2 stride-2 ceil-mode max pooling on split NHWC (pooling_layer.cu:11-47, pooling_layer.cpp:90-93). */
 int mnc_maxpool2x2_split(const void* in_hi, const void* in_lo, int batch, int H, int W, int C,

@@ -22,6 +22,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 
 #include "mnc_b200.h"
 #include "ptx.cuh"
@@ -210,10 +211,23 @@ __device__ __forceinline__ void run_epilogue(const IgemmArgs& p, const CUtensorM
         if (threadIdx.x == 128) ptx::tma_store_wait_read<1>();  // this buffer's previous store
         ptx::named_bar_sync(1, 128);
         if (ch0 < p.Cout) {
+          // bias: 8 x 16-byte loads when the chunk is whole and aligned (the usual case)
           float bv[32];
+          if (p.bias != nullptr && ch0 + 32 <= p.Cout &&
+              (reinterpret_cast<uintptr_t>(p.bias + ch0) & 15) == 0) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            bv[j] = (p.bias != nullptr && ch0 + j < p.Cout) ? __ldg(p.bias + ch0 + j) : 0.f;
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + ch0) + j4);
+              bv[4 * j4] = b4.x;
+              bv[4 * j4 + 1] = b4.y;
+              bv[4 * j4 + 2] = b4.z;
+              bv[4 * j4 + 3] = b4.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              bv[j] = (p.bias != nullptr && ch0 + j < p.Cout) ? __ldg(p.bias + ch0 + j) : 0.f;
+          }
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             uint32_t hw[4], lw[4];
@@ -225,14 +239,15 @@ __device__ __forceinline__ void run_epilogue(const IgemmArgs& p, const CUtensorM
                 x0 = fmaxf(x0, 0.f);
                 x1 = fmaxf(x1, 0.f);
               }
-              const __nv_bfloat16 h0b = __float2bfloat16_rn(x0);
-              const __nv_bfloat16 h1b = __float2bfloat16_rn(x1);
-              const __nv_bfloat16 l0b = __float2bfloat16_rn(x0 - __bfloat162float(h0b));
-              const __nv_bfloat16 l1b = __float2bfloat16_rn(x1 - __bfloat162float(h1b));
-              hw[e] = static_cast<uint32_t>(__bfloat16_as_ushort(h0b)) |
-                      (static_cast<uint32_t>(__bfloat16_as_ushort(h1b)) << 16);
-              lw[e] = static_cast<uint32_t>(__bfloat16_as_ushort(l0b)) |
-                      (static_cast<uint32_t>(__bfloat16_as_ushort(l1b)) << 16);
+              // packed conversions: (x0, x1) -> bf16x2 in one instruction; the hi values come back
+              // as floats by a shift / mask of the packed word
+              const __nv_bfloat162 hp = __floats2bfloat162_rn(x0, x1);
+              const uint32_t hbits = *reinterpret_cast<const uint32_t*>(&hp);
+              const float f0 = __uint_as_float(hbits << 16);
+              const float f1 = __uint_as_float(hbits & 0xffff0000u);
+              const __nv_bfloat162 lp = __floats2bfloat162_rn(x0 - f0, x1 - f1);
+              hw[e] = hbits;
+              lw[e] = *reinterpret_cast<const uint32_t*>(&lp);
             }
             const int off = row * 64 + ((g ^ ((row >> 1) & 3)) << 4);
             *reinterpret_cast<uint4*>(sb + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
@@ -663,6 +678,171 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
   }
 }
 
+// ------------------------------------------------------------------------------ conv1_1
+// conv1_1 (3 -> 64 channels, K = 27) on the tensor cores.  The SIMT kernel spends 0.65 ms per batch
+// of 8 on 8.3 G fp32 FMAs; as an MMA the layer is 37.5k tiles x 4 instructions and the kernel is
+// bound by writing its 1.23 GB of output.  There is nothing for TMA to im2col (3 channels), so
+// four producer warps build the A tile themselves: thread p gathers the 27-value patch of pixel p
+// from the fp32 NCHW blob (coalesced along the row; neighbours' re-reads hit L1), splits each value
+// into (hi, lo) bf16, pads K to 32 and writes the two 64-byte rows of the tile with the 64B swizzle
+// pattern the tcgen05 descriptor (SWIZZLE_64B, K-major) expects.  Weights: one [hi(64) ; lo(64)] x 32
+// tile, loaded once by TMA; per 16-wide k slice  A_hi x [B_hi ; B_lo]  (N = 128) and  A_lo x B_hi
+// (N = 64), the same stacked-N scheme as conv_halo_tc_kernel, so run_epilogue<.., ACC2> is reused
+// unchanged (bias, ReLU, re-split, swizzled staging, TMA store).  The image batch is viewed as
+// batch*H one-row images so that a tile is 128 consecutive pixels of a row.
+constexpr int kC11K = 32;                       // 27 padded
+constexpr int kC11ABytes = kBlockM * kC11K * 2; // one bf16 plane of the A tile: 8 KB
+constexpr int kC11Stages = 2;
+constexpr int kC11BBytes = 128 * kC11K * 2;     // stacked weight tile: 8 KB
+constexpr int kC11Ring = kC11Stages * 2 * kC11ABytes + kC11BBytes;  // 40 KB
+constexpr int kC11Staging = 2 * 2 * 128 * 64;
+constexpr int kC11Smem = kC11Ring + 1024 /*barriers*/ + kC11Staging + 1024 /*align*/;
+constexpr int kC11Threads = 384;
+
+__global__ void __launch_bounds__(kC11Threads, 1)
+conv1_1_tc_kernel(const float* __restrict__ data, int B, int H, int W,
+                  const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_o_hi,
+                  const __grid_constant__ CUtensorMap tm_o_lo, const IgemmArgs p) {
+  constexpr int BN = 64;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* a_ring = smem;
+  uint8_t* b_tile = smem + kC11Stages * 2 * kC11ABytes;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + kC11Ring);
+  uint64_t* a_empty = a_full + kC11Stages;
+  uint64_t* b_full = a_empty + kC11Stages;
+  uint64_t* tfull_bar = b_full + 1;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint8_t* staging = smem + kC11Ring + 1024;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.batch * p.tiles_w;   // p.batch = B*H one-row images
+  const int first = blockIdx.x, stride = gridDim.x;
+
+  if (warp == 0 && lane == 0) ptx::prefetch_tmap(&tm_b);
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kC11Stages; ++s) {
+      ptx::mbar_init(&a_full[s], 128);
+      ptx::mbar_init(&a_empty[s], 1);
+    }
+    ptx::mbar_init(b_full, 1);
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tfull_bar[a], 1);
+      ptx::mbar_init(&tempty_bar[a], 128);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) ptx::tmem_alloc<256>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // weights: once per CTA
+    ptx::mbar_arrive_expect_tx_w(b_full, kC11BBytes);
+    ptx::tma_load_2d_w(b_tile, &tm_b, b_full, 0, 0);
+  } else if (warp == 1) {
+    // -------------------------------------------------------------- MMA issuer (whole warp)
+    constexpr uint32_t idesc1 = ptx::umma_idesc_bf16_m128(2 * BN);
+    constexpr uint32_t idesc2 = ptx::umma_idesc_bf16_m128(BN);
+    ptx::mbar_wait(b_full, 0);
+    ptx::tc_fence_after();
+    const uint32_t b_addr = ptx::smem_u32(b_tile);
+    int as = 0, local = 0;
+    uint32_t aph = 0;
+    for (int t = first; t < total_tiles; t += stride, ++local) {
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      ptx::mbar_wait(&a_full[as], aph);
+      ptx::tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * (2 * BN);
+      const uint32_t a_hi = ptx::smem_u32(a_ring + as * 2 * kC11ABytes);
+      const uint32_t a_lo = a_hi + kC11ABytes;
+#pragma unroll
+      for (int kk = 0; kk < kC11K / 16; ++kk) {
+        const uint64_t da_hi = ptx::umma_desc_sw64(a_hi + kk * 32);
+        const uint64_t da_lo = ptx::umma_desc_sw64(a_lo + kk * 32);
+        const uint64_t db = ptx::umma_desc_sw64(b_addr + kk * 32);
+        ptx::umma_bf16_ss_w(tmem_d, da_hi, db, idesc1, kk > 0 ? 1u : 0u);
+        ptx::umma_bf16_ss_w(tmem_d, da_lo, db, idesc2, 1u);
+      }
+      ptx::umma_commit_w(&a_empty[as]);
+      ptx::umma_commit_w(&tfull_bar[acc]);
+      if (++as == kC11Stages) {
+        as = 0;
+        aph ^= 1;
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    run_epilogue<1, 128, BN, 1, true>(p, &tm_o_hi, &tm_o_lo, staging, tfull_bar, tempty_bar,
+                                      tmem_base, 0, first, stride, total_tiles);
+  } else if (warp >= 8) {
+    // -------------------------------------------------------------- A producers (128 threads)
+    const int pr = threadIdx.x - 256;   // tile row = pixel within the 128-pixel row segment
+    const long long plane = static_cast<long long>(H) * W;
+    int as = 0;
+    uint32_t aph = 0;
+    for (int t = first; t < total_tiles; t += stride) {
+      const int img = t / p.tiles_w;             // one-row image index = b*H + h
+      const int w = (t - img * p.tiles_w) * 128 + pr;
+      const int b = img / H, h = img - b * H;
+      // gather the patch first (global-load latency overlaps the wait for the stage)
+      float v[27];
+      const float* xb = data + static_cast<long long>(b) * 3 * plane;
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const int hh = h + ky - 1, ww = w + kx - 1;
+            const bool ok = hh >= 0 && hh < H && ww >= 0 && ww < W && w < W && p.taps != 0;
+            v[c * 9 + ky * 3 + kx] = ok ? __ldg(xb + c * plane + static_cast<long long>(hh) * W + ww) : 0.f;
+          }
+      uint32_t hw[16], lw[16];   // 32 bf16 each, k = 27..31 are zero
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const float x0 = (2 * e < 27) ? v[2 * e] : 0.f;
+        const float x1 = (2 * e + 1 < 27) ? v[(2 * e + 1 < 27) ? 2 * e + 1 : 0] : 0.f;
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+        const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
+        const __nv_bfloat16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+        hw[e] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) |
+                (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
+        lw[e] = static_cast<uint32_t>(__bfloat16_as_ushort(l0)) |
+                (static_cast<uint32_t>(__bfloat16_as_ushort(l1)) << 16);
+      }
+      ptx::mbar_wait(&a_empty[as], aph ^ 1);
+      uint8_t* sa = a_ring + as * 2 * kC11ABytes;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int off = pr * 64 + ((g ^ ((pr >> 1) & 3)) << 4);   // SWIZZLE_64B
+        *reinterpret_cast<uint4*>(sa + off) = make_uint4(hw[4 * g], hw[4 * g + 1], hw[4 * g + 2], hw[4 * g + 3]);
+        *reinterpret_cast<uint4*>(sa + kC11ABytes + off) =
+            make_uint4(lw[4 * g], lw[4 * g + 1], lw[4 * g + 2], lw[4 * g + 3]);
+      }
+      ptx::fence_proxy_async();      // generic-proxy writes -> visible to the tensor core's async proxy
+      ptx::mbar_arrive(&a_full[as]);
+      if (++as == kC11Stages) {
+        as = 0;
+        aph ^= 1;
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<256>(tmem_base);
+  }
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -932,4 +1112,57 @@ extern "C" int mnc_igemm_tc(const void* a_hi, const void* a_lo, int batch, int H
     MNC_LAUNCH(1, 128, 256, 64);
   }
 #undef MNC_LAUNCH
+}
+
+// conv1_1 on the tensor cores.  w_stacked: bf16 [128][32] = rows 0..63 the hi plane, 64..127 the lo
+// plane of weight.reshape(64, 27) (k = c*9 + ky*3 + kx), columns 27..31 zero.
+extern "C" int mnc_conv1_1_tc(const float* data_nchw, int batch, int H, int W, const void* w_stacked,
+                              const float* bias, void* out_hi, void* out_lo, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (batch <= 0 || H <= 0 || W <= 0) return MNC_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(out_hi) | reinterpret_cast<uintptr_t>(out_lo) |
+       reinterpret_cast<uintptr_t>(w_stacked)) % 16 != 0)
+    return MNC_ERR_ARG;
+  IgemmArgs a;
+  a.batch = batch * H;   // one-row images
+  a.H = 1;
+  a.W = W;
+  a.Cin = 32;
+  a.Cout = 64;
+  a.taps = 1;
+  a.tiles_h = 1;
+  a.tiles_w = (W + 127) / 128;
+  a.tiles_n = 1;
+  a.k_steps = 1;
+  a.split_k = 1;
+  a.relu = 1;
+  a.out_mode = 0;
+  if (const char* dbg = getenv("MNC_C11_MODE")) a.out_mode = atoi(dbg);      // 3: drain + discard
+  if (const char* dbg = getenv("MNC_C11_NOLOAD")) a.taps = atoi(dbg) ? 0 : 1;  // 0: constant patch
+  a.bias = bias;
+  a.out_hi = static_cast<__nv_bfloat16*>(out_hi);
+  a.out_lo = static_cast<__nv_bfloat16*>(out_lo);
+  a.out_f32 = nullptr;
+  a.out_pix_stride = 64;
+  a.out_ch_offset = 0;
+  a.split_stride = 0;
+  a.vec_ok = 1;
+  a.tma_store = 1;
+  CUtensorMap tb, to_hi, to_lo;
+  int rc;
+  if ((rc = make_wgt_map(&tb, w_stacked, 128, 32, 128, 32)) != MNC_OK) return rc;
+  if ((rc = make_out_map(&to_hi, out_hi, a.batch, 1, W, 64, 64, 1, 128)) != MNC_OK) return rc;
+  if ((rc = make_out_map(&to_lo, out_lo, a.batch, 1, W, 64, 64, 1, 128)) != MNC_OK) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(conv1_1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             kC11Smem) != cudaSuccess)
+      return MNC_ERR_CUDA;
+    attr_set = true;
+  }
+  const int total = a.batch * a.tiles_w;
+  int grid = sm_count();
+  if (total < grid) grid = total;
+  conv1_1_tc_kernel<<<grid, kC11Threads, kC11Smem, stream>>>(data_nchw, batch, H, W, tb, to_hi, to_lo, a);
+  return cudaGetLastError() == cudaSuccess ? MNC_OK : MNC_ERR_CUDA;
 }

@@ -140,6 +140,24 @@ def conv1_1(data, weight, bias, out):
     check(rc, "mnc_conv1_1")
 
 
+def conv1_1_weight_to_tc(weight):
+    """fp32 [64,3,3,3] -> bf16 [128,32]: hi plane rows 0..63, lo plane rows 64..127, K padded 27->32."""
+    assert tuple(weight.shape) == (64, 3, 3, 3)
+    w = torch.zeros((64, 32), dtype=torch.float32, device=weight.device)
+    w[:, :27] = weight.reshape(64, 27)
+    sp = split(w)                      # [2, 64, 32]
+    return sp.reshape(128, 32).contiguous()
+
+
+def conv1_1_tc(data, w_stacked, bias, out):
+    b, c, H, W = data.shape
+    assert c == 3 and data.dtype == torch.float32 and data.is_contiguous()
+    assert w_stacked.dtype == torch.bfloat16 and tuple(w_stacked.shape) == (128, 32)
+    rc = lib.mnc_conv1_1_tc(ptr(data), c_int(b), c_int(H), c_int(W), ptr(w_stacked), ptr(bias),
+                            ptr(out[0]), ptr(out[1]), cur_stream())
+    check(rc, "mnc_conv1_1_tc")
+
+
 def maxpool2x2(a, batch, H, W, C, out):
     rc = lib.mnc_maxpool2x2_split(ptr(a[0]), ptr(a[1]), c_int(batch), c_int(H), c_int(W), c_int(C),
                                   ptr(out[0]), ptr(out[1]), cur_stream())

@@ -45,6 +45,9 @@ class MNCEngine:
              for k, v in weights.items()}
         # conv1_1 stays fp32 (SIMT kernel); the other convs are split [2, Cout, 9*Cin]
         self.conv1_1 = w["conv1_1"]
+        # 64-channel conv1_1 runs on the tensor cores (stacked hi/lo weight tile, K padded to 32)
+        self.conv1_1_tc = (dense.conv1_1_weight_to_tc(w["conv1_1"][0])
+                           if impl == "tc" and w["conv1_1"][0].shape[0] == 64 else None)
         self.convs = []
         for name in TRUNK_NAMES[1:] + ["rpn_conv_3x3"]:
             if name in w:   # the CFM test net has no RPN (proposals are an input)
@@ -156,7 +159,10 @@ class MNCEngine:
         bufs = [self._split_buf("act0", big), self._split_buf("act1", big)]
         cur = 0
         x = bufs[cur].view(-1)[:2 * B * H * W * ch[0]].view(2, B, H, W, ch[0])
-        dense.conv1_1(data, self.conv1_1[0], self.conv1_1[1], x)
+        if self.conv1_1_tc is not None:
+            dense.conv1_1_tc(data.contiguous(), self.conv1_1_tc, self.conv1_1[1], x)
+        else:
+            dense.conv1_1(data, self.conv1_1[0], self.conv1_1[1], x)
         cin = ch[0]
         if "conv1_1" in POOL_AFTER:
             raise NotImplementedError

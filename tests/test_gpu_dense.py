@@ -94,6 +94,25 @@ def test_conv1_1_and_pool_and_layout():
     assert torch.equal(dense.merge(back), dense.merge(pooled))
 
 
+@pytest.mark.parametrize("B,H,W", [(2, 37, 53), (1, 5, 128), (3, 20, 300), (1, 600, 1000)])
+def test_conv1_1_tensor_core_form(B, H, W):
+    """conv1_1 as an MMA (producer warps build the swizzled A tile, K = 27 padded to 32) vs fp64,
+    and vs the fp32 FMA kernel; ragged row tiles (W % 128 != 0), image borders, batch > 1."""
+    import torch.nn.functional as F
+    from mnc_b200 import dense
+    torch.manual_seed(B * 1000 + W)
+    data = (torch.rand(B, 3, H, W, device="cuda") * 255 - 115).contiguous()   # mean-subtracted pixels
+    w = torch.randn(64, 3, 3, 3, device="cuda") * 0.02
+    b = torch.randn(64, device="cuda")
+    out = torch.zeros(2, B, H, W, 64, device="cuda", dtype=torch.bfloat16)
+    dense.conv1_1_tc(data, dense.conv1_1_weight_to_tc(w), b, out)
+    ref = F.relu(F.conv2d(data.double(), w.double(), b.double(), padding=1)).permute(0, 2, 3, 1)
+    assert relerr(dense.merge(out), ref) < 1e-4
+    simt = torch.zeros_like(out)
+    dense.conv1_1(data, w, b, simt)
+    assert relerr(dense.merge(out), dense.merge(simt).double()) < 1e-4
+
+
 @pytest.mark.parametrize("B,H,W,Cin,Cout,bn", [(1, 75, 125, 64, 128, 128), (2, 37, 53, 64, 64, 64),
                                                (1, 16, 32, 128, 256, 256), (1, 9, 17, 64, 72, 128)])
 def test_conv3x3_with_fused_ceil_mode_pool(B, H, W, Cin, Cout, bn):
