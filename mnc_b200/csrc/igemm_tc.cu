@@ -642,6 +642,9 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
             const uint32_t la_hi = ptx::desc_lo(a_hi0 + woff);
             const uint32_t la_lo = ptx::desc_lo(a_lo0 + woff);
             const uint32_t lb = ptx::desc_lo(ptx::smem_u32(b_ring + bs * Cfg::kBStage));  // [hi | lo]
+            // (all eight MMAs of a tap from one asm block -- one election, half the instructions
+            // between UTCHMMAs -- measured 17 % SLOWER on conv1_2; ptx::umma_halo_tap_w is kept
+            // for the record)
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
               const uint32_t accum = (kc > 0 || tap > 0 || kk > 0) ? 1u : 0u;

@@ -269,6 +269,48 @@ __device__ __forceinline__ void umma_bf16_ss_w32(uint32_t tmem_d, uint32_t desc_
       "r"(desc_a_lo), "r"(desc_b_lo), "r"(idesc), "r"(accumulate), "n"(kHiA), "n"(kHiB)
       : "memory");
 }
+// One filter tap of the halo kernel = four 16-wide k slices x {A_hi x [B_hi|B_lo] (idesc1),
+// A_lo x B_hi (idesc2)}: eight MMAs issued from ONE asm block -- one election, the three descriptor
+// low words + TMEM address + the two instruction descriptors cross into uniform registers once, the
+// per-slice descriptors are the bases + 2*kk.  `first` = 0 clears the accumulator on the very
+// first MMA.
+template <uint32_t kHiA, uint32_t kHiB>
+__device__ __forceinline__ void umma_halo_tap_w(uint32_t tmem_d, uint32_t la_hi, uint32_t la_lo,
+                                                uint32_t lb, uint32_t idesc1, uint32_t idesc2,
+                                                uint32_t first) {
+  asm volatile(
+      "{\n\t.reg .pred p, q, t;\n\t.reg .b32 x, y, z;\n\t.reg .b64 da, db;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "setp.eq.b32 t, 0, 0;\n\t"
+      // kk = 0
+      "mov.b64 da, {%1, %7};\n\tmov.b64 db, {%3, %8};\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t"
+      "mov.b64 da, {%2, %7};\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, t;\n\t"
+      // kk = 1
+      "add.u32 x, %1, 2;\n\tadd.u32 y, %2, 2;\n\tadd.u32 z, %3, 2;\n\t"
+      "mov.b64 da, {x, %7};\n\tmov.b64 db, {z, %8};\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, t;\n\t"
+      "mov.b64 da, {y, %7};\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, t;\n\t"
+      // kk = 2
+      "add.u32 x, %1, 4;\n\tadd.u32 y, %2, 4;\n\tadd.u32 z, %3, 4;\n\t"
+      "mov.b64 da, {x, %7};\n\tmov.b64 db, {z, %8};\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, t;\n\t"
+      "mov.b64 da, {y, %7};\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, t;\n\t"
+      // kk = 3
+      "add.u32 x, %1, 6;\n\tadd.u32 y, %2, 6;\n\tadd.u32 z, %3, 6;\n\t"
+      "mov.b64 da, {x, %7};\n\tmov.b64 db, {z, %8};\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, t;\n\t"
+      "mov.b64 da, {y, %7};\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, t;\n\t}"
+      ::"r"(tmem_d),
+      "r"(la_hi), "r"(la_lo), "r"(lb), "r"(idesc1), "r"(idesc2), "r"(first), "n"(kHiA), "n"(kHiB)
+      : "memory");
+}
+
 // high words of the two descriptor flavours
 constexpr uint32_t kDescHiSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);
 constexpr uint32_t kDescHiSw64 = (512u >> 4) | (1u << 14) | (4u << 29);
