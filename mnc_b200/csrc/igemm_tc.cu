@@ -114,7 +114,11 @@ __device__ __forceinline__ Tile decode_tile(const IgemmArgs& p, int t, int rank,
 // ---------------------------------------------------------------------------------- epilogue
 // Shared by the per-tap kernel and the halo kernel: warps 4..7 drain the TMEM accumulators of
 // every tile this CTA owns (bias, ReLU, optional 2x2 ceil-mode max pool, re-split, store).
-template <int TH, int TW, int BN, int CL, bool ACC2 = false>
+// NG = 2: two warp groups (warps 4..7 and 8..11; a warp may read the TMEM lane quarter warp_id % 4)
+// drain alternate 32-column chunks of every tile -- for the low-K layers (conv1_1, conv1_2) the
+// epilogue, not the MMA, is the longest stage of the pipeline.  Each group then owns ONE staging
+// buffer (waiting for its previous bulk store to finish reading it) instead of two.
+template <int TH, int TW, int BN, int CL, bool ACC2 = false, int NG = 1>
 __device__ __forceinline__ void run_epilogue(const IgemmArgs& p, const CUtensorMap* tm_o_hi_p,
                                              const CUtensorMap* tm_o_lo_p, uint8_t* staging,
                                              uint64_t* tfull_bar, uint64_t* tempty_bar,
@@ -122,7 +126,10 @@ __device__ __forceinline__ void run_epilogue(const IgemmArgs& p, const CUtensorM
                                              int total_tiles) {
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q = warp - 4;  // TMEM lane quarter == warp_id % 4
+  const int q = (warp - 4) & 3;   // TMEM lane quarter == warp_id % 4
+  const int grp = (warp - 4) >> 2;  // 0 .. NG-1
+  constexpr int NBUF = 2 / NG;      // staging buffers per group
+  const int lead = 128 + grp * 128; // the group's bulk-store thread
   const int row = q * 32 + lane;
   int local = 0;
   int chunk_ctr = 0;
@@ -138,7 +145,7 @@ __device__ __forceinline__ void run_epilogue(const IgemmArgs& p, const CUtensorM
     ptx::mbar_wait(&tfull_bar[acc], acc_phase);
     ptx::tc_fence_after();
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+    for (int c0 = grp * 32; c0 < BN; c0 += 32 * NG) {
       uint32_t r[32];
       // ACC2: the tile's sum is split over two column blocks (see conv_halo_tc_kernel)
       constexpr int kAccCols = ACC2 ? 2 * BN : BN;
@@ -206,10 +213,10 @@ __device__ __forceinline__ void run_epilogue(const IgemmArgs& p, const CUtensorM
         // pattern so the 16-byte stores are bank-conflict free); one elected thread then issues
         // two bulk tensor stores (hi, lo).  TMA clips ragged tiles, channel tails and the
         // cluster's dummy tile, and the global writes are whole 64-byte rows.
-        const int buf = chunk_ctr & 1;
-        uint8_t* sb = staging + buf * (2 * 128 * 64);
-        if (threadIdx.x == 128) ptx::tma_store_wait_read<1>();  // this buffer's previous store
-        ptx::named_bar_sync(1, 128);
+        const int buf = chunk_ctr % NBUF;
+        uint8_t* sb = staging + (grp * NBUF + buf) * (2 * 128 * 64);
+        if (threadIdx.x == lead) ptx::tma_store_wait_read<NBUF - 1>();  // this buffer's previous store
+        ptx::named_bar_sync(1 + grp, 128);
         if (ch0 < p.Cout) {
           // bias: 8 x 16-byte loads when the chunk is whole and aligned (the usual case)
           float bv[32];
@@ -255,8 +262,8 @@ __device__ __forceinline__ void run_epilogue(const IgemmArgs& p, const CUtensorM
           }
         }
         ptx::fence_proxy_async();
-        ptx::named_bar_sync(1, 128);
-        if (threadIdx.x == 128 && ch0 < p.Cout) {
+        ptx::named_bar_sync(1 + grp, 128);
+        if (threadIdx.x == lead && ch0 < p.Cout) {
           ptx::tma_store_4d(tm_o_hi_p, sb, ch0, w0, h0, img);
           ptx::tma_store_4d(tm_o_lo_p, sb + 128 * 64, ch0, w0, h0, img);
           ptx::tma_store_commit();
@@ -318,7 +325,7 @@ __device__ __forceinline__ void run_epilogue(const IgemmArgs& p, const CUtensorM
     ptx::tc_fence_before();
     ptx::mbar_arrive(&tempty_bar[acc]);
   }
-  if (threadIdx.x == 128) ptx::tma_store_wait_read<0>();  // smem must outlive the bulk stores
+  if (threadIdx.x == lead) ptx::tma_store_wait_read<0>();  // smem must outlive the bulk stores
 }
 
 template <int TH, int TW, int BN, int CL, int BK>
@@ -523,13 +530,14 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t smem_addr, uint
 }
 
 template <int BN>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(BN == 64 ? 384 : 256, 1)
 conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                     const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                     const __grid_constant__ CUtensorMap tm_o_hi, const __grid_constant__ CUtensorMap tm_o_lo,
                     const IgemmArgs p) {
   using Cfg = HaloCfg<BN>;
   constexpr int TH = kHaloTH, TW = kHaloTW, NB = Cfg::kNB;
+  constexpr int kNG = (BN == 64) ? 2 : 1;   // epilogue warp groups (warps 4..7 [, 8..11])
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -567,7 +575,7 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tfull_bar[a], 1);
-      ptx::mbar_init(&tempty_bar[a], 128);
+      ptx::mbar_init(&tempty_bar[a], 128 * kNG);
     }
     ptx::fence_barrier_init();
   }
@@ -637,7 +645,11 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
           for (int tap = 0; tap < 9; ++tap) {
             ptx::mbar_wait(&b_full[bs], bph);
             ptx::tc_fence_after();
-            const uint32_t woff = ((tap / 3) * (TW + 2) + (tap % 3)) * 128;  // shifted window
+            // shifted window (reading all taps from offset 0 instead is no faster: the windows cost
+            // nothing extra; what bounds the Cout = 64 layer is shared-memory bandwidth -- per
+            // 16-wide k slice the two MMAs read 14 KB of operands in 96 tensor cycles, and the
+            // TMA fills add 194 KB per tile: ~5450 cycles of 128 B/clk against 3456 of MMA)
+            const uint32_t woff = ((tap / 3) * (TW + 2) + (tap % 3)) * 128;
             // descriptor low words (start address >> 4); + 2 per 16-element k slice
             const uint32_t la_hi = ptx::desc_lo(a_hi0 + woff);
             const uint32_t la_lo = ptx::desc_lo(a_lo0 + woff);
@@ -669,8 +681,8 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
       }
     }
   } else if (warp >= 4) {
-    run_epilogue<TH, TW, BN, 1, true>(p, &tm_o_hi, &tm_o_lo, staging, tfull_bar, tempty_bar,
-                                      tmem_base, 0, first, stride, total_tiles);
+    run_epilogue<TH, TW, BN, 1, true, kNG>(p, &tm_o_hi, &tm_o_lo, staging, tfull_bar, tempty_bar,
+                                           tmem_base, 0, first, stride, total_tiles);
   }
 
   ptx::tc_fence_before();
@@ -700,7 +712,7 @@ constexpr int kC11BBytes = 128 * kC11K * 2;     // stacked weight tile: 8 KB
 constexpr int kC11Ring = kC11Stages * 2 * kC11ABytes + kC11BBytes;  // 40 KB
 constexpr int kC11Staging = 2 * 2 * 128 * 64;
 constexpr int kC11Smem = kC11Ring + 1024 /*barriers*/ + kC11Staging + 1024 /*align*/;
-constexpr int kC11Threads = 384;
+constexpr int kC11Threads = 512;
 
 __global__ void __launch_bounds__(kC11Threads, 1)
 conv1_1_tc_kernel(const float* __restrict__ data, int B, int H, int W,
@@ -734,7 +746,7 @@ conv1_1_tc_kernel(const float* __restrict__ data, int B, int H, int W,
     ptx::mbar_init(b_full, 1);
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tfull_bar[a], 1);
-      ptx::mbar_init(&tempty_bar[a], 128);
+      ptx::mbar_init(&tempty_bar[a], 256);
     }
     ptx::fence_barrier_init();
   }
@@ -781,12 +793,12 @@ conv1_1_tc_kernel(const float* __restrict__ data, int B, int H, int W,
         aph ^= 1;
       }
     }
-  } else if (warp >= 4 && warp < 8) {
-    run_epilogue<1, 128, BN, 1, true>(p, &tm_o_hi, &tm_o_lo, staging, tfull_bar, tempty_bar,
-                                      tmem_base, 0, first, stride, total_tiles);
-  } else if (warp >= 8) {
+  } else if (warp >= 4 && warp < 12) {
+    run_epilogue<1, 128, BN, 1, true, 2>(p, &tm_o_hi, &tm_o_lo, staging, tfull_bar, tempty_bar,
+                                         tmem_base, 0, first, stride, total_tiles);
+  } else if (warp >= 12) {
     // -------------------------------------------------------------- A producers (128 threads)
-    const int pr = threadIdx.x - 256;   // tile row = pixel within the 128-pixel row segment
+    const int pr = threadIdx.x - 384;   // tile row = pixel within the 128-pixel row segment
     const long long plane = static_cast<long long>(H) * W;
     int as = 0;
     uint32_t aph = 0;
@@ -980,7 +992,8 @@ static int launch_halo(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const
   int grid = sm_count();
   if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
   if (total < grid) grid = total;
-  kern<<<grid, 256, Cfg::kSmemBytes, stream>>>(ta_hi, ta_lo, tb_hi, tb_lo, to_hi, to_lo, a);
+  kern<<<grid, BN == 64 ? 384 : 256, Cfg::kSmemBytes, stream>>>(ta_hi, ta_lo, tb_hi, tb_lo, to_hi,
+                                                              to_lo, a);
   return cudaGetLastError() == cudaSuccess ? MNC_OK : MNC_ERR_CUDA;
 }
 
