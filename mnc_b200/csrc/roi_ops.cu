@@ -332,7 +332,7 @@ struct __align__(16) SampleTab {
 };
 
 template <int SUB>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 4)
 roi_warp_split_kernel(const float* __restrict__ feat, int C, int H, int W,
                       const float* __restrict__ rois, float spatial_scale,
                       __nv_bfloat16* __restrict__ o14_hi, __nv_bfloat16* __restrict__ o14_lo,
