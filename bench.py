@@ -104,6 +104,25 @@ def cpu_reference_time(weights, steps, warmup, images_per_step=1):
     return times, torch.get_num_threads()
 
 
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL announces its
+    version on the first communicator), so file descriptor 1 is pointed at stderr for the whole
+    run and the JSON line is written to a private duplicate of the original stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    sys.stdout.flush()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 def run_reference(args, rank):
     """--impl reference: the reference's own algorithm on the host cores.  The reference has no
     runnable CPU implementation (its MNC layers are NOT_IMPLEMENTED on CPU and Caffe does not
@@ -128,7 +147,7 @@ def run_reference(args, rank):
         "note": "reference has no runnable CPU path (BASELINE.md section 2); oracle port timed; "
                 "steps/warmup clamped to keep the run bounded",
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def workload_config(args, world):
@@ -153,6 +172,7 @@ def main():
                     help="write the ordered list of tensor-core launches of the timed region "
                          "(shape, algorithmic FLOPs / bytes) as JSON, for scripts/ncu_tc_summary.py")
     args = ap.parse_args()
+    _claim_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
@@ -347,7 +367,7 @@ def main():
         "speedup_vs_published_titanx": value / world * 0.33,
         "wall_s_timed_region": t_wall,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
