@@ -22,7 +22,6 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
-#include <cstdlib>
 
 #include "mnc_b200.h"
 #include "ptx.cuh"
@@ -816,7 +815,7 @@ conv1_1_tc_kernel(const float* __restrict__ data, int B, int H, int W,
 #pragma unroll
           for (int kx = 0; kx < 3; ++kx) {
             const int hh = h + ky - 1, ww = w + kx - 1;
-            const bool ok = hh >= 0 && hh < H && ww >= 0 && ww < W && w < W && p.taps != 0;
+            const bool ok = hh >= 0 && hh < H && ww >= 0 && ww < W && w < W;
             v[c * 9 + ky * 3 + kx] = ok ? __ldg(xb + c * plane + static_cast<long long>(hh) * W + ww) : 0.f;
           }
       uint32_t hw[16], lw[16];   // 32 bf16 each, k = 27..31 are zero
@@ -1153,8 +1152,6 @@ extern "C" int mnc_conv1_1_tc(const float* data_nchw, int batch, int H, int W, c
   a.split_k = 1;
   a.relu = 1;
   a.out_mode = 0;
-  if (const char* dbg = getenv("MNC_C11_MODE")) a.out_mode = atoi(dbg);      // 3: drain + discard
-  if (const char* dbg = getenv("MNC_C11_NOLOAD")) a.taps = atoi(dbg) ? 0 : 1;  // 0: constant patch
   a.bias = bias;
   a.out_hi = static_cast<__nv_bfloat16*>(out_hi);
   a.out_lo = static_cast<__nv_bfloat16*>(out_lo);

@@ -1,5 +1,6 @@
-"""conv1_1: tensor-core form vs fp32 FMA form, and which stage of the TC kernel bounds it
-(MNC_C11_MODE=3: epilogue drains TMEM and discards; MNC_C11_NOLOAD=1: producers skip the gathers)."""
+"""conv1_1: tensor-core form vs fp32 FMA form (batch 8, 600x1000, L2 flushed between launches).
+(The stage-elimination numbers in profiles/README.md finding 10 came from two temporary switches in
+mnc_conv1_1_tc -- epilogue drains and discards / producers skip the gathers -- since removed.)"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -26,6 +27,5 @@ def t(fn, n=6):
     return float(np.median(ts[2:]))
 
 
-print("MODE=%s NOLOAD=%s : tc %.3f ms   simt %.3f ms" % (
-    os.environ.get("MNC_C11_MODE", "0"), os.environ.get("MNC_C11_NOLOAD", "0"),
+print("conv1_1: tensor cores %.3f ms   fp32 FMA %.3f ms" % (
     t(lambda: dense.conv1_1_tc(data, wt, b, out)), t(lambda: dense.conv1_1(data, w, b, out))))
