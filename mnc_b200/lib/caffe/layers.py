@@ -90,3 +90,34 @@ class MaskPoolingLayer(_NativeLayer):
 
 LAYER_TYPES = {"ROIWarping": ROIWarpingLayer, "MaskResize": MaskResizeLayer,
                "MaskPooling": MaskPoolingLayer}
+
+
+class ROIPoolingLayer(_NativeLayer):
+    """roi_pooling_layer.cpp:20-44 (setup/reshape), roi_pooling_layer.cu:80-105 (forward); the
+    layer type of the CFM test net (models/VGG16/cfm/test.prototxt:399-465)."""
+
+    def LayerSetUp(self, bottom, top):
+        p = self.layer_param_.get("roi_pooling_param", {})
+        if p.get("pooled_h", 0) <= 0:
+            raise ValueError("pooled_h must be > 0")
+        if p.get("pooled_w", 0) <= 0:
+            raise ValueError("pooled_w must be > 0")
+        self.pooled_height_ = int(p["pooled_h"])
+        self.pooled_width_ = int(p["pooled_w"])
+        self.spatial_scale_ = float(p.get("spatial_scale", 1.0))
+
+    def Reshape(self, bottom, top):
+        self.channels_ = bottom[0].channels
+        self.height_ = bottom[0].height
+        self.width_ = bottom[0].width
+        top[0].reshape(bottom[1].num, self.channels_, self.pooled_height_, self.pooled_width_)
+        self.max_idx_ = np.zeros((bottom[1].num, self.channels_, self.pooled_height_,
+                                  self.pooled_width_), dtype=np.int32)
+
+    def Forward_gpu(self, bottom, top):
+        arg = torch.empty(self.max_idx_.shape, dtype=torch.int32, device="cuda")
+        out = ops.roi_pool_nchw(_dev(bottom[0].data), _dev(bottom[1].data).view(-1, 5),
+                                self.pooled_height_, self.pooled_width_, self.spatial_scale_,
+                                argmax=arg)
+        top[0].data[...] = out.cpu().numpy()
+        self.max_idx_[...] = arg.cpu().numpy()

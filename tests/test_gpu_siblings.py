@@ -41,6 +41,27 @@ def test_roi_pool_nchw_bit_exact(P):
     assert np.array_equal(ops.roi_pool_nchw(d_feat, d_rois, ph, pw).cpu().numpy(), want)  # argmax=NULL
 
 
+def test_roi_pooling_layer_mirror_contract():
+    """LayerSetUp / Reshape / Forward_gpu protocol of ROIPoolingLayer (roi_pooling_layer.cpp:20-44)."""
+    import mnc_b200.lib as L
+    L.install()
+    import caffe
+    from caffe.layers import ROIPoolingLayer
+    from oracle import oracle as O
+    rng = np.random.default_rng(2)
+    feat, rois, top = caffe.Blob(), caffe.Blob(), caffe.Blob()
+    feat.data = rng.normal(size=(2, 16, 20, 30)).astype(np.float32)
+    rois.data = _rois(12, 3, 480, 320, levels=2)
+    layer = ROIPoolingLayer(dict(roi_pooling_param=dict(pooled_w=7, pooled_h=7, spatial_scale=0.0625)))
+    layer.LayerSetUp([feat, rois], [top])
+    layer.Forward([feat, rois], [top])
+    want, want_arg = O.roi_pool(feat.data, rois.data, 7, 7, return_argmax=True)
+    assert top.shape == (12, 16, 7, 7) and np.array_equal(top.data, want)
+    assert np.array_equal(layer.max_idx_, want_arg)
+    with pytest.raises(ValueError):
+        ROIPoolingLayer(dict(roi_pooling_param=dict(pooled_w=7, pooled_h=0))).LayerSetUp([feat, rois], [top])
+
+
 @pytest.mark.parametrize("P", [7, 14])
 def test_roi_pool_and_sample_split_forms(P):
     """Engine forms (fp32 NHWC in, split-bf16 rows out) vs the NCHW layer kernels' oracle."""
