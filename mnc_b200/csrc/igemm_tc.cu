@@ -711,7 +711,7 @@ constexpr int kC11BBytes = 128 * kC11K * 2;     // stacked weight tile: 8 KB
 constexpr int kC11Ring = kC11Stages * 2 * kC11ABytes + kC11BBytes;  // 40 KB
 constexpr int kC11Staging = 2 * 2 * 128 * 64;
 constexpr int kC11Smem = kC11Ring + 1024 /*barriers*/ + kC11Staging + 1024 /*align*/;
-constexpr int kC11Threads = 512;
+constexpr int kC11Threads = 640;   // 4 control + 8 epilogue + 8 producer warps
 
 __global__ void __launch_bounds__(kC11Threads, 1)
 conv1_1_tc_kernel(const float* __restrict__ data, int B, int H, int W,
@@ -797,11 +797,14 @@ conv1_1_tc_kernel(const float* __restrict__ data, int B, int H, int W,
                                          tmem_base, 0, first, stride, total_tiles);
   } else if (warp >= 12) {
     // -------------------------------------------------------------- A producers (128 threads)
-    const int pr = threadIdx.x - 384;   // tile row = pixel within the 128-pixel row segment
+    // two producer groups (warps 12..15, 16..19): group g builds the tiles with local index
+    // parity g into ring stage g, so consecutive tiles are gathered / converted concurrently
+    const int pg = (warp - 12) >> 2;
+    const int pr = (threadIdx.x - 384) & 127;   // tile row = pixel within the 128-pixel row segment
     const long long plane = static_cast<long long>(H) * W;
-    int as = 0;
+    const int as = pg;
     uint32_t aph = 0;
-    for (int t = first; t < total_tiles; t += stride) {
+    for (int t = first + pg * stride; t < total_tiles; t += 2 * stride) {
       const int img = t / p.tiles_w;             // one-row image index = b*H + h
       const int w = (t - img * p.tiles_w) * 128 + pr;
       const int b = img / H, h = img - b * H;
@@ -842,10 +845,7 @@ conv1_1_tc_kernel(const float* __restrict__ data, int B, int H, int W,
       }
       ptx::fence_proxy_async();      // generic-proxy writes -> visible to the tensor core's async proxy
       ptx::mbar_arrive(&a_full[as]);
-      if (++as == kC11Stages) {
-        as = 0;
-        aph ^= 1;
-      }
+      aph ^= 1;
     }
   }
 
