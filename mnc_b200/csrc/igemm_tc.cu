@@ -25,6 +25,7 @@
 
 #include "mnc_b200.h"
 #include "ptx.cuh"
+#include "launch_util.h"
 
 namespace mnc {
 
@@ -944,13 +945,8 @@ static int launch_igemm(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo,
                         int max_ctas, cudaStream_t stream) {
   using Cfg = IgemmCfg<BN, BK>;
   auto kern = igemm_tc_kernel<TH, TW, BN, CL, BK>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e =
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-    if (e != cudaSuccess) return MNC_ERR_CUDA;
-    attr_set = true;
-  }
+  static SmemGrant grant;
+  if (!ensure_dynamic_smem(kern, Cfg::kSmemBytes, grant)) return MNC_ERR_CUDA;
   const int spatial = a.batch * a.tiles_h * a.tiles_w;
   const int total = a.split_k * a.tiles_n * ((spatial + CL - 1) / CL);
   int grid = sm_count();
@@ -980,13 +976,8 @@ static int launch_halo(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const
                        const IgemmArgs& a, int max_ctas, cudaStream_t stream) {
   using Cfg = HaloCfg<BN>;
   auto kern = conv_halo_tc_kernel<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) !=
-        cudaSuccess)
-      return MNC_ERR_CUDA;
-    attr_set = true;
-  }
+  static SmemGrant grant;
+  if (!ensure_dynamic_smem(kern, Cfg::kSmemBytes, grant)) return MNC_ERR_CUDA;
   const int total = a.tiles_n * a.batch * a.tiles_h * a.tiles_w;
   int grid = sm_count();
   if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
@@ -1166,13 +1157,8 @@ extern "C" int mnc_conv1_1_tc(const float* data_nchw, int batch, int H, int W, c
   if ((rc = make_wgt_map(&tb, w_stacked, 128, 32, 128, 32)) != MNC_OK) return rc;
   if ((rc = make_out_map(&to_hi, out_hi, a.batch, 1, W, 64, 64, 1, 128)) != MNC_OK) return rc;
   if ((rc = make_out_map(&to_lo, out_lo, a.batch, 1, W, 64, 64, 1, 128)) != MNC_OK) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(conv1_1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             kC11Smem) != cudaSuccess)
-      return MNC_ERR_CUDA;
-    attr_set = true;
-  }
+  static SmemGrant grant;
+  if (!ensure_dynamic_smem(conv1_1_tc_kernel, kC11Smem, grant)) return MNC_ERR_CUDA;
   const int total = a.batch * a.tiles_w;
   int grid = sm_count();
   if (total < grid) grid = total;

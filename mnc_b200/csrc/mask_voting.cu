@@ -21,6 +21,7 @@
 #include <cstdint>
 
 #include "mnc_b200.h"
+#include "launch_util.h"
 
 namespace mnc {
 
@@ -520,15 +521,10 @@ extern "C" int mnc_mv_device(const float* boxes, const float* masks, int nb, int
   if (nb <= 0 || max_results <= 0 || batch <= 0) return MNC_ERR_ARG;
   const int smem = nb * (16 + 4 + 4 + 8 + 4);
   if (smem > 200 * 1024) return MNC_ERR_ARG;
-  static int attr_smem = 40 * 1024;
-  if (smem > attr_smem) {
-    if (cudaFuncSetAttribute(mv_aggregate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             smem) != cudaSuccess ||
-        cudaFuncSetAttribute(mv_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             smem) != cudaSuccess)
-      return MNC_ERR_CUDA;
-    attr_smem = smem;
-  }
+  static SmemGrant grant_agg, grant_fin;   // (static shared memory counts against the 48 KB default)
+  if (!ensure_dynamic_smem(mv_aggregate_kernel, smem, grant_agg) ||
+      !ensure_dynamic_smem(mv_finalize_kernel, smem, grant_fin))
+    return MNC_ERR_CUDA;
   const int total = batch * max_results;
   int* unit = bbox_ws + static_cast<long long>(total) * 4;   // [batch] flags after the boxes
   mv_init_bbox_kernel<<<(total + 255) / 256, 256, 0, stream>>>(bbox_ws, total, unit, batch);

@@ -16,6 +16,7 @@
 #include <cstring>
 
 #include "mnc_b200.h"
+#include "launch_util.h"
 
 namespace mnc {
 
@@ -124,13 +125,16 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const int* __restri
       unsigned long long cur = remv[blk];
       int num = s_num, nk = 0;
       const int rows = min(64, n - r0);
-#pragma unroll 8
-      for (int i = 0; i < rows; ++i) {
-        if (!((cur >> i) & 1ull) && num < max_keep) {
-          keep[num++] = r0 + i;
-          s_rows[nk++] = r0 + i;
-          cur |= diag[buf][i];
-        }
+      const unsigned long long rowmask = rows == 64 ? ~0ull : ((1ull << rows) - 1ull);
+      // visit only the candidates that are still alive: one iteration per KEPT box (typically a
+      // handful per block), not one per candidate
+      unsigned long long avail = ~cur & rowmask;
+      while (avail && num < max_keep) {
+        const int i = __ffsll(static_cast<long long>(avail)) - 1;
+        keep[num++] = r0 + i;
+        s_rows[nk++] = r0 + i;
+        cur |= diag[buf][i];
+        avail = ~cur & rowmask & ~((2ull << i) - 1ull);   // alive candidates after i
       }
       s_nk = nk;
       s_num = num;
@@ -449,13 +453,8 @@ extern "C" int mnc_rank_sort_desc(const float* keys, long long outer_stride,
     int np2 = 1;
     while (np2 < n) np2 <<= 1;
     const int smem = np2 * 6;
-    static int attr_smem = 40 * 1024;   // opt in early: static shared memory counts against 48 KB
-    if (smem > attr_smem) {
-      if (cudaFuncSetAttribute(bitonic_sort_desc_kernel,
-                               cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
-        return MNC_ERR_CUDA;
-      attr_smem = smem;
-    }
+    static SmemGrant grant;   // always opt in: static shared memory counts against the 48 KB default
+    if (!ensure_dynamic_smem(bitonic_sort_desc_kernel, smem, grant)) return MNC_ERR_CUDA;
     bitonic_sort_desc_kernel<<<problems, 1024, smem, static_cast<cudaStream_t>(stream_)>>>(
         keys, outer_stride, inner_stride, inner, key_stride, valid, n, np2, order, n_valid);
     return check_launch();
@@ -476,13 +475,8 @@ extern "C" int mnc_topk_sort_desc(const float* keys, long long outer_stride, lon
   while (np2 < (k < n ? k : n)) np2 <<= 1;
   const size_t smem = static_cast<size_t>(np2) * 8 + static_cast<size_t>(n) * 4;
   if (smem > 200 * 1024) return MNC_ERR_ARG;   // callers fall back to mnc_rank_sort_desc
-  static int attr_smem = 40 * 1024;     // opt in early: static shared memory counts against 48 KB
-  if (static_cast<int>(smem) > attr_smem) {
-    if (cudaFuncSetAttribute(topk_sort_desc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             static_cast<int>(smem)) != cudaSuccess)
-      return MNC_ERR_CUDA;
-    attr_smem = static_cast<int>(smem);
-  }
+  static SmemGrant grant;
+  if (!ensure_dynamic_smem(topk_sort_desc_kernel, static_cast<int>(smem), grant)) return MNC_ERR_CUDA;
   topk_sort_desc_kernel<<<problems, kTopkThreads, smem, static_cast<cudaStream_t>(stream_)>>>(
       keys, outer_stride, inner_stride, inner, key_stride, valid, n, k, np2, order, order_stride,
       n_out);
