@@ -215,3 +215,117 @@ def test_golden_fixtures(name):
     else:
         out = O.stage_bridge_forward(g["rois"], g["deltas"], g["prob"], g["im_info"])
         assert np.array_equal(out, g["rois_ext"])
+
+
+# ------------------------------------------------------------------ SURVEY.md section 8f rows 3 and 4
+def test_roi_pool_against_bruteforce_numpy():
+    """ROIPooling restatement (roi_pooling_layer.cu:17-77) vs an independent numpy version:
+    round-half-away start/end, +1 sizes forced to >= 1, floor/ceil bin edges, clipping, empty -> 0,
+    first maximum wins (argmax)."""
+    from oracle import oracle as O
+    rng = np.random.default_rng(0)
+    feat = rng.normal(size=(2, 6, 20, 30)).astype(np.float32)
+    feat[0, 0, 3:6, 4:9] = 7.0     # a plateau: the FIRST maximum must be reported
+    rois = np.array([[0, 10, 20, 200, 150], [1, 0, 0, 479, 319], [0, 300, 100, 310, 105],
+                     [1, 470, 300, 600, 400], [0, 50, 50, 40, 40], [0, 56, 40, 150, 100],
+                     [0, 900, 900, 950, 950]], np.float32)
+
+    def rnd(v):  # CUDA round(): half away from zero
+        return int(np.floor(v + 0.5)) if v >= 0 else int(np.ceil(v - 0.5))
+
+    for P in (7, 14, 3):
+        out, arg = O.roi_pool(feat, rois, P, P, return_argmax=True)
+        for i, roi in enumerate(rois):
+            b = int(roi[0])
+            sw, sh, ew, eh = (rnd(np.float32(v) * np.float32(0.0625)) for v in roi[1:])
+            rw, rh = max(ew - sw + 1, 1), max(eh - sh + 1, 1)
+            bh, bw = np.float32(rh) / np.float32(P), np.float32(rw) / np.float32(P)
+            for ph in range(P):
+                for pw in range(P):
+                    h0 = min(max(int(np.floor(np.float32(ph) * bh)) + sh, 0), 20)
+                    h1 = min(max(int(np.ceil(np.float32(ph + 1) * bh)) + sh, 0), 20)
+                    w0 = min(max(int(np.floor(np.float32(pw) * bw)) + sw, 0), 30)
+                    w1 = min(max(int(np.ceil(np.float32(pw + 1) * bw)) + sw, 0), 30)
+                    if h1 <= h0 or w1 <= w0:
+                        assert np.all(out[i, :, ph, pw] == 0) and np.all(arg[i, :, ph, pw] == -1)
+                        continue
+                    win = feat[b, :, h0:h1, w0:w1].reshape(6, -1)
+                    assert np.array_equal(out[i, :, ph, pw], win.max(axis=1))
+                    k = win.argmax(axis=1)                       # numpy argmax = first maximum
+                    want_arg = (h0 + k // (w1 - w0)) * 30 + (w0 + k % (w1 - w0))
+                    assert np.array_equal(arg[i, :, ph, pw], want_arg)
+
+
+def test_convert_pred_to_image_known_answers():
+    """`_convert_pred_to_image` restatement (vis_seg.py:101-131) on hand-checkable cases: painting
+    order, the 150 outline including its numpy `[a-1:a+1]` slices (empty when a == 0), rounding
+    half-to-even and clipping of the box."""
+    from oracle import oracle as O
+    ones = np.ones((21, 21), np.float32)
+    pred = {"cls_name": [3, 7], "masks": [ones, ones],
+            "boxes": [np.array([10, 10, 29, 24, 0.9], np.float32), np.array([20, 5, 40, 15, 0.8], np.float32)]}
+    inst, cls = O.convert_pred_to_image(64, 48, pred)
+    assert inst.dtype.kind == "i" and inst.shape == (48, 64)
+    assert np.all(inst[5:16, 20:41] == 2)                    # the later instance overwrites
+    assert np.all(inst[16:25, 10:30] == 1) and inst[4, 20] == 0
+    assert np.all(cls[7:14, 22:39] == 7)                     # interior of instance 2
+    assert np.all(cls[5:16, 19:21] == 150) and np.all(cls[4:6, 20:41] == 150)   # its outline
+    assert np.all(cls[17:23, 12:28] == 3)                    # instance 1 interior below instance 2
+    # box touching the top-left corner: the [-1:1] slices are empty, only x2 / y2 sides are drawn
+    pred0 = {"cls_name": [5], "masks": [ones], "boxes": [np.array([0, 0, 9.5, 6.5, 1.0], np.float32)]}
+    inst0, cls0 = O.convert_pred_to_image(32, 24, pred0)     # round-half-even: 9.5 -> 10, 6.5 -> 6
+    assert np.all(inst0[0:7, 0:11] == 1) and inst0[7, 0] == 0 and inst0[0, 11] == 0
+    assert cls0[0, 0] == 5 and cls0[3, 0] == 5               # no outline at x = 0 / y = 0
+    assert np.all(cls0[0:7, 9:11] == 150) and np.all(cls0[5:7, 0:11] == 150)
+    # a mask that is 0 everywhere paints nothing but its outline
+    predz = {"cls_name": [9], "masks": [np.zeros((21, 21), np.float32)],
+             "boxes": [np.array([4, 4, 12, 12, 1.0], np.float32)]}
+    instz, clsz = O.convert_pred_to_image(20, 20, predz)
+    assert instz.sum() == 0 and set(np.unique(clsz)) == {0, 150}
+    # binarisation is >= 0.4 on the resized mask
+    m = np.full((21, 21), 0.4, np.float32)
+    predt = {"cls_name": [2], "masks": [m], "boxes": [np.array([2, 2, 9, 9, 1.0], np.float32)]}
+    assert O.convert_pred_to_image(16, 16, predt)[0][5, 5] == 1
+
+
+def test_voc_ap_and_eval_sds_known_answers():
+    from oracle import oracle as O
+    # perfect ranking: AP = 1 under both metrics
+    rec = np.array([0.25, 0.5, 0.75, 1.0])
+    prec = np.ones(4)
+    assert O.voc_ap(rec, prec, True) == pytest.approx(1.0) and O.voc_ap(rec, prec, False) == pytest.approx(1.0)
+    # never more than half the ground truth found, precision 0.5 throughout
+    rec, prec = np.array([0.25, 0.25, 0.5, 0.5]), np.array([1.0, 0.5, 2 / 3, 0.5])
+    assert O.voc_ap(rec, prec, True) == pytest.approx((3 * 1.0 + 3 * (2 / 3)) / 11)   # t = 0, .1, .2 | .3, .4, .5
+    assert O.voc_ap(rec, prec, False) == pytest.approx(0.25 * 1.0 + 0.25 * (2 / 3))
+    # one image, one ground-truth square; a matching prediction, a duplicate and a miss
+    gt = {"a": [{"mask_bound": np.array([10, 10, 29, 29]), "mask": np.ones((20, 20), bool)}]}
+    ones = np.ones((1, 21, 21), np.float32)
+    boxes = [np.array([[10, 10, 29, 29, 0.9], [11, 11, 30, 30, 0.8], [40, 40, 50, 50, 0.7]], np.float32)]
+    masks = [np.stack([ones, ones, ones])]
+    ap = O.eval_sds(boxes, masks, ["a"], gt, ov_thresh=0.5)
+    # tp, fp (duplicate), fp: recall reaches 1 at precision 1 -> 11-point AP = 1
+    assert ap == pytest.approx(1.0)
+    ap2 = O.eval_sds([boxes[0][::-1].copy()], [masks[0]], ["a"], gt, ov_thresh=0.5)   # same scores order kept
+    assert ap2 == pytest.approx(1.0)
+    worse = [np.array([[40, 40, 50, 50, 0.95], [10, 10, 29, 29, 0.9]], np.float32)]
+    assert O.eval_sds(worse, [np.stack([ones, ones])], ["a"], gt) == pytest.approx(0.5)
+    assert O.eval_sds([np.zeros((0, 5), np.float32)], [np.zeros((0, 1, 21, 21), np.float32)], ["a"], gt) == 0.0
+    # an image missing from the ground-truth cache only produces false positives
+    assert O.eval_sds(boxes, masks, ["zzz"], gt) == 0.0
+
+
+def test_cfm_blob_helpers():
+    """prep_im_for_blob_cfm / pred_rois_for_blob restatements (blob.py:53-106): scale rule with the
+    MAX_SIZE cap, zero padding to the largest level, level = scale closest to a 224x224 box."""
+    from oracle import oracle as O
+    im = O.synthetic_image(0, 100, 400)
+    blob, scales = O.prep_im_for_blob_cfm(im, (200, 300), max_size=1000)
+    assert np.allclose(scales, [2.0, 2.5])                 # 300/100 = 3 would make 1200 > 1000 -> 1000/400
+    assert blob.shape == (2, 3, 250, 1000) and np.all(blob[0, :, 200:, :] == 0) and np.all(blob[0, :, :, 800:] == 0)
+    rois = O.pred_rois_for_blob(np.array([[0, 0, 111, 111], [0, 0, 89, 89], [0, 0, 99, 99]], float), scales)
+    # areas x scale^2 vs 224^2 = 50176: 112^2 -> 50176 | 78400;  90^2 -> 32400 | 50625;  100^2 -> 40000 | 62500
+    assert rois[:, 0].tolist() == [0.0, 1.0, 0.0]
+    assert np.allclose(rois[0, 1:], [0, 0, 222, 222]) and np.allclose(rois[1, 1:], [0, 0, 222.5, 222.5])
+    one = O.pred_rois_for_blob(np.array([[1, 2, 3, 4]], float), np.array([1.5]))
+    assert one.tolist() == [[0.0, 1.5, 3.0, 4.5, 6.0]]
