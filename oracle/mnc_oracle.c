@@ -12,8 +12,9 @@
  * Pinning: the reference ships no forward known-answer vectors for these kernels
  * (SURVEY.md section 8c).  orc_nms and orc_mv are pinned against the reference's own
  * nms_kernel.cu / mv_kernel.cu compiled unmodified into oracle/_ref (tests/test_ref_pin.py, GPU);
- * orc_roi_warp / orc_mask_resize / orc_mask_pool have no runnable reference here (Caffe cannot be
- * built): "parity unpinned" for those three, the .cu source lines are the only spec.
+ * orc_roi_warp / orc_mask_resize / orc_mask_pool / orc_roi_pool have no runnable reference here
+ * (Caffe cannot be built): "parity unpinned" for those four, the .cu source lines are the only
+ * spec (orc_roi_pool is cross-checked against a numpy brute force in tests/test_oracle_golden.py).
  */
 #include <math.h>
 #include <stdlib.h>

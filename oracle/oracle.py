@@ -18,6 +18,10 @@ against the reference's own nms_kernel.cu / mv_kernel.cu built unmodified into o
 Everything else on the path (ProposalLayer, StageBridgeLayer, ROIWarping, MaskResize, MaskPooling,
 gpu_mask_voting host logic) is "parity unpinned": the reference has no tests or vectors for it and
 its code cannot run here (Python 2, Caffe unbuildable), so the source lines are the only spec.
+The same is true of the SURVEY.md section 8f additions at the end of this file and in
+mnc_oracle.c (ROIPooling, the Faster R-CNN / CFM test nets and their blob helpers, result
+rendering, the AP^r evaluator): "parity unpinned" by the reference, cross-checked by brute-force
+and hand-computed known answers in tests/test_oracle_golden.py.
 
 Tie rule: the reference sorts with `scores.argsort()[::-1]` (proposal_layer.py:139,
 gpu_nms.pyx:26), numpy's unstable introsort, so the order of equal scores is unspecified there.
