@@ -129,6 +129,13 @@ def run_reference(args, rank):
     build here), so this is the oracle port, all host threads (torch CPU), 1 image per step."""
     if rank != 0:
         return
+    # torchrun pins OMP_NUM_THREADS to 1 for its workers; this arm is the CPU implementation with
+    # all the host threads it can use, so undo that before torch / the OpenMP oracle library load
+    ncpu = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(ncpu)
+    os.environ["MKL_NUM_THREADS"] = str(ncpu)
+    import torch
+    torch.set_num_threads(ncpu)
     from mnc_b200 import weights as Wt
     w = Wt.make_weights(Wt.FULL_ARCH)
     steps = max(1, min(args.steps, 3))
