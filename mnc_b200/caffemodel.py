@@ -11,8 +11,8 @@ from caffe-mnc/src/caffe/proto/caffe.proto:
     BlobProto      : shape = 7 (BlobShape), data = 5 (packed float), double_data = 8,
                      legacy dims num/channels/height/width = 1..4    (:10-22)
     BlobShape      : dim = 1 (packed int64)                          (:6-8)
-`.caffemodel.h5` (HDF5, what fetch_mnc_model.sh downloads) needs h5py, which is not installed:
-convert with Caffe's own tools or `save_caffemodel` on a machine that has it.
+`.caffemodel.h5` (HDF5, what data/scripts/fetch_mnc_model.sh downloads; written by Net::ToHDF5,
+net.cpp:920-975) is read by the small HDF5 parser in mnc_b200/hdf5_min.py -- no h5py needed.
 """
 import struct
 
@@ -130,7 +130,11 @@ def weights_from_caffemodel(path, kind="mnc_5stage"):
     only the owners are read.  (The reference's snapshots already hold un-normalised bbox_pred
     weights, lib/caffeWrapper/SolverWrapper.py:67-115.)"""
     import torch
-    layers = load_caffemodel(path)
+    if path.endswith((".h5", ".hdf5")):
+        from .hdf5_min import load_caffemodel_h5
+        layers = load_caffemodel_h5(path)      # {layer: [blobs]} from /data/<layer>/<index>
+    else:
+        layers = load_caffemodel(path)
     for name, others in _ALIASES.items():
         for o in others:
             if name not in layers and o in layers:
@@ -146,7 +150,8 @@ def weights_from_caffemodel(path, kind="mnc_5stage"):
         b = blobs[1].reshape(-1) if len(blobs) > 1 else np.zeros(w.shape[0], np.float32)
         if w.ndim == 4 and not n.startswith(("conv", "rpn_")):
             w = w.reshape(w.shape[-2], w.shape[-1])   # legacy (1,1,N,K) InnerProduct blobs
-        out[n] = (torch.from_numpy(np.ascontiguousarray(w)), torch.from_numpy(np.ascontiguousarray(b)))
+        out[n] = (torch.from_numpy(np.array(w, dtype=np.float32, order="C")),
+                  torch.from_numpy(np.array(b, dtype=np.float32, order="C")))   # owned, writable copies
     return out
 
 

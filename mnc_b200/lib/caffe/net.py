@@ -22,7 +22,7 @@ def load_weights(prototxt=None, weights=None, return_kind=False):
     if weights is None:
         kind = kind or "mnc_5stage"
         weights = make_weights() if kind == "mnc_5stage" else make_sibling_weights(kind)
-    elif isinstance(weights, str) and weights.endswith(".caffemodel"):
+    elif isinstance(weights, str) and weights.endswith((".caffemodel", ".caffemodel.h5", ".h5")):
         from mnc_b200.caffemodel import weights_from_caffemodel
         weights = weights_from_caffemodel(weights, kind or "mnc_5stage")   # by layer name
     elif isinstance(weights, str):
@@ -47,8 +47,8 @@ class Net(object):
                faster_rcnn_end2end/test.prototxt or cfm/test.prototxt (checked layer by layer
                against mnc_graph) -- or None (graph implied by the weights; default 5-stage).
     weights  : {caffe layer name: (weight, bias)} dict, a binary `.caffemodel`
-               (mnc_b200/caffemodel.py), a torch-saved file of such a dict, or None for the seeded
-               random initialiser (mnc_b200/weights.py).  `.caffemodel.h5` needs h5py (absent).
+               or HDF5 `.caffemodel.h5` (mnc_b200/caffemodel.py, hdf5_min.py), a torch-saved file of
+               such a dict, or None for the seeded random initialiser (mnc_b200/weights.py).
     """
 
     def __init__(self, prototxt=None, weights=None, phase=1):

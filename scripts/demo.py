@@ -5,9 +5,9 @@ with everything between the uint8 frames and the rendered label images resident 
 
     python scripts/demo.py --images a.jpg b.jpg [--net model.caffemodel] [--out out_dir]
 
-Images of the same size are batched.  Without --net the seeded random initialiser is used (the
-trained `.caffemodel.h5` of fetch_mnc_model.sh needs converting to binary `.caffemodel` first:
-no h5py in this image).  Outputs per image: `cls_<name>.png` (VOC palette) and `final_<name>.jpg`
+Images of the same size are batched.  --net takes a binary `.caffemodel` or the `.caffemodel.h5`
+that data/scripts/fetch_mnc_model.sh downloads; without it the seeded random initialiser is used.
+Outputs per image: `cls_<name>.png` (VOC palette) and `final_<name>.jpg`
 (0.2 * image + 0.8 * class colours, as demo.py:165-169 blends them)."""
 import argparse
 import os
@@ -25,7 +25,7 @@ from mnc_b200.api import Detector
 def main():
     ap = argparse.ArgumentParser(description="MNC demo on mnc_b200")
     ap.add_argument("--images", nargs="+", required=True)
-    ap.add_argument("--net", default=None, help="binary .caffemodel of the 5-stage net")
+    ap.add_argument("--net", default=None, help=".caffemodel or .caffemodel.h5 of the 5-stage net")
     ap.add_argument("--out", default="demo_out")
     ap.add_argument("--gpu", type=int, default=0)
     ap.add_argument("--vis-thresh", type=float, default=0.5)

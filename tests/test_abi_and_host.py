@@ -269,3 +269,55 @@ def test_eval_host_helpers_match_oracle_and_voc_palette():
     segs = [np.ones((2, 1, 21, 21), np.float32), np.zeros((0, 1, 21, 21), np.float32)]
     d = get_vis_dict(dets, segs, "n", ["a", "b"], vis_thresh=0.5)
     assert d["cls_name"] == [1] and d["boxes"][0][4] == np.float32(0.9) and d["masks"][0].shape == (21, 21)
+
+
+def test_hdf5_reader_on_reference_test_files_and_caffemodel_h5(tmp_path):
+    """mnc_b200/hdf5_min.py (`.caffemodel.h5`): (1) the reference's own HDF5 test
+    files, whose contents its generator script defines (caffe-mnc/src/caffe/test/test_data/
+    generate_sample_data.py:13-52) -- contiguous float32, and gzip-chunked float32 / uint8;
+    (2) a Net::ToHDF5-shaped weight file (net.cpp:920-975: /data/<layer>/<param id>, empty groups for
+    parameter-sharing layers, a /diff group) assembled byte by byte, 26 layer groups so the group
+    B-tree spans several symbol-table nodes; (3) the engine weight dict from it."""
+    from mnc_b200 import hdf5_min, weights as Wt, caffemodel as CM
+    from tests.util import write_h5_tree
+    base = "/root/reference/caffe-mnc/src/caffe/test/test_data/"
+    if os.path.exists(base + "sample_data.h5"):   # build container only
+        data = np.arange(10 * 8 * 6 * 5).reshape(10, 8, 6, 5).astype(np.float32)
+        label = (1 + np.arange(10)[:, None]).astype(np.float32)
+        d = hdf5_min.read_hdf5(base + "sample_data.h5")
+        assert set(d) == {"/data", "/label", "/label2"}
+        assert np.array_equal(d["/data"], data) and np.array_equal(d["/label"], label)
+        assert np.array_equal(d["/label2"], label + 1)
+        g = hdf5_min.read_hdf5(base + "sample_data_2_gzip.h5")
+        assert np.array_equal(g["/data"], data + data.size) and g["/label"].dtype == np.uint8
+        assert np.array_equal(g["/label2"], (label + 1).astype(np.uint8))
+        s = hdf5_min.read_hdf5(base + "solver_data.h5")
+        assert s["/data"].shape == (8, 3, 10, 10) and s["/targets"].shape == (8, 1)
+    w = Wt.make_weights(Wt.TINY_ARCH)
+    tree = {"data": {}, "diff": {}}
+    for name, (wt, b) in w.items():
+        tree["data"][name] = {"0": wt.numpy(), "1": b.numpy()}
+    tree["data"]["fc6_ext"] = {}                      # parameter-sharing layer: group without datasets
+    tree["data"]["relu1_1"] = {}
+    p = str(tmp_path / "mnc_tiny.caffemodel.h5")
+    write_h5_tree(p, tree)
+    layers = hdf5_min.load_caffemodel_h5(p)
+    assert set(layers) == set(w) and len(w) >= 25
+    back = CM.weights_from_caffemodel(p)
+    assert all(torch.equal(back[k][0], w[k][0]) and torch.equal(back[k][1], w[k][1]) for k in w)
+    # layer names with '/' are nested groups in the file (faster_rcnn_end2end: "rpn_conv/3x3")
+    wf = Wt.make_sibling_weights("faster_rcnn", Wt.TINY_ARCH)
+    tf = {"data": {}}
+    for name, (wt, b) in wf.items():
+        if name == "rpn_conv_3x3":
+            tf["data"]["rpn_conv"] = {"3x3": {"0": wt.numpy(), "1": b.numpy()}}
+        else:
+            tf["data"][name] = {"0": wt.numpy(), "1": b.numpy()}
+    pf = str(tmp_path / "frcnn_tiny.caffemodel.h5")
+    write_h5_tree(pf, tf)
+    bf = CM.weights_from_caffemodel(pf, "faster_rcnn")
+    assert set(bf) == set(wf) and torch.equal(bf["rpn_conv_3x3"][0], wf["rpn_conv_3x3"][0])
+    with pytest.raises(ValueError):
+        bad = tmp_path / "x.h5"
+        bad.write_bytes(b"not hdf5" * 100)
+        hdf5_min.read_hdf5(str(bad))
