@@ -120,3 +120,35 @@ def voc_eval_sds(det_file, seg_file, devkit_path, image_list, cls_name, cache_di
     with open(seg_file, "rb") as f:
         masks_pkl = pickle.load(f, encoding="latin1")
     return eval_sds_arrays(boxes_pkl, masks_pkl, image_names, gt_pkl, ov_thresh)
+
+
+def reformat_result(all_boxes, all_masks, num_classes, num_images):
+    """`PascalVOCSeg._reformat_result` (lib/datasets/pascal_voc_seg.py:179-193): masks to
+    (n, M, M) and binarised at cfg.BINARIZE_THRESH before they are written out."""
+    M = cfg.MASK_SIZE
+    out = [[[] for _ in range(num_images)] for _ in range(num_classes)]
+    for c in range(1, num_classes):
+        for i in range(num_images):
+            m = all_masks[c][i]
+            if len(m) == 0:
+                continue
+            out[c][i] = np.asarray(m).reshape(len(m), M, M) >= cfg.BINARIZE_THRESH
+    return all_boxes, out
+
+
+def write_voc_seg_results_file(all_boxes, all_masks, classes, output_dir):
+    """Per-class result pickles `<cls>_det.pkl` / `<cls>_seg.pkl`, the files `voc_eval_sds` reads
+    (`PascalVOCSeg._write_voc_seg_results_file`, pascal_voc_seg.py:160-177).  -> list of paths."""
+    num_images = len(all_boxes[1]) if len(all_boxes) > 1 else 0
+    boxes, masks = reformat_result(all_boxes, all_masks, len(classes), num_images)
+    os.makedirs(output_dir, exist_ok=True)
+    written = []
+    for c, cls in enumerate(classes):
+        if cls == "__background__":
+            continue
+        for suffix, payload in (("_det.pkl", boxes[c]), ("_seg.pkl", masks[c])):
+            path = os.path.join(output_dir, cls + suffix)
+            with open(path, "wb") as f:
+                pickle.dump(payload, f, pickle.HIGHEST_PROTOCOL)
+            written.append(path)
+    return written

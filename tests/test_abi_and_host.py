@@ -321,3 +321,32 @@ def test_hdf5_reader_on_reference_test_files_and_caffemodel_h5(tmp_path):
         bad = tmp_path / "x.h5"
         bad.write_bytes(b"not hdf5" * 100)
         hdf5_min.read_hdf5(str(bad))
+
+
+def test_voc_seg_result_files_writer(tmp_path):
+    """`<cls>_det.pkl` / `<cls>_seg.pkl` as PascalVOCSeg writes them (pascal_voc_seg.py:160-193):
+    masks reshaped to (n, 21, 21) and binarised at 0.4, empty entries stay empty lists."""
+    import pickle
+    import mnc_b200.lib as L
+    L.install()
+    from utils.voc_eval import write_voc_seg_results_file
+    classes = ["__background__", "aeroplane", "bicycle"]
+    rng = np.random.default_rng(0)
+    boxes = [[[] for _ in range(2)] for _ in range(3)]
+    masks = [[[] for _ in range(2)] for _ in range(3)]
+    boxes[1][0] = rng.uniform(0, 50, (3, 5)).astype(np.float32)
+    masks[1][0] = rng.uniform(0, 1, (3, 1, 21, 21)).astype(np.float32)
+    boxes[2][1] = rng.uniform(0, 50, (1, 5)).astype(np.float32)
+    masks[2][1] = rng.uniform(0, 1, (1, 441)).astype(np.float32)      # (n, sz*sz) is accepted too
+    paths = write_voc_seg_results_file(boxes, masks, classes, str(tmp_path / "res"))
+    assert sorted(os.path.basename(p) for p in paths) == ["aeroplane_det.pkl", "aeroplane_seg.pkl",
+                                                          "bicycle_det.pkl", "bicycle_seg.pkl"]
+    with open(tmp_path / "res" / "aeroplane_seg.pkl", "rb") as f:
+        seg = pickle.load(f)
+    with open(tmp_path / "res" / "aeroplane_det.pkl", "rb") as f:
+        det = pickle.load(f)
+    assert seg[0].shape == (3, 21, 21) and seg[0].dtype == bool and len(seg[1]) == 0
+    assert np.array_equal(seg[0], masks[1][0].reshape(3, 21, 21) >= 0.4)
+    assert np.array_equal(det[0], boxes[1][0]) and len(det[1]) == 0
+    with open(tmp_path / "res" / "bicycle_seg.pkl", "rb") as f:
+        assert pickle.load(f)[1].shape == (1, 21, 21)
