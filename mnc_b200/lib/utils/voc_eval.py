@@ -3,9 +3,9 @@ segmentation task: `voc_ap` (:19-55) and `voc_eval_sds` (:195-283).
 
 The per-prediction `cv2.resize(mask, box size) >= cfg.BINARIZE_THRESH` (:249-251) runs for all
 predictions in one device launch (csrc/render.cu, mnc_binarize_masks); the greedy
-true/false-positive assignment stays on the host, as in the reference.  Building the ground-truth
-cache from the VOC/SBD `inst`/`cls` .mat files (`check_voc_sds_cache`, :351-391) needs the dataset
-and scipy.io and is not part of this path: the `<cls>_mask_gt.pkl` files are read if they exist.
+true/false-positive assignment stays on the host, as in the reference.  The ground-truth cache
+(`parse_inst` :306-348, `check_voc_sds_cache` :351-391) is built from the SBD `inst/` and `cls/`
+.mat files with scipy.io, as upstream does, when the `<cls>_mask_gt.pkl` files do not exist yet.
 """
 import os
 import pickle
@@ -102,17 +102,53 @@ def eval_sds_arrays(boxes_pkl, masks_pkl, image_names, gt_pkl, ov_thresh=0.5, de
     return voc_ap(rec, prec, True)
 
 
+def parse_inst(image_name, devkit_path):
+    """Instances of one SBD image: [{'mask': bool (h,w) inside the tight bound, 'mask_cls': class id,
+    'mask_bound': [x1,y1,x2,y2]}] from `inst/<name>.mat` (GTinst.Segmentation = instance ids) and
+    `cls/<name>.mat` (GTcls.Segmentation = class ids)."""
+    import scipy.io as sio
+    inst = sio.loadmat(os.path.join(devkit_path, "inst", image_name + ".mat"))["GTinst"]["Segmentation"][0][0]
+    clsm = sio.loadmat(os.path.join(devkit_path, "cls", image_name + ".mat"))["GTcls"]["Segmentation"][0][0]
+    record = []
+    for inst_id in np.unique(inst):
+        if inst_id == 0:                      # background
+            continue
+        where = inst == inst_id
+        rows, cols = np.where(where)
+        x1, y1, x2, y2 = cols.min(), rows.min(), cols.max(), rows.max()
+        mask = where[y1:y2 + 1, x1:x2 + 1]
+        classes = np.unique(clsm[y1:y2 + 1, x1:x2 + 1][mask])
+        assert classes.shape[0] == 1, "instance %d of %s spans several classes" % (inst_id, image_name)
+        record.append({"mask": mask, "mask_cls": classes[0],
+                       "mask_bound": np.array([x1, y1, x2, y2], dtype=np.float64)})
+    return record
+
+
+def check_voc_sds_cache(cache_dir, devkit_path, image_names, class_names):
+    """Write `<cls>_mask_gt.pkl` ({image name: [instance dicts]}) for every class unless all of
+    them already exist."""
+    os.makedirs(cache_dir, exist_ok=True)
+    fg = [(i, n) for i, n in enumerate(class_names) if n != "__background__"]
+    if all(os.path.isfile(os.path.join(cache_dir, n + "_mask_gt.pkl")) for _, n in fg):
+        return
+    per_class = [{} for _ in class_names]
+    for image_name in image_names:
+        for rec in parse_inst(image_name, devkit_path):
+            rec["already_detect"] = False
+            per_class[int(rec["mask_cls"])].setdefault(image_name, []).append(rec)
+    for i, n in fg:
+        with open(os.path.join(cache_dir, n + "_mask_gt.pkl"), "wb") as f:
+            pickle.dump(per_class[i], f)
+
+
 def voc_eval_sds(det_file, seg_file, devkit_path, image_list, cls_name, cache_dir, class_names,
                  ov_thresh=0.5):
     """File-level entry with the reference's signature: `det_file` / `seg_file` are the per-class
     pickles ([image] -> arrays) that `PascalVOCSeg._write_voc_seg_results_file` writes."""
     with open(image_list) as f:
         image_names = [x.strip() for x in f.readlines()]
+    check_voc_sds_cache(cache_dir, devkit_path, image_names, class_names)
     gt_cache = os.path.join(cache_dir, cls_name + "_mask_gt.pkl")
-    if not os.path.isfile(gt_cache):
-        raise FileNotFoundError(
-            "%s missing: build the ground-truth cache with the reference's check_voc_sds_cache "
-            "(needs VOCdevkit + SBD)" % gt_cache)
     with open(gt_cache, "rb") as f:
         gt_pkl = pickle.load(f, encoding="latin1")
     with open(det_file, "rb") as f:

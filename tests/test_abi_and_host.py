@@ -350,3 +350,42 @@ def test_voc_seg_result_files_writer(tmp_path):
     assert np.array_equal(det[0], boxes[1][0]) and len(det[1]) == 0
     with open(tmp_path / "res" / "bicycle_seg.pkl", "rb") as f:
         assert pickle.load(f)[1].shape == (1, 21, 21)
+
+
+def test_sbd_ground_truth_cache(tmp_path):
+    """parse_inst / check_voc_sds_cache (voc_eval.py:306-391) on SBD-shaped .mat files: tight bounds,
+    masks cropped to them, class from the class map, per-class {image: [instances]} pickles, and the
+    cache is not rebuilt when complete."""
+    import pickle
+    import scipy.io as sio
+    import mnc_b200.lib as L
+    L.install()
+    from utils.voc_eval import parse_inst, check_voc_sds_cache
+    dev = tmp_path / "sbd"
+    (dev / "inst").mkdir(parents=True)
+    (dev / "cls").mkdir()
+    inst = np.zeros((40, 60), np.uint8)
+    cls = np.zeros((40, 60), np.uint8)
+    inst[5:15, 10:30] = 1; cls[5:15, 10:30] = 2          # instance 1: class 2, a full rectangle
+    inst[20:35, 40:55] = 2; cls[20:35, 40:55] = 1        # instance 2: class 1 ...
+    inst[22:25, 42:45] = 0; cls[22:25, 42:45] = 0        # ... with a hole
+    inst[0:3, 0:3] = 3; cls[0:3, 0:3] = 2                # instance 3: class 2 again
+    for name in ("im_a", "im_b"):
+        sio.savemat(str(dev / "inst" / (name + ".mat")), {"GTinst": {"Segmentation": inst, "Categories": np.array([2, 1, 2])}})
+        sio.savemat(str(dev / "cls" / (name + ".mat")), {"GTcls": {"Segmentation": cls}})
+    rec = parse_inst("im_a", str(dev))
+    assert [int(r["mask_cls"]) for r in rec] == [2, 1, 2]
+    assert rec[0]["mask_bound"].tolist() == [10, 5, 29, 14] and rec[0]["mask"].all()
+    assert rec[1]["mask_bound"].tolist() == [40, 20, 54, 34] and rec[1]["mask"].shape == (15, 15)
+    assert rec[1]["mask"].sum() == 15 * 15 - 9 and rec[2]["mask_bound"].tolist() == [0, 0, 2, 2]
+    names = ["__background__", "aeroplane", "bicycle"]
+    cache = tmp_path / "cache"
+    check_voc_sds_cache(str(cache), str(dev), ["im_a", "im_b"], names)
+    with open(cache / "bicycle_mask_gt.pkl", "rb") as f:
+        gt = pickle.load(f)
+    assert set(gt) == {"im_a", "im_b"} and len(gt["im_a"]) == 2 and gt["im_a"][0]["already_detect"] is False
+    with open(cache / "aeroplane_mask_gt.pkl", "rb") as f:
+        assert [len(v) for v in pickle.load(f).values()] == [1, 1]
+    stamp = (cache / "bicycle_mask_gt.pkl").stat().st_mtime_ns
+    check_voc_sds_cache(str(cache), str(tmp_path / "nowhere"), ["im_a"], names)   # complete: not rebuilt
+    assert (cache / "bicycle_mask_gt.pkl").stat().st_mtime_ns == stamp
