@@ -298,9 +298,15 @@ class MNCEngine:
     def detect(self, data, im_info, im_hw, im_scale):
         """forward + im_detect tail (tools/demo.py:92-100): boxes (B,600,4), masks (B,600,1,21,21),
         scores (B,600,21), valid (B,600) uint8."""
-        B = data.shape[0]
         o = self.forward(data, im_info)
-        n = ROIS_PER_IMAGE
+        return self.detect_tail(o, data.shape[0], im_hw, im_scale) + (o,)
+
+    def detect_tail(self, o, B, im_hw, im_scale, n=ROIS_PER_IMAGE):
+        """The `im_detect` tail on the blobs of `forward` (tools/demo.py:84-100 ==
+        TesterWrapper.py:244-260): rois / im_scale (fp32 division, the numpy-1.x evaluation of
+        `rois[:, 1:5] / im_scales[0]`), clip_boxes to the ORIGINAL image shape im_hw, stage 1 rows
+        then stage 2 rows.  o: dict with rois, rois_ext (B*n,5), mask_proposal(_ext),
+        seg_cls_prob(_ext), roi_counts (B,); n rows per image and stage."""
         b1 = ops.unscale_clip(o["rois"], n, im_scale, im_hw).view(B, n, 4)
         b2 = ops.unscale_clip(o["rois_ext"], n, im_scale, im_hw).view(B, n, 4)
         boxes = torch.cat([b1, b2], dim=1).contiguous()
@@ -311,4 +317,4 @@ class MNCEngine:
         ar = torch.arange(n, device=self.device, dtype=torch.int32).view(1, n)
         v = (ar < o["roi_counts"].view(B, 1)).to(torch.uint8)
         valid = torch.cat([v, v], dim=1).contiguous()
-        return boxes, masks, scores, valid, o
+        return boxes, masks, scores, valid

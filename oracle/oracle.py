@@ -360,14 +360,17 @@ def mv(all_boxes, all_masks, candidate_inds, candidate_start, candidate_weights,
     return result_mask, result_box
 
 
-def mask_voting_candidates(boxes, scores, num_classes, max_per_image):
+def mask_voting_candidates(boxes, scores, num_classes, max_per_image, numpy2=False):
     """Host half of gpu_mask_voting -- lib/transform/mask_transform.py:213-274.
     Returns (candidate_inds i32, candidate_start i32 END offsets, candidate_weights f32,
     candidate_scores f32, class_bar list).
 
     Weight normalisation (`cur_weights / sum(cur_weights)`, :266-267): the reference ran under
     numpy 1.x where builtin sum() over fp32 scalars starting from int 0 accumulates in float64,
-    and `f32_array / f64_scalar` is evaluated in fp32 with the scalar cast to fp32; restated so."""
+    and `f32_array / f64_scalar` is evaluated in fp32 with the scalar cast to fp32; restated so
+    (numpy2=False, the semantics the CUDA path implements).  numpy2=True is the same line as
+    numpy >= 2 evaluates it (NEP 50: the int 0 is weak, the sum stays float32).  Both are pinned
+    to the reference's own function run under each rule (tests/golden/ref_voting.npz)."""
     sup_boxes, sup_scores, tobesort = [], [], []
     for i in range(num_classes):
         if i == 0:
@@ -400,9 +403,14 @@ def mask_voting_candidates(boxes, scores, num_classes, max_per_image):
             cur_inds = np.where(cur_ov >= CFG.MASK_MERGE_IOU_THRESH)[0]
             candidate_inds.extend(cur_inds)
             cur_weights = scores[cur_inds, c].astype(np.float32)
-            total = np.float64(0.0)
-            for v in cur_weights:  # builtin sum(): sequential, float64 accumulator
-                total = total + np.float64(v)
+            if numpy2:
+                total = np.float32(0.0)
+                for v in cur_weights:  # builtin sum(): sequential, float32 accumulator
+                    total = np.float32(total + v)
+            else:
+                total = np.float64(0.0)
+                for v in cur_weights:  # builtin sum(): sequential, float64 accumulator
+                    total = total + np.float64(v)
             cur_weights = cur_weights / np.float32(total)
             candidate_weights.extend(cur_weights)
             candidate_start.append(len(candidate_inds))
@@ -413,10 +421,11 @@ def mask_voting_candidates(boxes, scores, num_classes, max_per_image):
             np.array(candidate_scores, dtype=np.float32), class_bar)
 
 
-def gpu_mask_voting(masks, boxes, scores, num_classes, max_per_image, im_width, im_height):
+def gpu_mask_voting(masks, boxes, scores, num_classes, max_per_image, im_width, im_height,
+                    numpy2=False):
     """lib/transform/mask_transform.py:213-286."""
     inds, start, weights, cscores, class_bar = mask_voting_candidates(
-        boxes, scores, num_classes, max_per_image)
+        boxes, scores, num_classes, max_per_image, numpy2=numpy2)
     result_mask, result_box = mv(boxes.astype(np.float32), masks, inds, start, weights,
                                  im_height, im_width)
     result_box = np.hstack((result_box, cscores[:, np.newaxis]))
@@ -667,14 +676,28 @@ def pred_rois_for_blob(im_rois, im_scales):
     return np.hstack((levels.astype(np.float64), im_rois))
 
 
-def im_detect_tail(blobs, im_shape, im_scale=1.0):
-    """tools/demo.py:84-100 (== TesterWrapper.py:244-260)."""
-    rois1 = blobs["rois"][:, 1:5] / im_scale
-    rois2 = blobs["rois_ext"][:, 1:5] / im_scale
+def im_detect_tail(blobs, im_shape, im_scale=1.0, numpy2=False):
+    """tools/demo.py:84-100 (== TesterWrapper.py:244-260).
+
+    `rois[:, 1:5] / im_scales[0]` divides a float32 array by a 0-d float64 array: under the numpy
+    1.x the reference ran on that is a float32 division by float32(scale) (value-based casting)
+    and boxes stay float32 -- numpy2=False, what the CUDA path implements; under numpy >= 2 it is a
+    float64 division and boxes come out float64 -- numpy2=True, pinned bit-exact to the reference's
+    own im_detect run here (tests/golden/ref_prep_tail.npz).  The two agree to 1 float32 ulp."""
+    if numpy2:
+        div = np.float64(im_scale)
+        rois1 = blobs["rois"][:, 1:5].astype(np.float64) / div
+        rois2 = blobs["rois_ext"][:, 1:5].astype(np.float64) / div
+    else:
+        div = np.float32(im_scale)
+        rois1 = blobs["rois"][:, 1:5] / div
+        rois2 = blobs["rois_ext"][:, 1:5] / div
     rois1, _ = clip_boxes(rois1, im_shape)
     rois2, _ = clip_boxes(rois2, im_shape)
     masks = np.concatenate((blobs["mask_proposal"], blobs["mask_proposal_ext"]), axis=0)
-    boxes = np.concatenate((rois1, rois2), axis=0).astype(np.float32)
+    boxes = np.concatenate((rois1, rois2), axis=0)
+    if not numpy2:
+        boxes = boxes.astype(np.float32)
     scores = np.concatenate((blobs["seg_cls_prob"], blobs["seg_cls_prob_ext"]), axis=0)
     return boxes, masks, scores
 
