@@ -3,7 +3,7 @@
 // cv2.resize(fx = fy = scale, INTER_LINEAR), HWC -> NCHW blob.
 //
 // OpenCV's float INTER_LINEAR rule is restated (OpenCV is a dependency of the reference, not part
-// of it): source coordinate fx = (dx + 0.5) / scale - 0.5, sx = floor(fx); sx < 0 -> (0, frac 0);
+// of it): source coordinate fx = (dx + 0.5) / scale - 0.5 in double, sx = floor(fx); sx < 0 -> (0, frac 0);
 // sx >= W-1 -> (W-1, frac 0); horizontal interpolation first, then vertical, in fp32.
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -18,9 +18,11 @@ struct LinTap {
 };
 
 __device__ __forceinline__ LinTap lin_tap(int d, double inv_scale, int n) {
-  float f = static_cast<float>((d + 0.5) * inv_scale - 0.5);
-  int s = static_cast<int>(floorf(f));
-  f -= s;
+  // the fraction is taken in double and rounded once (OpenCV 4.x resize.cpp; an fp32 coordinate
+  // would lose 1e-5 of the fraction at x ~ 200 and 3e-3 of a pixel value -- measured against cv2)
+  const double fd = (d + 0.5) * inv_scale - 0.5;
+  int s = static_cast<int>(floor(fd));
+  float f = static_cast<float>(fd - s);
   if (s < 0) {
     f = 0.f;
     s = 0;

@@ -9,7 +9,7 @@
 // same result without the n read-modify-write passes over the image.
 //
 // cv2.resize (OpenCV, a dependency of the reference, not part of it) is restated as in
-// preprocess.cu: fx = (dx + 0.5) * (src / dst) - 0.5 in fp32, floor, clamp (sx < 0 -> 0, frac 0;
+// preprocess.cu: fx = (dx + 0.5) * (src / dst) - 0.5 in double, floor, clamp (sx < 0 -> 0, frac 0;
 // sx >= src - 1 -> src - 1, frac 0), horizontal pass then vertical pass in fp32.
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -25,9 +25,9 @@ struct InstRec {
 
 __device__ __forceinline__ void cv_tap(int d, double scale, int n, int& i0, int& i1, float& a0,
                                        float& a1) {
-  float f = static_cast<float>((d + 0.5) * scale - 0.5);
-  int s = static_cast<int>(floorf(f));
-  f -= s;
+  const double fd = (d + 0.5) * scale - 0.5;   // fraction in double, rounded once (see preprocess.cu)
+  int s = static_cast<int>(floor(fd));
+  float f = static_cast<float>(fd - s);
   if (s < 0) {
     f = 0.f;
     s = 0;

@@ -98,19 +98,52 @@ def test_tiny_arch_batch3_stagewise():
         assert n > 50
 
 
-def test_tiny_arch_pixels_to_outputs_close_to_oracle():
-    """No teacher forcing: when the RoI lists agree (they do unless a near-tie flips), every output
-    blob the callers read matches the pure oracle run within 1e-3."""
+def _match_rois(got, want, tol=0.05):
+    """Pair RoIs of two lists by coordinates (different anchors are many pixels apart): returns
+    index pairs (i, j) with max |got[i] - want[j]| < tol, each row used once."""
+    d = np.abs(got[:, None, 1:] - want[None, :, 1:]).max(axis=2)
+    j = d.argmin(axis=1)
+    ok = d[np.arange(len(got)), j] < tol
+    i = np.where(ok)[0]
+    assert len(set(j[i])) == len(i)
+    return i, j[i]
+
+
+@pytest.mark.parametrize("arch,H,W", [("TINY_ARCH", 224, 320), ("TINY_ARCH", 375, 500)])
+def test_pixels_to_outputs_free_running(arch, H, W):
+    """No teacher forcing: pixels -> every blob the callers read, engine vs pure oracle run.
+    A 1e-6 score or 1e-4 px box difference may flip an NMS decision or swap two near-equal scores,
+    after which a few RoIs differ between the two runs (legal); so RoIs are paired by coordinates,
+    the unpaired remainder is bounded, and every paired RoI's outputs must agree within tolerance
+    through BOTH stages.  A wrong kernel anywhere fails this."""
     from oracle import oracle as O
-    w, ims, data, im_info, eng, out = _run("TINY_ARCH", 224, 320, 1)
+    w, ims, data, im_info, eng, out = _run(arch, H, W, 1)
     (boxes, masks, scores), blobs = O.im_detect(w, ims[0])
     n = int(out["roi_counts"][0].item())
+    want_n = blobs["rois"].shape[0]
+    assert abs(n - want_n) <= 3, (n, want_n)
     rois = out["rois"][:n].cpu().numpy()
-    if rois.shape == blobs["rois"].shape and np.abs(rois - blobs["rois"]).max() < 0.05:
-        assert np.abs(out["mask_proposal"][:n].cpu().numpy() - blobs["mask_proposal"]).max() < 5 * TOL
-        assert np.abs(out["seg_cls_prob"][:n].cpu().numpy() - blobs["seg_cls_prob"]).max() < 5 * TOL
-    else:
-        pytest.skip("a near-tie reordered proposals between oracle and engine (legal; see docstring)")
+    i, j = _match_rois(rois, blobs["rois"])
+    assert len(i) >= want_n - 6, "only %d of %d RoIs found in the oracle's list" % (len(i), want_n)
+    # rank agreement: paired RoIs appear in the same relative order, except where two scores
+    # within ~1e-6 of each other swap (bounded)
+    assert (np.diff(j) <= 0).sum() <= 3, np.where(np.diff(j) <= 0)[0]
+    for name, tol in (("mask_proposal", 5 * TOL), ("seg_cls_prob", 5 * TOL), ("cls_prob", 5 * TOL)):
+        g = out[name][:n].cpu().numpy()[i]
+        assert np.abs(g - blobs[name][j]).max() < tol, name
+    bb = out["bbox_pred"][:n].cpu().numpy()[i]
+    assert np.abs(bb - blobs["bbox_pred"][j]).max() < 5 * TOL * max(1.0, np.abs(blobs["bbox_pred"]).max())
+    # stage 2: rois_ext and the _ext outputs of the paired rows (argmax class may only differ
+    # where the top-2 seg_cls_prob are within tolerance of each other)
+    ext = out["rois_ext"][:n].cpu().numpy()[i]
+    want_ext = blobs["rois_ext"][j]
+    p = np.sort(blobs["seg_cls_prob"][j], axis=1)
+    decided = (p[:, -1] - p[:, -2]) > 20 * TOL
+    assert decided.sum() >= 0.8 * len(j)
+    assert np.abs(ext[decided, 1:] - want_ext[decided, 1:]).max() < 0.05
+    for name in ("mask_proposal_ext", "seg_cls_prob_ext"):
+        g = out[name][:n].cpu().numpy()[i][decided]
+        assert np.abs(g - blobs[name][j][decided]).max() < 10 * TOL, name
 
 
 def test_full_vgg16_600x1000_stagewise_and_roi_count():
@@ -122,6 +155,17 @@ def test_full_vgg16_600x1000_stagewise_and_roi_count():
     # equal fp32 scores do occur among 21546 anchors (about 10 pairs in the top 6000 here); their
     # order is fixed by the documented rule (score desc, index asc), which the teacher-forced
     # proposal check above has just verified index for index.
+
+
+def test_full_vgg16_600x1000_batch8_stagewise():
+    """BASELINE.json configs[1] exactly: FULL_ARCH, batch 8, 600x1000 -- the benchmarked
+    configuration (tile / wave / split-K choices depend on the batch).  Stage-wise parity of three
+    of the eight images (first, middle, last: the CPU oracle needs ~10 s per image)."""
+    w, ims, data, im_info, eng, out = _run("FULL_ARCH", 600, 1000, 8)
+    counts = out["roi_counts"].cpu().numpy()
+    assert counts.shape == (8,) and np.all(counts == 300)
+    for img in (0, 3, 7):
+        assert _check_stagewise(w, data, im_info, eng, out, img) == 300
 
 
 def test_caffe_net_shim_and_detect_tail():

@@ -66,10 +66,11 @@ def test_proposal_layer_mirror(H, W, imh, imw):
     forced_boxes, forced_idx = _oracle_from_device_decode(props, scores, valid)
     assert rois.shape[0] == forced_boxes.shape[0] == int(cnt[0].item())
     assert np.array_equal(rois[:, 1:], forced_boxes)            # bit-exact RoIs
-    # the same RoI *indices* as the pure oracle unless an ulp moved a box across a threshold
-    same = np.array_equal(forced_idx, inter["roi_anchor_index"])
-    if same:
-        assert np.allclose(rois, want_rois, rtol=1e-5, atol=2e-3)
+    # the same RoI *indices* as the pure oracle: these seeded inputs have no IoU within 1e-6 of the
+    # threshold among the decisions taken (margin-checked fixtures of the same generator are in
+    # tests/test_gpu_ref_fixtures.py), so the expf-vs-exp ulp cannot move a decision
+    assert np.array_equal(forced_idx, inter["roi_anchor_index"])
+    assert np.allclose(rois, want_rois, rtol=1e-5, atol=2e-3)
 
 
 def test_rpn_decode_softmax_from_nhwc_logits():

@@ -35,12 +35,9 @@ def test_mv_host_matches_oracle(nb, H, W, seed):
     rm, rb = mv(boxes, masks, inds, start, weights, H, W)
     rm_o, rb_o, agg = O.mv(boxes, masks, inds, start, weights, H, W, return_agg=True)
     assert rm.shape == (len(start), 1, 21, 21) and rb.dtype == np.int32
-    # int boxes must match unless an aggregated pixel lies within float noise of the 0.4 threshold
-    near = np.abs(agg - 0.4) < 2e-6
-    if not near.any():
-        assert np.array_equal(rb, rb_o)
-    else:
-        assert (rb != rb_o).sum() <= 2
+    # int boxes match exactly: on these seeded inputs no aggregated pixel that bounds a result box
+    # sits within float noise of the 0.4 threshold (checked: the nearest is reported on failure)
+    assert np.array_equal(rb, rb_o), "nearest aggregate to 0.4: %.3e" % np.abs(agg - 0.4).min()
     assert util.rel_err(rm, rm_o) < 1e-4
 
 
@@ -94,5 +91,5 @@ def test_gpu_mask_voting_matches_oracle(nb, H, W, seed):
         assert lb[c].shape == lb_o[c].shape and lm[c].shape == lm_o[c].shape
         if lb[c].shape[0]:
             assert np.array_equal(lb[c][:, 4], lb_o[c][:, 4])
-            assert np.abs(lb[c][:, :4] - lb_o[c][:, :4]).max() <= 1   # see test_mv_host note
+            assert np.array_equal(lb[c][:, :4], lb_o[c][:, :4])
             assert util.rel_err(lm[c], lm_o[c]) < 1e-3

@@ -160,9 +160,8 @@ def test_mv_against_naive_render():
         assert np.allclose(a, agg[k], atol=1e-6)
         ys, xs = np.where(a > np.float32(0.4))
         want = [xs.min(), ys.min(), xs.max(), ys.max()] if len(xs) else [W // 2, H // 2, W // 2, H // 2]
-        near = np.abs(a - 0.4) < 1e-6
-        if not near.any():
-            assert list(rb[k]) == [int(v) for v in want]
+        assert not (np.abs(a - 0.4) < 1e-6).any()   # seeded input: no pixel inside float noise of 0.4
+        assert list(rb[k]) == [int(v) for v in want]
     assert list(rb[1]) == [W // 2, H // 2, W // 2, H // 2]   # empty list -> defaults (mv_kernel.cu:148,172)
 
 
