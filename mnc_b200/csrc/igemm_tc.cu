@@ -19,6 +19,8 @@
 //    raw fp32 (split-K partials / final logits).
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
@@ -37,11 +39,18 @@ struct IgemmArgs {
   int k_steps;  // taps * Cin / 64
   int split_k;
   int relu;
-  int out_mode;  // 0: split bf16 (hi, lo); 1: fp32; 2: split bf16 after a fused 2x2/2 ceil-mode max pool
+  // 0: split bf16 (hi, lo); 1: fp32; 2: split bf16 after a fused 2x2/2 ceil-mode max pool;
+  // 4: tri-plane (fp16 hi, e4m3 lo, e4m3 hi copy -- see "precision mode 1" below); 5: tri-plane
+  // after the fused max pool
+  int out_mode;
   const float* bias;
-  __nv_bfloat16* out_hi;
-  __nv_bfloat16* out_lo;
+  __nv_bfloat16* out_hi;   // modes 4/5: the fp16 plane
+  __nv_bfloat16* out_lo;   // modes 4/5: the e4m3 residual plane
+  uint8_t* out_x;          // modes 4/5: the e4m3 copy of the value
   float* out_f32;
+  float acc_scale;         // accumulator -> true value (1 for bf16 operands; 2^-(ea+ew) in mode 1)
+  float out_scale;         // modes 4/5: 2^ea of the tensor being written
+  unsigned int* amax;      // optional: atomicMax of |output| as float bits (scale calibration)
   long long out_pix_stride;  // elements between consecutive pixels (rows)
   int out_ch_offset;
   long long split_stride;  // elements between split-K partial planes (fp32 mode)
@@ -53,10 +62,15 @@ constexpr int kBlockM = 128;
 
 // BK = K elements per pipeline stage: 64 (128-byte rows, SWIZZLE_128B) or 32 (64-byte rows,
 // SWIZZLE_64B: half-size stages, i.e. twice the pipeline depth in the same shared memory).
-template <int BN, int BK>
+// CL = 2: the CTA pair of a cluster runs ONE M = 256 MMA per instruction (cta_group::2): each CTA
+// holds its own 128 pixel rows of A and only HALF of the weight tile (BN / 2 rows), so per MAC an
+// SM takes in 2/3 of the operand bytes of the single-CTA 128 x 256 tile -- operand delivery into
+// the SM (~61 B/clk measured from L2), not the tensor pipe, is what bounds these kernels once the
+// tensor work per MAC drops (profiles/README.md, r02 findings).
+template <int BN, int BK, int CL = 1>
 struct IgemmCfg {
-  static constexpr int kABytes = kBlockM * BK * 2;  // one bf16 plane of the A tile
-  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kABytes = kBlockM * BK * 2;  // one 2-byte plane of the A tile
+  static constexpr int kBBytes = (BN / CL) * BK * 2;  // one 2-byte plane of this CTA's part of B
   static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
   static constexpr int kStagesRaw = (192 * 1024) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
@@ -111,6 +125,32 @@ __device__ __forceinline__ Tile decode_tile(const IgemmArgs& p, int t, int rank,
   return tl;
 }
 
+// ---------------------------------------------------------------------- precision mode 1 format
+// "tri-plane" activations / weights: a tensor with per-tensor exponent e is
+// stored as   h = fp16(x * 2^e)            (main operand, kind::f16)
+//             l = e4m3((x*2^e - h) * 2^6)  (residual, 2^-11 of h at most)
+//             c = e4m3(x * 2^e * 2^-5)     (low-precision copy of the value)
+// for activations, and with the residual scaled by 2^5 / the copy by 2^-6 for weights, so that
+//   X.W * 2^(ex+ew) = Xh.Wh  +  Xl.Wc  +  Xc.Wl      (2^6 * 2^-6 = 2^-5 * 2^5 = 1)
+// The first product runs as fp16 MMAs, the two corrections as ONE K-concatenated chain of FP8
+// MMAs at twice the rate: 2 tensor-work units per MAC instead of the 3 of the split-bf16 scheme,
+// at 1.1e-5 relative error per layer (scripts/fp8_correction_model.py; measured in tests).
+struct Tri2 {
+  uint32_t h;      // two fp16
+  uint16_t l, c;   // two e4m3 each
+};
+__device__ __forceinline__ Tri2 tri_pack2(float x0, float x1, float scale) {
+  const float a0 = fminf(fmaxf(x0 * scale, -65504.f), 65504.f);
+  const float a1 = fminf(fmaxf(x1 * scale, -65504.f), 65504.f);
+  const __half2 h = __floats2half2_rn(a0, a1);
+  const float2 hf = __half22float2(h);
+  Tri2 t;
+  t.h = *reinterpret_cast<const uint32_t*>(&h);
+  t.l = __nv_cvt_float2_to_fp8x2(make_float2((a0 - hf.x) * 64.f, (a1 - hf.y) * 64.f), __NV_SATFINITE, __NV_E4M3);
+  t.c = __nv_cvt_float2_to_fp8x2(make_float2(a0 * 0.03125f, a1 * 0.03125f), __NV_SATFINITE, __NV_E4M3);
+  return t;
+}
+
 // ---------------------------------------------------------------------------------- epilogue
 // Shared by the per-tap kernel and the halo kernel: warps 4..7 drain the TMEM accumulators of
 // every tile this CTA owns (bias, ReLU, optional 2x2 ceil-mode max pool, re-split, store).
@@ -120,7 +160,8 @@ __device__ __forceinline__ Tile decode_tile(const IgemmArgs& p, int t, int rank,
 // buffer (waiting for its previous bulk store to finish reading it) instead of two.
 template <int TH, int TW, int BN, int CL, bool ACC2 = false, int NG = 1>
 __device__ __forceinline__ void run_epilogue(const IgemmArgs& p, const CUtensorMap* tm_o_hi_p,
-                                             const CUtensorMap* tm_o_lo_p, uint8_t* staging,
+                                             const CUtensorMap* tm_o_lo_p,
+                                             const CUtensorMap* tm_o_x_p, uint8_t* staging,
                                              uint64_t* tfull_bar, uint64_t* tempty_bar,
                                              uint32_t tmem_base, int rank, int first, int stride,
                                              int total_tiles) {
@@ -133,6 +174,8 @@ __device__ __forceinline__ void run_epilogue(const IgemmArgs& p, const CUtensorM
   const int row = q * 32 + lane;
   int local = 0;
   int chunk_ctr = 0;
+  float amx = 0.f;   // max |output| seen by this thread (valid pixels only)
+  const float asc = p.acc_scale;
   for (int t = first; t < total_tiles; t += stride, ++local) {
     const Tile tl = decode_tile<CL>(p, t, rank, TH, TW, BN);
     const int img = tl.img, h0 = tl.h0, w0 = tl.w0, n0 = tl.n0, ks = tl.ks;
@@ -163,7 +206,7 @@ __device__ __forceinline__ void run_epilogue(const IgemmArgs& p, const CUtensorM
       }
       const int ch0 = n0 + c0;
       if (p.out_mode == 3) continue;  // diagnostic: accumulators are drained and discarded
-      if (p.out_mode == 2) {
+      if (p.out_mode == 2 || p.out_mode == 5) {
         // Fused 2x2 stride-2 ceil-mode max pool (pooling_layer.cu:11-47).  A warp holds 32/TW
         // whole image rows of the pixel tile (TW = 16: two rows, TW = 8: four), so the pool window
         // of an even (row, column) is lanes {l, l^1, l^TW, l^(TW+1)}: two shuffles per channel.
@@ -174,10 +217,11 @@ __device__ __forceinline__ void run_epilogue(const IgemmArgs& p, const CUtensorM
         float m[8];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(r[j]);
+          float x = __uint_as_float(r[j]) * asc;
           if (p.bias != nullptr && ch0 + j < p.Cout) x += __ldg(p.bias + ch0 + j);
           if (p.relu) x = fmaxf(x, 0.f);
           if (!valid) x = -3.402823466e+38f;
+          else amx = fmaxf(amx, fabsf(x));
           x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 1));
           x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, TW));
           if ((j >> 3) == part) m[j & 7] = x;
@@ -189,8 +233,29 @@ __device__ __forceinline__ void run_epilogue(const IgemmArgs& p, const CUtensorM
         if (!tl.dummy && hp < Ho && wp < Wo && (h0 + hl) < p.H && (w0 + wl) < p.W &&
             chp < p.Cout) {
           const long long ppix = (static_cast<long long>(img) * Ho + hp) * Wo + wp;
-          __nv_bfloat16* ph = p.out_hi + ppix * p.out_pix_stride + p.out_ch_offset + chp;
-          __nv_bfloat16* pl = p.out_lo + ppix * p.out_pix_stride + p.out_ch_offset + chp;
+          const long long poff = ppix * p.out_pix_stride + p.out_ch_offset + chp;
+          if (p.out_mode == 5) {
+            uint32_t hw[4], lw[2], cw[2];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const Tri2 tr = tri_pack2(m[2 * e], m[2 * e + 1], p.out_scale);
+              hw[e] = tr.h;
+              if (e & 1) {
+                lw[e >> 1] |= static_cast<uint32_t>(tr.l) << 16;
+                cw[e >> 1] |= static_cast<uint32_t>(tr.c) << 16;
+              } else {
+                lw[e >> 1] = tr.l;
+                cw[e >> 1] = tr.c;
+              }
+            }
+            *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out_hi) + poff) =
+                make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(p.out_lo) + poff) = make_uint2(lw[0], lw[1]);
+            *reinterpret_cast<uint2*>(p.out_x + poff) = make_uint2(cw[0], cw[1]);
+            continue;
+          }
+          __nv_bfloat16* ph = p.out_hi + poff;
+          __nv_bfloat16* pl = p.out_lo + poff;
           uint32_t hw[4], lw[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -208,11 +273,13 @@ __device__ __forceinline__ void run_epilogue(const IgemmArgs& p, const CUtensorM
           *reinterpret_cast<uint4*>(pl) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
         }
       } else if (p.tma_store) {
-        // ---- out_mode 0 via shared-memory staging + TMA store: each thread owns one pixel row
-        // of the 128 x 32-channel chunk (64 B per bf16 plane, written with the 64B-swizzle
-        // pattern so the 16-byte stores are bank-conflict free); one elected thread then issues
-        // two bulk tensor stores (hi, lo).  TMA clips ragged tiles, channel tails and the
-        // cluster's dummy tile, and the global writes are whole 64-byte rows.
+        // ---- out_mode 0 / 4 via shared-memory staging + TMA store: each thread owns one pixel row
+        // of the 128 x 32-channel chunk (64 B per 2-byte plane, written with the 64B-swizzle
+        // pattern so the 16-byte stores are bank-conflict free; the one-byte planes of mode 4 are
+        // 32 B per row, unswizzled); one elected thread then issues the bulk tensor stores.  TMA
+        // clips ragged tiles, channel tails and the cluster's dummy tile, and the global writes
+        // are whole rows.
+        const bool tri = (p.out_mode == 4);
         const int buf = chunk_ctr % NBUF;
         uint8_t* sb = staging + (grp * NBUF + buf) * (2 * 128 * 64);
         if (threadIdx.x == lead) ptx::tma_store_wait_read<NBUF - 1>();  // this buffer's previous store
@@ -235,37 +302,59 @@ __device__ __forceinline__ void run_epilogue(const IgemmArgs& p, const CUtensorM
             for (int j = 0; j < 32; ++j)
               bv[j] = (p.bias != nullptr && ch0 + j < p.Cout) ? __ldg(p.bias + ch0 + j) : 0.f;
           }
+          float mx = 0.f;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             uint32_t hw[4], lw[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              float x0 = __uint_as_float(r[g * 8 + 2 * e]) + bv[g * 8 + 2 * e];
-              float x1 = __uint_as_float(r[g * 8 + 2 * e + 1]) + bv[g * 8 + 2 * e + 1];
+              float x0 = __uint_as_float(r[g * 8 + 2 * e]) * asc + bv[g * 8 + 2 * e];
+              float x1 = __uint_as_float(r[g * 8 + 2 * e + 1]) * asc + bv[g * 8 + 2 * e + 1];
               if (p.relu) {
                 x0 = fmaxf(x0, 0.f);
                 x1 = fmaxf(x1, 0.f);
               }
-              // packed conversions: (x0, x1) -> bf16x2 in one instruction; the hi values come back
-              // as floats by a shift / mask of the packed word
-              const __nv_bfloat162 hp = __floats2bfloat162_rn(x0, x1);
-              const uint32_t hbits = *reinterpret_cast<const uint32_t*>(&hp);
-              const float f0 = __uint_as_float(hbits << 16);
-              const float f1 = __uint_as_float(hbits & 0xffff0000u);
-              const __nv_bfloat162 lp = __floats2bfloat162_rn(x0 - f0, x1 - f1);
-              hw[e] = hbits;
-              lw[e] = *reinterpret_cast<const uint32_t*>(&lp);
+              mx = fmaxf(mx, fmaxf(fabsf(x0), fabsf(x1)));
+              if (tri) {
+                const Tri2 tr = tri_pack2(x0, x1, p.out_scale);
+                hw[e] = tr.h;
+                // lw[0..1]: residual bytes, lw[2..3]: copy bytes (8 channels each)
+                if (e & 1) {
+                  lw[e >> 1] |= static_cast<uint32_t>(tr.l) << 16;
+                  lw[2 + (e >> 1)] |= static_cast<uint32_t>(tr.c) << 16;
+                } else {
+                  lw[e >> 1] = tr.l;
+                  lw[2 + (e >> 1)] = tr.c;
+                }
+              } else {
+                // packed conversions: (x0, x1) -> bf16x2 in one instruction; the hi values come
+                // back as floats by a shift / mask of the packed word
+                const __nv_bfloat162 hp = __floats2bfloat162_rn(x0, x1);
+                const uint32_t hbits = *reinterpret_cast<const uint32_t*>(&hp);
+                const float f0 = __uint_as_float(hbits << 16);
+                const float f1 = __uint_as_float(hbits & 0xffff0000u);
+                const __nv_bfloat162 lp = __floats2bfloat162_rn(x0 - f0, x1 - f1);
+                hw[e] = hbits;
+                lw[e] = *reinterpret_cast<const uint32_t*>(&lp);
+              }
             }
             const int off = row * 64 + ((g ^ ((row >> 1) & 3)) << 4);
             *reinterpret_cast<uint4*>(sb + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-            *reinterpret_cast<uint4*>(sb + 128 * 64 + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            if (tri) {
+              *reinterpret_cast<uint2*>(sb + 128 * 64 + row * 32 + g * 8) = make_uint2(lw[0], lw[1]);
+              *reinterpret_cast<uint2*>(sb + 128 * 96 + row * 32 + g * 8) = make_uint2(lw[2], lw[3]);
+            } else {
+              *reinterpret_cast<uint4*>(sb + 128 * 64 + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            }
           }
+          if (valid) amx = fmaxf(amx, mx);
         }
         ptx::fence_proxy_async();
         ptx::named_bar_sync(1 + grp, 128);
         if (threadIdx.x == lead && ch0 < p.Cout) {
           ptx::tma_store_4d(tm_o_hi_p, sb, ch0, w0, h0, img);
           ptx::tma_store_4d(tm_o_lo_p, sb + 128 * 64, ch0, w0, h0, img);
+          if (tri) ptx::tma_store_4d(tm_o_x_p, sb + 128 * 96, ch0, w0, h0, img);
           ptx::tma_store_commit();
         }
         ++chunk_ctr;
@@ -273,10 +362,11 @@ __device__ __forceinline__ void run_epilogue(const IgemmArgs& p, const CUtensorM
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(r[j]);
+          float x = __uint_as_float(r[j]) * asc;
           if (p.bias != nullptr && ch0 + j < p.Cout) x += __ldg(p.bias + ch0 + j);
           if (p.relu) x = fmaxf(x, 0.f);
           v[j] = x;
+          if (ch0 + j < p.Cout) amx = fmaxf(amx, fabsf(x));
         }
         const bool fullchunk = (ch0 + 32 <= p.Cout) && p.vec_ok;
         if (p.out_mode == 0) {
@@ -323,22 +413,38 @@ __device__ __forceinline__ void run_epilogue(const IgemmArgs& p, const CUtensorM
       }
     }
     ptx::tc_fence_before();
-    ptx::mbar_arrive(&tempty_bar[acc]);
+    if (CL == 2)   // CTA pair: the leader's MMA warp waits for the accumulators of BOTH CTAs
+      ptx::mbar_arrive_cluster(ptx::mapa_u32(ptx::smem_u32(&tempty_bar[acc]), 0));
+    else
+      ptx::mbar_arrive(&tempty_bar[acc]);
   }
   if (threadIdx.x == lead) ptx::tma_store_wait_read<0>();  // smem must outlive the bulk stores
+  if (p.amax != nullptr) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amx = fmaxf(amx, __shfl_xor_sync(0xffffffffu, amx, o));
+    if (lane == 0 && amx > 0.f) atomicMax(p.amax, __float_as_uint(amx));
+  }
 }
 
-template <int TH, int TW, int BN, int CL, int BK>
+// PM (precision mode): 0 = split-bf16 operands (planes hi, lo; 3 bf16 MMAs per k slice);
+// 1 = tri-plane operands (fp16 value, e4m3 residual, e4m3 copy; see above): per 64 K-elements
+// 4 fp16 MMAs + 4 FP8 MMAs (K = 32 each, double rate) instead of 12 bf16 MMAs.  A stage holds
+// A:[h | l | c] then B:[h | c | l] -- same bytes as mode 0 (one 2-byte and two 1-byte planes).
+template <int TH, int TW, int BN, int CL, int BK, int PM = 0>
 __global__ void __launch_bounds__(256, 1)
 igemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                const __grid_constant__ CUtensorMap tm_a_x,
                 const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                const __grid_constant__ CUtensorMap tm_b_x,
                 const __grid_constant__ CUtensorMap tm_o_hi, const __grid_constant__ CUtensorMap tm_o_lo,
+                const __grid_constant__ CUtensorMap tm_o_x,
                 const IgemmArgs p) {
   static_assert(TH * TW == kBlockM, "pixel tile must have 128 rows");
-  using Cfg = IgemmCfg<BN, BK>;
+  using Cfg = IgemmCfg<BN, BK, CL>;
   constexpr int kStages = Cfg::kStages;
   constexpr int kABytes = Cfg::kABytes;
   constexpr int kBlockK = BK;
+  constexpr bool kPair = (CL == 2);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -355,7 +461,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
   const int spatial_tiles = p.batch * p.tiles_h * p.tiles_w;
   const int total_tiles = p.split_k * p.tiles_n * ((spatial_tiles + CL - 1) / CL);
   const int kchunks = p.Cin / kBlockK;
-  const int rank = (CL > 1) ? static_cast<int>(ptx::cluster_ctarank()) : 0;
+  const int rank = kPair ? static_cast<int>(ptx::cluster_ctarank()) : 0;
   const int first = blockIdx.x / CL;      // work items are owned by clusters
   const int stride = gridDim.x / CL;
   constexpr uint16_t kMask = static_cast<uint16_t>((1u << CL) - 1u);
@@ -365,24 +471,31 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     ptx::prefetch_tmap(&tm_a_lo);
     ptx::prefetch_tmap(&tm_b_hi);
     ptx::prefetch_tmap(&tm_b_lo);
+    if (PM == 1) {
+      ptx::prefetch_tmap(&tm_a_x);
+      ptx::prefetch_tmap(&tm_b_x);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
-      ptx::mbar_init(&full_bar[s], 1);
-      ptx::mbar_init(&empty_bar[s], CL);  // every CTA of the cluster must release the stage
+      ptx::mbar_init(&full_bar[s], 1);    // pair: only the leader's is used (both CTAs' bytes)
+      ptx::mbar_init(&empty_bar[s], 1);   // pair: released in both CTAs by the leader's commit
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tfull_bar[a], 1);
-      ptx::mbar_init(&tempty_bar[a], 128);
+      ptx::mbar_init(&tempty_bar[a], 128 * CL);  // pair: the leader's collects both epilogues
     }
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
-    ptx::tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+    if (kPair)
+      ptx::tmem_alloc_2sm<Cfg::kTmemCols>(tmem_slot);
+    else
+      ptx::tmem_alloc<Cfg::kTmemCols>(tmem_slot);
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (CL > 1) ptx::cluster_sync_all();  // peers' barriers are initialised before any remote arrive
+  if (kPair) ptx::cluster_sync_all();  // peers' barriers are initialised before any remote arrive
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -391,12 +504,19 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     {  // whole warp, warp-uniform arguments; one lane is elected inside each issue (ptx.cuh)
       int stage = 0;
       uint32_t phase = 0;
+      // B planes: mode 0 [hi | lo] of kBBytes each; mode 1 [h (kBBytes) | c | l (kBBytes/2 each)]
+      constexpr int kNP = (PM == 0) ? 2 : 3;
+      const CUtensorMap* amaps[3] = {&tm_a_hi, &tm_a_lo, &tm_a_x};
+      const CUtensorMap* bmaps[3] = {&tm_b_hi, &tm_b_lo, &tm_b_x};
       for (int t = first; t < total_tiles; t += stride) {
         const Tile tl = decode_tile<CL>(p, t, rank, TH, TW, BN);
         for (int i = 0, k = tl.kb; i < tl.kn; ++i, k += tl.kstride) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + stage * Cfg::kStageBytes;
-          ptx::mbar_arrive_expect_tx_w(&full_bar[stage], Cfg::kStageBytes);
+          // pair: the leader's barrier counts the bytes of both CTAs' loads
+          if (!kPair || rank == 0)
+            ptx::mbar_arrive_expect_tx_w(&full_bar[stage], CL * Cfg::kStageBytes);
+          const uint32_t bar_cl = kPair ? ptx::mapa_u32(ptx::smem_u32(&full_bar[stage]), 0) : 0u;
           const int tap = k / kchunks;
           const int kc = k - tap * kchunks;
           int dy = 0, dx = 0;
@@ -404,23 +524,22 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
             dy = tap / 3 - 1;
             dx = tap % 3 - 1;
           }
-          ptx::tma_load_4d_w(st, &tm_a_hi, &full_bar[stage], kc * kBlockK, tl.w0 + dx, tl.h0 + dy,
-                           tl.img);
-          ptx::tma_load_4d_w(st + kABytes, &tm_a_lo, &full_bar[stage], kc * kBlockK, tl.w0 + dx,
-                           tl.h0 + dy, tl.img);
-          if (CL == 1) {
-            ptx::tma_load_2d_w(st + 2 * kABytes, &tm_b_hi, &full_bar[stage],
-                             tap * p.Cin + kc * kBlockK, tl.n0);
-            ptx::tma_load_2d_w(st + 2 * kABytes + Cfg::kBBytes, &tm_b_lo, &full_bar[stage],
-                             tap * p.Cin + kc * kBlockK, tl.n0);
-          } else {
-            // each CTA fetches 1/CL of the weight tile and multicasts it to the whole cluster
-            constexpr int kSlice = Cfg::kBBytes / CL;
-            const int nrow = tl.n0 + rank * (BN / CL);
-            ptx::tma_load_2d_mcast_w(st + 2 * kABytes + rank * kSlice, &tm_b_hi, &full_bar[stage],
-                                   tap * p.Cin + kc * kBlockK, nrow, kMask);
-            ptx::tma_load_2d_mcast_w(st + 2 * kABytes + Cfg::kBBytes + rank * kSlice, &tm_b_lo,
-                                   &full_bar[stage], tap * p.Cin + kc * kBlockK, nrow, kMask);
+#pragma unroll
+          for (int pl = 0; pl < kNP; ++pl) {
+            const int aoff = (PM == 0) ? pl * kABytes : (pl == 0 ? 0 : kABytes + (pl - 1) * (kABytes / 2));
+            const int boff = (PM == 0) ? pl * Cfg::kBBytes
+                                       : (pl == 0 ? 0 : Cfg::kBBytes + (pl - 1) * (Cfg::kBBytes / 2));
+            if (kPair) {
+              ptx::tma_load_4d_2sm_w(st + aoff, amaps[pl], bar_cl, kc * kBlockK, tl.w0 + dx,
+                                     tl.h0 + dy, tl.img);
+              ptx::tma_load_2d_2sm_w(st + 2 * kABytes + boff, bmaps[pl], bar_cl,
+                                     tap * p.Cin + kc * kBlockK, tl.n0 + rank * (BN / CL));
+            } else {
+              ptx::tma_load_4d_w(st + aoff, amaps[pl], &full_bar[stage], kc * kBlockK, tl.w0 + dx,
+                                 tl.h0 + dy, tl.img);
+              ptx::tma_load_2d_w(st + 2 * kABytes + boff, bmaps[pl], &full_bar[stage],
+                                 tap * p.Cin + kc * kBlockK, tl.n0);
+            }
           }
           if (++stage == kStages) {
             stage = 0;
@@ -429,10 +548,13 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         }
       }
     }
-  } else if (warp == 1) {
-    // -------------------------------------------------------------- MMA issuer
+  } else if (warp == 1 && rank == 0) {
+    // -------------------------------------------------------------- MMA issuer (pair: leader only)
     {  // whole warp, warp-uniform arguments; one lane is elected inside each issue (ptx.cuh)
-      constexpr uint32_t idesc = ptx::umma_idesc_bf16_m128(BN);
+      // mode 1: format code 0 = fp16 for kind::f16 and E4M3 for kind::f8f6f4 (same descriptor)
+      constexpr uint32_t idesc1 = (PM == 0) ? ptx::umma_idesc_bf16_m128(BN) : ptx::umma_idesc_fmt0_m128(BN);
+      // pair: M = 256 (m_dim field = M >> 4 at bit 24)
+      constexpr uint32_t idesc = kPair ? ((idesc1 & ~(0x1Fu << 24)) | ((256u >> 4) << 24)) : idesc1;
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
@@ -448,44 +570,88 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
           const uint32_t a_hi = ptx::smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t a_lo = a_hi + kABytes;
           const uint32_t b_hi = a_hi + 2 * kABytes;
-          const uint32_t b_lo = b_hi + Cfg::kBBytes;
+          if (PM == 0) {
+            const uint32_t a_lo = a_hi + kABytes;
+            const uint32_t b_lo = b_hi + Cfg::kBBytes;
 #pragma unroll
-          for (int kk = 0; kk < kBlockK / 16; ++kk) {
-            const uint64_t da_hi = (BK == 64) ? ptx::umma_desc_sw128(a_hi + kk * 32) : ptx::umma_desc_sw64(a_hi + kk * 32);
-            const uint64_t da_lo = (BK == 64) ? ptx::umma_desc_sw128(a_lo + kk * 32) : ptx::umma_desc_sw64(a_lo + kk * 32);
-            const uint64_t db_hi = (BK == 64) ? ptx::umma_desc_sw128(b_hi + kk * 32) : ptx::umma_desc_sw64(b_hi + kk * 32);
-            const uint64_t db_lo = (BK == 64) ? ptx::umma_desc_sw128(b_lo + kk * 32) : ptx::umma_desc_sw64(b_lo + kk * 32);
-            // small cross terms first, then the dominant product
-            ptx::umma_bf16_ss_w(tmem_d, da_lo, db_hi, idesc, (i > 0 || kk > 0) ? 1u : 0u);
-            ptx::umma_bf16_ss_w(tmem_d, da_hi, db_lo, idesc, 1u);
-            ptx::umma_bf16_ss_w(tmem_d, da_hi, db_hi, idesc, 1u);
+            for (int kk = 0; kk < kBlockK / 16; ++kk) {
+              const uint64_t da_hi = ptx::umma_desc_rows<BK * 2>(a_hi + kk * 32);
+              const uint64_t da_lo = ptx::umma_desc_rows<BK * 2>(a_lo + kk * 32);
+              const uint64_t db_hi = ptx::umma_desc_rows<BK * 2>(b_hi + kk * 32);
+              const uint64_t db_lo = ptx::umma_desc_rows<BK * 2>(b_lo + kk * 32);
+              // small cross terms first, then the dominant product
+              const uint32_t acc0 = (i > 0 || kk > 0) ? 1u : 0u;
+              if (kPair) {
+                ptx::umma_f16_ss_2sm_w(tmem_d, da_lo, db_hi, idesc, acc0);
+                ptx::umma_f16_ss_2sm_w(tmem_d, da_hi, db_lo, idesc, 1u);
+                ptx::umma_f16_ss_2sm_w(tmem_d, da_hi, db_hi, idesc, 1u);
+              } else {
+                ptx::umma_bf16_ss_w(tmem_d, da_lo, db_hi, idesc, acc0);
+                ptx::umma_bf16_ss_w(tmem_d, da_hi, db_lo, idesc, 1u);
+                ptx::umma_bf16_ss_w(tmem_d, da_hi, db_hi, idesc, 1u);
+              }
+            }
+          } else {
+            const uint32_t a_l = a_hi + kABytes, a_c = a_l + kABytes / 2;
+            const uint32_t b_c = b_hi + Cfg::kBBytes, b_l = b_c + Cfg::kBBytes / 2;
+            // corrections (FP8, K = 32 per instruction): residual x copy, copy x residual
+#pragma unroll
+            for (int kk = 0; kk < kBlockK / 32; ++kk) {
+              const uint64_t da_l = ptx::umma_desc_rows<BK>(a_l + kk * 32);
+              const uint64_t db_c = ptx::umma_desc_rows<BK>(b_c + kk * 32);
+              const uint64_t da_c = ptx::umma_desc_rows<BK>(a_c + kk * 32);
+              const uint64_t db_l = ptx::umma_desc_rows<BK>(b_l + kk * 32);
+              const uint32_t acc0 = (i > 0 || kk > 0) ? 1u : 0u;
+              if (kPair) {
+                ptx::umma_f8_ss_2sm_w(tmem_d, da_l, db_c, idesc, acc0);
+                ptx::umma_f8_ss_2sm_w(tmem_d, da_c, db_l, idesc, 1u);
+              } else {
+                ptx::umma_f8_ss_w(tmem_d, da_l, db_c, idesc, acc0);
+                ptx::umma_f8_ss_w(tmem_d, da_c, db_l, idesc, 1u);
+              }
+            }
+            // main product (fp16, K = 16 per instruction)
+#pragma unroll
+            for (int kk = 0; kk < kBlockK / 16; ++kk) {
+              const uint64_t da = ptx::umma_desc_rows<BK * 2>(a_hi + kk * 32);
+              const uint64_t db = ptx::umma_desc_rows<BK * 2>(b_hi + kk * 32);
+              if (kPair)
+                ptx::umma_f16_ss_2sm_w(tmem_d, da, db, idesc, 1u);
+              else
+                ptx::umma_bf16_ss_w(tmem_d, da, db, idesc, 1u);
+            }
           }
-          if (CL == 1)
-            ptx::umma_commit_w(&empty_bar[stage]);
+          if (kPair)
+            ptx::umma_commit_2sm_w(&empty_bar[stage], kMask);  // frees the stage in both CTAs
           else
-            ptx::umma_commit_mcast_w(&empty_bar[stage], kMask);  // frees the stage in every CTA
+            ptx::umma_commit_w(&empty_bar[stage]);
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        ptx::umma_commit_w(&tfull_bar[acc]);
+        if (kPair)
+          ptx::umma_commit_2sm_w(&tfull_bar[acc], kMask);      // both epilogues may drain
+        else
+          ptx::umma_commit_w(&tfull_bar[acc]);
       }
     }
   } else if (warp >= 4) {
     // ---------------------------------------------------------------- epilogue
-    run_epilogue<TH, TW, BN, CL>(p, &tm_o_hi, &tm_o_lo, staging, tfull_bar, tempty_bar, tmem_base,
-                                 rank, first, stride, total_tiles);
+    run_epilogue<TH, TW, BN, CL>(p, &tm_o_hi, &tm_o_lo, &tm_o_x, staging, tfull_bar, tempty_bar,
+                                 tmem_base, rank, first, stride, total_tiles);
   }
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (CL > 1) ptx::cluster_sync_all();  // no CTA leaves while a peer may still signal its barriers
+  if (kPair) ptx::cluster_sync_all();  // no CTA leaves while a peer may still signal its barriers
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    if (kPair)
+      ptx::tmem_dealloc_2sm<Cfg::kTmemCols>(tmem_base);
+    else
+      ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
 }
 
@@ -534,7 +700,7 @@ __global__ void __launch_bounds__(BN == 64 ? 384 : 256, 1)
 conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                     const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                     const __grid_constant__ CUtensorMap tm_o_hi, const __grid_constant__ CUtensorMap tm_o_lo,
-                    const IgemmArgs p) {
+                    const __grid_constant__ CUtensorMap tm_o_x, const IgemmArgs p) {
   using Cfg = HaloCfg<BN>;
   constexpr int TH = kHaloTH, TW = kHaloTW, NB = Cfg::kNB;
   constexpr int kNG = (BN == 64) ? 2 : 1;   // epilogue warp groups (warps 4..7 [, 8..11])
@@ -681,8 +847,8 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
       }
     }
   } else if (warp >= 4) {
-    run_epilogue<TH, TW, BN, 1, true, kNG>(p, &tm_o_hi, &tm_o_lo, staging, tfull_bar, tempty_bar,
-                                           tmem_base, 0, first, stride, total_tiles);
+    run_epilogue<TH, TW, BN, 1, true, kNG>(p, &tm_o_hi, &tm_o_lo, &tm_o_x, staging, tfull_bar,
+                                           tempty_bar, tmem_base, 0, first, stride, total_tiles);
   }
 
   ptx::tc_fence_before();
@@ -794,8 +960,8 @@ conv1_1_tc_kernel(const float* __restrict__ data, int B, int H, int W,
       }
     }
   } else if (warp >= 4 && warp < 12) {
-    run_epilogue<1, 128, BN, 1, true, 2>(p, &tm_o_hi, &tm_o_lo, staging, tfull_bar, tempty_bar,
-                                         tmem_base, 0, first, stride, total_tiles);
+    run_epilogue<1, 128, BN, 1, true, 2>(p, &tm_o_hi, &tm_o_lo, &tm_o_lo, staging, tfull_bar,
+                                         tempty_bar, tmem_base, 0, first, stride, total_tiles);
   } else if (warp >= 12) {
     // -------------------------------------------------------------- A producers (128 threads)
     // two producer groups (warps 12..15, 16..19): group g builds the tiles with local index
@@ -879,51 +1045,59 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// bf16 [N][H][W][C] activation plane, box [1][TH][TW][64], 128B swizzle, zero OOB fill.
+static CUtensorMapSwizzle swizzle_for_row(int row_bytes) {
+  return row_bytes >= 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+// [N][H][W][C] activation plane of `eb`-byte elements (2: bf16 / fp16, 1: e4m3), box
+// [1][TH][TW][bk], swizzle mode = the box row width (bk * eb bytes), zero OOB fill.
 static int make_act_map(CUtensorMap* m, const void* base, int N, int H, int W, int C, int TH,
-                        int TW, int bk) {
+                        int TW, int bk, int eb = 2) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return MNC_ERR_DRIVER;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint64_t strides[3] = {(cuuint64_t)C * eb, (cuuint64_t)W * C * eb, (cuuint64_t)H * W * C * eb};
   cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)TW, (cuuint32_t)TH, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides,
-                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(m, eb == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 4,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle_for_row(bk * eb), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? MNC_OK : MNC_ERR_DRIVER;
 }
 
-// bf16 [Cout][Ktot] weight plane, box [BN][64].
+// [Cout][Ktot] weight plane, box [box_rows][bk].
 static int make_wgt_map(CUtensorMap* m, const void* base, int Cout, long long Ktot, int box_rows,
-                        int bk) {
+                        int bk, int eb = 2) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return MNC_ERR_DRIVER;
   cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)Cout};
-  cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
+  cuuint64_t strides[1] = {(cuuint64_t)Ktot * eb};
   cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
-                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(m, eb == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle_for_row(bk * eb), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? MNC_OK : MNC_ERR_DRIVER;
 }
 
-// bf16 output plane seen as [N][H][W][Cout] with pixel stride `pix_stride` elements; box
-// [1][TH][TW][32], 64-byte swizzle (matches the epilogue's staging layout).
+// output plane seen as [N][H][W][Cout] with pixel stride `pix_stride` elements; box
+// [1][TH][TW][32]: 2-byte planes with the 64-byte swizzle of the epilogue's staging layout,
+// 1-byte planes (32-byte rows) unswizzled.
 static int make_out_map(CUtensorMap* m, const void* base, int N, int H, int W, int Cout,
-                        long long pix_stride, int TH, int TW) {
+                        long long pix_stride, int TH, int TW, int eb = 2) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return MNC_ERR_DRIVER;
   cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-  cuuint64_t strides[3] = {(cuuint64_t)pix_stride * 2, (cuuint64_t)W * pix_stride * 2,
-                           (cuuint64_t)H * W * pix_stride * 2};
+  cuuint64_t strides[3] = {(cuuint64_t)pix_stride * eb, (cuuint64_t)W * pix_stride * eb,
+                           (cuuint64_t)H * W * pix_stride * eb};
   cuuint32_t box[4] = {32, (cuuint32_t)TW, (cuuint32_t)TH, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides,
-                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+  CUresult r = enc(m, eb == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 4,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   eb == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE,
                    CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? MNC_OK : MNC_ERR_DRIVER;
 }
@@ -938,13 +1112,14 @@ static int sm_count() {
   return n;
 }
 
-template <int TH, int TW, int BN, int CL, int BK>
-static int launch_igemm(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo,
-                        const CUtensorMap& tb_hi, const CUtensorMap& tb_lo,
-                        const CUtensorMap& to_hi, const CUtensorMap& to_lo, const IgemmArgs& a,
-                        int max_ctas, cudaStream_t stream) {
-  using Cfg = IgemmCfg<BN, BK>;
-  auto kern = igemm_tc_kernel<TH, TW, BN, CL, BK>;
+struct Maps {
+  CUtensorMap a[3], b[3], o[3];
+};
+
+template <int TH, int TW, int BN, int CL, int BK, int PM>
+static int launch_igemm(const Maps& m, const IgemmArgs& a, int max_ctas, cudaStream_t stream) {
+  using Cfg = IgemmCfg<BN, BK, CL>;
+  auto kern = igemm_tc_kernel<TH, TW, BN, CL, BK, PM>;
   static SmemGrant grant;
   if (!ensure_dynamic_smem(kern, Cfg::kSmemBytes, grant)) return MNC_ERR_CUDA;
   const int spatial = a.batch * a.tiles_h * a.tiles_w;
@@ -966,14 +1141,13 @@ static int launch_igemm(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo,
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta_hi, ta_lo, tb_hi, tb_lo, to_hi, to_lo, a);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, m.a[0], m.a[1], m.a[2], m.b[0], m.b[1], m.b[2],
+                                     m.o[0], m.o[1], m.o[2], a);
   return e == cudaSuccess ? MNC_OK : MNC_ERR_CUDA;
 }
 
 template <int BN>
-static int launch_halo(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CUtensorMap& tb_hi,
-                       const CUtensorMap& tb_lo, const CUtensorMap& to_hi, const CUtensorMap& to_lo,
-                       const IgemmArgs& a, int max_ctas, cudaStream_t stream) {
+static int launch_halo(const Maps& m, const IgemmArgs& a, int max_ctas, cudaStream_t stream) {
   using Cfg = HaloCfg<BN>;
   auto kern = conv_halo_tc_kernel<BN>;
   static SmemGrant grant;
@@ -982,8 +1156,8 @@ static int launch_halo(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const
   int grid = sm_count();
   if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
   if (total < grid) grid = total;
-  kern<<<grid, BN == 64 ? 384 : 256, Cfg::kSmemBytes, stream>>>(ta_hi, ta_lo, tb_hi, tb_lo, to_hi,
-                                                              to_lo, a);
+  kern<<<grid, BN == 64 ? 384 : 256, Cfg::kSmemBytes, stream>>>(m.a[0], m.a[1], m.b[0], m.b[1],
+                                                              m.o[0], m.o[1], m.o[2], a);
   return cudaGetLastError() == cudaSuccess ? MNC_OK : MNC_ERR_CUDA;
 }
 
@@ -1019,23 +1193,40 @@ extern "C" int mnc_igemm_set_block_k(int bk) {
   return MNC_OK;
 }
 
-extern "C" int mnc_igemm_tc(const void* a_hi, const void* a_lo, int batch, int H, int W, int Cin,
-                            const void* w_hi, const void* w_lo, int Cout, int taps,
-                            const float* bias, int relu, int out_mode, void* out0, void* out1,
-                            long long out_pix_stride, int out_ch_offset, int split_k,
-                            long long split_stride, int bn, int max_ctas, void* stream_) {
+// General form.  in_fmt 0: operands are split-bf16 planes (a0 = hi, a1 = lo; w0 = hi, w1 = lo);
+// in_fmt 1: tri-plane operands (a0 = fp16 value, a1 = e4m3 residual, a2 = e4m3 copy; w0 = fp16,
+// w1 = e4m3 copy, w2 = e4m3 residual -- layouts above).  out_mode 0 / 2: split-bf16 (out0 = hi,
+// out1 = lo), 1: fp32 (out0), 4 / 5: tri-plane (out0 = fp16, out1 = residual, out2 = copy) with
+// exponent scale `out_scale`; 2 and 5 apply the fused 2x2 ceil-mode max pool.  acc_scale turns the
+// accumulator into the true value (2^-(ea+ew) for tri-plane operands, 1 otherwise).  amax
+// (optional, device) receives atomicMax(|output|) as float bits.
+extern "C" int mnc_igemm_tc2(int in_fmt, const void* a0, const void* a1, const void* a2, int batch,
+                             int H, int W, int Cin, const void* w0, const void* w1, const void* w2,
+                             int Cout, int taps, const float* bias, int relu, int out_mode,
+                             void* out0, void* out1, void* out2, long long out_pix_stride,
+                             int out_ch_offset, int split_k, long long split_stride, int bn,
+                             int max_ctas, float acc_scale, float out_scale, unsigned int* amax,
+                             void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (Cin % 64 != 0 || (taps != 1 && taps != 9) || batch <= 0 || H <= 0 || W <= 0 || Cout <= 0)
     return MNC_ERR_ARG;
+  if (in_fmt != 0 && in_fmt != 1) return MNC_ERR_ARG;
+  if (out_mode != 0 && out_mode != 1 && out_mode != 2 && out_mode != 3 && out_mode != 4 && out_mode != 5)
+    return MNC_ERR_ARG;
+  const bool tri_out = (out_mode == 4 || out_mode == 5);
+  const bool pooled = (out_mode == 2 || out_mode == 5);
   int bk = g_igemm_bk;
   if (split_k < 1) split_k = 1;
   if (split_k > 1 && out_mode != 1) return MNC_ERR_ARG;
-  if (out_mode == 2 && (taps != 9 || Cout % 8 != 0 || out_pix_stride % 8 != 0 ||
-                        out_ch_offset % 8 != 0))
+  if (pooled && (taps != 9 || Cout % 8 != 0 || out_pix_stride % 8 != 0 || out_ch_offset % 8 != 0))
+    return MNC_ERR_ARG;
+  if (tri_out && (out_pix_stride % 16 != 0 || out_ch_offset % 16 != 0 ||
+                  (reinterpret_cast<uintptr_t>(out0) | reinterpret_cast<uintptr_t>(out1) |
+                   reinterpret_cast<uintptr_t>(out2)) % 16 != 0))
     return MNC_ERR_ARG;
   const bool conv = (taps == 9);
   if (bn == 0) bn = (Cout <= 64) ? 64 : (Cout <= 128 ? 128 : 256);
-  const bool halo = conv && g_igemm_halo && (bn == 64 || bn == 128) && split_k == 1;
+  const bool halo = in_fmt == 0 && conv && g_igemm_halo && (bn == 64 || bn == 128) && split_k == 1;
   const int TH = conv ? (halo ? kHaloTH : 8) : 1, TW = conv ? (halo ? kHaloTW : 16) : 128;
   if (bn != 64 && bn != 128 && bn != 192 && bn != 256) return MNC_ERR_ARG;
   if (bk == 0) bk = 64;              // measured: BLOCK_K 64 wins at BN 256 (profiles/r01_igemm_bk32_bn192.log)
@@ -1060,49 +1251,74 @@ extern "C" int mnc_igemm_tc(const void* a_hi, const void* a_lo, int batch, int H
   a.bias = bias;
   a.out_hi = static_cast<__nv_bfloat16*>(out0);
   a.out_lo = static_cast<__nv_bfloat16*>(out1);
+  a.out_x = static_cast<uint8_t*>(out2);
   a.out_f32 = static_cast<float*>(out0);
   a.out_pix_stride = out_pix_stride;
   a.out_ch_offset = out_ch_offset;
   a.split_stride = split_stride;
+  a.acc_scale = acc_scale;
+  a.out_scale = out_scale;
+  a.amax = amax;
   const int vec = (out_mode == 1) ? 4 : 8;
   a.vec_ok = (out_pix_stride % vec == 0) && (out_ch_offset % vec == 0) &&
              (reinterpret_cast<uintptr_t>(out0) % 16 == 0) &&
              (out_mode == 1 || reinterpret_cast<uintptr_t>(out1) % 16 == 0) &&
              (split_stride % vec == 0);
 
-  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+  Maps m;
   int rc;
   if (halo) bk = 64;
   // halo kernel: the activation box is the pixel tile plus a one-pixel border
   const int box_h = halo ? TH + 2 : TH, box_w = halo ? TW + 2 : TW;
-  if ((rc = make_act_map(&ta_hi, a_hi, batch, H, W, Cin, box_h, box_w, bk)) != MNC_OK) return rc;
-  if ((rc = make_act_map(&ta_lo, a_lo, batch, H, W, Cin, box_h, box_w, bk)) != MNC_OK) return rc;
+  if ((rc = make_act_map(&m.a[0], a0, batch, H, W, Cin, box_h, box_w, bk, 2)) != MNC_OK) return rc;
+  if ((rc = make_act_map(&m.a[1], a1, batch, H, W, Cin, box_h, box_w, bk, in_fmt ? 1 : 2)) != MNC_OK)
+    return rc;
+  m.a[2] = m.a[1];
+  if (in_fmt == 1 && (rc = make_act_map(&m.a[2], a2, batch, H, W, Cin, box_h, box_w, bk, 1)) != MNC_OK)
+    return rc;
   const long long ktot = static_cast<long long>(taps) * Cin;
   // epilogue through shared memory + TMA store when the output planes allow a tensor map
-  CUtensorMap to_hi = ta_hi, to_lo = ta_lo;  // placeholders when unused
+  m.o[0] = m.a[0];  // placeholders when unused
+  m.o[1] = m.a[1];
+  m.o[2] = m.a[1];
   a.tma_store = 0;
   if (out_mode == 0 && g_igemm_tma_store && out_pix_stride % 8 == 0 && out_ch_offset % 8 == 0 &&
       reinterpret_cast<uintptr_t>(out0) % 16 == 0 && reinterpret_cast<uintptr_t>(out1) % 16 == 0) {
     const __nv_bfloat16* bh = static_cast<const __nv_bfloat16*>(out0) + out_ch_offset;
     const __nv_bfloat16* bl = static_cast<const __nv_bfloat16*>(out1) + out_ch_offset;
-    if (make_out_map(&to_hi, bh, batch, H, W, Cout, out_pix_stride, TH, TW) == MNC_OK &&
-        make_out_map(&to_lo, bl, batch, H, W, Cout, out_pix_stride, TH, TW) == MNC_OK)
+    if (make_out_map(&m.o[0], bh, batch, H, W, Cout, out_pix_stride, TH, TW) == MNC_OK &&
+        make_out_map(&m.o[1], bl, batch, H, W, Cout, out_pix_stride, TH, TW) == MNC_OK)
       a.tma_store = 1;
   }
+  if (out_mode == 4) {
+    const __nv_bfloat16* bh = static_cast<const __nv_bfloat16*>(out0) + out_ch_offset;
+    const uint8_t* bl = static_cast<const uint8_t*>(out1) + out_ch_offset;
+    const uint8_t* bc = static_cast<const uint8_t*>(out2) + out_ch_offset;
+    if (make_out_map(&m.o[0], bh, batch, H, W, Cout, out_pix_stride, TH, TW, 2) != MNC_OK ||
+        make_out_map(&m.o[1], bl, batch, H, W, Cout, out_pix_stride, TH, TW, 1) != MNC_OK ||
+        make_out_map(&m.o[2], bc, batch, H, W, Cout, out_pix_stride, TH, TW, 1) != MNC_OK)
+      return MNC_ERR_DRIVER;
+    a.tma_store = 1;
+  }
   const int cl = halo ? 1 : g_igemm_cluster;
-  if ((rc = make_wgt_map(&tb_hi, w_hi, Cout, ktot, bn / cl, bk)) != MNC_OK) return rc;
-  if ((rc = make_wgt_map(&tb_lo, w_lo, Cout, ktot, bn / cl, bk)) != MNC_OK) return rc;
+  if ((rc = make_wgt_map(&m.b[0], w0, Cout, ktot, bn / cl, bk, 2)) != MNC_OK) return rc;
+  if ((rc = make_wgt_map(&m.b[1], w1, Cout, ktot, bn / cl, bk, in_fmt ? 1 : 2)) != MNC_OK) return rc;
+  m.b[2] = m.b[1];
+  if (in_fmt == 1 && (rc = make_wgt_map(&m.b[2], w2, Cout, ktot, bn / cl, bk, 1)) != MNC_OK) return rc;
   if (halo) {
     a.k_steps = 9 * (Cin / 64);
-    if (bn == 64) return launch_halo<64>(ta_hi, ta_lo, tb_hi, tb_lo, to_hi, to_lo, a, max_ctas, stream);
-    return launch_halo<128>(ta_hi, ta_lo, tb_hi, tb_lo, to_hi, to_lo, a, max_ctas, stream);
+    if (bn == 64) return launch_halo<64>(m, a, max_ctas, stream);
+    return launch_halo<128>(m, a, max_ctas, stream);
   }
 
-#define MNC_LAUNCH(TH_, TW_, BN_, BK_)                                                            \
-  return (cl == 2) ? launch_igemm<TH_, TW_, BN_, 2, BK_>(ta_hi, ta_lo, tb_hi, tb_lo, to_hi, to_lo, \
-                                                         a, max_ctas, stream)                     \
-                   : launch_igemm<TH_, TW_, BN_, 1, BK_>(ta_hi, ta_lo, tb_hi, tb_lo, to_hi, to_lo, \
-                                                         a, max_ctas, stream)
+#define MNC_LAUNCH_PM(TH_, TW_, BN_, BK_, PM_)                                      \
+  return (cl == 2) ? launch_igemm<TH_, TW_, BN_, 2, BK_, PM_>(m, a, max_ctas, stream) \
+                   : launch_igemm<TH_, TW_, BN_, 1, BK_, PM_>(m, a, max_ctas, stream)
+#define MNC_LAUNCH(TH_, TW_, BN_, BK_)                          \
+  do {                                                          \
+    if (in_fmt == 1) MNC_LAUNCH_PM(TH_, TW_, BN_, BK_, 1);      \
+    MNC_LAUNCH_PM(TH_, TW_, BN_, BK_, 0);                       \
+  } while (0)
   if (conv) {
     if (bn == 64) MNC_LAUNCH(8, 16, 64, 64);
     if (bn == 128) MNC_LAUNCH(8, 16, 128, 64);
@@ -1118,6 +1334,18 @@ extern "C" int mnc_igemm_tc(const void* a_hi, const void* a_lo, int batch, int H
     MNC_LAUNCH(1, 128, 256, 64);
   }
 #undef MNC_LAUNCH
+#undef MNC_LAUNCH_PM
+}
+
+// Split-bf16 operands, outputs 0 / 1 / 2 (the round-1 entry point; kept for its callers).
+extern "C" int mnc_igemm_tc(const void* a_hi, const void* a_lo, int batch, int H, int W, int Cin,
+                            const void* w_hi, const void* w_lo, int Cout, int taps,
+                            const float* bias, int relu, int out_mode, void* out0, void* out1,
+                            long long out_pix_stride, int out_ch_offset, int split_k,
+                            long long split_stride, int bn, int max_ctas, void* stream_) {
+  return mnc_igemm_tc2(0, a_hi, a_lo, nullptr, batch, H, W, Cin, w_hi, w_lo, nullptr, Cout, taps,
+                       bias, relu, out_mode, out0, out1, nullptr, out_pix_stride, out_ch_offset,
+                       split_k, split_stride, bn, max_ctas, 1.0f, 1.0f, nullptr, stream_);
 }
 
 // conv1_1 on the tensor cores.  w_stacked: bf16 [128][32] = rows 0..63 the hi plane, 64..127 the lo
@@ -1152,6 +1380,10 @@ extern "C" int mnc_conv1_1_tc(const float* data_nchw, int batch, int H, int W, c
   a.split_stride = 0;
   a.vec_ok = 1;
   a.tma_store = 1;
+  a.out_x = nullptr;
+  a.acc_scale = 1.0f;
+  a.out_scale = 1.0f;
+  a.amax = nullptr;
   CUtensorMap tb, to_hi, to_lo;
   int rc;
   if ((rc = make_wgt_map(&tb, w_stacked, 128, 32, 128, 32)) != MNC_OK) return rc;

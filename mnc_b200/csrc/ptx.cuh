@@ -110,6 +110,92 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// shared::cluster address of `smem_addr` (a shared::cta address of this CTA) in CTA `rank`.
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+// arrive on an mbarrier given by its shared::cluster address (possibly in the peer CTA)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
+               : "memory");
+}
+
+// ------------------------------------------------------------------ CTA pair (cta_group::2)
+// Two CTAs of a cluster on one TPC execute ONE M = 256 MMA: CTA r supplies rows [128r, 128r+128)
+// of A and rows [N/2 * r, N/2 * (r+1)) of B from the same offsets of its own shared memory and
+// receives its 128 accumulator rows in its own TMEM.  Only the leader (rank 0) issues; both load.
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_result) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   smem_u32(smem_result)),
+               "n"(kCols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols)
+               : "memory");
+}
+// TMA loads whose completion bytes are counted on the LEADER's mbarrier (`bar_cluster` = its
+// shared::cluster address); the data lands in the executing CTA's own shared memory.
+__device__ __forceinline__ void tma_load_4d_2sm_w(void* smem_dst, const void* tmap,
+                                                  uint32_t bar_cluster, int c0, int c1, int c2,
+                                                  int c3) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];\n\t}"
+      ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm_w(void* smem_dst, const void* tmap,
+                                                  uint32_t bar_cluster, int c0, int c1) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];\n\t}"
+      ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_ss_2sm_w(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                                  uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f8_ss_2sm_w(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                                 uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// commit of the pair's MMAs: arrives on the barrier at this offset in every CTA of `cta_mask`
+__device__ __forceinline__ void umma_commit_2sm_w(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+      ::"r"(smem_u32(bar)), "h"(cta_mask)
+      : "memory");
+}
+
 // ------------------------------------------------------------------ tcgen05
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result) {
@@ -250,6 +336,20 @@ __device__ __forceinline__ void tma_load_2d_mcast_w(void* smem_dst, const void* 
       : "memory");
 }
 
+// kind::f8f6f4 (dense FP8: E4M3 / E5M2 operands, one byte per element in shared memory, K = 32 per
+// instruction, fp32 accumulate in TMEM): twice the MAC rate of kind::f16.
+__device__ __forceinline__ void umma_f8_ss_w(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // Same, with the descriptors passed as their 32-bit low words (14-bit start address field; the
 // caller adds 2 per 32 bytes) and the high words -- stride-byte-offset, version, swizzle mode:
 // compile-time constants -- as template arguments, so only two 32-bit values travel to the
@@ -337,6 +437,28 @@ __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(1) << 46;
   d |= static_cast<uint64_t>(4) << 61;
   return d;
+}
+// 32-byte rows (32 FP8 or 16 fp16 elements per row): 8-row atoms of 256 B, layout type 6 = SWIZZLE_32B.
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(256u >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(6) << 61;
+  return d;
+}
+// Descriptor of a K-major tile whose rows are `row_bytes` (128 / 64 / 32) long, swizzled with the
+// mode of the same width.
+template <int kRowBytes>
+__device__ __forceinline__ uint64_t umma_desc_rows(uint32_t smem_addr) {
+  static_assert(kRowBytes == 128 || kRowBytes == 64 || kRowBytes == 32, "row width");
+  return kRowBytes == 128 ? umma_desc_sw128(smem_addr)
+                          : (kRowBytes == 64 ? umma_desc_sw64(smem_addr) : umma_desc_sw32(smem_addr));
+}
+// Instruction descriptor with A/B format code 0 and fp32 D, M = 128: kind::f16 reads it as fp16
+// operands, kind::f8f6f4 as E4M3 operands (same bit pattern: c_format = 1 at bit 4, formats 0).
+__host__ __device__ constexpr uint32_t umma_idesc_fmt0_m128(uint32_t n) {
+  return (1u << 4) | ((n >> 3) << 17) | ((128u >> 4) << 24);
 }
 // Instruction descriptor for kind::f16 with bf16 A/B (K-major both), fp32 D, M=128.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16_m128(uint32_t n) {

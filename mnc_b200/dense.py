@@ -3,6 +3,8 @@
 Activations and weights are "split" tensors: a torch bf16 tensor of shape [2, ...] holding the
 (hi, lo) planes with x ~= hi + lo.
 """
+import ctypes
+
 import torch
 
 from ._lib import lib, ptr, cur_stream, check, c_int, c_ll
@@ -34,6 +36,123 @@ def fc_weight_to_split(w, chw=None):
         c, h, wd = chw
         w = w.reshape(w.shape[0], c, h, wd).permute(0, 2, 3, 1).reshape(w.shape[0], -1)
     return split(w)
+
+
+# ------------------------------------------------------------------ precision mode 1 ("tri-plane")
+class Tri:
+    """A tensor in the tri-plane format of csrc/igemm_tc.cu: x * 2^exp = h + l / l_scale, with a
+    low-precision copy c = x * 2^exp * c_scale (activations: l_scale 2^6, c_scale 2^-5; weights:
+    l_scale 2^5, c_scale 2^-6).  h: fp16, l / c: e4m3 bytes (uint8 tensors), all of one shape."""
+    __slots__ = ("h", "l", "c", "exp")
+
+    def __init__(self, h, l, c, exp):
+        self.h, self.l, self.c, self.exp = h, l, c, int(exp)
+
+    @property
+    def shape(self):
+        return self.h.shape
+
+    def view(self, *shape):
+        return Tri(self.h.view(*shape), self.l.view(*shape), self.c.view(*shape), self.exp)
+
+    def flat(self, n):
+        return Tri(self.h.view(-1)[:n], self.l.view(-1)[:n], self.c.view(-1)[:n], self.exp)
+
+    def float(self):
+        """fp32 value carried by the two precise planes: (h + l / 2^6) * 2^-exp (activations)."""
+        l = self.l.view(torch.float8_e4m3fn).float()
+        return (self.h.float() + l * (1.0 / 64.0)) * (2.0 ** -self.exp)
+
+
+def tri_alloc(shape, device, exp=0):
+    n = 1
+    for s_ in shape:
+        n *= int(s_)
+    buf = torch.empty(4 * n, dtype=torch.uint8, device=device)
+    return Tri(buf[:2 * n].view(torch.float16).view(*shape), buf[2 * n:3 * n].view(*shape),
+               buf[3 * n:].view(*shape), exp)
+
+
+def _e4m3(x):
+    return x.clamp(-448.0, 448.0).to(torch.float8_e4m3fn).view(torch.uint8)
+
+
+def exp_for(amax, target_log2=12):
+    """Power-of-two exponent e with amax * 2^e in (2^(target-1), 2^target]."""
+    import math
+    if not (amax > 0) or math.isinf(amax):
+        return 0
+    return target_log2 - int(math.ceil(math.log2(amax)))
+
+
+def tri_from_f32(x, exp=None, weight=False):
+    """torch restatement of the device conversion (tests, weights at load time)."""
+    x = x.float()
+    if exp is None:
+        exp = exp_for(float(x.abs().max()), 13 if weight else 12)
+    xs = (x * (2.0 ** exp)).clamp(-65504.0, 65504.0)
+    h = xs.half()
+    r = xs - h.float()
+    if weight:
+        return Tri(h.contiguous(), _e4m3(r * 32.0).contiguous(), _e4m3(xs * (1.0 / 64.0)).contiguous(), exp)
+    return Tri(h.contiguous(), _e4m3(r * 64.0).contiguous(), _e4m3(xs * (1.0 / 32.0)).contiguous(), exp)
+
+
+def conv_weight_to_tri(w):
+    cout, cin, kh, kw = w.shape
+    return tri_from_f32(w.permute(0, 2, 3, 1).reshape(cout, kh * kw * cin), weight=True)
+
+
+def fc_weight_to_tri(w, chw=None):
+    if chw is not None:
+        c, h, wd = chw
+        w = w.reshape(w.shape[0], c, h, wd).permute(0, 2, 3, 1).reshape(w.shape[0], -1)
+    return tri_from_f32(w, weight=True)
+
+
+def igemm2(a, batch, H, W, cin, w, cout, taps, bias=None, relu=False, out=None, out_f32=None,
+           out_pix_stride=None, out_ch_offset=0, split_k=1, split_stride=0, bn=0, max_ctas=0,
+           pool=False, out_exp=0, amax=None):
+    """General tensor-core launch (mnc_igemm_tc2).  a / w: split bf16 tensors ([2, ...]) or Tri;
+    out: split bf16 tensor, or Tri (written with exponent out_exp), or out_f32."""
+    tri_in = isinstance(a, Tri)
+    assert tri_in == isinstance(w, Tri)
+    if tri_in:
+        ap = (a.h, a.l, a.c)
+        wp = (w.h, w.c, w.l)          # kernel order: value, copy, residual
+        acc_scale = 2.0 ** -(a.exp + w.exp)
+    else:
+        ap, wp, acc_scale = (a[0], a[1], None), (w[0], w[1], None), 1.0
+    if out_f32 is not None:
+        mode, op = 1, (out_f32, None, None)
+    elif isinstance(out, Tri):
+        mode, op = (5 if pool else 4), (out.h, out.l, out.c)
+        out.exp = int(out_exp)
+    else:
+        mode, op = (2 if pool else 0), (out[0], out[1], None)
+    stride = out_pix_stride if out_pix_stride is not None else cout
+    if timer is not None:
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ev1 = torch.cuda.Event(enable_timing=True)
+        ev0.record()
+    rc = lib.mnc_igemm_tc2(c_int(int(tri_in)), ptr(ap[0]), ptr(ap[1]), ptr(ap[2]), c_int(batch),
+                           c_int(H), c_int(W), c_int(cin), ptr(wp[0]), ptr(wp[1]), ptr(wp[2]),
+                           c_int(cout), c_int(taps), ptr(bias), c_int(int(relu)), c_int(mode),
+                           ptr(op[0]), ptr(op[1]), ptr(op[2]), c_ll(stride), c_int(out_ch_offset),
+                           c_int(split_k), c_ll(split_stride), c_int(bn), c_int(max_ctas),
+                           ctypes.c_float(acc_scale), ctypes.c_float(2.0 ** out_exp), ptr(amax),
+                           cur_stream())
+    check(rc, "mnc_igemm_tc2")
+    if timer is not None:
+        ev1.record()
+        timer.records.append((ev0, ev1, 2.0 * batch * H * W * cout * taps * cin,
+                              "%dx%dx%d" % (batch * H * W, cout, taps * cin)))
+        m_out = batch * ((H + 1) // 2) * ((W + 1) // 2) if pool else batch * H * W
+        timer.manifest.append(dict(
+            M=batch * H * W, N=cout, K=taps * cin, taps=taps, bn=bn, split_k=split_k,
+            pooled=bool(pool), fp32_out=out_f32 is not None, tri_in=tri_in,
+            flops=2.0 * batch * H * W * cout * taps * cin,
+            bytes=4.0 * (batch * H * W * cin + cout * taps * cin + m_out * cout * max(split_k, 1))))
 
 
 import os as _os
