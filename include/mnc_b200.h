@@ -56,8 +56,47 @@ int mnc_igemm_tc(const void* a_hi, const void* a_lo, int batch, int H, int W, in
                  int out_ch_offset, int split_k, long long split_stride, int bn, int max_ctas,
                  void* stream);
 
-/* Thread-block-cluster size of mnc_igemm_tc launches: 2 (default) = CTA pairs share each weight
- * tile via TMA multicast; 1 = no clusters. */
+/* General form of mnc_igemm_tc (same layers replaced: cudnn_conv_layer.cu:11-54 / conv_layer.cu:8-23 +
+ * im2col.cu:9-39, inner_product_layer.cu:21-27, relu_layer.cu:9-14, pooling_layer.cu:11-47).
+ * in_fmt 0: split-bf16 operands (a0 = hi, a1 = lo, a2 unused; w0 = hi, w1 = lo) -- 3 bf16 MMAs per
+ *   k slice.  in_fmt 1 ("precision mode 1"): tri-plane operands: a0 = fp16(x * 2^ea), a1 = e4m3 of
+ *   the fp16 residual * 2^6, a2 = e4m3(x * 2^ea * 2^-5); w0 = fp16(w * 2^ew), w1 = e4m3(w * 2^ew *
+ *   2^-6), w2 = e4m3 of the residual * 2^5.  X.W * 2^(ea+ew) = a0.w0 + a1.w1 + a2.w2: one fp16
+ *   product plus two FP8 products (kind::f8f6f4, twice the rate), 2 tensor-work units per MAC.
+ * out_mode 0 / 2: split-bf16 (out0, out1); 1: fp32 (out0); 4 / 5: tri-plane activation (out0 fp16,
+ *   out1 residual, out2 copy) with scale out_scale = 2^e; 2 and 5 fuse the 2x2 ceil-mode max pool.
+ * acc_scale: accumulator -> true value (2^-(ea+ew) for tri-plane operands, 1 otherwise).
+ * amax: optional device word receiving atomicMax(|output|) as float bits (scale calibration). */
+int mnc_igemm_tc2(int in_fmt, const void* a0, const void* a1, const void* a2, int batch, int H,
+                  int W, int Cin, const void* w0, const void* w1, const void* w2, int Cout, int taps,
+                  const float* bias, int relu, int out_mode, void* out0, void* out1, void* out2,
+                  long long out_pix_stride, int out_ch_offset, int split_k, long long split_stride,
+                  int bn, int max_ctas, float acc_scale, float out_scale, unsigned int* amax,
+                  void* stream);
+
+/* Tri-plane helpers.  fp32 -> (fp16 h, e4m3 l, e4m3 c) with scale 2^e and back (h + l / 2^6) *
+ * inv_scale; n % 4 == 0. */
+int mnc_f32_to_tri(const float* in, long long n, float scale, void* h, void* l, void* c,
+                   unsigned int* amax, void* stream);
+int mnc_tri_to_f32(const void* h, const void* l, long long n, float inv_scale, float* out, void* stream);
+/* mnc_splitk_reduce with a tri-plane result. */
+int mnc_splitk_reduce_tri(const float* partial, int splits, long long split_stride, long long rows,
+                          int cols, const float* bias, int relu, float scale, void* h, void* l,
+                          void* c, long long out_row_stride, int out_ch_offset, unsigned int* amax,
+                          void* stream);
+/* MaskPooling (mask_pooling_layer.cu:13-26) + 2x2 max pool on tri-plane NHWC RoI features
+ * (R,14,14,C) x mask14 (R,196) -> (R,7,7,C), same exponent in and out. */
+int mnc_mask_pool_tri(const void* f_h, const void* f_l, const float* mask14, int R, int C, void* o_h,
+                      void* o_l, void* o_c, void* stream);
+/* mnc_roi_warp_split (ROIWarping roi_warping_layer.cu:67-107 + the 2x2 pools) with tri-plane
+ * outputs scaled by `scale`. */
+int mnc_roi_warp_tri(const float* feat_nhwc, int C, int H, int W, const float* rois, int R, int sub,
+                     float spatial_scale, float scale, void* o14_h, void* o14_l, void* o14_c,
+                     void* o7_h, void* o7_l, void* o7_c, void* stream);
+
+/* Thread-block-cluster size of mnc_igemm_tc launches: 2 (default) = CTA pairs (cta_group::2): one
+ * M = 256 MMA per instruction, each CTA holds its 128 pixel rows and half of the weight tile;
+ * 1 = single-CTA 128-row tiles. */
 int mnc_igemm_set_cluster(int cluster_size);
 /* K elements per pipeline stage: 64 (SWIZZLE_128B), 32 (SWIZZLE_64B, twice the stages) or
  * 0 = default (64; the 192-wide Cout tile always uses 32).  bn also accepts 192. */

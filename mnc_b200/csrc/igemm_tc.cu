@@ -27,6 +27,7 @@
 
 #include "mnc_b200.h"
 #include "ptx.cuh"
+#include "tri.cuh"
 #include "launch_util.h"
 
 namespace mnc {
@@ -135,21 +136,7 @@ __device__ __forceinline__ Tile decode_tile(const IgemmArgs& p, int t, int rank,
 // The first product runs as fp16 MMAs, the two corrections as ONE K-concatenated chain of FP8
 // MMAs at twice the rate: 2 tensor-work units per MAC instead of the 3 of the split-bf16 scheme,
 // at 1.1e-5 relative error per layer (scripts/fp8_correction_model.py; measured in tests).
-struct Tri2 {
-  uint32_t h;      // two fp16
-  uint16_t l, c;   // two e4m3 each
-};
-__device__ __forceinline__ Tri2 tri_pack2(float x0, float x1, float scale) {
-  const float a0 = fminf(fmaxf(x0 * scale, -65504.f), 65504.f);
-  const float a1 = fminf(fmaxf(x1 * scale, -65504.f), 65504.f);
-  const __half2 h = __floats2half2_rn(a0, a1);
-  const float2 hf = __half22float2(h);
-  Tri2 t;
-  t.h = *reinterpret_cast<const uint32_t*>(&h);
-  t.l = __nv_cvt_float2_to_fp8x2(make_float2((a0 - hf.x) * 64.f, (a1 - hf.y) * 64.f), __NV_SATFINITE, __NV_E4M3);
-  t.c = __nv_cvt_float2_to_fp8x2(make_float2(a0 * 0.03125f, a1 * 0.03125f), __NV_SATFINITE, __NV_E4M3);
-  return t;
-}
+// (element conversions: tri.cuh)
 
 // ---------------------------------------------------------------------------------- epilogue
 // Shared by the per-tap kernel and the halo kernel: warps 4..7 drain the TMEM accumulators of
@@ -1229,8 +1216,12 @@ extern "C" int mnc_igemm_tc2(int in_fmt, const void* a0, const void* a1, const v
   const bool halo = in_fmt == 0 && conv && g_igemm_halo && (bn == 64 || bn == 128) && split_k == 1;
   const int TH = conv ? (halo ? kHaloTH : 8) : 1, TW = conv ? (halo ? kHaloTW : 16) : 128;
   if (bn != 64 && bn != 128 && bn != 192 && bn != 256) return MNC_ERR_ARG;
+  const bool bk_forced = (bk != 0);
   if (bk == 0) bk = 64;              // measured: BLOCK_K 64 wins at BN 256 (profiles/r01_igemm_bk32_bn192.log)
-  if (bn == 192) bk = 32;            // instantiated: (64|128|256, 64), (192|256, 32), FC only (128, 32)
+  // BN 192: a CTA pair holds 96 weight rows each, so 64-wide stages fit three deep (and keep the
+  // FP8 planes' rows at 64 B -- 32-byte rows cost 27 % more L2 sectors, r02 ncu); a single CTA
+  // needs the half-size stages
+  if (bn == 192 && !bk_forced) bk = (g_igemm_cluster == 2) ? 64 : 32;
   if (bn < 128 || (bn == 128 && conv)) bk = 64;
 
   IgemmArgs a;
@@ -1322,14 +1313,16 @@ extern "C" int mnc_igemm_tc2(int in_fmt, const void* a0, const void* a1, const v
   if (conv) {
     if (bn == 64) MNC_LAUNCH(8, 16, 64, 64);
     if (bn == 128) MNC_LAUNCH(8, 16, 128, 64);
-    if (bn == 192) MNC_LAUNCH(8, 16, 192, 32);
+    if (bn == 192 && bk == 32) MNC_LAUNCH(8, 16, 192, 32);
+    if (bn == 192) MNC_LAUNCH(8, 16, 192, 64);
     if (bk == 32) MNC_LAUNCH(8, 16, 256, 32);
     MNC_LAUNCH(8, 16, 256, 64);
   } else {
     if (bn == 64) MNC_LAUNCH(1, 128, 64, 64);
     if (bn == 128 && bk == 32) MNC_LAUNCH(1, 128, 128, 32);
     if (bn == 128) MNC_LAUNCH(1, 128, 128, 64);
-    if (bn == 192) MNC_LAUNCH(1, 128, 192, 32);
+    if (bn == 192 && bk == 32) MNC_LAUNCH(1, 128, 192, 32);
+    if (bn == 192) MNC_LAUNCH(1, 128, 192, 64);
     if (bk == 32) MNC_LAUNCH(1, 128, 256, 32);
     MNC_LAUNCH(1, 128, 256, 64);
   }

@@ -22,6 +22,7 @@
 #include <cstdint>
 
 #include "mnc_b200.h"
+#include "tri.cuh"
 
 namespace mnc {
 
@@ -331,12 +332,24 @@ struct __align__(16) SampleTab {
   float w[4];    // bilinear weights; all four are 0 for an out-of-range sample
 };
 
-template <int SUB>
+// output planes of the fused RoI kernels: split-bf16 (hi, lo) or tri-plane (h, l, c; scale 2^exp)
+struct RoiOut {
+  void* p14[3];
+  void* p7[3];
+  float scale;
+};
+template <bool TRI>
+__device__ __forceinline__ void st_feat4(void* const (&pl)[3], long long off, const float4 v, float scale) {
+  if (TRI)
+    st_tri4(static_cast<__half*>(pl[0]), static_cast<uint8_t*>(pl[1]), static_cast<uint8_t*>(pl[2]), off, v, scale);
+  else
+    st_split4(static_cast<__nv_bfloat16*>(pl[0]), static_cast<__nv_bfloat16*>(pl[1]), off, v);
+}
+
+template <int SUB, bool TRI>
 __global__ void __launch_bounds__(256, 4)
 roi_warp_split_kernel(const float* __restrict__ feat, int C, int H, int W,
-                      const float* __restrict__ rois, float spatial_scale,
-                      __nv_bfloat16* __restrict__ o14_hi, __nv_bfloat16* __restrict__ o14_lo,
-                      __nv_bfloat16* __restrict__ o7_hi, __nv_bfloat16* __restrict__ o7_lo) {
+                      const float* __restrict__ rois, float spatial_scale, const RoiOut o) {
   constexpr int P = 14 * SUB;
   constexpr int NS = 2 * SUB * P;  // samples handled by this CTA
   __shared__ SampleTab tab[NS];
@@ -389,11 +402,11 @@ roi_warp_split_kernel(const float* __restrict__ feat, int C, int H, int W,
             cell = max4(cell, bilerp4(wg.x, wg.y, wg.z, wg.w, v1, v2, v3, v4));
           }
         }
-        st_split4(o14_hi, o14_lo, ((static_cast<long long>(r) * 14 + (2 * t + dy)) * 14 + j) * C + c, cell);
+        st_feat4<TRI>(o.p14, ((static_cast<long long>(r) * 14 + (2 * t + dy)) * 14 + j) * C + c, cell, o.scale);
         best7 = max4(best7, cell);
       }
     }
-    st_split4(o7_hi, o7_lo, ((static_cast<long long>(r) * 7 + t) * 7 + jp) * C + c, best7);
+    st_feat4<TRI>(o.p7, ((static_cast<long long>(r) * 7 + t) * 7 + jp) * C + c, best7, o.scale);
   }
 }
 
@@ -783,17 +796,36 @@ extern "C" int mnc_roi_warp_split(const float* feat_nhwc, int C, int H, int W, c
           static_cast<__nv_bfloat16*>(o7_lo));
     return check_launch();
   }
+  RoiOut o;
+  o.p14[0] = o14_hi; o.p14[1] = o14_lo; o.p14[2] = nullptr;
+  o.p7[0] = o7_hi; o.p7[1] = o7_lo; o.p7[2] = nullptr;
+  o.scale = 1.0f;
   dim3 grid(R, 7);
   if (sub == 2)
-    roi_warp_split_kernel<2><<<grid, 256, 0, s>>>(
-        feat_nhwc, C, H, W, rois, spatial_scale, static_cast<__nv_bfloat16*>(o14_hi),
-        static_cast<__nv_bfloat16*>(o14_lo), static_cast<__nv_bfloat16*>(o7_hi),
-        static_cast<__nv_bfloat16*>(o7_lo));
+    roi_warp_split_kernel<2, false><<<grid, 256, 0, s>>>(feat_nhwc, C, H, W, rois, spatial_scale, o);
   else
-    roi_warp_split_kernel<1><<<grid, 256, 0, s>>>(
-        feat_nhwc, C, H, W, rois, spatial_scale, static_cast<__nv_bfloat16*>(o14_hi),
-        static_cast<__nv_bfloat16*>(o14_lo), static_cast<__nv_bfloat16*>(o7_hi),
-        static_cast<__nv_bfloat16*>(o7_lo));
+    roi_warp_split_kernel<1, false><<<grid, 256, 0, s>>>(feat_nhwc, C, H, W, rois, spatial_scale, o);
+  return check_launch();
+}
+
+// Same, writing tri-plane outputs (fp16 value, e4m3 residual, e4m3 copy) scaled by `scale` = 2^exp.
+extern "C" int mnc_roi_warp_tri(const float* feat_nhwc, int C, int H, int W, const float* rois,
+                                int R, int sub, float spatial_scale, float scale, void* o14_h,
+                                void* o14_l, void* o14_c, void* o7_h, void* o7_l, void* o7_c,
+                                void* stream) {
+  if (R <= 0) return MNC_OK;
+  if (C % 4 != 0 || (sub != 1 && sub != 2) || (reinterpret_cast<uintptr_t>(feat_nhwc) & 15))
+    return MNC_ERR_ARG;
+  auto s = static_cast<cudaStream_t>(stream);
+  RoiOut o;
+  o.p14[0] = o14_h; o.p14[1] = o14_l; o.p14[2] = o14_c;
+  o.p7[0] = o7_h; o.p7[1] = o7_l; o.p7[2] = o7_c;
+  o.scale = scale;
+  dim3 grid(R, 7);
+  if (sub == 2)
+    roi_warp_split_kernel<2, true><<<grid, 256, 0, s>>>(feat_nhwc, C, H, W, rois, spatial_scale, o);
+  else
+    roi_warp_split_kernel<1, true><<<grid, 256, 0, s>>>(feat_nhwc, C, H, W, rois, spatial_scale, o);
   return check_launch();
 }
 

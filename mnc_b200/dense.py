@@ -19,6 +19,9 @@ def split(x):
 
 
 def merge(s):
+    """fp32 value of a split-bf16 tensor ([2, ...]) or of a Tri."""
+    if isinstance(s, Tri):
+        return s.float()
     return s[0].float() + s[1].float()
 
 
@@ -62,6 +65,12 @@ class Tri:
         """fp32 value carried by the two precise planes: (h + l / 2^6) * 2^-exp (activations)."""
         l = self.l.view(torch.float8_e4m3fn).float()
         return (self.h.float() + l * (1.0 / 64.0)) * (2.0 ** -self.exp)
+
+    def clone(self):
+        return Tri(self.h.clone(), self.l.clone(), self.c.clone(), self.exp)
+
+    def __getitem__(self, idx):
+        return Tri(self.h[idx], self.l[idx], self.c[idx], self.exp)
 
 
 def tri_alloc(shape, device, exp=0):
@@ -284,6 +293,9 @@ def maxpool2x2(a, batch, H, W, C, out):
 
 
 def split_to_nchw(a, batch, H, W, C, out):
+    if isinstance(a, Tri):     # blob read-back path (not hot): torch does the layout change
+        out.copy_(a.float().view(batch, H, W, C).permute(0, 3, 1, 2))
+        return
     rc = lib.mnc_split_to_nchw(ptr(a[0]), ptr(a[1]), c_int(batch), c_int(H), c_int(W), c_int(C),
                                ptr(out), cur_stream())
     check(rc, "mnc_split_to_nchw")
@@ -297,7 +309,31 @@ def nchw_to_split(x, out):
 
 
 def split_to_f32(a, out):
-    """out (fp32, same element order) = hi + lo."""
+    """out (fp32, same element order) = hi + lo (split bf16) or (h + l / 2^6) * 2^-exp (Tri)."""
     n = out.numel()
+    if isinstance(a, Tri):
+        rc = lib.mnc_tri_to_f32(ptr(a.h), ptr(a.l), c_ll(n), ctypes.c_float(2.0 ** -a.exp), ptr(out),
+                                cur_stream())
+        check(rc, "mnc_tri_to_f32")
+        return
     rc = lib.mnc_split_to_f32(ptr(a[0]), ptr(a[1]), c_ll(n), ptr(out), cur_stream())
     check(rc, "mnc_split_to_f32")
+
+
+def f32_to_tri(x, out, exp, amax=None):
+    """Device conversion fp32 -> Tri `out` (same element order) with exponent exp."""
+    out.exp = int(exp)
+    rc = lib.mnc_f32_to_tri(ptr(x), c_ll(x.numel()), ctypes.c_float(2.0 ** exp), ptr(out.h), ptr(out.l),
+                            ptr(out.c), ptr(amax), cur_stream())
+    check(rc, "mnc_f32_to_tri")
+
+
+def splitk_reduce_tri(partial, splits, split_stride, rows, cols, out, out_exp, bias=None, relu=False,
+                      out_row_stride=None, out_ch_offset=0, amax=None):
+    out.exp = int(out_exp)
+    stride = out_row_stride if out_row_stride is not None else cols
+    rc = lib.mnc_splitk_reduce_tri(ptr(partial), c_int(splits), c_ll(split_stride), c_ll(rows),
+                                   c_int(cols), ptr(bias), c_int(int(relu)),
+                                   ctypes.c_float(2.0 ** out_exp), ptr(out.h), ptr(out.l), ptr(out.c),
+                                   c_ll(stride), c_int(out_ch_offset), ptr(amax), cur_stream())
+    check(rc, "mnc_splitk_reduce_tri")

@@ -31,12 +31,27 @@ def _ceil_half(x):
     return (x + 1) // 2
 
 
+HALO_MAX_COUT = 128    # 3x3 convs with Cout <= 128 run the halo kernel (split-bf16 operands)
+
+
 class MNCEngine:
-    def __init__(self, weights, device="cuda", impl="tc", sm_count=None):
+    # "f16f8": precision mode 1 on every launch of the per-tap / inner-product kernel -- tri-plane
+    # operands, fp16 main product + two FP8 correction products (2 tensor-work units per MAC);
+    # "bf16x3": split-bf16 operands everywhere (3 units per MAC).  The halo kernel (Cout <= 128)
+    # and conv1_1 use split-bf16 operands in both.
+    DEFAULT_PRECISION = "f16f8"
+
+    def __init__(self, weights, device="cuda", impl="tc", sm_count=None, precision=None):
         """weights: {caffe name: (weight, bias)} fp32 tensors in Caffe layouts (see weights.py)."""
         self.device = torch.device(device)
         self.impl = impl
+        self.precision = (precision or self.DEFAULT_PRECISION) if impl == "tc" else "bf16x3"
+        self.tri = self.precision == "f16f8"
         self.fuse_pool = True
+        # per-tensor exponents of the tri-plane activations, measured on the first forward
+        self.exp = {}
+        self._calibrating = False
+        self._calibrated = not self.tri
         self.arch = arch_of(weights)
         self.sms = sm_count or torch.cuda.get_device_properties(self.device).multi_processor_count
         dev = self.device
@@ -53,27 +68,33 @@ class MNCEngine:
         self.convs = []
         for name in TRUNK_NAMES[1:] + ["rpn_conv_3x3"]:
             if name in w:   # the CFM test net has no RPN (proposals are an input)
-                self.convs.append((name, dense.conv_weight_to_split(w[name][0]), w[name][1]))
+                tri = self.tri and w[name][0].shape[0] > HALO_MAX_COUT
+                cw = dense.conv_weight_to_tri(w[name][0]) if tri else dense.conv_weight_to_split(w[name][0])
+                self.convs.append((name, cw, w[name][1]))
         self.trunk_convs = [c for c in self.convs if c[0] != "rpn_conv_3x3"]
         if "rpn_conv_3x3" in w:
             r = self.arch["rpn"]
             rpn_w = torch.cat([w["rpn_cls_score"][0].reshape(18, r), w["rpn_bbox_pred"][0].reshape(36, r)])
-            self.rpn_head = (dense.split(rpn_w), torch.cat([w["rpn_cls_score"][1], w["rpn_bbox_pred"][1]]).contiguous())
+            self.rpn_head = (self._fc_w(rpn_w), torch.cat([w["rpn_cls_score"][1], w["rpn_bbox_pred"][1]]).contiguous())
         c5 = self.c5
-        self.fc6 = (dense.fc_weight_to_split(w["fc6"][0], (c5, 7, 7)), w["fc6"][1])
-        self.fc7 = (dense.split(w["fc7"][0]), w["fc7"][1])
+        self.fc6 = (self._fc_w(w["fc6"][0], (c5, 7, 7)), w["fc6"][1])
+        self.fc7 = (self._fc_w(w["fc7"][0]), w["fc7"][1])
         if "fc6_maskest" in w:
-            self.fc6_maskest = (dense.fc_weight_to_split(w["fc6_maskest"][0], (c5, 14, 14)), w["fc6_maskest"][1])
-            self.mask_pred = (dense.split(w["mask_pred"][0]), w["mask_pred"][1])
-            self.fc6_mask = (dense.fc_weight_to_split(w["fc6_mask"][0], (c5, 7, 7)), w["fc6_mask"][1])
-            self.fc7_mask = (dense.split(w["fc7_mask"][0]), w["fc7_mask"][1])
+            self.fc6_maskest = (self._fc_w(w["fc6_maskest"][0], (c5, 14, 14)), w["fc6_maskest"][1])
+            self.mask_pred = (self._fc_w(w["mask_pred"][0]), w["mask_pred"][1])
+            self.fc6_mask = (self._fc_w(w["fc6_mask"][0], (c5, 7, 7)), w["fc6_mask"][1])
+            self.fc7_mask = (self._fc_w(w["fc7_mask"][0]), w["fc7_mask"][1])
         # cls_score | seg_cls_score | bbox_pred share their input: one inner product for all of them
         names = [n for n in ("cls_score", "seg_cls_score", "bbox_pred") if n in w]
         self.cls_head_names = names
         cls_w = torch.cat([w[n][0] for n in names])
         cls_b = torch.cat([w[n][1] for n in names])
-        self.cls_heads = (dense.split(cls_w), cls_b.contiguous())
+        self.cls_heads = (self._fc_w(cls_w), cls_b.contiguous())
         self._buf = {}
+        self._amax = torch.zeros(2, dtype=torch.int32, device=dev)
+
+    def _fc_w(self, w, chw=None):
+        return dense.fc_weight_to_tri(w, chw) if self.tri else dense.fc_weight_to_split(w, chw)
 
     # ------------------------------------------------------------------ helpers
     def _split_buf(self, key, *shape):
@@ -86,6 +107,38 @@ class MNCEngine:
             self._buf[key] = t
         return t[:2 * need].view(2, *shape)
 
+    def _act_buf(self, key, *shape, tri=None, exp_key=None):
+        """Activation buffer in the format its consumer wants: split bf16 [2, *shape] or Tri."""
+        if not (self.tri if tri is None else tri):
+            return self._split_buf(key, *shape)
+        need = 1
+        for s_ in shape:
+            need *= s_
+        t = self._buf.get("tri_" + key)
+        if t is None or t.numel() < 4 * need:
+            t = torch.empty(4 * need, dtype=torch.uint8, device=self.device)
+            self._buf["tri_" + key] = t
+        return dense.Tri(t[:2 * need].view(torch.float16).view(*shape), t[2 * need:3 * need].view(*shape),
+                         t[3 * need:4 * need].view(*shape), self.exp.get(exp_key or key, 0))
+
+    def _scaled(self, exp_key, fn):
+        """Run fn(out_exp, amax) -- the launch(es) that write the tri-plane tensor `exp_key`.  Normal
+        operation: the frozen exponent.  Calibration (first forward): launch, read the measured
+        max |value|, choose the exponent that puts it at 2^12 (fp16 has 16x headroom above, the
+        e4m3 planes saturate gracefully), relaunch if it changed."""
+        if not self._calibrating:
+            fn(self.exp[exp_key], None)
+            return
+        slot = self._amax[:1]
+        slot.zero_()
+        e0 = self.exp.get(exp_key, 0)
+        fn(e0, slot)
+        amax = float(slot.view(torch.float32).item())
+        e = dense.exp_for(amax, 12) if amax > 0 else e0
+        self.exp[exp_key] = e
+        if e != e0:
+            fn(e, None)
+
     def _f32_buf(self, key, *shape):
         t = self._buf.get(key)
         need = 1
@@ -97,31 +150,50 @@ class MNCEngine:
         return t[:need].view(*shape)
 
     def _linear(self, a, M, K, wgt, N, bias, relu, out=None, out_f32=None, out_stride=None,
-                out_ch_offset=0, key="lin", block_k=0, bn=0):
+                out_ch_offset=0, key="lin", block_k=0, bn=0, exp_key=None):
         """y = act(a @ W^T + b) through the implicit-GEMM kernel; split-K when the tile count
-        cannot fill the GPU (e.g. fc6_maskest: K = 100352, N = 256)."""
-        # Cout tile: 192 (BLOCK_K 32, 5 stages) for the wide layers -- at M = 2400, N = 4096 it gives
-        # 19 x 22 = 418 tiles = 2.8 waves of 148 CTAs, against 4.1 (-> 5) waves at 128 and 2.05
-        # (-> 3, at twice the tile cost) at 256; measured 480 vs 404 vs 347 TF/s on the fc6 shape
-        # (profiles/r01_igemm_bk32_bn192.log)
+        cannot fill the GPU (e.g. fc6_maskest: K = 100352, N = 256).  a / wgt / out: split-bf16
+        tensors or dense.Tri (out written with the exponent of `exp_key`)."""
+        tri_in = isinstance(a, dense.Tri)
+        # Cout tile: 192 for the wide layers -- at M = 2400, N = 4096 it gives 19 x 22 = 418 tiles
+        # (220 CTA-pair items = 2.97 waves of 74 pairs), against 2.16 (-> 3) waves at 256
         bn = bn or (64 if N <= 64 else (128 if N <= 128 else (192 if N >= 1024 else 256)))
         tiles = math.ceil(M / 128) * math.ceil(N / bn)
         k_steps = K // 64
         split = self._pick_split(tiles, k_steps) if self.impl == "tc" else 1
-        a4 = a.view(2, 1, 1, M, K)
+        a4 = a.view(1, 1, M, K) if tri_in else a.view(2, 1, 1, M, K)
+        tri_out = isinstance(out, dense.Tri)
+        ek = exp_key or key
         if split == 1:
-            dense.igemm(a4, 1, 1, M, K, wgt, N, 1, bias=bias, relu=relu, out=out, out_f32=out_f32,
-                        out_pix_stride=out_stride, out_ch_offset=out_ch_offset, bn=bn,
-                        impl=self.impl)
+            if self.impl != "tc":
+                dense.igemm(a4, 1, 1, M, K, wgt, N, 1, bias=bias, relu=relu, out=out, out_f32=out_f32,
+                            out_pix_stride=out_stride, out_ch_offset=out_ch_offset, bn=bn, impl=self.impl)
+                return
+
+            def run(e, amax):
+                dense.igemm2(a4, 1, 1, M, K, wgt, N, 1, bias=bias, relu=relu, out=out, out_f32=out_f32,
+                             out_pix_stride=out_stride, out_ch_offset=out_ch_offset, bn=bn,
+                             out_exp=e, amax=amax)
+            if tri_out:
+                self._scaled(ek, run)
+            else:
+                run(0, None)
             return
         part = self._f32_buf("splitk_" + key, split, M, N)
-        if block_k:
+        if block_k and not tri_in:
             dense.set_block_k(block_k)
-        dense.igemm(a4, 1, 1, M, K, wgt, N, 1, out_f32=part, split_k=split, split_stride=M * N, bn=bn)
-        if block_k:
-            dense.set_block_k(0)
-        dense.splitk_reduce(part, split, M * N, M, N, bias=bias, relu=relu, out=out,
-                            out_f32=out_f32, out_row_stride=out_stride, out_ch_offset=out_ch_offset)
+        try:
+            dense.igemm2(a4, 1, 1, M, K, wgt, N, 1, out_f32=part, split_k=split, split_stride=M * N, bn=bn)
+        finally:
+            if block_k and not tri_in:
+                dense.set_block_k(0)
+        if tri_out:
+            self._scaled(ek, lambda e, amax: dense.splitk_reduce_tri(
+                part, split, M * N, M, N, out, e, bias=bias, relu=relu, out_row_stride=out_stride,
+                out_ch_offset=out_ch_offset, amax=amax))
+        else:
+            dense.splitk_reduce(part, split, M * N, M, N, bias=bias, relu=relu, out=out,
+                                out_f32=out_f32, out_row_stride=out_stride, out_ch_offset=out_ch_offset)
 
     def _pick_split(self, tiles, k_steps, max_split=32):
         """Split-K only when the launch cannot fill the GPU (e.g. fc6_maskest: 19 row tiles,
@@ -139,28 +211,56 @@ class MNCEngine:
                 best, best_cost = s, cost
         return best
 
-    def _conv(self, x, B, H, W, cin, wgt, cout, bias, out, key):
-        """3x3 conv + bias + ReLU -> split NHWC, split-K when whole waves would idle."""
-        bn = 64 if cout <= 64 else (128 if cout <= 128 else 256)
-        tiles = B * math.ceil(H / 8) * math.ceil(W / 16) * math.ceil(cout / bn)
-        split = self._pick_split(tiles, 9 * cin // 64, max_split=4) if self.impl == "tc" else 1
-        if split == 1:
+    def _conv(self, x, B, H, W, cin, wgt, cout, bias, out, key, pool=False):
+        """3x3 conv + bias + ReLU (+ fused 2x2 ceil-mode max pool) -> `out` (split-bf16 or Tri),
+        split-K when whole waves would idle."""
+        if self.impl != "tc":
             dense.igemm(x, B, H, W, cin, wgt, cout, 9, bias=bias, relu=True, out=out, impl=self.impl)
             return
+        bn = 64 if cout <= 64 else (128 if cout <= 128 else 256)
+        tiles = B * math.ceil(H / 8) * math.ceil(W / 16) * math.ceil(cout / bn)
+        split = 1 if pool else self._pick_split(tiles, 9 * cin // 64, max_split=4)
+        tri_out = isinstance(out, dense.Tri)
+        if split == 1:
+            def run(e, amax):
+                dense.igemm2(x, B, H, W, cin, wgt, cout, 9, bias=bias, relu=True, out=out, pool=pool,
+                             out_exp=e, amax=amax)
+            if tri_out:
+                self._scaled(key, run)
+            else:
+                run(0, None)
+            return
         M = B * H * W
-        part = self._f32_buf("splitk_" + key, split, M, cout)
-        dense.igemm(x, B, H, W, cin, wgt, cout, 9, out_f32=part, split_k=split, split_stride=M * cout)
-        dense.splitk_reduce(part, split, M * cout, M, cout, bias=bias, relu=True, out=out)
+        part = self._f32_buf("splitk_conv", split, M, cout)
+        dense.igemm2(x, B, H, W, cin, wgt, cout, 9, out_f32=part, split_k=split, split_stride=M * cout)
+        if tri_out:
+            self._scaled(key, lambda e, amax: dense.splitk_reduce_tri(
+                part, split, M * cout, M, cout, out, e, bias=bias, relu=True, amax=amax))
+        else:
+            dense.splitk_reduce(part, split, M * cout, M, cout, bias=bias, relu=True, out=out)
 
     # ------------------------------------------------------------------ trunk
+    def _conv_in_tri(self, cout):
+        """Does the conv with `cout` output channels read tri-plane operands?"""
+        return self.tri and cout > HALO_MAX_COUT
+
     def trunk(self, data):
-        """conv1_1 .. conv5_3 (test.prototxt:19-387).  data fp32 (B,3,H,W) -> split NHWC conv5_3."""
+        """conv1_1 .. conv5_3 (test.prototxt:19-387).  data fp32 (B,3,H,W) -> NHWC conv5_3 in the
+        format its consumers read (split bf16, or Tri when rpn_conv_3x3 takes tri-plane operands)."""
         B, _, H, W = data.shape
         ch = self.arch["trunk"]
         big = B * H * W * max(ch[0], ch[1])
-        bufs = [self._split_buf("act0", big), self._split_buf("act1", big)]
         cur = 0
-        x = bufs[cur].view(-1)[:2 * B * H * W * ch[0]].view(2, B, H, W, ch[0])
+        names = [c[0] for c in self.trunk_convs]
+        couts = [c[1].shape[-2] for c in self.trunk_convs]
+
+        # the two ping-pong buffers are raw bytes: 4 per element in either format
+        self._act_buf("act0", big, tri=False)
+        self._act_buf("act1", big, tri=False)
+        first_next = couts[0] if couts else 0
+        x = self._pp_buf(cur, self._conv_in_tri(first_next), "conv1_1", B, H, W, ch[0])
+        if isinstance(x, dense.Tri):
+            raise NotImplementedError("conv1_1 feeds a halo-kernel layer in every supported net")
         if self.conv1_1_tc is not None:
             dense.conv1_1_tc(data.contiguous(), self.conv1_1_tc, self.conv1_1[1], x)
         else:
@@ -168,58 +268,89 @@ class MNCEngine:
         cin = ch[0]
         if "conv1_1" in POOL_AFTER:
             raise NotImplementedError
-        for (name, wgt, bias) in self.trunk_convs:
-            cout = wgt.shape[1]
+        for li, (name, wgt, bias) in enumerate(self.trunk_convs):
+            cout = couts[li]
             nxt = 1 - cur
+            pool_here = name in POOL_AFTER
+            fuse = pool_here and self.impl == "tc" and self.fuse_pool
+            Ho, Wo = (_ceil_half(H), _ceil_half(W)) if pool_here else (H, W)
+            # the consumer of this layer's output decides its format
             if name == "conv5_3":
-                y = self._split_buf("conv5_3", B, H, W, cout)
+                nxt_tri = self._conv_in_tri(self.arch["rpn"]) if self.arch["rpn"] else False
             else:
-                y = bufs[nxt].view(-1)[:2 * B * H * W * cout].view(2, B, H, W, cout)
-            fuse = (name in POOL_AFTER) and self.impl == "tc" and self.fuse_pool
-            if fuse:
-                # Pooling fused into the conv epilogue: the full-resolution map is never written
-                Ho, Wo = _ceil_half(H), _ceil_half(W)
-                y = bufs[nxt].view(-1)[:2 * B * Ho * Wo * cout].view(2, B, Ho, Wo, cout)
-                dense.igemm(x, B, H, W, cin, wgt, cout, 9, bias=bias, relu=True, out=y, pool=True)
+                nxt_tri = self._conv_in_tri(couts[li + 1])
+            if fuse or not pool_here:
+                if name == "conv5_3":
+                    y = self._act_buf("conv5_3", B, Ho, Wo, cout, tri=nxt_tri, exp_key="conv5_3")
+                else:
+                    y = self._pp_buf(nxt, nxt_tri, name, B, Ho, Wo, cout)
+                self._conv(x, B, H, W, cin, wgt, cout, bias, y, name, pool=fuse)
                 x, cur, cin, H, W = y, nxt, cout, Ho, Wo
                 continue
-            self._conv(x, B, H, W, cin, wgt, cout, bias, y, "conv")
+            # un-fused pooling (SIMT cross-check path): split-bf16 only
+            y = self._pp_buf(nxt, False, name, B, H, W, cout)
+            self._conv(x, B, H, W, cin, wgt, cout, bias, y, name)
             x, cur, cin = y, nxt, cout
-            if name in POOL_AFTER:
-                Ho, Wo = _ceil_half(H), _ceil_half(W)
-                nxt = 1 - cur
-                y = bufs[nxt].view(-1)[:2 * B * Ho * Wo * cout].view(2, B, Ho, Wo, cout)
-                dense.maxpool2x2(x, B, H, W, cout, y)
-                x, cur, H, W = y, nxt, Ho, Wo
+            nxt = 1 - cur
+            y = self._pp_buf(nxt, False, name + "_pool", B, Ho, Wo, cout)
+            dense.maxpool2x2(x, B, H, W, cout, y)
+            x, cur, H, W = y, nxt, Ho, Wo
         return x, H, W
+
+    def _pp_buf(self, slot, tri, exp_key, *shape):
+        """View of ping-pong activation buffer `slot` (raw bytes, 4 per element) as split bf16 or Tri."""
+        need = 1
+        for s_ in shape:
+            need *= s_
+        raw = self._buf["act%d" % slot]          # bf16 tensor of 2 * big elements
+        if not tri:
+            return raw[:2 * need].view(2, *shape)
+        b = raw.view(torch.uint8)
+        return dense.Tri(b[:2 * need].view(torch.float16).view(*shape), b[2 * need:3 * need].view(*shape),
+                         b[3 * need:4 * need].view(*shape), self.exp.get(exp_key, 0))
 
     # ------------------------------------------------------------------ one cascade stage head
     def head(self, feat14, box7, R, tag):
-        """test.prototxt:509-785 on R RoIs.  feat14 split [2,R,14,14,C5], box7 split [2,R,7,7,C5]."""
+        """test.prototxt:509-785 on R RoIs.  feat14 [R,14,14,C5], box7 [R,7,7,C5] NHWC RoI features
+        (split bf16 or Tri)."""
         c5, fc, me = self.c5, self.fc, self.me
-        h_me = self._split_buf("h_me", R, me)
+        h_me = self._act_buf("h_me", R, me, exp_key="h_me_" + tag)
         # fc6_maskest streams its 963 MB activation matrix from HBM exactly once (a single Cout
-        # tile: no L2 reuse), so it wants loads in flight rather than big stages: BLOCK_K 32 gives a
-        # 4-deep ring at BN 256 (2-deep at 64 left every k-step waiting ~2 us for DRAM).  A 6-deep
-        # ring (BN 128) is no faster: what remains (2.7 TB/s) is the DRAM efficiency of 128-byte
-        # row segments 200 KB apart, the price of K-major rows with K = 100352.
+        # tile: no L2 reuse), so it wants loads in flight rather than big stages (split-bf16 mode:
+        # BLOCK_K 32 gives a 4-deep ring at BN 256).  What remains (2.7 TB/s) is the DRAM efficiency
+        # of 128-byte row segments 200 KB apart, the price of K-major rows with K = 100352.
         self._linear(feat14, R, 196 * c5, self.fc6_maskest[0], me, self.fc6_maskest[1], True,
-                     out=h_me, key="me", block_k=32)
+                     out=h_me, key="me", block_k=32, exp_key="h_me_" + tag)
         logits = self._f32_buf("mask_logits_" + tag, R, 448)
         self._linear(h_me, R, me, self.mask_pred[0], 441, self.mask_pred[1], False,
                      out_f32=logits, out_stride=448, key="mp")
         mask_proposal, mask14 = ops.sigmoid_mask_resize(logits, R, MASK_SIZE, 14)
-        join = self._split_buf("join", R, 2 * fc)
-        h6 = self._split_buf("h6", R, fc)
-        self._linear(box7, R, 49 * c5, self.fc6[0], fc, self.fc6[1], True, out=h6, key="fc6")
-        self._linear(h6, R, fc, self.fc7[0], fc, self.fc7[1], True, out=join, out_stride=2 * fc,
-                     out_ch_offset=fc, key="fc7")
-        m7 = self._split_buf("m7", R, 7, 7, c5)
-        ops.mask_pool_split(feat14, mask14, R, c5, m7)
-        self._linear(m7, R, 49 * c5, self.fc6_mask[0], fc, self.fc6_mask[1], True, out=h6, key="fc6")
-        self._linear(h6, R, fc, self.fc7_mask[0], fc, self.fc7_mask[1], True, out=join,
-                     out_stride=2 * fc, out_ch_offset=0, key="fc7")
-        heads = torch.empty((R, 128), dtype=torch.float32, device=self.device)
+        join = self._act_buf("join", R, 2 * fc, exp_key="join_" + tag)
+        h6 = self._act_buf("h6", R, fc, exp_key="h6_box_" + tag)
+        self._linear(box7, R, 49 * c5, self.fc6[0], fc, self.fc6[1], True, out=h6, key="fc6",
+                     exp_key="h6_box_" + tag)
+        m7 = self._act_buf("m7", R, 7, 7, c5, exp_key="roi_feat")
+        if isinstance(feat14, dense.Tri):
+            ops.mask_pool_tri(feat14, mask14, R, c5, m7)
+        else:
+            ops.mask_pool_split(feat14, mask14, R, c5, m7)
+        h6m = self._act_buf("h6m", R, fc, exp_key="h6_mask_" + tag)
+        self._linear(m7, R, 49 * c5, self.fc6_mask[0], fc, self.fc6_mask[1], True, out=h6m, key="fc6",
+                     exp_key="h6_mask_" + tag)
+        # Concat [fc7_mask | fc7] (test.prototxt:700-705): both halves of `join` share one exponent
+        if isinstance(join, dense.Tri):
+            def both(e, amax):
+                for src, wb, off in ((h6, self.fc7, fc), (h6m, self.fc7_mask, 0)):
+                    dense.igemm2(src.view(1, 1, R, fc), 1, 1, R, fc, wb[0], fc, 1, bias=wb[1], relu=True,
+                                 out=join, out_pix_stride=2 * fc, out_ch_offset=off,
+                                 bn=self._fc_bn(fc), out_exp=e, amax=amax)
+            self._scaled("join_" + tag, both)
+        else:
+            self._linear(h6, R, fc, self.fc7[0], fc, self.fc7[1], True, out=join, out_stride=2 * fc,
+                         out_ch_offset=fc, key="fc7")
+            self._linear(h6m, R, fc, self.fc7_mask[0], fc, self.fc7_mask[1], True, out=join,
+                         out_stride=2 * fc, out_ch_offset=0, key="fc7")
+        heads = self._f32_buf("heads_" + tag, R, 128)
         self._linear(join, R, 2 * fc, self.cls_heads[0], 126, self.cls_heads[1], False,
                      out_f32=heads, out_stride=128, key="cls")
         cls_prob = ops.softmax_rows(heads[:, 0:21], 21)
@@ -229,25 +360,35 @@ class MNCEngine:
                     cls_prob=cls_prob, seg_cls_prob=seg_cls_prob, bbox_pred=bbox_pred,
                     seg_cls_score=heads[:, 21:42], join=join)
 
+    @staticmethod
+    def _fc_bn(N):
+        return 64 if N <= 64 else (128 if N <= 128 else (192 if N >= 1024 else 256))
+
     # ------------------------------------------------------------------ trunk + RPN + proposals
     def conv5_f32(self, conv5_3, B, H5, W5):
-        """fp32 copy of conv5_3 (= hi + lo, exact) for the RoI gathers: 39 MB per batch of 8."""
+        """fp32 copy of conv5_3 (exact value of the stored planes) for the RoI gathers: 39 MB per
+        batch of 8."""
         c5f = self._f32_buf("conv5_f32", B, H5, W5, self.c5)
         dense.split_to_f32(conv5_3, c5f)
+        if self._calibrating:
+            # RoI features are interpolations of conv5_3 (and their products with masks <= 1):
+            # they take conv5_3's range
+            amax = float(c5f.abs().max().item())
+            self.exp["roi_feat"] = dense.exp_for(amax, 12) if amax > 0 else 0
         return c5f
 
     def rpn_rois(self, data, im_info, keep_intermediate=False):
         """test.prototxt:19-476: trunk, rpn_conv_3x3, rpn_cls_score | rpn_bbox_pred, softmax,
-        ProposalLayer.  -> conv5_3 (split NHWC), H5, W5, fp32 conv5_3, rois (B*300,5), counts."""
+        ProposalLayer.  -> conv5_3 (NHWC), H5, W5, fp32 conv5_3, rois (B*300,5), counts."""
         B = data.shape[0]
         conv5_3, H5, W5 = self.trunk(data)
         c5, r = self.c5, self.arch["rpn"]
         name, wgt, bias = self.convs[-1]
-        rpn = self._split_buf("rpn", B, H5, W5, r)
-        self._conv(conv5_3, B, H5, W5, c5, wgt, r, bias, rpn, "conv")
+        rpn = self._act_buf("rpn", B, H5, W5, r, exp_key="rpn")     # consumer: the 54-wide head
+        self._conv(conv5_3, B, H5, W5, c5, wgt, r, bias, rpn, "rpn")
         rpn_out = self._f32_buf("rpn_out", B, H5, W5, 64)
         self._linear(rpn, B * H5 * W5, r, self.rpn_head[0], 54, self.rpn_head[1], False,
-                     out_f32=rpn_out, out_stride=64, key="rpn")
+                     out_f32=rpn_out, out_stride=64, key="rpn_head")
         res = ops.proposals_from_rpn(rpn_out, None, im_info, B, H5, W5, "nhwc", True,
                                      pre_nms_top_n=PRE_NMS_TOP_N, post_nms_top_n=ROIS_PER_IMAGE,
                                      nms_thresh=RPN_NMS_THRESH, min_size=RPN_MIN_SIZE,
@@ -255,12 +396,33 @@ class MNCEngine:
         rois = res[0].view(B * ROIS_PER_IMAGE, 5)
         return conv5_3, H5, W5, self.conv5_f32(conv5_3, B, H5, W5), rois, res[1], res, rpn_out
 
+    def roi_features(self, c5f, H5, W5, rois, sub, feat14, box7):
+        """ROIWarping (+ 28->14 pool when sub == 2) + 14->7 pool into the FC operand buffers."""
+        if isinstance(feat14, dense.Tri):
+            ops.roi_warp_tri(c5f, self.c5, H5, W5, rois, sub, feat14, box7, self.exp["roi_feat"])
+        else:
+            ops.roi_warp_split(c5f, self.c5, H5, W5, rois, sub, feat14, box7)
+
     # ------------------------------------------------------------------ whole forward
     def forward(self, data, im_info, keep_intermediate=False):
         """data fp32 (B,3,H,W) device, im_info fp32 (B,3) device [h, w, scale].
         Returns device tensors named after the blobs callers read (tools/demo.py:84-90):
         rois (B*300,5), mask_proposal (B*300,1,21,21), seg_cls_prob (B*300,21) and the `_ext`
-        versions, plus roi_counts (B,) = number of real (non-padding) RoIs per image."""
+        versions, plus roi_counts (B,) = number of real (non-padding) RoIs per image.
+
+        Precision mode 1 needs one exponent per tri-plane activation tensor: the first call
+        measures them layer by layer on its own input (a few dozen host syncs, once) and freezes
+        them; every later call is the sync-free launch sequence."""
+        if not self._calibrated:
+            self._calibrating = True
+            try:
+                self._forward(data, im_info, False)
+            finally:
+                self._calibrating = False
+            self._calibrated = True
+        return self._forward(data, im_info, keep_intermediate)
+
+    def _forward(self, data, im_info, keep_intermediate=False):
         B = data.shape[0]
         out = {}
         conv5_3, H5, W5, c5f, rois, roi_counts, res, rpn_out = self.rpn_rois(data, im_info, keep_intermediate)
@@ -268,9 +430,9 @@ class MNCEngine:
         R = B * ROIS_PER_IMAGE
         out["rois"] = rois
         out["roi_counts"] = roi_counts
-        feat14 = self._split_buf("feat14", R, 14, 14, c5)
-        box7 = self._split_buf("box7", R, 7, 7, c5)
-        ops.roi_warp_split(c5f, c5, H5, W5, rois, 2, feat14, box7)
+        feat14 = self._act_buf("feat14", R, 14, 14, c5, exp_key="roi_feat")
+        box7 = self._act_buf("box7", R, 7, 7, c5, exp_key="roi_feat")
+        self.roi_features(c5f, H5, W5, rois, 2, feat14, box7)
         s1 = self.head(feat14, box7, R, "s1")
         rois_ext = ops.stage_bridge(rois, s1["bbox_pred"], s1["seg_cls_prob"], im_info,
                                     ROIS_PER_IMAGE)
@@ -286,7 +448,7 @@ class MNCEngine:
             out["_mask_logits"] = s1["mask_logits"].clone()
             out["_mask_resize"] = s1["mask_resize"]
             out["_join"] = s1["join"].clone()
-        ops.roi_warp_split(c5f, c5, H5, W5, rois_ext, 1, feat14, box7)
+        self.roi_features(c5f, H5, W5, rois_ext, 1, feat14, box7)
         s2 = self.head(feat14, box7, R, "s2")
         for k in ("mask_proposal", "seg_cls_prob", "cls_prob", "bbox_pred"):
             out[k + "_ext"] = s2[k]

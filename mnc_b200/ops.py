@@ -230,6 +230,24 @@ def roi_warp_split(feat, C, H, W, rois, sub, out14, out7, spatial_scale=0.0625):
                                  cur_stream()), "mnc_roi_warp_split")
 
 
+def roi_warp_tri(feat, C, H, W, rois, sub, out14, out7, exp, spatial_scale=0.0625):
+    """roi_warp_split with tri-plane outputs (mnc_b200.dense.Tri) written with exponent `exp`."""
+    R = rois.shape[0]
+    assert feat.dtype == torch.float32
+    out14.exp = out7.exp = int(exp)
+    check(lib.mnc_roi_warp_tri(ptr(feat), c_int(C), c_int(H), c_int(W), ptr(rois), c_int(R), c_int(sub),
+                               c_float(spatial_scale), c_float(2.0 ** exp), ptr(out14.h), ptr(out14.l),
+                               ptr(out14.c), ptr(out7.h), ptr(out7.l), ptr(out7.c), cur_stream()),
+          "mnc_roi_warp_tri")
+
+
+def mask_pool_tri(feat14, mask14, R, C, out7):
+    """MaskPooling + 2x2 max pool on tri-plane features; the output takes the input's exponent."""
+    out7.exp = feat14.exp
+    check(lib.mnc_mask_pool_tri(ptr(feat14.h), ptr(feat14.l), ptr(mask14), c_int(R), c_int(C),
+                                ptr(out7.h), ptr(out7.l), ptr(out7.c), cur_stream()), "mnc_mask_pool_tri")
+
+
 def sigmoid_mask_resize(logits, R, mask_size=21, out_size=14):
     dev = logits.device
     mp = torch.empty((R, 1, mask_size, mask_size), dtype=torch.float32, device=dev)

@@ -20,6 +20,8 @@ from .engine import MNCEngine, ROIS_PER_IMAGE, NUM_CLASSES, MASK_SIZE
 
 
 class FasterRCNNEngine(MNCEngine):
+    DEFAULT_PRECISION = "bf16x3"   # RoI producers of this graph write split-bf16 features
+
     def forward(self, data, im_info, keep_intermediate=False):
         """-> rois (B*300,5), roi_counts (B,), cls_prob (B*300,21), bbox_pred (B*300,84)."""
         B = data.shape[0]
@@ -56,6 +58,8 @@ class FasterRCNNEngine(MNCEngine):
 
 
 class CFMEngine(MNCEngine):
+    DEFAULT_PRECISION = "bf16x3"
+
     def forward(self, data, rois, masks, keep_intermediate=False):
         """data fp32 (S,3,H,W) image pyramid; rois fp32 (R,5) [level,x1,y1,x2,y2] in the level's
         scaled coordinates; masks fp32 (R,1,14,14).  -> mask_prob (R,1,21,21), seg_cls_prob,
