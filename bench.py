@@ -4,14 +4,20 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
   (N > 1: launched by torchrun, one rank per GPU; reads RANK/LOCAL_RANK/WORLD_SIZE/MASTER_*)
 
-A "step" = one pass of the hot path (im_detect: trunk -> RPN proposals -> two cascade stages,
-tools/demo.py:79-100) over one batch of B synthetic 600x1000 images per GPU (weak scaling: the
-batch is sharded over images, one all-gather of per-image records at the end of each step).
-`value`  : whole-job images/s with the inputs resident in HBM (CUDA events, max over ranks).
-`e2e`    : same metric through the public host-buffer API (mnc_b200.api.Detector.im_detect_batch):
-           pinned-host inputs H2D + results D2H inside the timed region.
-`roofline`: the dominant kernel (tcgen05 implicit GEMM, all conv + FC launches of the step):
-           algorithmic FLOPs (2*M*N*K, real dims) / summed per-launch CUDA-event time.
+A "step" = one pass of the hot path (im_detect: trunk -> RPN proposals -> two cascade stages ->
+im_detect tail, tools/demo.py:79-100) over one batch of B synthetic 600x1000 images per GPU (weak
+scaling: the batch is sharded over images; the one collective is an all-gather of the per-step
+output records, issued on a side stream so that it overlaps the next step's trunk).
+`value`  : whole-job images/s with the inputs resident in HBM (CUDA events, max over ranks); the
+           step is replayed from a CUDA graph (mnc_b200.engine.MNCEngine.detect_graphed).
+`e2e`    : same metric through the public host-buffer API (mnc_b200.api.Detector.im_detect_images):
+           uint8 frames in host memory -> H2D -> prep + forward -> results D2H, all inside the
+           timed region; reported from page-locked and from pageable caller memory.
+`roofline`: the dominant kernel (tcgen05 implicit GEMM: all conv + inner-product launches of a step):
+           algorithmic FLOPs (2*M*N*K, real dims) / summed per-launch CUDA-event time (measured in
+           an eager pass of the same step); `roofline_roi_warp`: the RoI-warp HBM roofline.
+`micro`  : BASELINE.json configs[3] (RoI-warp / mask-pool GB/s) and configs[4] (gpu_nms 10k boxes,
+           gpu_mask_voting 600 x 21; ms + bit-exactness against the reference's own kernels).
 `cpu_baseline`: the oracle (port of the reference path; the reference has no runnable CPU path,
            BASELINE.md section 2) timed on this box's host cores on a bounded sample (rank 0, N=1).
 --impl reference prints the same line for the CPU oracle alone.
@@ -40,6 +46,28 @@ def _peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
 
 
+def physical_cores():
+    """Physical cores of the box (SMT siblings counted once)."""
+    try:
+        seen = set()
+        phys = core = None
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("physical id"):
+                    phys = line.split(":")[1].strip()
+                elif line.startswith("core id"):
+                    core = line.split(":")[1].strip()
+                elif not line.strip():
+                    if phys is not None and core is not None:
+                        seen.add((phys, core))
+                    phys = core = None
+        if seen:
+            return len(seen)
+    except Exception:
+        pass
+    return max(1, (os.cpu_count() or 2) // 2)
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -56,7 +84,7 @@ class ClockSampler(threading.Thread):
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 if self.stop_flag:
@@ -88,20 +116,25 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_time(weights, steps, warmup, images_per_step=1):
-    """The CPU oracle on `images_per_step` images per step (bounded sample of the batch)."""
-    import torch
+def cpu_reference_time(weights, images, warmup):
+    """The CPU oracle, one image per step: `warmup` untimed images, then `images` timed ones.
+    Returns the per-image seconds."""
     from oracle import oracle as O
     times = []
-    for it in range(warmup + steps):
+    for it in range(warmup + images):
+        im = O.synthetic_image(it, H, W)
         t0 = time.perf_counter()
-        for i in range(images_per_step):
-            im = O.synthetic_image(i, H, W)
-            O.im_detect(weights, im)
+        O.im_detect(weights, im)
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
-    return times, torch.get_num_threads()
+    return times
+
+
+def _summ(times):
+    s = sorted(times)
+    n = len(s)
+    return {"median_s": s[n // 2], "p10_s": s[max(0, int(0.1 * n))], "p90_s": s[min(n - 1, int(0.9 * n))], "n": n}
 
 
 _JSON_FD = None
@@ -123,36 +156,46 @@ def _emit(line):
     os.write(_JSON_FD if _JSON_FD is not None else 1, (json.dumps(line) + "\n").encode())
 
 
+def _pin_cpu_threads():
+    """One software thread per physical core, before torch / OpenMP start (torchrun pins
+    OMP_NUM_THREADS to 1 for its workers; oversubscribing SMT siblings made this arm swing 6x)."""
+    n = physical_cores()
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    os.environ["MKL_NUM_THREADS"] = str(n)
+    os.environ.setdefault("OMP_PROC_BIND", "spread")
+    os.environ.setdefault("OMP_PLACES", "cores")
+    return n
+
+
 def run_reference(args, rank):
     """--impl reference: the reference's own algorithm on the host cores.  The reference has no
     runnable CPU implementation (its MNC layers are NOT_IMPLEMENTED on CPU and Caffe does not
-    build here), so this is the oracle port, all host threads (torch CPU), 1 image per step."""
+    build here), so this is the oracle port on all physical cores; a step = one image."""
     if rank != 0:
         return
-    # torchrun pins OMP_NUM_THREADS to 1 for its workers; this arm is the CPU implementation with
-    # all the host threads it can use, so undo that before torch / the OpenMP oracle library load
-    ncpu = os.cpu_count() or 1
-    os.environ["OMP_NUM_THREADS"] = str(ncpu)
-    os.environ["MKL_NUM_THREADS"] = str(ncpu)
+    ncpu = _pin_cpu_threads()
     import torch
     torch.set_num_threads(ncpu)
     from mnc_b200 import weights as Wt
     w = Wt.make_weights(Wt.FULL_ARCH)
-    steps = max(1, min(args.steps, 3))
-    warm = min(args.warmup, 1)
-    times, threads = cpu_reference_time(w, steps, warm, 1)
-    tot = sum(times)
-    v = steps * 1 / tot
+    images = max(5, min(args.steps, 8))
+    warm = max(2, min(args.warmup, 3))
+    times = cpu_reference_time(w, images, warm)
+    st = _summ(times)
+    v = 1.0 / st["median_s"]
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": warm, "ms_per_step": 1000.0 * tot / steps,
+        "steps": images, "warmup": warm, "ms_per_step": 1000.0 * st["median_s"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": workload_config(args, 1),
-        "cpu_baseline": {"value": v, "unit": "images/s", "cores": threads, "kind": "port",
-                         "sample": "1 image (600x1000, 300 RoIs/stage) per step, %d steps" % steps},
+        "cpu_baseline": {"value": v, "unit": "images/s", "cores": ncpu, "kind": "port",
+                         "sample": "%d images (600x1000, 300 RoIs/stage) one per step after %d "
+                                   "warm-up images; value = 1 / median per-image time" % (images, warm),
+                         "per_image_s": st},
         "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "reference has no runnable CPU path (BASELINE.md section 2); oracle port timed; "
-                "steps/warmup clamped to keep the run bounded",
+        "note": "reference has no runnable CPU path (BASELINE.md section 2); oracle port timed on "
+                "%d physical cores (torch CPU fp32 conv/FC + numpy layers + C/OpenMP kernels); "
+                "steps/warmup clamped to keep the run bounded" % ncpu,
     }
     _emit(line)
 
@@ -161,21 +204,119 @@ def workload_config(args, world):
     return {"workload": "configs[1]: VGG16 MNC 5-stage inference (im_detect), batch %d per GPU, "
                         "600x1000 synthetic, 300 RoIs/stage" % args.batch,
             "global_batch": args.batch * world, "image": [H, W], "rois_per_stage": 300,
-            "parallelism": "dp%d (images sharded, 1 all-gather of records)" % world,
-            "l2": "L2 flushed (256 MiB write) between timed steps; per-step working set >> L2",
-            "weights": "seeded random init (mnc_b200/weights.py), fp32 -> split-bf16"}
+            "parallelism": "dp%d (images sharded, 1 all-gather of records per step, overlapped)" % world,
+            "l2": "inputs larger than L2: every step streams 1.13 GB of weights and > 5 GB of "
+                  "activations through the 126 MB L2, nothing of a step survives to the next",
+            "weights": "seeded random init (mnc_b200/weights.py), fp32 -> fp16 + 2 x e4m3 planes "
+                       "(halo-kernel layers: split bf16)"}
+
+
+def median_ms(fn, iters=20, warm=3, flush=None):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ms = []
+    for i in range(iters):
+        if flush is not None:
+            flush.fill_(i & 0xff)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    ms.sort()
+    return ms[len(ms) // 2]
+
+
+def microbench(hbm_gbs):
+    """BASELINE.json configs[3] and configs[4] (SURVEY.md section 8d inputs), one GPU."""
+    import ctypes
+    import numpy as np
+    import torch
+    from mnc_b200 import ops
+    from oracle import oracle as O
+    from tests import util
+    res = {}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    g = torch.Generator(device="cpu").manual_seed(7)
+    feat = torch.randn(1, 512, 38, 63, generator=g).clamp_min(0).cuda()
+    rng = np.random.default_rng(8)
+    x1, y1 = rng.uniform(0, 999, 2000), rng.uniform(0, 599, 2000)
+    w, h = rng.uniform(16, 600, 2000), rng.uniform(16, 600, 2000)
+    rois = np.stack([np.zeros(2000), x1, y1, np.clip(x1 + w, 0, 999), np.clip(y1 + h, 0, 599)], 1).astype(np.float32)
+    trois = torch.from_numpy(rois).cuda()
+    for P in (28, 14):
+        out = torch.empty(2000, 512, P, P, device="cuda")
+        ms = median_ms(lambda: ops.roi_warp_nchw(feat, trois, P, P, out=out), flush=flush)
+        alg = 2000 * 512 * P * P * 4 + 512 * 38 * 63 * 4 + 2000 * 20
+        res["roi_warp_P%d" % P] = {"ms": ms, "algorithmic_bytes": alg, "GBps": alg / ms / 1e6,
+                                   "frac_of_hbm": alg / ms / 1e6 / hbm_gbs}
+        del out
+    f14 = torch.randn(2000, 512, 14, 14, device="cuda")
+    m14 = torch.rand(2000, 1, 14, 14, device="cuda")
+    o14 = torch.empty_like(f14)
+    ms = median_ms(lambda: ops.mask_pool_nchw(f14, m14, out=o14), flush=flush)
+    alg = 2 * 2000 * 512 * 196 * 4 + 2000 * 196 * 4
+    res["mask_pool"] = {"ms": ms, "algorithmic_bytes": alg, "GBps": alg / ms / 1e6,
+                        "frac_of_hbm": alg / ms / 1e6 / hbm_gbs}
+    del f14, o14
+    # ---- configs[4]: gpu_nms, 10 000 boxes, keep 300 at 0.7, vs the reference's own _nms
+    boxes = util.random_boxes(10000, seed=10)
+    scores = util.tie_free_scores(10000, seed=11)
+    order = O.order_desc(scores)
+    sorted_dets = np.ascontiguousarray(np.hstack([boxes, scores[:, None]]).astype(np.float32)[order])
+    sb = torch.from_numpy(np.ascontiguousarray(sorted_dets[:, :4])).cuda()[None].contiguous()
+    ms = median_ms(lambda: ops.nms_sorted(sb, None, 0.7, 300))
+    keep, num = ops.nms_sorted(sb, None, 0.7, 300)
+    got = keep[0, :int(num[0].item())].cpu().numpy()
+    ref_so = os.path.join(ROOT, "oracle", "_ref", "libmnc_ref.so")
+    exact, against = None, None
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    if os.path.exists(ref_so):
+        ref = ctypes.CDLL(ref_so)
+        k_ref = np.zeros(10000, dtype=np.int32)
+        n_ref = ctypes.c_int(0)
+        ref._Z4_nmsPiS_PKfiifi(p(k_ref), ctypes.byref(n_ref), p(sorted_dets), 10000, 5, ctypes.c_float(0.7), 0)
+        exact, against = bool(np.array_equal(got, k_ref[:300])), "reference _nms (oracle/_ref)"
+    else:
+        exact, against = bool(np.array_equal(got, O.nms_sorted(sorted_dets, 0.7)[:300])), "oracle"
+    res["nms_10k_keep300"] = {"ms": ms, "kept": int(len(got)), "bit_exact": exact, "against": against,
+                              "algorithmic_bytes": 10000 * 20 + 2 * 10000 * 157 * 8}
+    # ---- configs[4]: gpu_mask_voting, 600 boxes x 21 classes at 600x1000
+    from tests.test_ref_pin import _voting_inputs
+    vb, vm, vs = _voting_inputs(600, 600, 1000, 11)
+    tb, tm, ts = (torch.from_numpy(a).cuda()[None] for a in (vb, vm, vs))
+    hw = torch.tensor([[600, 1000]], dtype=torch.int32, device="cuda")
+    ms = median_ms(lambda: ops.mask_voting(tb, tm, ts, hw), iters=10)
+    r = ops.mask_voting(tb, tm, ts, hw)
+    inds, start, wts, cs, bar = O.mask_voting_candidates(vb, vs, 21, 100)
+    k = int(r["n_res"][0])
+    beg, end = r["cand_begin"][0, :k].cpu().numpy(), r["cand_end"][0, :k].cpu().numpy()
+    ci, cw = r["cand_inds"][0].cpu().numpy().ravel(), r["cand_weights"][0].cpu().numpy().ravel()
+    lists_ok = bool(k == len(start) and np.array_equal(np.concatenate([ci[b:e] for b, e in zip(beg, end)]), inds)
+                    and np.array_equal(np.concatenate([cw[b:e] for b, e in zip(beg, end)]), wts))
+    rm_o, rb_o = O.mv(vb, vm, inds, start, wts, 600, 1000)
+    boxes_ok = bool(np.array_equal(r["result_box"][0, :k].cpu().numpy(), rb_o))
+    res["mask_voting_600x21"] = {"ms": ms, "results": k, "candidates": int(len(inds)),
+                                 "lists_bit_exact": lists_ok, "result_boxes_exact": boxes_ok,
+                                 "against": "oracle (itself == reference _mv built -fmad=false, tests/test_ref_pin.py)"}
+    return res
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=8, help="images per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-micro", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--dump-igemm", default=None,
-                    help="write the ordered list of tensor-core launches of the timed region "
+                    help="write the ordered list of tensor-core launches of one step "
                          "(shape, algorithmic FLOPs / bytes) as JSON, for scripts/ncu_tc_summary.py")
     args = ap.parse_args()
     _claim_stdout()
@@ -186,6 +327,7 @@ def main():
         run_reference(args, rank)
         return
 
+    ncpu = _pin_cpu_threads() if int(os.environ.get("WORLD_SIZE", "1")) == 1 else None
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -198,31 +340,31 @@ def main():
     dev = torch.device("cuda", local)
     B = args.batch
     w = Wt.make_weights(Wt.FULL_ARCH)
-    det = Detector(w, device=dev, max_batch=B, height=H, width=W)
+    det = Detector(w, device=dev, max_batch=B, height=H, width=W, use_graph=not args.no_graph)
     eng = det.engine
 
     # synthetic inputs: image i of the global batch = seed 1234 + i
     start, _ = mdist.shard_range(B * world, rank, world)
-    rng_imgs = []
-    for i in range(B):
-        rng = np.random.default_rng(1234 + start + i)
-        im = rng.integers(0, 256, size=(H, W, 3), dtype=np.uint8).astype(np.float32)
-        im -= np.array([[[102.9801, 115.9465, 122.7717]]], dtype=np.float32)
-        rng_imgs.append(im.transpose(2, 0, 1))
-    host_blob = torch.from_numpy(np.stack(rng_imgs)).contiguous()
-    data = host_blob.to(dev)
+    u8 = np.stack([np.random.default_rng(1234 + start + i).integers(0, 256, size=(H, W, 3), dtype=np.uint8)
+                   for i in range(B)])
+    data = ops.prep_images(torch.from_numpy(u8).to(dev), 1.0)
     im_info = torch.tensor([[H, W, 1.0]] * B, dtype=torch.float32, device=dev)
     im_hw = torch.tensor([[H, W]] * B, dtype=torch.float32, device=dev)
     im_scale = torch.ones(B, dtype=torch.float32, device=dev)
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    pipe = mdist.GatherPipe(dev, mdist.record_len(B))
 
-    def step():
-        boxes, masks, scores, valid, o = eng.detect(data, im_info, im_hw, im_scale)
-        rec = mdist.pack_records(boxes, masks, scores, valid)
-        return mdist.all_gather_records(rec), o
+    def step(graph=not args.no_graph):
+        rec = pipe.send_buffer()
+        if graph:
+            outs = eng.detect_graphed(data, im_info, im_hw, im_scale, rec=rec)
+        else:
+            o = eng.forward(data, im_info)
+            outs = eng.detect_tail(o, B, im_hw, im_scale, rec=rec) + (o,)
+        return outs, pipe.submit()
 
-    for _ in range(args.warmup):
-        out, o = step()
+    for _ in range(args.warmup + 2):      # + 2: one graph capture per send buffer of the gather pipe
+        (boxes, masks, scores, valid, o), gathered = step()
+    pipe.drain()
     torch.cuda.synchronize()
     counts = o["roi_counts"].cpu().numpy()
 
@@ -235,27 +377,23 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    dense.timer = dense.KernelTimer()
-    launches0 = _lib.launch_count
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-          for _ in range(args.steps)]
+        time.sleep(0.2)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     barrier()
     torch.cuda.nvtx.range_push("timed")
     t_wall0 = time.perf_counter()
+    ev[0].record()
     for k in range(args.steps):
-        flush.fill_(k & 0xff)          # evict L2 between timed steps (outside the event pair)
-        ev[k][0].record()
         step()
-        ev[k][1].record()
+        if k + 1 < args.steps:
+            ev[k + 1].record()
+    pipe.drain()                           # the last step's gather is inside the timed region
+    ev[args.steps].record()
     barrier()
     torch.cuda.nvtx.range_pop()
     t_wall = time.perf_counter() - t_wall0
-    launches = _lib.launch_count - launches0
-    ktimer, dense.timer = dense.timer, None
-    if args.dump_igemm and rank == 0:
-        with open(args.dump_igemm, "w") as f:
-            json.dump({"steps": args.steps, "launches": ktimer.manifest}, f)
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    dev_ms = ev[0].elapsed_time(ev[args.steps])
+    step_ms = sorted(ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps))
     clocks = sampler.finish() if rank == 0 else None
     tms = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -263,14 +401,37 @@ def main():
     total_ms = float(tms.item())
     value = world * B * args.steps / (total_ms / 1000.0)
 
+    # the collective alone (same buffers, main stream, nothing to overlap with)
+    comm_ms = 0.0
+    if world > 1:
+        rec = pipe.send[0]
+        out = pipe.recv[0]
+        comm_ms = median_ms(lambda: mdist.all_gather_records(rec, out), iters=10)
+
+    # ------------------------------------------------------------- eager pass: per-kernel roofline
+    dense.timer = dense.KernelTimer()
+    launches0 = _lib.launch_count
+    n_eager = 3
+    for _ in range(n_eager):
+        step(graph=False)
+    pipe.drain()
+    torch.cuda.synchronize()
+    launches_per_step = (_lib.launch_count - launches0) // n_eager
+    ktimer, dense.timer = dense.timer, None
+    if args.dump_igemm and rank == 0:
+        per = len(ktimer.manifest) // n_eager
+        with open(args.dump_igemm, "w") as f:
+            json.dump({"steps": 1, "launches": ktimer.manifest[-per:]}, f)
+
     # ------------------------------------------------------------- forward + gpu_mask_voting
     # (the published 0.33 s/img covers im_detect only, tools/demo.py:144-147; BASELINE.md asks for
     # both numbers)
     im_hw_i = torch.tensor([[H, W]] * B, dtype=torch.int32, device=dev)
 
     def step_vote():
-        boxes, masks, scores, valid, _ = eng.detect(data, im_info, im_hw, im_scale)
-        return ops.mask_voting(boxes, masks, scores, im_hw_i, box_valid=valid)
+        bx, mk, sc, vl, _ = eng.detect_graphed(data, im_info, im_hw, im_scale) if not args.no_graph \
+            else eng.detect(data, im_info, im_hw, im_scale)
+        return ops.mask_voting(bx, mk, sc, im_hw_i, box_valid=vl)
 
     for _ in range(2):
         vr = step_vote()
@@ -289,22 +450,40 @@ def main():
 
     # ------------------------------------------------------------- e2e: host buffers in and out
     # the reference's callers hand im_detect the raw uint8 image (tools/demo.py:143-146); so does
-    # this: uint8 BGR frames in host memory -> boxes / masks / scores in host memory
-    host_u8 = np.stack([np.random.default_rng(1234 + start + i).integers(
-        0, 256, size=(H, W, 3), dtype=np.uint8) for i in range(B)])
-    host_u8 = torch.from_numpy(host_u8).pin_memory()   # the step's inputs live in pinned host memory
-    for _ in range(2):
-        det.im_detect_images(host_u8)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        det.im_detect_images(host_u8)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * args.steps / float(te.item())
+    # this: uint8 BGR frames in host memory -> boxes / masks / scores in host memory (+ the
+    # all-gather of the records when N > 1)
+    def e2e_run(src):
+        def once():
+            det.im_detect_images(src)
+            if world > 1:
+                mdist.all_gather_records(eng.last_record, pipe.recv[0])
+                torch.cuda.synchronize()
+        for _ in range(2):
+            once()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            once()
+        torch.cuda.synchronize()
+        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        return world * B * args.steps / float(te.item())
+
+    e2e_pinned = e2e_run(torch.from_numpy(u8).pin_memory())
+    e2e_pageable = e2e_run(u8)             # a plain numpy array, as cv2.imread returns
+
+    # ------------------------------------------------------------- batch-1 latency (configs[0])
+    lat1 = None
+    if world == 1:
+        d1, i1, h1, s1 = data[:1].contiguous(), im_info[:1].contiguous(), im_hw[:1].contiguous(), im_scale[:1].contiguous()
+        fn = (lambda: eng.detect_graphed(d1, i1, h1, s1)) if not args.no_graph else (lambda: eng.detect(d1, i1, h1, s1))
+        lat1 = median_ms(fn, iters=20, warm=4)
+        t0 = time.perf_counter()
+        for _ in range(20):
+            fn()
+        host_ms1 = (time.perf_counter() - t0) * 1000.0 / 20      # host time to issue a step
+        torch.cuda.synchronize()
 
     if rank != 0:
         if world > 1:
@@ -313,58 +492,96 @@ def main():
 
     # ------------------------------------------------------------- roofline of the dominant kernel
     k_ms, k_flops, k_n = ktimer.totals()
-    # per launch site (order of launch within a step): mean ms over the timed steps
-    per_step = k_n // args.steps if args.steps else 0
+    per_step = k_n // n_eager
     site_ms = [0.0] * per_step
     for i, (e0, e1, _, _) in enumerate(ktimer.records):
-        site_ms[i % per_step] += e0.elapsed_time(e1) / args.steps
+        site_ms[i % per_step] += e0.elapsed_time(e1) / n_eager
     site_tags = [ktimer.records[i][3] for i in range(per_step)]
+    man = ktimer.manifest[:per_step]
+    work = sum(m["flops"] * (2 if m.get("tri_in") else 3) for m in man)
+    flops_step = sum(m["flops"] for m in man)
+    k_ms_step = k_ms / n_eager
     peaks, peak_src = _peaks()
     peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
-    ach = k_flops / (k_ms / 1000.0) / 1e12 if k_ms > 0 else 0.0
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    ach = flops_step / (k_ms_step / 1000.0) / 1e12 if k_ms_step > 0 else 0.0
     traffic, traffic_note = None, None
-    summ = os.path.join(ROOT, "profiles", "r01_ncu_tc_summary.json")
-    if os.path.exists(summ):
-        with open(summ) as f:
-            sj = json.load(f)
-        traffic = sj["mean_traffic_bytes_per_launch"]
-        traffic_note = ("dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the %d "
-                        "tensor-core launches of one step in the committed ncu --set full capture "
-                        "(profiles/r01_ncu_tc_summary.json); algorithmic bytes of the same launches: "
-                        "%.3e per launch" % (sj["n_launches"], sj["mean_algorithmic_bytes_per_launch"]))
+    for nm in ("r02_ncu_tc_summary.json", "r01_ncu_tc_summary.json"):
+        summ = os.path.join(ROOT, "profiles", nm)
+        if os.path.exists(summ):
+            with open(summ) as f:
+                sj = json.load(f)
+            traffic = sj["mean_traffic_bytes_per_launch"]
+            traffic_note = ("dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the %d "
+                            "tensor-core launches of one step in the committed ncu --set full capture "
+                            "(profiles/%s); algorithmic bytes of the same launches: %.3e per launch"
+                            % (sj["n_launches"], nm, sj["mean_algorithmic_bytes_per_launch"]))
+            break
+    ms_step = total_ms / args.steps
     roofline = {
-        "kernel": "igemm_tc_kernel (tcgen05 implicit GEMM: 13 conv3x3 + 11 inner-product launch "
-                  "sites per step)",
+        "kernel": "igemm_tc_kernel / conv_halo_tc_kernel (tcgen05 implicit GEMM: 13 conv3x3 + 15 "
+                  "inner-product launches per step)",
         "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
         "frac": ach / peak_tf, "traffic": traffic, "traffic_note": traffic_note,
         "peak_source": peak_src + ", bf16 dense sustained (kernel timed inside a long step)",
-        "launches_timed": k_n, "share_of_step": k_ms / total_ms,
+        "launches_timed": k_n, "share_of_step": k_ms_step / ms_step,
         "ms_by_launch_site": [[t, round(m, 4)] for t, m in zip(site_tags, site_ms)],
-        "algorithmic_flops_per_step": k_flops / args.steps,
-        "tensor_work_factor": 3,
-        "frac_tensor_pipe": 3 * ach / peak_tf,
-        "note": "fp32-parity mode issues 3 bf16 MMAs per algorithmic MAC (hi*hi + hi*lo + lo*hi); "
-                "frac counts algorithmic FLOPs only, frac_tensor_pipe counts issued tensor work",
+        "algorithmic_flops_per_step": flops_step,
+        "tensor_work_factor": work / flops_step,
+        "frac_tensor_pipe": (work / flops_step) * ach / peak_tf,
+        "note": "fp32-parity arithmetic: launches with tri-plane operands issue one fp16 MMA + two "
+                "FP8 MMAs (double rate) per algorithmic MAC = 2 bf16-equivalent units, the three "
+                "halo-kernel layers (Cout <= 128) and conv1_1 three bf16 MMAs = 3 units; frac counts "
+                "algorithmic FLOPs only, frac_tensor_pipe counts issued tensor work; per-launch "
+                "times from CUDA events around each launch in an eager pass of the same step",
     }
+
+    micro, roof_warp = None, None
+    if world == 1 and not args.no_micro:
+        micro = microbench(hbm)
+        rw = micro["roi_warp_P28"]
+        roof_warp = {"kernel": "roi_warp_nchw_kernel (ROIWarping layer form, 2000 RoIs, 28x28, "
+                               "512x38x63 map: BASELINE.json configs[3])",
+                     "bound": "hbm", "achieved": rw["GBps"], "peak": hbm, "unit": "GB/s",
+                     "frac": rw["frac_of_hbm"], "traffic": None,
+                     "algorithmic_bytes": rw["algorithmic_bytes"], "peak_source": peak_src + ", copy bandwidth"}
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        times, threads = cpu_reference_time(w, 1, 1, 1)
-        cpu = {"value": 1.0 / times[0], "unit": "images/s", "cores": threads, "kind": "port",
-               "sample": "1 image (600x1000, 300 RoIs/stage) after 1 warm-up, oracle port "
-                         "(torch CPU fp32 conv/FC + numpy layers + C kernels)"}
+        torch.set_num_threads(ncpu)
+        times = cpu_reference_time(w, 5, 2)
+        st = _summ(times)
+        cpu = {"value": 1.0 / st["median_s"], "unit": "images/s", "cores": ncpu, "kind": "port",
+               "sample": "5 images (600x1000, 300 RoIs/stage) after 2 warm-up images, oracle port "
+                         "(torch CPU fp32 conv/FC + numpy layers + C kernels); 1 / median",
+               "per_image_s": st}
 
     line = {
         "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16x3 (split-bf16 tensor cores, fp32 accumulate, fp32-parity)",
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16+2xf8 (fp16 main product + two e4m3 correction products on tcgen05, fp32 "
+                 "accumulate, fp32-parity; Cout<=128 convs: bf16x3)",
         "data": "synthetic", "config": workload_config(args, world),
-        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": det.h2d_bytes,
+        "e2e": {"value": e2e_pinned, "unit": "images/s", "h2d_bytes_per_step": det.h2d_bytes,
                 "d2h_bytes_per_step": det.d2h_bytes,
-                "api": "mnc_b200.api.Detector.im_detect_images: uint8 BGR host frames in (pinned "
-                       "staging, H2D), mean/resize/NCHW on device, forward, im_detect tail, "
-                       "boxes+masks+scores D2H to host"},
-        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+                "value_pageable_input": e2e_pageable,
+                "api": "mnc_b200.api.Detector.im_detect_images: uint8 BGR host frames in (value: "
+                       "page-locked caller memory; value_pageable_input: a plain numpy array, staged "
+                       "through the Detector's pinned buffer), H2D, mean/resize/NCHW on device, "
+                       "forward (CUDA-graph replay), im_detect tail, one record D2H to host"
+                       + ("; + all-gather of the records" if world > 1 else "")},
+        "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
+        "clocks": clocks, "roofline": roofline, "roofline_roi_warp": roof_warp, "micro": micro,
+        "cpu_baseline": cpu,
+        "step_ms": {"median": step_ms[len(step_ms) // 2], "p10": step_ms[int(0.1 * len(step_ms))],
+                    "p90": step_ms[min(len(step_ms) - 1, int(0.9 * len(step_ms)))]},
+        "comm_ms_per_step": comm_ms,
+        "comm_note": "all_gather_into_tensor of the %d-float record per rank, alone on an idle GPU; "
+                     "in the timed loop it runs on a side stream under the next step's trunk"
+                     % mdist.record_len(B),
+        "latency_batch1_ms": lat1, "host_issue_ms_batch1": host_ms1 if world == 1 else None,
+        "cuda_graph": not args.no_graph,
         "forward_plus_voting": {"value": vote_value, "unit": "images/s",
                                 "instances_per_image": n_instances,
                                 "note": "im_detect + batched device gpu_mask_voting (100 per image)"},

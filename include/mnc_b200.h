@@ -210,6 +210,14 @@ int mnc_softmax_rows(const float* in, int in_stride, int rows, int cols, float* 
                      int out_stride, void* stream);
 int mnc_unscale_clip(const float* rois, int total, int rois_per_img, const float* im_scale,
                      const float* im_hw, float* boxes, void* stream);
+/* The im_detect tail (tools/demo.py:84-100) in one launch, into the per-step output record:
+ * counts[B] (valid detections, as float), boxes[B][2n][4] = clip(rois[:,1:5] / im_scale, image),
+ * scores[B][2n][ncls], masks[B][2n][msz] -- stage 1 rows, then stage 2 rows -- and valid[B][2n]. */
+int mnc_detect_tail(const float* rois, const float* rois_ext, const float* mask, const float* mask_ext,
+                    const float* prob, const float* prob_ext, const int* roi_counts,
+                    const float* im_scale, const float* im_hw, int batch, int n, int msz, int ncls,
+                    float* counts, float* boxes, float* scores, float* masks, unsigned char* valid,
+                    void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * The three MNC Caffe layers, Forward_gpu contract (fp32 NCHW device blobs):

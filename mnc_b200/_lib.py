@@ -35,7 +35,8 @@ c_float = ctypes.c_float
 
 
 # kernels launched by each C-ABI entry point (for bench.py's `gpu_launches` claim)
-_LAUNCHES = {"mnc_nms_sorted": 2, "mnc_mv_device": 3}
+# (checked against the ncu launch list of a bench step, profiles/r02_launches_*.csv)
+_LAUNCHES = {"mnc_nms_sorted": 2, "mnc_mv_device": 4}
 launch_count = 0
 
 

@@ -15,15 +15,16 @@ from .engine import MNCEngine, ROIS_PER_IMAGE, MASK_SIZE, NUM_CLASSES
 
 
 class Detector:
-    def __init__(self, weights, device="cuda", max_batch=8, height=600, width=1000):
+    def __init__(self, weights, device="cuda", max_batch=8, height=600, width=1000, use_graph=True):
         self.device = torch.device(device)
         self.engine = MNCEngine(weights, device=self.device)
+        # a step is ~60 launches on static buffers: replayed from a CUDA graph per input shape
+        self.use_graph = use_graph
         self.max_batch = max_batch
         B, n = max_batch, 2 * ROIS_PER_IMAGE
         self._h_in = torch.empty((B, 3, height, width), dtype=torch.float32).pin_memory()
-        self._h_boxes = torch.empty((B, n, 4), dtype=torch.float32).pin_memory()
-        self._h_masks = torch.empty((B, n, 1, MASK_SIZE, MASK_SIZE), dtype=torch.float32).pin_memory()
-        self._h_scores = torch.empty((B, n, NUM_CLASSES), dtype=torch.float32).pin_memory()
+        # results come back as ONE record (ops.record_layout) + the valid flags: two D2H copies
+        self._h_rec = torch.empty(ops.record_layout(B, ROIS_PER_IMAGE)[3], dtype=torch.float32).pin_memory()
         self._h_valid = torch.empty((B, n), dtype=torch.uint8).pin_memory()
         self._d_in = torch.empty((B, 3, height, width), dtype=torch.float32, device=self.device)
         self.h2d_bytes = 0
@@ -49,7 +50,11 @@ class Detector:
             im_info = np.tile(np.array([[H, W, 1.0]], dtype=np.float32), (B, 1))
         info_h = torch.as_tensor(np.asarray(im_info, dtype=np.float32))
         scale_h = info_h[:, 2].contiguous() if im_scales is None else torch.as_tensor(np.asarray(im_scales, np.float32))
-        hw_h = info_h[:, :2].contiguous() if im_shapes is None else torch.as_tensor(np.asarray(im_shapes, np.float32))
+        if im_shapes is None:
+            # boxes are clipped to the ORIGINAL image (TesterWrapper.py:254-255): blob size / scale
+            hw_h = torch.round(info_h[:, :2] / scale_h[:, None]).contiguous()
+        else:
+            hw_h = torch.as_tensor(np.asarray(im_shapes, np.float32))
         if blob.is_pinned():
             src = blob                                   # caller already handed page-locked memory
         else:
@@ -58,17 +63,26 @@ class Detector:
         with torch.cuda.device(dev):
             self._d_in[:B].copy_(src, non_blocking=True)
             info = info_h.to(dev, non_blocking=True)
-            boxes, masks, scores, valid, _ = self.engine.detect(
+            boxes, masks, scores, valid, _ = self._detect(
                 self._d_in[:B], info, hw_h.to(dev), scale_h.to(dev))
-            self._h_boxes[:B].copy_(boxes, non_blocking=True)
-            self._h_masks[:B].copy_(masks, non_blocking=True)
-            self._h_scores[:B].copy_(scores, non_blocking=True)
-            self._h_valid[:B].copy_(valid, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+            out = self._results_to_host(B, valid)
         self.h2d_bytes = blob.numel() * 4 + info_h.numel() * 4 + scale_h.numel() * 4 + hw_h.numel() * 4
-        self.d2h_bytes = (boxes.numel() + masks.numel() + scores.numel()) * 4 + valid.numel()
-        return (self._h_boxes[:B].numpy(), self._h_masks[:B].numpy(), self._h_scores[:B].numpy(),
-                self._h_valid[:B].numpy())
+        return out
+
+    def _detect(self, data, info, hw, sc):
+        if self.use_graph:
+            return self.engine.detect_graphed(data, info, hw, sc)
+        return self.engine.detect(data, info, hw, sc)
+
+    def _results_to_host(self, B, valid):
+        rec = self.engine.last_record
+        n = rec.numel()
+        self._h_rec[:n].copy_(rec, non_blocking=True)
+        self._h_valid[:B].copy_(valid, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        self.d2h_bytes = n * 4 + valid.numel()
+        _, boxes, scores, masks = ops.record_views(self._h_rec[:n], B, ROIS_PER_IMAGE)
+        return boxes.numpy(), masks.numpy(), scores.numpy(), self._h_valid[:B].numpy()
 
     def im_detect_images(self, images_u8):
         """Batched `im_detect(im, net)` on raw images, as the reference's callers hand them over
@@ -102,20 +116,15 @@ class Detector:
         with torch.cuda.device(dev):
             self._d_u8[:B].copy_(pinned_src, non_blocking=True)
             ops.prep_images(self._d_u8[:B], scale, out=self._d_in[:B])
-            boxes, masks, scores, valid, _ = self.engine.detect(
+            boxes, masks, scores, valid, _ = self._detect(
                 self._d_in[:B], info.to(dev, non_blocking=True), hw.to(dev, non_blocking=True),
                 sc.to(dev, non_blocking=True))
-            self._h_boxes[:B].copy_(boxes, non_blocking=True)
-            self._h_masks[:B].copy_(masks, non_blocking=True)
-            self._h_scores[:B].copy_(scores, non_blocking=True)
-            self._h_valid[:B].copy_(valid, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+            out = self._results_to_host(B, valid)
         self.h2d_bytes = images_u8.nbytes + (info.numel() + hw.numel() + sc.numel()) * 4
-        self.d2h_bytes = (boxes.numel() + masks.numel() + scores.numel()) * 4 + valid.numel()
-        return (self._h_boxes[:B].numpy(), self._h_masks[:B].numpy(), self._h_scores[:B].numpy(),
-                self._h_valid[:B].numpy(), scale)
+        return out + (scale,)
 
     def mask_voting(self, boxes, masks, scores, valid, im_hw, max_per_image=100):
         """Device-resident batched gpu_mask_voting on `engine.detect` outputs (device tensors)."""
         hw = torch.as_tensor(np.asarray(im_hw, dtype=np.int32)).to(self.device)
-        return ops.mask_voting(boxes, masks, scores, hw, max_per_image=max_per_image, box_valid=valid)
+        return ops.mask_voting_checked(boxes, masks, scores, hw, max_per_image=max_per_image,
+                                       box_valid=valid)

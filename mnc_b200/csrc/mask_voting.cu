@@ -36,37 +36,40 @@ __device__ __forceinline__ float2 mv_ratio(const float4 box, int mask_size) {
   return make_float2((float)mask_size / box_width, (float)mask_size / box_height);
 }
 
-// mask_render (mv_kernel.cu:36-91) for one pixel of one box.
+// One pixel of one candidate's 21x21 mask pasted into its box -- the value `mask_render` produces
+// (mv_kernel.cu:36-91).  The operation order inside each expression is the reference's (products
+// of the two 1-D weights first, then the four weighted taps summed left to right) because results
+// are compared bit for bit with the reference built without FMA contraction; the structure is
+// ours: outside test, 1-D cell / fraction per axis, last-cell rule, 4-tap blend.
+struct MvAxis {
+  int cell;     // floor of the mask coordinate
+  float frac;   // coordinate - cell
+};
+__device__ __forceinline__ MvAxis mv_axis(int p, float box_lo, float ratio) {
+  const float pos = ((float)p - box_lo) * ratio;
+  MvAxis a;
+  a.cell = floor(pos);
+  a.frac = pos - a.cell;
+  return a;
+}
 __device__ __forceinline__ float mv_render(const float4 box, const float2 ratio,
                                            const float* __restrict__ mask, int mask_size, int h,
                                            int w) {
-  const float box_x1 = box.x, box_y1 = box.y, box_x2 = box.z, box_y2 = box.w;
-  if (w < box_x1 || w > box_x2 || h < box_y1 || h > box_y2) return 0.0f;
-  const float ratio_w = ratio.x;
-  const float ratio_h = ratio.y;
-  const float inverse_x = ((float)w - box_x1) * ratio_w;
-  const float inverse_y = ((float)h - box_y1) * ratio_h;
-  int start_x = floor(inverse_x);
-  int start_y = floor(inverse_y);
-  if (start_x == mask_size - 1 && start_y == mask_size - 1) {
-    return __ldg(mask + mask_size * mask_size - 1);
-  } else if (start_x == mask_size - 1 || start_y == mask_size - 1) {
-    return __ldg(mask + start_y * mask_size + start_x);
-  } else {
-    int top_left_ind = start_y * mask_size + start_x;
-    int top_right_ind = top_left_ind + 1;
-    int bot_left_ind = top_left_ind + mask_size;
-    int bot_right_ind = bot_left_ind + 1;
-    float top_left_weight = (1 - (inverse_x - start_x)) * (1 - (inverse_y - start_y));
-    float top_right_weight = (inverse_x - start_x) * (1 - (inverse_y - start_y));
-    float bot_left_weight = (1 - (inverse_x - start_x)) * (inverse_y - start_y);
-    float bot_right_weight = (inverse_x - start_x) * (inverse_y - start_y);
-    float val = top_left_weight * __ldg(mask + top_left_ind) +
-                top_right_weight * __ldg(mask + top_right_ind) +
-                bot_left_weight * __ldg(mask + bot_left_ind) +
-                bot_right_weight * __ldg(mask + bot_right_ind);
-    return val;
-  }
+  if (w < box.x || w > box.z || h < box.y || h > box.w) return 0.0f;   // unrounded box, float compare
+  const MvAxis ax = mv_axis(w, box.x, ratio.x);
+  const MvAxis ay = mv_axis(h, box.y, ratio.y);
+  const int last = mask_size - 1;
+  // a sample in the last mask row or column is not interpolated along either axis (:66-74)
+  if (ax.cell == last || ay.cell == last)
+    return __ldg(mask + (ax.cell == last && ay.cell == last ? last * mask_size + last
+                                                           : ay.cell * mask_size + ax.cell));
+  const float* tap = mask + ay.cell * mask_size + ax.cell;
+  const float w00 = (1 - ax.frac) * (1 - ay.frac);
+  const float w01 = ax.frac * (1 - ay.frac);
+  const float w10 = (1 - ax.frac) * ay.frac;
+  const float w11 = ax.frac * ay.frac;
+  return w00 * __ldg(tap) + w01 * __ldg(tap + 1) + w10 * __ldg(tap + mask_size) +
+         w11 * __ldg(tap + mask_size + 1);
 }
 
 struct CandList {
@@ -151,14 +154,13 @@ mv_range_kernel(const float* __restrict__ masks, long long masks_per_img,
     ok &= (v >= 0.f && v <= 1.f);
   }
   if (blockIdx.x == 0) {
+    // only the entries of the lists themselves: the gaps between lists are never written
     const int nr = min(n_res[img], max_results);
-    int lo = INT_MAX, hi = 0;
     for (int t = 0; t < nr; ++t) {
-      lo = min(lo, cand_begin[img * max_results + t]);
-      hi = max(hi, cand_end[img * max_results + t]);
+      const int lo = cand_begin[img * max_results + t], hi = cand_end[img * max_results + t];
+      for (int i = lo + threadIdx.x; i < hi; i += blockDim.x)
+        ok &= (cand_weights[img * cand_img_stride + i] >= 0.f);
     }
-    for (int i = lo + threadIdx.x; i < hi; i += blockDim.x)
-      ok &= (cand_weights[img * cand_img_stride + i] >= 0.f);
   }
   if (!__syncthreads_and(ok) && threadIdx.x == 0) atomicAnd(&unit[img], 0);
 }

@@ -213,6 +213,40 @@ __global__ void unscale_clip_kernel(const float* __restrict__ rois, int total, i
   b[3] = clipf(__fdiv_rn(r[4], s), hmax);
 }
 
+// The whole im_detect tail (tools/demo.py:84-100 == TesterWrapper.py:244-260) in one launch: boxes =
+// clip(rois[:, 1:5] / im_scale, original image shape) for stage 1 then stage 2, masks and scores
+// concatenated in the same order, written straight into the per-step output record (the buffer
+// that is copied to the host / handed to the all-gather):
+//   counts[B] | boxes[B][2n][4] | scores[B][2n][ncls] | masks[B][2n][msz]      (+ valid[B][2n] u8)
+// One CTA per output row.
+__global__ void __launch_bounds__(128)
+detect_tail_kernel(const float* __restrict__ rois, const float* __restrict__ rois_ext,
+                   const float* __restrict__ mask, const float* __restrict__ mask_ext,
+                   const float* __restrict__ prob, const float* __restrict__ prob_ext,
+                   const int* __restrict__ roi_counts, const float* __restrict__ im_scale,
+                   const float* __restrict__ im_hw, int n, int msz, int ncls,
+                   float* __restrict__ counts, float* __restrict__ boxes, float* __restrict__ scores,
+                   float* __restrict__ masks, unsigned char* __restrict__ valid) {
+  const int img = blockIdx.y;
+  const int row = blockIdx.x;            // 0 .. 2n-1: stage 1 rows then stage 2 rows
+  const int stage = row >= n;
+  const long long src = static_cast<long long>(img) * n + (row - stage * n);
+  const long long dst = static_cast<long long>(img) * 2 * n + row;
+  const float* r = (stage ? rois_ext : rois) + src * 5;
+  const float* m = (stage ? mask_ext : mask) + src * msz;
+  const float* p = (stage ? prob_ext : prob) + src * ncls;
+  const int cnt = roi_counts[img];
+  if (threadIdx.x < 4) {
+    const float s = im_scale[img];
+    const float lim = __fsub_rn(im_hw[img * 2 + ((threadIdx.x & 1) ? 0 : 1)], 1.0f);  // x: W-1, y: H-1
+    boxes[dst * 4 + threadIdx.x] = clipf(__fdiv_rn(r[1 + threadIdx.x], s), lim);
+  }
+  if (threadIdx.x == 4) valid[dst] = (row - stage * n) < cnt ? 1 : 0;
+  if (threadIdx.x == 5 && row == 0) counts[img] = static_cast<float>(2 * cnt);
+  for (int i = threadIdx.x; i < ncls; i += blockDim.x) scores[dst * ncls + i] = p[i];
+  for (int i = threadIdx.x; i < msz; i += blockDim.x) masks[dst * msz + i] = m[i];
+}
+
 // TesterWrapper._detection_forward tail (lib/caffeWrapper/TesterWrapper.py:229-234): boxes =
 // rois[:,1:5] / im_scale; pred = bbox_transform_inv(boxes, deltas) for every class; clip to the
 // original image.  One thread per (RoI, class).
@@ -305,6 +339,19 @@ extern "C" int mnc_unscale_clip(const float* rois, int total, int rois_per_img,
   if (total <= 0) return MNC_OK;
   unscale_clip_kernel<<<(total + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
       rois, total, rois_per_img, im_scale, im_hw, boxes);
+  return check_launch();
+}
+
+extern "C" int mnc_detect_tail(const float* rois, const float* rois_ext, const float* mask,
+                               const float* mask_ext, const float* prob, const float* prob_ext,
+                               const int* roi_counts, const float* im_scale, const float* im_hw,
+                               int batch, int n, int msz, int ncls, float* counts, float* boxes,
+                               float* scores, float* masks, unsigned char* valid, void* stream) {
+  if (batch <= 0 || n <= 0) return MNC_OK;
+  dim3 grid(2 * n, batch);
+  detect_tail_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      rois, rois_ext, mask, mask_ext, prob, prob_ext, roi_counts, im_scale, im_hw, n, msz, ncls,
+      counts, boxes, scores, masks, valid);
   return check_launch();
 }
 

@@ -164,16 +164,6 @@ def igemm2(a, batch, H, W, cin, w, cout, taps, bias=None, relu=False, out=None, 
             bytes=4.0 * (batch * H * W * cin + cout * taps * cin + m_out * cout * max(split_k, 1))))
 
 
-import os as _os
-
-if _os.environ.get("MNC_IGEMM_HALO"):
-    check(lib.mnc_igemm_set_halo(c_int(int(_os.environ["MNC_IGEMM_HALO"]))), "mnc_igemm_set_halo")
-if _os.environ.get("MNC_IGEMM_BK"):
-    check(lib.mnc_igemm_set_block_k(c_int(int(_os.environ["MNC_IGEMM_BK"]))), "mnc_igemm_set_block_k")
-if _os.environ.get("MNC_IGEMM_CLUSTER"):
-    check(lib.mnc_igemm_set_cluster(c_int(int(_os.environ["MNC_IGEMM_CLUSTER"]))),
-          "mnc_igemm_set_cluster")
-
 
 class KernelTimer:
     """Optional per-launch CUDA-event timing of the implicit-GEMM kernel (bench.py's roofline):

@@ -206,6 +206,8 @@ class _File(object):
         for f in filters:
             if f[0] not in (1, 2):
                 raise NotImplementedError("HDF5 filter id %d" % f[0])
+        if btree == (1 << (8 * self.so)) - 1:
+            return out                    # undefined address: the dataset was never written (fill value 0)
         self._chunk_btree(btree, ndim, cdims, dtype, filters, out)
         return out
 

@@ -178,6 +178,36 @@ def unscale_clip(rois, rois_per_img, im_scale, im_hw):
     return boxes
 
 
+def record_layout(B, n, msz=441, ncls=21):
+    """Offsets (in floats) of the sections of the per-step output record and its length."""
+    o_boxes = (B + 3) // 4 * 4
+    o_scores = o_boxes + B * 2 * n * 4
+    o_masks = o_scores + B * 2 * n * ncls
+    return o_boxes, o_scores, o_masks, o_masks + B * 2 * n * msz
+
+
+def record_views(rec, B, n, msz=441, ncls=21):
+    ob, os_, om, end = record_layout(B, n, msz, ncls)
+    side = int(round(msz ** 0.5))
+    return (rec[:B], rec[ob:os_].view(B, 2 * n, 4), rec[os_:om].view(B, 2 * n, ncls),
+            rec[om:end].view(B, 2 * n, 1, side, side))
+
+
+def detect_tail(o, B, n, im_scale, im_hw, rec, valid):
+    """im_detect tail into the record buffer `rec` (fp32, record_layout(B, n)[3] floats) and
+    `valid` (uint8 [B, 2n]).  Returns (counts, boxes, scores, masks) views of rec."""
+    msz = o["mask_proposal"].shape[-1] * o["mask_proposal"].shape[-2]
+    ncls = o["seg_cls_prob"].shape[-1]
+    counts, boxes, scores, masks = record_views(rec, B, n, msz, ncls)
+    check(lib.mnc_detect_tail(ptr(o["rois"]), ptr(o["rois_ext"]), ptr(o["mask_proposal"]),
+                              ptr(o["mask_proposal_ext"]), ptr(o["seg_cls_prob"]),
+                              ptr(o["seg_cls_prob_ext"]), ptr(o["roi_counts"]), ptr(im_scale),
+                              ptr(im_hw), c_int(B), c_int(n), c_int(msz), c_int(ncls), ptr(counts),
+                              ptr(boxes), ptr(scores), ptr(masks), ptr(valid), cur_stream()),
+          "mnc_detect_tail")
+    return counts, boxes, scores, masks
+
+
 def decode_class_boxes(rois, bbox_pred, rois_per_img, im_scale, im_hw, ncls=21):
     """-> (R, ncls*4) fp32: per-class decoded boxes in original-image coordinates, clipped."""
     R = rois.shape[0]
@@ -326,7 +356,7 @@ def mask_voting(boxes, masks, scores, im_hw, max_per_image=100, nms_thresh=0.3, 
                               ptr(res_score), ptr(n_res), ptr(class_bar), ptr(overflow),
                               cur_stream()), "mnc_vote_select")
     cand_inds = _i32(B, max_results, nb, device=dev)
-    cand_w = torch.empty((B, max_results, nb), dtype=torch.float32, device=dev)
+    cand_w = torch.empty((B, max_results, nb), dtype=torch.float32, device=dev)   # lists only; gaps unread
     cand_begin = _i32(B, max_results, device=dev)
     cand_end = _i32(B, max_results, device=dev)
     check(lib.mnc_vote_candidates(ptr(boxes), ptr(scores), ptr(box_valid), c_int(nb), c_int(ncls),
@@ -346,6 +376,22 @@ def mask_voting(boxes, masks, scores, im_hw, max_per_image=100, nms_thresh=0.3, 
                 res_box_idx=res_idx, result_mask=out_mask, result_box=out_box,
                 cand_inds=cand_inds, cand_weights=cand_w, cand_begin=cand_begin, cand_end=cand_end,
                 overflow=overflow, order=order, keep=keep, num_keep=num)
+
+
+def mask_voting_checked(boxes, masks, scores, im_hw, max_per_image=100, box_valid=None, **kw):
+    """mask_voting that never truncates: the reference keeps EVERY kept row whose score ties the
+    global threshold (mask_transform.py:258), so when more rows tie than `max_results` has slots
+    the device reports it and the call is repeated with room (one host read of a 4-byte flag)."""
+    cap = kw.pop("max_results", max(128, max_per_image + 28))
+    nb = boxes.shape[1]
+    while True:
+        r = mask_voting(boxes, masks, scores, im_hw, max_per_image=max_per_image, max_results=cap,
+                        box_valid=box_valid, **kw)
+        if int(r["overflow"].item()) == 0:
+            return r
+        if cap >= nb * (scores.shape[2] - 1):
+            raise VotingOverflow("mask voting overflow at max_results = %d" % cap)
+        cap = min(2 * cap, nb * (scores.shape[2] - 1))
 
 
 # ----------------------------------------------------------------------------- input preparation

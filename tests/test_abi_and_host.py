@@ -159,8 +159,8 @@ def test_shard_range_and_records():
     scores = torch.rand(B, 600, 21)
     valid = (torch.rand(B, 600) > 0.3).to(torch.uint8)
     rec = D.pack_records(boxes, masks, scores, valid)
-    assert rec.shape == (B, D.REC_FLOATS)
-    c, b2, m2, s2 = D.unpack_records(rec)
+    assert rec.shape == (D.record_len(B),)
+    c, b2, m2, s2 = D.unpack_records(rec.view(1, -1), B)
     assert torch.equal(b2, boxes) and torch.equal(m2, masks) and torch.equal(s2, scores)
     assert torch.equal(c, valid.sum(1).to(torch.int64))
 

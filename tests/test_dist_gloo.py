@@ -30,8 +30,8 @@ def _worker(rank, world, port, q):
     valid = (torch.rand(total, 600, generator=g) > 0.5).to(torch.uint8)
     rec = D.pack_records(boxes[s:e], masks[s:e], scores[s:e], valid[s:e])
     allrec = D.all_gather_records(rec)
-    c, b2, m2, s2 = D.unpack_records(allrec)
-    ok = (allrec.shape[0] == total and torch.equal(b2, boxes) and torch.equal(m2, masks)
+    c, b2, m2, s2 = D.unpack_records(allrec, e - s)
+    ok = (tuple(allrec.shape) == (w, D.record_len(e - s)) and torch.equal(b2, boxes) and torch.equal(m2, masks)
           and torch.equal(s2, scores) and torch.equal(c, valid.sum(1).to(torch.int64)))
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
