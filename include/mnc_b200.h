@@ -227,6 +227,12 @@ int mnc_detect_tail(const float* rois, const float* rois_ext, const float* mask,
  */
 int mnc_roi_warp_nchw(const float* feat, int C, int H, int W, const float* rois, int R,
                       int pooled_h, int pooled_w, float spatial_scale, float* out, void* stream);
+/* ROIWarping 28x28 / 14x14 kernel choice (all bit-identical; scripts/gpu_roi_stage_ab.py measures them):
+ * 2 (default) = row walk (a warp per output plane keeps the two live feature rows in registers:
+ * ~1.5 loads per output); 1 = RoI window staged in shared memory (28x28 only; 4-byte cp.async,
+ * channel pairs interleaved, packed fp32x2 arithmetic); 0 = per-tap gathers through L1 (round-1
+ * kernel; other pooled sizes always use it).  Returns the previous value. */
+int mnc_roi_warp_set_stage(int on);
 int mnc_mask_resize_nchw(const float* in, int N, int C, int in_h, int in_w, int out_h, int out_w,
                          float* out, void* stream);
 int mnc_mask_pool_nchw(const float* feat, const float* mask, int N, int C, int H, int W,

@@ -23,6 +23,7 @@
 
 #include "mnc_b200.h"
 #include "tri.cuh"
+#include "launch_util.h"
 
 namespace mnc {
 
@@ -162,6 +163,264 @@ roi_warp_nchw_kernel(const float* __restrict__ feat, int C, int H, int W,
     } else {
 #pragma unroll
       for (int e = 0; e < EPT; ++e) __stcs(o + e, v[e]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// ROIWarping 28x28 with the RoI's feature window STAGED IN SHARED MEMORY (the design
+// BASELINE.json's north_star names): one CTA per (RoI, 16-channel group).  The taps of a RoI only
+// touch the window rows [r0, r1] x columns [c0, c1] of the map (<= 38 x 63 floats per channel);
+// the CTA copies that window with 4-byte cp.async (all copies in flight together) for as many
+// channels as fit a 48 KB budget (all 16 for a typical proposal, 4 for a full-map RoI), stored
+// CHANNEL-PAIR INTERLEAVED: one 8-byte LDS returns a tap of two channels.  Every thread owns 4
+// consecutive outputs of the 28 x 28 plane with their window offsets and bilinear weights in
+// registers (weights formed first, products summed left to right: the operation order of
+// roi_warping_layer.cu:56) and walks the channel pairs with PACKED fp32x2 arithmetic
+// (__fmul2_rn / __fadd2_rn: two IEEE operations per instruction, no FMA contraction -- still
+// bit-exact with the reference built with -fmad=false): 4 LDS.64 + 7 packed ops per TWO outputs
+// instead of 4 LDG + 7 ops per output, one 16-byte streaming store per 4 outputs.  3.2 x fewer
+// instructions per output than the gather kernel; the window is read once from L2 instead of
+// ~7 times through L1.
+constexpr int kStageGroup = 16;            // channels per CTA
+constexpr int kStageFloats = 12 * 1024;    // 48 KB window budget
+
+// Packed fp32x2 arithmetic WITHOUT fusion.  sm_100 has FMUL2 and FFMA2 but no packed add, and
+// ptxas folds every mul.rn.f32x2 -> add.rn.f32x2 (or fma by a literal 1.0) chain into one FFMA2 --
+// a single rounding, which would break bit-exactness with the reference's separately rounded
+// products and sums (measured: -fmad=false does not stop it).  So the products are FMUL2 and each
+// sum is fma(p, one, acc) with `one` = 1.0f handed in as a KERNEL ARGUMENT: p * 1.0 is exact, the
+// fma rounds once = an IEEE add, and the compiler cannot see the value, so nothing is folded.
+__device__ __forceinline__ float2 mul2_rn(float2 a, float2 b) {
+  float2 r;
+  asm("{\n\t.reg .b64 ra, rb, rc;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "mul.rn.f32x2 rc, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rc;\n\t}"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+__device__ __forceinline__ float2 add2_rn(float2 a, float2 b, float one) {
+  float2 r;
+  asm("{\n\t.reg .b64 ra, rb, rc, ro;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 ro, {%6, %6};\n\t"
+      "fma.rn.f32x2 rc, rb, ro, ra;\n\t"
+      "mov.b64 {%0, %1}, rc;\n\t}"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(one));
+  return r;
+}
+
+// One staged pass of NP channel pairs: window layout [pixel][S] float2 with S = NP + 1 (the odd
+// pitch spreads neighbouring pixels over the banks); a tap's pairs sit at compile-time offsets of
+// its address, so the pair loop has no address arithmetic.
+template <int NP>
+__device__ __forceinline__ void warp28_pass(const float2* __restrict__ win2, const int (&off)[4][4],
+                                            const float2 (&wgt)[4][4], const bool (&ok)[4],
+                                            float* __restrict__ o, int n_c, float one) {
+  constexpr int S = NP + 1, PP = 28 * 28;
+  const float2* t[4][4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) t[e][k] = win2 + off[e][k] * S;
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    if (2 * p >= n_c) break;
+    float2 v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float2 val = mul2_rn(wgt[e][0], t[e][0][p]);
+      val = add2_rn(val, mul2_rn(wgt[e][1], t[e][1][p]), one);
+      val = add2_rn(val, mul2_rn(wgt[e][2], t[e][2][p]), one);
+      val = add2_rn(val, mul2_rn(wgt[e][3], t[e][3][p]), one);
+      v[e] = ok[e] ? val : make_float2(0.f, 0.f);
+    }
+    __stcs(reinterpret_cast<float4*>(o + 2 * p * PP), make_float4(v[0].x, v[1].x, v[2].x, v[3].x));
+    if (2 * p + 1 < n_c)   // odd channel tail: the second half of the last pair holds stale data
+      __stcs(reinterpret_cast<float4*>(o + (2 * p + 1) * PP), make_float4(v[0].y, v[1].y, v[2].y, v[3].y));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+roi_warp28_stage_kernel(const float* __restrict__ feat, int C, int H, int W,
+                        const float* __restrict__ rois, float spatial_scale, float* __restrict__ out,
+                        float one) {
+  constexpr int P = 28, PP = P * P, EPT = 4, TPC = PP / EPT;   // 196 threads compute
+  extern __shared__ float2 win2[];                             // [pixel][pairs + 1] (2 channels)
+  __shared__ AxisTap tap_h[P], tap_w[P];
+  __shared__ int bounds[4];
+  const int r = blockIdx.x;
+  const int cg0 = blockIdx.y * kStageGroup;
+  const int tid = threadIdx.x;
+  const RoiGeom g = roi_geom(rois + static_cast<long long>(r) * 5, spatial_scale, P, P);
+  if (tid < P) tap_h[tid] = axis_tap(__fadd_rn(g.start_h, __fmul_rn(static_cast<float>(tid), g.bin_h)), H);
+  if (tid >= 32 && tid < 32 + P)
+    tap_w[tid - 32] = axis_tap(__fadd_rn(g.start_w, __fmul_rn(static_cast<float>(tid - 32), g.bin_w)), W);
+  __syncthreads();
+  if (tid < 32) {   // window bounds: warp-wide min / max over the valid taps
+    int r0 = H, r1 = -1, c0 = W, c1 = -1;
+    if (tid < P) {
+      if (tap_h[tid].ok) { r0 = tap_h[tid].lo; r1 = tap_h[tid].hi; }
+      if (tap_w[tid].ok) { c0 = tap_w[tid].lo; c1 = tap_w[tid].hi; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      r0 = min(r0, __shfl_xor_sync(0xffffffffu, r0, o));
+      r1 = max(r1, __shfl_xor_sync(0xffffffffu, r1, o));
+      c0 = min(c0, __shfl_xor_sync(0xffffffffu, c0, o));
+      c1 = max(c1, __shfl_xor_sync(0xffffffffu, c1, o));
+    }
+    if (tid == 0) { bounds[0] = r0; bounds[1] = r1; bounds[2] = c0; bounds[3] = c1; }
+  }
+  __syncthreads();
+  const int r0 = bounds[0], r1 = bounds[1], c0 = bounds[2], c1 = bounds[3];
+  const int nch = min(kStageGroup, C - cg0);
+  const int q = tid;                       // output quad (threads >= TPC only help staging)
+  float* obase = out + (static_cast<long long>(r) * C + cg0) * PP + q * EPT;
+  if (r1 < r0 || c1 < c0) {                // no sample inside the map: the RoI's output is zero
+    if (q < TPC)
+      for (int c = 0; c < nch; ++c)
+        __stcs(reinterpret_cast<float4*>(obase + c * PP), make_float4(0.f, 0.f, 0.f, 0.f));
+    return;
+  }
+  const int wh = r1 - r0 + 1, ww = c1 - c0 + 1;
+  const int per_ch = wh * ww;
+  // pairs per pass: the largest of 8 / 4 / 2 / 1 whose padded window fits the budget
+  // (a full 38 x 63 map: 2394 px x 2 float2 x 8 B = 38 KB -> 1 pair)
+  const int budget_px = (kStageFloats / 2) / per_ch;    // float2 slots per pixel
+  const int np = budget_px >= 9 ? 8 : (budget_px >= 5 ? 4 : (budget_px >= 3 ? 2 : 1));
+  const int S = np + 1;
+  int off[EPT][4];
+  float2 wgt[EPT][4];
+  bool ok[EPT];
+  if (q < TPC) {
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+      const int i = q * EPT + e;
+      const int ph = i / P, pw = i - ph * P;
+      const AxisTap th = tap_h[ph];
+      const AxisTap tw = tap_w[pw];
+      ok[e] = th.ok && tw.ok;
+      const int lo_h = ok[e] ? th.lo - r0 : 0, hi_h = ok[e] ? th.hi - r0 : 0;
+      const int lo_w = ok[e] ? tw.lo - c0 : 0, hi_w = ok[e] ? tw.hi - c0 : 0;
+      off[e][0] = lo_h * ww + lo_w;
+      off[e][1] = lo_h * ww + hi_w;
+      off[e][2] = hi_h * ww + lo_w;
+      off[e][3] = hi_h * ww + hi_w;
+      const float w1 = __fmul_rn(th.h, tw.h), w2 = __fmul_rn(th.h, tw.l);
+      const float w3 = __fmul_rn(th.l, tw.h), w4 = __fmul_rn(th.l, tw.l);
+      wgt[e][0] = make_float2(w1, w1);
+      wgt[e][1] = make_float2(w2, w2);
+      wgt[e][2] = make_float2(w3, w3);
+      wgt[e][3] = make_float2(w4, w4);
+    }
+  }
+  const int HW = H * W;
+  const float* fbase = feat + (static_cast<long long>(g.level) * C + cg0) * HW + r0 * W + c0;
+  float* winf = reinterpret_cast<float*>(win2);
+  for (int cb = 0; cb < nch; cb += 2 * np) {
+    const int n_c = min(2 * np, nch - cb);
+    {  // stage: thread = (column, row lane); channel ch -> half (ch & 1) of pair (ch >> 1)
+      const int x = tid & 63, rl = tid >> 6;
+      if (x < ww) {
+        int ch = 0, y = rl;
+        while (y >= wh) { y -= wh; ++ch; }
+        while (ch < n_c) {
+          const float* src = fbase + static_cast<long long>(cb + ch) * HW + y * W + x;
+          const uint32_t dst = static_cast<uint32_t>(
+              __cvta_generic_to_shared(winf + (((y * ww + x) * S + (ch >> 1)) << 1) + (ch & 1)));
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+          y += 4;
+          while (y >= wh) { y -= wh; ++ch; }
+        }
+      }
+      asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    if (q < TPC) {
+      float* o = obase + cb * PP;
+      if (np == 8) warp28_pass<8>(win2, off, wgt, ok, o, n_c, one);
+      else if (np == 4) warp28_pass<4>(win2, off, wgt, ok, o, n_c, one);
+      else if (np == 2) warp28_pass<2>(win2, off, wgt, ok, o, n_c, one);
+      else warp28_pass<1>(win2, off, wgt, ok, o, n_c, one);
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// ROIWarping by ROW WALK: a warp owns one output plane (RoI, channel); lane = output column pw, and
+// the warp walks the P sample rows top to bottom.  The four taps of (ph, pw) are (row lo / hi) x
+// (column lo / hi); consecutive sample rows advance by bin_h < 1.4 feature rows, so the two feature
+// rows a lane needs are kept in registers and re-read only when the row taps move on -- ~2 loads
+// per new feature row instead of 4 per output: 1.5 loads per output for a typical proposal, and
+// each load is one coalesced row segment (lanes = neighbouring columns).  Control flow depends only
+// on the RoI: the warp never diverges.  The value formula is unchanged (weights first, products
+// summed left to right, no FMA): bit-exact with the reference built with -fmad=false.
+// Stores: one 4 x P byte row segment per sample row, consecutive rows contiguous (whole plane
+// written once, streaming).  P = 14 packs two planes into one warp (lanes 0-13 and 16-29).
+template <int P>
+__global__ void __launch_bounds__(256)
+roi_warp_rowwalk_kernel(const float* __restrict__ feat, int C, int H, int W,
+                        const float* __restrict__ rois, float spatial_scale, int ch_per_cta,
+                        float* __restrict__ out) {
+  constexpr int PP = P * P;
+  constexpr int PPW = (P <= 16) ? 2 : 1;          // planes per warp
+  __shared__ AxisTap tap_h[P];
+  const int r = blockIdx.x;
+  const int cbase = blockIdx.y * ch_per_cta;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const RoiGeom g = roi_geom(rois + static_cast<long long>(r) * 5, spatial_scale, P, P);
+  if (tid < P) tap_h[tid] = axis_tap(__fadd_rn(g.start_h, __fmul_rn(static_cast<float>(tid), g.bin_h)), H);
+  const int sub = (PPW == 2) ? (lane >> 4) : 0;     // which plane of the warp
+  const int pw = (PPW == 2) ? (lane & 15) : lane;
+  const bool live = pw < P;
+  const AxisTap tw = axis_tap(__fadd_rn(g.start_w, __fmul_rn(static_cast<float>(live ? pw : 0), g.bin_w)), W);
+  __syncthreads();
+  const int HW = H * W;
+  const int nch = min(ch_per_cta, C - cbase);
+  for (int c = warp * PPW + sub; c < nch; c += 8 * PPW) {
+    const float* plane = feat + (static_cast<long long>(g.level) * C + cbase + c) * HW;
+    float* o = out + (static_cast<long long>(r) * C + cbase + c) * PP + pw;
+    int cur_lo = -1, cur_hi = -1;
+    float a_lo = 0.f, a_hi = 0.f, b_lo = 0.f, b_hi = 0.f;   // rows cur_lo / cur_hi at columns lo / hi
+#pragma unroll 4
+    for (int ph = 0; ph < P; ++ph) {
+      const AxisTap th = tap_h[ph];
+      float val = 0.f;
+      if (th.ok) {
+        if (th.lo != cur_lo) {
+          if (th.lo == cur_hi) {
+            a_lo = b_lo;
+            a_hi = b_hi;
+          } else {
+            a_lo = __ldg(plane + th.lo * W + tw.lo);
+            a_hi = __ldg(plane + th.lo * W + tw.hi);
+          }
+          cur_lo = th.lo;
+          cur_hi = -1;
+        }
+        if (th.hi != cur_hi) {
+          if (th.hi == th.lo) {
+            b_lo = a_lo;
+            b_hi = a_hi;
+          } else {
+            b_lo = __ldg(plane + th.hi * W + tw.lo);
+            b_hi = __ldg(plane + th.hi * W + tw.hi);
+          }
+          cur_hi = th.hi;
+        }
+        const float w1 = __fmul_rn(th.h, tw.h), w2 = __fmul_rn(th.h, tw.l);
+        const float w3 = __fmul_rn(th.l, tw.h), w4 = __fmul_rn(th.l, tw.l);
+        val = __fmul_rn(w1, a_lo);
+        val = __fadd_rn(val, __fmul_rn(w2, a_hi));
+        val = __fadd_rn(val, __fmul_rn(w3, b_lo));
+        val = __fadd_rn(val, __fmul_rn(w4, b_hi));
+        if (!tw.ok) val = 0.f;
+      }
+      if (live) __stcs(o + ph * P, val);
     }
   }
 }
@@ -721,6 +980,13 @@ static inline int grid_for(long long n, int block, int cap) {
 
 using namespace mnc;
 
+static int g_roi_stage = 2;   // 2: row walk (default, fastest measured); 1: staged window; 0: gather
+extern "C" int mnc_roi_warp_set_stage(int on) {
+  const int prev = g_roi_stage;
+  g_roi_stage = on;   // 0: gather kernel, 1: shared-memory staged window (28x28), 2: row walk
+  return prev;
+}
+
 extern "C" int mnc_roi_warp_nchw(const float* feat, int C, int H, int W, const float* rois, int R,
                                  int pooled_h, int pooled_w, float spatial_scale, float* out,
                                  void* stream) {
@@ -729,6 +995,28 @@ extern "C" int mnc_roi_warp_nchw(const float* feat, int C, int H, int W, const f
     return MNC_ERR_ARG;
   dim3 grid(R, (C + kWarpSlab - 1) / kWarpSlab);
   auto s = static_cast<cudaStream_t>(stream);
+  // the two sizes of the MNC graph: shared-memory staged windows (needs 16-byte aligned planes and
+  // a window that fits the budget: H * W <= 2457 floats covers every map up to 39 x 63)
+  const bool stage = g_roi_stage && (reinterpret_cast<uintptr_t>(out) % 16 == 0) &&
+                     static_cast<long long>(H) * W * 5 <= kStageFloats;
+  if (g_roi_stage == 2 && pooled_h == pooled_w && (pooled_h == 28 || pooled_h == 14)) {
+    const int cpc = 32;
+    dim3 wgrid(R, (C + cpc - 1) / cpc);
+    if (pooled_h == 28)
+      roi_warp_rowwalk_kernel<28><<<wgrid, 256, 0, s>>>(feat, C, H, W, rois, spatial_scale, cpc, out);
+    else
+      roi_warp_rowwalk_kernel<14><<<wgrid, 256, 0, s>>>(feat, C, H, W, rois, spatial_scale, cpc, out);
+    return check_launch();
+  }
+  // (14x14: 784 taps per channel against a ~440-float window -- staging does not pay, measured)
+  if (stage && g_roi_stage == 1 && pooled_h == 28 && pooled_w == 28) {
+    dim3 sgrid(R, (C + kStageGroup - 1) / kStageGroup);
+    static SmemGrant grant28;
+    const int smem = kStageFloats * 4;
+    if (!ensure_dynamic_smem(roi_warp28_stage_kernel, smem, grant28)) return MNC_ERR_CUDA;
+    roi_warp28_stage_kernel<<<sgrid, 256, smem, s>>>(feat, C, H, W, rois, spatial_scale, out, 1.0f);
+    return check_launch();
+  }
   if (pooled_h == 28 && pooled_w == 28)
     roi_warp_nchw_kernel<28, 28, 4><<<grid, 256, 0, s>>>(feat, C, H, W, rois, spatial_scale, out);
   else if (pooled_h == 14 && pooled_w == 14)

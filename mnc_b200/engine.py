@@ -481,7 +481,8 @@ class MNCEngine:
                 self.detect(st[0], st[1], st[2], st[3])
             torch.cuda.synchronize(self.device)
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            # thread_local: a NCCL watchdog thread may poll events while this thread captures
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 o = self.forward(st[0], st[1])
                 outs = self.detect_tail(o, data.shape[0], st[2], st[3], rec=rec) + (o,)
             ent = (g, st, outs, self.last_record)
