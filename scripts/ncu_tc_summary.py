@@ -1,14 +1,14 @@
 """Join an `ncu --set full` capture of the tensor-core kernels of one bench step with the launch
 manifest bench.py wrote (`--dump-igemm`), and emit the per-launch table + means that
-`bench.py` reports as `roofline.traffic` (profiles/r01_ncu_tc_summary.json).
+`bench.py` reports as `roofline.traffic` (profiles/r02_ncu_tc_summary.json).
 
   ncu --set full --clock-control none --import-source on \\
       -k regex:"igemm_tc_kernel|conv_halo_tc_kernel" --nvtx --nvtx-include "timed/" -c 28 \\
-      -o gpurun_out/r01_ncu_tc python bench.py --steps 1 --warmup 3 --no-cpu-baseline \\
+      -o gpurun_out/r02_ncu_tc python bench.py --steps 1 --warmup 3 --no-cpu-baseline \\
       --dump-igemm gpurun_out/igemm_manifest.json
-  ncu -i gpurun_out/r01_ncu_tc.ncu-rep --page raw --csv > profiles/r01_ncu_tc_raw.csv
-  python scripts/ncu_tc_summary.py profiles/r01_ncu_tc_raw.csv gpurun_out/igemm_manifest.json \\
-      > profiles/r01_ncu_tc_summary.json
+  ncu -i gpurun_out/r02_ncu_tc.ncu-rep --page raw --csv > profiles/r02_ncu_tc_raw.csv
+  python scripts/ncu_tc_summary.py profiles/r02_ncu_tc_raw.csv gpurun_out/igemm_manifest.json \\
+      > profiles/r02_ncu_tc_summary.json
 """
 import csv
 import json
@@ -16,7 +16,7 @@ import sys
 
 LAYERS = ["conv1_2", "conv2_1", "conv2_2", "conv3_1", "conv3_2", "conv3_3", "conv4_1", "conv4_2",
           "conv4_3", "conv5_1", "conv5_2", "conv5_3", "rpn_conv_3x3", "rpn_cls_score|rpn_bbox_pred"]
-HEAD = ["fc6_maskest", "mask_pred", "fc6", "fc7", "fc6_mask", "fc7_mask", "cls_score|seg_cls_score|bbox_pred"]
+HEAD = ["fc6_maskest", "mask_pred", "fc6", "fc6_mask", "fc7", "fc7_mask", "cls_score|seg_cls_score|bbox_pred"]
 
 
 def main(raw_csv, manifest_json):
@@ -69,7 +69,7 @@ def main(raw_csv, manifest_json):
     n = len(out)
     summary = {
         "source": "ncu --set full --clock-control none over the tensor-core launches of one bench.py step "
-                  "(batch 8, 600x1000); raw: profiles/r01_ncu_tc_raw.csv; made by scripts/ncu_tc_summary.py",
+                  "(batch 8, 600x1000); raw: profiles/r02_ncu_tc_raw.csv; made by scripts/ncu_tc_summary.py",
         "n_launches": n,
         "mean_traffic_bytes_per_launch": sum(o["traffic_bytes"] for o in out) / n,
         "mean_algorithmic_bytes_per_launch": sum(o["algorithmic_bytes"] for o in out) / n,
