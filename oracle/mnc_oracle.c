@@ -10,11 +10,15 @@
  * contraction happens behind our back.
  *
  * Pinning: the reference ships no forward known-answer vectors for these kernels
- * (SURVEY.md section 8c).  orc_nms and orc_mv are pinned against the reference's own
- * nms_kernel.cu / mv_kernel.cu compiled unmodified into oracle/_ref (tests/test_ref_pin.py, GPU);
- * orc_roi_warp / orc_mask_resize / orc_mask_pool / orc_roi_pool have no runnable reference here
- * (Caffe cannot be built): "parity unpinned" for those four, the .cu source lines are the only
- * spec (orc_roi_pool is cross-checked against a numpy brute force in tests/test_oracle_golden.py).
+ * (SURVEY.md section 8c), so every function here is pinned against the reference's own SOURCES
+ * compiled unmodified into oracle/_ref (oracle/Makefile `ref`; tests/test_ref_pin.py on the GPU):
+ * orc_nms / orc_mv against lib/nms/{nms,mv}_kernel.cu; orc_roi_warp / orc_mask_resize /
+ * orc_mask_pool / orc_roi_pool against caffe-mnc/src/caffe/layers/{roi_warping,mask_resize,
+ * mask_pooling,roi_pooling}_layer.{cu,cpp} (built against the Caffe-runtime stand-in
+ * oracle/ref_stub).  Built with -fmad=false the reference equals this file BIT FOR BIT; built with
+ * nvcc's default FMA contraction it differs by the rounding of one fused product (<= 2e-5).
+ * orc_roi_pool is additionally checked on the CPU against the reference's ROIPooling Forward_cpu
+ * (tests/test_ref_fixtures.py).
  */
 #include <math.h>
 #include <stdlib.h>

@@ -11,17 +11,22 @@ Nothing under mnc_b200/ imports this module.
    torch CPU fp32 (im2col + sgemm class; caffe-mnc/src/caffe/util/im2col.cpp:19-55,
    util/math_functions.cpp:19, layers/base_conv_layer.cpp:257-279, inner_product_layer.cpp:31-34).
 
-Pinning status: the reference holds known-answer data only for anchors
-(lib/transform/anchors.py:15-35) and Caffe max-pooling (test_pooling_layer.cpp:60-118); both are
-checked in tests/test_oracle_golden.py.  orc_nms / orc_mv are additionally pinned on the GPU box
-against the reference's own nms_kernel.cu / mv_kernel.cu built unmodified into oracle/_ref.
-Everything else on the path (ProposalLayer, StageBridgeLayer, ROIWarping, MaskResize, MaskPooling,
-gpu_mask_voting host logic) is "parity unpinned": the reference has no tests or vectors for it and
-its code cannot run here (Python 2, Caffe unbuildable), so the source lines are the only spec.
-The same is true of the SURVEY.md section 8f additions at the end of this file and in
-mnc_oracle.c (ROIPooling, the Faster R-CNN / CFM test nets and their blob helpers, result
-rendering, the AP^r evaluator): "parity unpinned" by the reference, cross-checked by brute-force
-and hand-computed known answers in tests/test_oracle_golden.py.
+Pinning status: pinned to the reference's own code throughout.
+ * The Python restatements (anchors, bbox transforms, ProposalLayer, StageBridgeLayer, MaskLayer,
+   gpu_mask_voting host logic, prep_im_for_blob, im_detect tail, bbox_overlaps, the cfg constants)
+   are held bit for bit to fixtures the REFERENCE's own Python produced, run in the build container
+   from /root/reference (scripts/make_ref_fixtures.py -> tests/golden/ref_*.npz;
+   tests/test_ref_fixtures.py).  Two lines evaluate differently under numpy 1.x (what the reference
+   ran on) and numpy 2 (this image); both evaluations are recorded and reproduced (`numpy2=`).
+ * The C restatements of the CUDA kernels are held to the reference's sources compiled unmodified
+   into oracle/_ref (tests/test_ref_pin.py): bit-exact against the -fmad=false build.
+ * Known answers the reference itself holds (anchors table lib/transform/anchors.py:15-35, Caffe
+   max-pooling test_pooling_layer.cpp:60-118, conv-vs-naive) are in tests/test_oracle_golden.py.
+ * conv / inner-product arithmetic lives in cuDNN / cuBLAS / a CBLAS the reference does not pin:
+   tolerance parity (1e-3 relative, north_star) against torch CPU fp32 is the only meaningful bar.
+ * The SURVEY.md section 8f additions (rendering, the AP^r evaluator, the CFM blob helpers) are
+   cross-checked by brute-force and hand-computed known answers in tests/test_oracle_golden.py;
+   ROIPooling is pinned like the other layers.
 
 Tie rule: the reference sorts with `scores.argsort()[::-1]` (proposal_layer.py:139,
 gpu_nms.pyx:26), numpy's unstable introsort, so the order of equal scores is unspecified there.
