@@ -452,26 +452,33 @@ def main():
     # the reference's callers hand im_detect the raw uint8 image (tools/demo.py:143-146); so does
     # this: uint8 BGR frames in host memory -> boxes / masks / scores in host memory (+ the
     # all-gather of the records when N > 1)
-    def e2e_run(src):
-        def once():
-            det.im_detect_images(src)
-            if world > 1:
-                mdist.all_gather_records(eng.last_record, pipe.recv[0])
-                torch.cuda.synchronize()
-        for _ in range(2):
-            once()
+    def e2e_run(src, pipelined):
+        def run(n):
+            if pipelined:    # Detector.im_detect_stream: two batches in flight, copies off the critical path
+                for res in det.im_detect_stream(src for _ in range(n)):
+                    if world > 1:
+                        mdist.all_gather_records(eng.last_record, pipe.recv[0])
+                        torch.cuda.synchronize()
+            else:            # one synchronous call per step
+                for _ in range(n):
+                    det.im_detect_images(src)
+                    if world > 1:
+                        mdist.all_gather_records(eng.last_record, pipe.recv[0])
+                        torch.cuda.synchronize()
+        run(3)
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            once()
+        run(args.steps)
         torch.cuda.synchronize()
         te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         return world * B * args.steps / float(te.item())
 
-    e2e_pinned = e2e_run(torch.from_numpy(u8).pin_memory())
-    e2e_pageable = e2e_run(u8)             # a plain numpy array, as cv2.imread returns
+    u8_pinned = torch.from_numpy(u8).pin_memory()
+    e2e_pinned = e2e_run(u8_pinned, True)
+    e2e_pageable = e2e_run(u8, True)       # a plain numpy array, as cv2.imread returns
+    e2e_sync = e2e_run(u8_pinned, False)   # one blocking im_detect_images call per step
 
     # ------------------------------------------------------------- batch-1 latency (configs[0])
     lat1 = None
@@ -565,11 +572,14 @@ def main():
         "data": "synthetic", "config": workload_config(args, world),
         "e2e": {"value": e2e_pinned, "unit": "images/s", "h2d_bytes_per_step": det.h2d_bytes,
                 "d2h_bytes_per_step": det.d2h_bytes,
-                "value_pageable_input": e2e_pageable,
-                "api": "mnc_b200.api.Detector.im_detect_images: uint8 BGR host frames in (value: "
-                       "page-locked caller memory; value_pageable_input: a plain numpy array, staged "
-                       "through the Detector's pinned buffer), H2D, mean/resize/NCHW on device, "
-                       "forward (CUDA-graph replay), im_detect tail, one record D2H to host"
+                "value_pageable_input": e2e_pageable, "value_blocking_calls": e2e_sync,
+                "api": "mnc_b200.api.Detector.im_detect_stream (value, value_pageable_input: every "
+                       "step's uint8 BGR host frames -> H2D -> mean/resize/NCHW on device -> forward "
+                       "(CUDA-graph replay) -> im_detect tail -> one record D2H -> host arrays; two "
+                       "batches in flight so the copies overlap the previous batch's compute; value: "
+                       "page-locked caller memory, value_pageable_input: a plain numpy array staged "
+                       "through the Detector's pinned buffer) and Detector.im_detect_images "
+                       "(value_blocking_calls: one synchronous call per step)"
                        + ("; + all-gather of the records" if world > 1 else "")},
         "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
         "clocks": clocks, "roofline": roofline, "roofline_roi_warp": roof_warp, "micro": micro,
