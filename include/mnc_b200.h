@@ -153,6 +153,12 @@ int mnc_split_to_f32(const void* in_hi, const void* in_lo, long long n, float* o
  */
 int mnc_nms_host(int* keep_out, int* num_out, const float* boxes_host, int boxes_num,
                  int boxes_dim, float nms_overlap_thresh, int device_id);
+/* nms.gpu_nms.gpu_nms (lib/nms/gpu_nms.pyx:16-31) in one call: UNSORTED dets (n x dim, dim >= 5,
+ * score in column 4) in host memory -> keep_out = indices of the kept rows in score order
+ * (`order[keep]`), *num_out their number.  Sort (score descending, ties by ascending index), gather,
+ * NMS and scan run on the device. */
+int mnc_gpu_nms_host(int* keep_out, int* num_out, const float* dets_host, int n, int dim,
+                     float nms_overlap_thresh, int device_id);
 
 /* Device form, batched over `problems` independent box lists (images x classes):
  *   boxes + p*problem_stride : n_max x box_stride floats (x1,y1,x2,y2,...), score-sorted

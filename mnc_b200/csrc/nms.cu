@@ -13,6 +13,7 @@
 // boxes visited in the given (score-sorted) order.
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 
 #include "mnc_b200.h"
@@ -557,6 +558,71 @@ extern "C" int mnc_nms_host(int* keep_out, int* num_out, const float* boxes_host
   if (num > 0 &&
       cudaMemcpy(keep_out, d_keep, sizeof(int) * num, cudaMemcpyDeviceToHost) != cudaSuccess)
     return MNC_ERR_CUDA;
+  *num_out = num;
+  return MNC_OK;
+}
+
+
+// nms.gpu_nms.gpu_nms in one call (lib/nms/gpu_nms.pyx:16-31): UNSORTED dets (n, dim >= 5, score in
+// column 4) in host memory -> indices of the kept rows, in score order.  The sort
+// (`scores.argsort()[::-1]`, ties by ascending index), the gather, the NMS and the greedy scan all
+// run on the device; the host sees one H2D of the dets and one D2H of the order + keep lists
+// (the numpy sort + fancy indexing of the .pyx wrapper were most of the drop-in's 12-35 ms).
+extern "C" int mnc_gpu_nms_host(int* keep_out, int* num_out, const float* dets_host, int n, int dim,
+                                float nms_overlap_thresh, int device_id) {
+  if (n < 0 || dim < 5 || !keep_out || !num_out) return MNC_ERR_ARG;
+  if (n == 0) {
+    *num_out = 0;
+    return MNC_OK;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return MNC_ERR_NOGPU;
+  int cur = 0;
+  cudaGetDevice(&cur);
+  if (cur != device_id && cudaSetDevice(device_id) != cudaSuccess) return MNC_ERR_CUDA;
+  auto al = [](size_t b) { return (b + 255) & ~static_cast<size_t>(255); };
+  const size_t dets_b = al(static_cast<size_t>(n) * dim * sizeof(float));
+  const size_t sorted_b = al(static_cast<size_t>(n) * 4 * sizeof(float));
+  const size_t ints_b = al((static_cast<size_t>(n) + 4) * sizeof(int));
+  const size_t mask_b = al(static_cast<size_t>(mnc_nms_workspace_bytes(n, 1)));
+  int rc = ensure_scratch(dets_b + sorted_b + 2 * ints_b + mask_b + 256, device_id);
+  if (rc != MNC_OK) return rc;
+  char* base = static_cast<char*>(g_scratch.dev);
+  float* d_dets = reinterpret_cast<float*>(base);
+  float* d_sorted = reinterpret_cast<float*>(base + dets_b);
+  int* d_order = reinterpret_cast<int*>(base + dets_b + sorted_b);       // [n] + n_valid + count
+  int* d_keep = reinterpret_cast<int*>(base + dets_b + sorted_b + ints_b);  // [n] + num
+  void* d_mask = base + dets_b + sorted_b + 2 * ints_b;
+  if (cudaMemcpy(d_dets, dets_host, static_cast<size_t>(n) * dim * sizeof(float),
+                 cudaMemcpyHostToDevice) != cudaSuccess)
+    return MNC_ERR_CUDA;
+  if ((rc = mnc_rank_sort_desc(d_dets + 4, 0, 0, 1, dim, nullptr, n, 1, d_order, d_order + n,
+                               nullptr)) != MNC_OK)
+    return rc;
+  if ((rc = mnc_gather_boxes(d_dets, dim, 0, 1, d_order, n, nullptr, n, 1, d_sorted,
+                             d_order + n + 1, nullptr)) != MNC_OK)
+    return rc;
+  if ((rc = mnc_nms_sorted(d_sorted, 4, 0, nullptr, n, 1, nms_overlap_thresh, n, d_mask, d_keep, n,
+                           d_keep + n, nullptr)) != MNC_OK)
+    return rc;
+  int num = 0;
+  if (cudaMemcpy(&num, d_keep + n, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess)
+    return MNC_ERR_CUDA;
+  if (num > 0) {
+    // keep (positions in the sorted list) -> original row indices, on the host: two small copies
+    static thread_local int* h_order = nullptr;
+    static thread_local int h_cap = 0;
+    if (h_cap < n) {
+      free(h_order);
+      h_order = static_cast<int*>(malloc(sizeof(int) * n));
+      h_cap = h_order ? n : 0;
+      if (!h_order) return MNC_ERR_ARG;
+    }
+    if (cudaMemcpy(h_order, d_order, sizeof(int) * n, cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(keep_out, d_keep, sizeof(int) * num, cudaMemcpyDeviceToHost) != cudaSuccess)
+      return MNC_ERR_CUDA;
+    for (int i = 0; i < num; ++i) keep_out[i] = h_order[keep_out[i]];
+  }
   *num_out = num;
   return MNC_OK;
 }

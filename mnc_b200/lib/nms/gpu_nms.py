@@ -1,4 +1,8 @@
-"""nms.gpu_nms -- reference lib/nms/gpu_nms.pyx:16-31 over mnc_nms_host (the `_nms` drop-in)."""
+"""nms.gpu_nms -- reference lib/nms/gpu_nms.pyx:16-31: `gpu_nms(dets, thresh, device_id=0)` ->
+list of kept row indices in score order.  One native call (mnc_gpu_nms_host): the
+`scores.argsort()[::-1]` sort (ties resolved score descending / index ascending), the gather, the
+bitmask NMS and the greedy scan all run on the device -- the .pyx wrapper's host-side sort and fancy
+indexing were most of this entry point's time."""
 import ctypes
 
 import numpy as np
@@ -6,23 +10,17 @@ import numpy as np
 from mnc_b200._lib import lib, check
 
 
-def _order_desc(scores):
-    # `scores.argsort()[::-1]` (gpu_nms.pyx:26) with ties resolved (score desc, index asc)
-    return np.lexsort((np.arange(scores.shape[0]), -scores.astype(np.float64)))
-
-
 def gpu_nms(dets, thresh, device_id=0):
     if dets.dtype != np.float32 or dets.ndim != 2:
         raise ValueError("Buffer dtype mismatch, expected 'float32_t' 2-D")  # cython's check
     boxes_num, boxes_dim = dets.shape
+    if boxes_dim < 5:
+        raise IndexError("dets needs 5 columns (x1, y1, x2, y2, score)")      # dets[:, 4] in the .pyx
+    dets = np.ascontiguousarray(dets)
     keep = np.zeros(boxes_num, dtype=np.int32)
     num_out = ctypes.c_int(0)
-    scores = dets[:, 4]
-    order = _order_desc(scores)
-    sorted_dets = np.ascontiguousarray(dets[order, :])
-    check(lib.mnc_nms_host(keep.ctypes.data_as(ctypes.c_void_p), ctypes.byref(num_out),
-                           sorted_dets.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(boxes_num),
-                           ctypes.c_int(boxes_dim), ctypes.c_float(thresh),
-                           ctypes.c_int(device_id)), "mnc_nms_host")
-    keep = keep[:num_out.value]
-    return list(order[keep])
+    check(lib.mnc_gpu_nms_host(keep.ctypes.data_as(ctypes.c_void_p), ctypes.byref(num_out),
+                               dets.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(boxes_num),
+                               ctypes.c_int(boxes_dim), ctypes.c_float(thresh),
+                               ctypes.c_int(device_id)), "mnc_gpu_nms_host")
+    return [int(i) for i in keep[:num_out.value]]

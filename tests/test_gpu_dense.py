@@ -24,7 +24,10 @@ def test_inner_product(M, K, N, bn, split):
     w = torch.randn(N, K, device="cuda") / K ** 0.5
     b = torch.randn(N, device="cuda")
     xs, ws = dense.split(x), dense.split(w)
-    ref = (dense.merge(xs).double() @ dense.merge(ws).double().t() + b.double()).clamp_min(0)
+    # reference from the ORIGINAL fp32 operands (so the 2^-17 operand-split error is inside the
+    # tolerance being asserted), and from the split-rounded ones for the exact-arithmetic SIMT check
+    ref = (x.double() @ w.double().t() + b.double()).clamp_min(0)
+    ref_q = (dense.merge(xs).double() @ dense.merge(ws).double().t() + b.double()).clamp_min(0)
     stride = ((N + 7) // 8) * 8
     if split > 1:
         part = torch.zeros(split, M, N, device="cuda")
@@ -43,7 +46,13 @@ def test_inner_product(M, K, N, bn, split):
     # on-device cross-check: SIMT fp32 path on the same operands
     chk = torch.zeros(M, N, device="cuda")
     dense.igemm(xs.view(2, 1, 1, M, K), 1, 1, M, K, ws, N, 1, bias=b, relu=True, out_f32=chk, impl="simt")
-    assert relerr(chk, ref) < 1e-5
+    assert relerr(chk, ref_q) < 1e-5
+    # precision mode 1 (fp16 + 2 x FP8, tri-plane operands) on the same layer, fp32 out
+    if split == 1:
+        xt, wt = dense.tri_from_f32(x), dense.tri_from_f32(w, weight=True)
+        o1 = torch.zeros(M, N, device="cuda")
+        dense.igemm2(xt.view(1, 1, M, K), 1, 1, M, K, wt, N, 1, bias=b, relu=True, out_f32=o1, bn=bn)
+        assert relerr(o1, ref) < 1e-4
 
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout,bn", [(1, 8, 16, 64, 64, 64), (2, 38, 63, 128, 256, 0),
@@ -59,12 +68,17 @@ def test_conv3x3(B, H, W, Cin, Cout, bn):
     b = torch.randn(Cout, device="cuda")
     xs = dense.split(x.permute(0, 2, 3, 1).contiguous())
     ws = dense.conv_weight_to_split(w)
-    xr = dense.merge(xs).permute(0, 3, 1, 2).double()
-    wr = dense.merge(ws).view(Cout, 3, 3, Cin).permute(0, 3, 1, 2).double()
-    ref = torch.nn.functional.conv2d(xr, wr, b.double(), padding=1).clamp_min(0).permute(0, 2, 3, 1)
+    # reference from the ORIGINAL fp32 operands: the operand-split error is inside the tolerance
+    ref = torch.nn.functional.conv2d(x.double(), w.double(), b.double(), padding=1).clamp_min(0).permute(0, 2, 3, 1)
     out = torch.zeros(2, B, H, W, Cout, device="cuda", dtype=torch.bfloat16)
     dense.igemm(xs, B, H, W, Cin, ws, Cout, 9, bias=b, relu=True, out=out, bn=bn)
     assert relerr(dense.merge(out), ref) < 1e-4
+    # precision mode 1 on the same layer (per-tap kernel, CTA pairs), tri-plane in and out
+    xt, wt = dense.tri_from_f32(x.permute(0, 2, 3, 1).contiguous()), dense.conv_weight_to_tri(w)
+    ot = dense.tri_alloc((B, H, W, Cout), "cuda")
+    dense.igemm2(xt, B, H, W, Cin, wt, Cout, 9, bias=b, relu=True, out=ot,
+                 out_exp=dense.exp_for(float(ref.max())), bn=bn)
+    assert relerr(ot.float(), ref) < 1e-4
 
 
 def test_conv1_1_and_pool_and_layout():
