@@ -315,6 +315,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-micro", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
+    ap.add_argument("--no-overlap-heads", action="store_true",
+                    help="A/B: issue the box branch in line instead of on the side stream")
     ap.add_argument("--dump-igemm", default=None,
                     help="write the ordered list of tensor-core launches of one step "
                          "(shape, algorithmic FLOPs / bytes) as JSON, for scripts/ncu_tc_summary.py")
@@ -342,6 +344,7 @@ def main():
     w = Wt.make_weights(Wt.FULL_ARCH)
     det = Detector(w, device=dev, max_batch=B, height=H, width=W, use_graph=not args.no_graph)
     eng = det.engine
+    eng.overlap_heads = not args.no_overlap_heads
 
     # synthetic inputs: image i of the global batch = seed 1234 + i
     start, _ = mdist.shard_range(B * world, rank, world)

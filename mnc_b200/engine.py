@@ -92,6 +92,11 @@ class MNCEngine:
         self.cls_heads = (self._fc_w(cls_w), cls_b.contiguous())
         self._buf = {}
         self._amax = torch.zeros(2, dtype=torch.int32, device=dev)
+        # the box branch (fc6 on the 7x7 features: tensor-bound) is issued on a side stream so that
+        # the mask branch's small / HBM-bound kernels (mask_pred, sigmoid + resize, MaskPooling) run
+        # under it instead of in front of it; in a captured graph the fork becomes parallel branches
+        self.overlap_heads = True
+        self._side = None
 
     def _fc_w(self, w, chw=None):
         return dense.fc_weight_to_tri(w, chw) if self.tri else dense.fc_weight_to_split(w, chw)
@@ -314,6 +319,9 @@ class MNCEngine:
         """test.prototxt:509-785 on R RoIs.  feat14 [R,14,14,C5], box7 [R,7,7,C5] NHWC RoI features
         (split bf16 or Tri)."""
         c5, fc, me = self.c5, self.fc, self.me
+        join = self._act_buf("join", R, 2 * fc, exp_key="join_" + tag)
+        h6 = self._act_buf("h6", R, fc, exp_key="h6_box_" + tag)
+        fork = self.overlap_heads and not self._calibrating and self.device.type == "cuda"
         h_me = self._act_buf("h_me", R, me, exp_key="h_me_" + tag)
         # fc6_maskest streams its 963 MB activation matrix from HBM exactly once (a single Cout
         # tile: no L2 reuse), so it wants loads in flight rather than big stages (split-bf16 mode:
@@ -324,11 +332,26 @@ class MNCEngine:
         logits = self._f32_buf("mask_logits_" + tag, R, 448)
         self._linear(h_me, R, me, self.mask_pred[0], 441, self.mask_pred[1], False,
                      out_f32=logits, out_stride=448, key="mp")
+        box_done = None
+        if fork:
+            # fork behind mask_pred (a second persistent GEMM would only queue behind fc6's CTAs):
+            # sigmoid + resize and MaskPooling then run UNDER the tensor-bound fc6
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.device)
+            main = torch.cuda.current_stream(self.device)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            with torch.cuda.stream(self._side):
+                self._side.wait_event(ev)
+                # (own split-K scratch: this launch overlaps the mask branch's fc6_mask)
+                self._linear(box7, R, 49 * c5, self.fc6[0], fc, self.fc6[1], True, out=h6, key="fc6_box",
+                             exp_key="h6_box_" + tag)
+                box_done = torch.cuda.Event()
+                box_done.record(self._side)
         mask_proposal, mask14 = ops.sigmoid_mask_resize(logits, R, MASK_SIZE, 14)
-        join = self._act_buf("join", R, 2 * fc, exp_key="join_" + tag)
-        h6 = self._act_buf("h6", R, fc, exp_key="h6_box_" + tag)
-        self._linear(box7, R, 49 * c5, self.fc6[0], fc, self.fc6[1], True, out=h6, key="fc6",
-                     exp_key="h6_box_" + tag)
+        if not fork:
+            self._linear(box7, R, 49 * c5, self.fc6[0], fc, self.fc6[1], True, out=h6, key="fc6_box",
+                         exp_key="h6_box_" + tag)
         m7 = self._act_buf("m7", R, 7, 7, c5, exp_key="roi_feat")
         if isinstance(feat14, dense.Tri):
             ops.mask_pool_tri(feat14, mask14, R, c5, m7)
@@ -337,6 +360,8 @@ class MNCEngine:
         h6m = self._act_buf("h6m", R, fc, exp_key="h6_mask_" + tag)
         self._linear(m7, R, 49 * c5, self.fc6_mask[0], fc, self.fc6_mask[1], True, out=h6m, key="fc6",
                      exp_key="h6_mask_" + tag)
+        if box_done is not None:
+            torch.cuda.current_stream(self.device).wait_event(box_done)
         # Concat [fc7_mask | fc7] (test.prototxt:700-705): both halves of `join` share one exponent
         if isinstance(join, dense.Tri):
             def both(e, amax):
