@@ -239,6 +239,10 @@ int mnc_roi_warp_nchw(const float* feat, int C, int H, int W, const float* rois,
  * channel pairs interleaved, packed fp32x2 arithmetic); 0 = per-tap gathers through L1 (round-1
  * kernel; other pooled sizes always use it).  Returns the previous value. */
 int mnc_roi_warp_set_stage(int on);
+/* Fused engine form (mnc_roi_warp_split / mnc_roi_warp_tri): 0 (default) = per-cell gathers,
+ * 1 = row walk (bit-identical outputs, 2.5x fewer loads, measured no faster:
+ * scripts/gpu_roi_rows_ab.py).  Returns the previous value. */
+int mnc_roi_warp_set_rows(int on);
 int mnc_mask_resize_nchw(const float* in, int N, int C, int in_h, int in_w, int out_h, int out_w,
                          float* out, void* stream);
 int mnc_mask_pool_nchw(const float* feat, const float* mask, int N, int C, int H, int W,

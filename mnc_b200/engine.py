@@ -321,7 +321,8 @@ class MNCEngine:
         c5, fc, me = self.c5, self.fc, self.me
         join = self._act_buf("join", R, 2 * fc, exp_key="join_" + tag)
         h6 = self._act_buf("h6", R, fc, exp_key="h6_box_" + tag)
-        fork = self.overlap_heads and not self._calibrating and self.device.type == "cuda"
+        # (not worth a fork / join for a handful of RoIs: single-image latency is launch-count bound)
+        fork = self.overlap_heads and not self._calibrating and R >= 4 * ROIS_PER_IMAGE
         h_me = self._act_buf("h_me", R, me, exp_key="h_me_" + tag)
         # fc6_maskest streams its 963 MB activation matrix from HBM exactly once (a single Cout
         # tile: no L2 reuse), so it wants loads in flight rather than big stages (split-bf16 mode:
