@@ -704,7 +704,7 @@ roi_warp_split_kernel(const float* __restrict__ feat, int C, int H, int W,
 // is L1-bandwidth bound: l1tex 94 %, r02 ncu).  Same 4-tap formula as the gather form (weights
 // first, FMA chain).  The 2x2 pooling to 7x7 pairs neighbouring columns by one warp shuffle.
 // grid (R, C/64), 224 threads = 7 warps x (2 columns x 16 channel quads).
-template <int SUB, bool TRI>
+template <int SUB, bool TRI, int NQ>
 __global__ void __launch_bounds__(224)
 roi_warp_rows_kernel(const float* __restrict__ feat, int C, int H, int W,
                      const float* __restrict__ rois, float spatial_scale, const RoiOut o) {
@@ -718,37 +718,54 @@ roi_warp_rows_kernel(const float* __restrict__ feat, int C, int H, int W,
     rowq[tid] = make_int4(t.ok ? t.lo : -1, t.hi, __float_as_int(t.h), __float_as_int(t.l));
   }
   const int j = 2 * warp + (lane >> 4);              // pooled column 0..13
-  const int c_raw = blockIdx.y * 64 + (lane & 15) * 4;   // first channel of this thread's quad
-  const bool chan_ok = c_raw < C;                         // (no early exit: the warp shuffles below)
-  const int c = chan_ok ? c_raw : 0;
+  // NQ channel quads per thread, 64 channels apart (independent load chains: ILP)
+  const int c_raw = blockIdx.y * (64 * NQ) + (lane & 15) * 4;
+  bool chan_ok[NQ];
+  int c[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    chan_ok[q] = c_raw + 64 * q < C;                 // (no early exit: the warp shuffles below)
+    c[q] = chan_ok[q] ? c_raw + 64 * q : 0;
+  }
   AxisTap tw[SUB];
 #pragma unroll
   for (int sx = 0; sx < SUB; ++sx)
     tw[sx] = axis_tap(__fadd_rn(g.start_w, __fmul_rn(static_cast<float>(j * SUB + sx), g.bin_w)), W);
   __syncthreads();
-  const float* fimg = feat + static_cast<long long>(g.level) * H * W * C + c;
+  const float* fimg = feat + static_cast<long long>(g.level) * H * W * C;
   const float kNeg = -3.402823466e+38f;
   int cur_lo = -1, cur_hi = -1;
-  float4 a_lo[SUB], a_hi[SUB], b_lo[SUB], b_hi[SUB];
+  float4 a_lo[NQ][SUB], a_hi[NQ][SUB], b_lo[NQ][SUB], b_hi[NQ][SUB];
+  float4 acc14[NQ], acc7[NQ];
 #pragma unroll
-  for (int sx = 0; sx < SUB; ++sx) a_lo[sx] = a_hi[sx] = b_lo[sx] = b_hi[sx] = make_float4(0.f, 0.f, 0.f, 0.f);
-  float4 acc14 = make_float4(kNeg, kNeg, kNeg, kNeg), acc7 = acc14;
+  for (int q = 0; q < NQ; ++q) {
+#pragma unroll
+    for (int sx = 0; sx < SUB; ++sx)
+      a_lo[q][sx] = a_hi[q][sx] = b_lo[q][sx] = b_hi[q][sx] = make_float4(0.f, 0.f, 0.f, 0.f);
+    acc14[q] = acc7[q] = make_float4(kNeg, kNeg, kNeg, kNeg);
+  }
 #pragma unroll 2
   for (int ph = 0; ph < P; ++ph) {
     const int4 tq = rowq[ph];
-    float4 rowmax = make_float4(0.f, 0.f, 0.f, 0.f);   // an out-of-range sample is 0 (and it pools)
+    float4 rowmax[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) rowmax[q] = make_float4(0.f, 0.f, 0.f, 0.f);   // out of range: 0 (and it pools)
     if (tq.x >= 0) {
       if (tq.x != cur_lo) {
         if (tq.x == cur_hi) {
 #pragma unroll
-          for (int sx = 0; sx < SUB; ++sx) { a_lo[sx] = b_lo[sx]; a_hi[sx] = b_hi[sx]; }
+          for (int q = 0; q < NQ; ++q)
+#pragma unroll
+            for (int sx = 0; sx < SUB; ++sx) { a_lo[q][sx] = b_lo[q][sx]; a_hi[q][sx] = b_hi[q][sx]; }
         } else {
           const float* row = fimg + static_cast<long long>(tq.x) * W * C;
 #pragma unroll
-          for (int sx = 0; sx < SUB; ++sx) {
-            a_lo[sx] = __ldg(reinterpret_cast<const float4*>(row + tw[sx].lo * C));
-            a_hi[sx] = __ldg(reinterpret_cast<const float4*>(row + tw[sx].hi * C));
-          }
+          for (int q = 0; q < NQ; ++q)
+#pragma unroll
+            for (int sx = 0; sx < SUB; ++sx) {
+              a_lo[q][sx] = __ldg(reinterpret_cast<const float4*>(row + tw[sx].lo * C + c[q]));
+              a_hi[q][sx] = __ldg(reinterpret_cast<const float4*>(row + tw[sx].hi * C + c[q]));
+            }
         }
         cur_lo = tq.x;
         cur_hi = -1;
@@ -756,48 +773,76 @@ roi_warp_rows_kernel(const float* __restrict__ feat, int C, int H, int W,
       if (tq.y != cur_hi) {
         if (tq.y == tq.x) {
 #pragma unroll
-          for (int sx = 0; sx < SUB; ++sx) { b_lo[sx] = a_lo[sx]; b_hi[sx] = a_hi[sx]; }
+          for (int q = 0; q < NQ; ++q)
+#pragma unroll
+            for (int sx = 0; sx < SUB; ++sx) { b_lo[q][sx] = a_lo[q][sx]; b_hi[q][sx] = a_hi[q][sx]; }
         } else {
           const float* row = fimg + static_cast<long long>(tq.y) * W * C;
 #pragma unroll
-          for (int sx = 0; sx < SUB; ++sx) {
-            b_lo[sx] = __ldg(reinterpret_cast<const float4*>(row + tw[sx].lo * C));
-            b_hi[sx] = __ldg(reinterpret_cast<const float4*>(row + tw[sx].hi * C));
-          }
+          for (int q = 0; q < NQ; ++q)
+#pragma unroll
+            for (int sx = 0; sx < SUB; ++sx) {
+              b_lo[q][sx] = __ldg(reinterpret_cast<const float4*>(row + tw[sx].lo * C + c[q]));
+              b_hi[q][sx] = __ldg(reinterpret_cast<const float4*>(row + tw[sx].hi * C + c[q]));
+            }
         }
         cur_hi = tq.y;
       }
       const float th_h = __int_as_float(tq.z), th_l = __int_as_float(tq.w);
-      rowmax = make_float4(kNeg, kNeg, kNeg, kNeg);
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) rowmax[q] = make_float4(kNeg, kNeg, kNeg, kNeg);
 #pragma unroll
       for (int sx = 0; sx < SUB; ++sx) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (tw[sx].ok)
-          v = bilerp4(__fmul_rn(th_h, tw[sx].h), __fmul_rn(th_h, tw[sx].l), __fmul_rn(th_l, tw[sx].h),
-                      __fmul_rn(th_l, tw[sx].l), a_lo[sx], a_hi[sx], b_lo[sx], b_hi[sx]);
-        rowmax = max4(rowmax, v);
+        const float w1 = __fmul_rn(th_h, tw[sx].h), w2 = __fmul_rn(th_h, tw[sx].l);
+        const float w3 = __fmul_rn(th_l, tw[sx].h), w4 = __fmul_rn(th_l, tw[sx].l);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (tw[sx].ok) v = bilerp4(w1, w2, w3, w4, a_lo[q][sx], a_hi[q][sx], b_lo[q][sx], b_hi[q][sx]);
+          rowmax[q] = max4(rowmax[q], v);
+        }
       }
     }
-    acc14 = max4(acc14, rowmax);
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) acc14[q] = max4(acc14[q], rowmax[q]);
     if (ph % SUB == SUB - 1) {
       const int i = ph / SUB;                        // row of the 14x14 grid
-      if (chan_ok)
-        st_feat4<TRI>(o.p14, ((static_cast<long long>(r) * 14 + i) * 14 + j) * C + c, acc14, o.scale);
-      acc7 = max4(acc7, acc14);
-      acc14 = make_float4(kNeg, kNeg, kNeg, kNeg);
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        if (chan_ok[q])
+          st_feat4<TRI>(o.p14, ((static_cast<long long>(r) * 14 + i) * 14 + j) * C + c[q], acc14[q], o.scale);
+        acc7[q] = max4(acc7[q], acc14[q]);
+        acc14[q] = make_float4(kNeg, kNeg, kNeg, kNeg);
+      }
       if (i & 1) {
-        float4 oth;
-        oth.x = __shfl_xor_sync(0xffffffffu, acc7.x, 16);
-        oth.y = __shfl_xor_sync(0xffffffffu, acc7.y, 16);
-        oth.z = __shfl_xor_sync(0xffffffffu, acc7.z, 16);
-        oth.w = __shfl_xor_sync(0xffffffffu, acc7.w, 16);
-        if ((lane >> 4) == 0 && chan_ok)
-          st_feat4<TRI>(o.p7, ((static_cast<long long>(r) * 7 + (i >> 1)) * 7 + (j >> 1)) * C + c,
-                        max4(acc7, oth), o.scale);
-        acc7 = make_float4(kNeg, kNeg, kNeg, kNeg);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          float4 oth;
+          oth.x = __shfl_xor_sync(0xffffffffu, acc7[q].x, 16);
+          oth.y = __shfl_xor_sync(0xffffffffu, acc7[q].y, 16);
+          oth.z = __shfl_xor_sync(0xffffffffu, acc7[q].z, 16);
+          oth.w = __shfl_xor_sync(0xffffffffu, acc7[q].w, 16);
+          if ((lane >> 4) == 0 && chan_ok[q])
+            st_feat4<TRI>(o.p7, ((static_cast<long long>(r) * 7 + (i >> 1)) * 7 + (j >> 1)) * C + c[q],
+                          max4(acc7[q], oth), o.scale);
+          acc7[q] = make_float4(kNeg, kNeg, kNeg, kNeg);
+        }
       }
     }
   }
+}
+
+template <bool TRI>
+static void launch_roi_rows(int nq, int sub, const float* feat, int C, int H, int W, const float* rois,
+                            int R, float spatial_scale, const RoiOut& o, cudaStream_t s) {
+  dim3 grid(R, (C + 64 * nq - 1) / (64 * nq));
+#define MNC_ROWS(SUB_, NQ_) roi_warp_rows_kernel<SUB_, TRI, NQ_><<<grid, 224, 0, s>>>(feat, C, H, W, rois, spatial_scale, o)
+  if (sub == 2) {
+    if (nq == 2) MNC_ROWS(2, 2); else MNC_ROWS(2, 1);
+  } else {
+    if (nq == 2) MNC_ROWS(1, 2); else MNC_ROWS(1, 1);
+  }
+#undef MNC_ROWS
 }
 
 // Same outputs, fewer loads.  The sample grid of a RoI is regular, so bilinear sampling separates:
@@ -1187,10 +1232,11 @@ extern "C" int mnc_mask_pool_nchw(const float* feat, const float* mask, int N, i
 }
 
 static int g_roi_rows = 0;   // fused engine form: 0 = per-cell gathers (default), 1 = row walk (bit-identical,
-                             // 2.5x fewer loads, not faster: 0.634 vs 0.639 ms at 28x28, 0.377 vs 0.304 at 14x14)
+                             // 2.5x fewer loads, not faster: 0.625-0.641 vs 0.639 ms at 28x28, 0.38-0.41 vs 0.305 at 14x14:
+                             // the kernel is bound by its 1.2 GB of output and the 4x sample arithmetic, not by taps)
 extern "C" int mnc_roi_warp_set_rows(int on) {
   const int prev = g_roi_rows;
-  g_roi_rows = on ? 1 : 0;
+  g_roi_rows = (on == 1 || on == 2) ? on : 0;   // channel quads per thread
   return prev;
 }
 static int g_roi_walk = 0;  // measured slower on real proposals (profiles/README.md): latency-bound
@@ -1226,11 +1272,7 @@ extern "C" int mnc_roi_warp_split(const float* feat_nhwc, int C, int H, int W, c
   o.p7[0] = o7_hi; o.p7[1] = o7_lo; o.p7[2] = nullptr;
   o.scale = 1.0f;
   if (g_roi_rows && C % 4 == 0) {
-    dim3 rgrid(R, (C + 63) / 64);
-    if (sub == 2)
-      roi_warp_rows_kernel<2, false><<<rgrid, 224, 0, s>>>(feat_nhwc, C, H, W, rois, spatial_scale, o);
-    else
-      roi_warp_rows_kernel<1, false><<<rgrid, 224, 0, s>>>(feat_nhwc, C, H, W, rois, spatial_scale, o);
+    launch_roi_rows<false>(g_roi_rows, sub, feat_nhwc, C, H, W, rois, R, spatial_scale, o, s);
     return check_launch();
   }
   dim3 grid(R, 7);
@@ -1255,11 +1297,7 @@ extern "C" int mnc_roi_warp_tri(const float* feat_nhwc, int C, int H, int W, con
   o.p7[0] = o7_h; o.p7[1] = o7_l; o.p7[2] = o7_c;
   o.scale = scale;
   if (g_roi_rows) {
-    dim3 rgrid(R, (C + 63) / 64);
-    if (sub == 2)
-      roi_warp_rows_kernel<2, true><<<rgrid, 224, 0, s>>>(feat_nhwc, C, H, W, rois, spatial_scale, o);
-    else
-      roi_warp_rows_kernel<1, true><<<rgrid, 224, 0, s>>>(feat_nhwc, C, H, W, rois, spatial_scale, o);
+    launch_roi_rows<true>(g_roi_rows, sub, feat_nhwc, C, H, W, rois, R, spatial_scale, o, s);
     return check_launch();
   }
   dim3 grid(R, 7);

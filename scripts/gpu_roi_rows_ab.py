@@ -17,11 +17,11 @@ rois = torch.from_numpy(np.stack([np.repeat(np.arange(B), R // B), x1, y1, np.cl
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 for sub in (2, 1):
     res, outs = {}, {}
-    for rows in (1, 0):
+    for rows in (2, 1, 0):
         lib.mnc_roi_warp_set_rows(rows)
         o14, o7 = dense.tri_alloc((R, 14, 14, C), "cuda"), dense.tri_alloc((R, 7, 7, C), "cuda")
         ms = bench.median_ms(lambda: ops.roi_warp_tri(feat, C, H, W, rois, sub, o14, o7, 9), flush=flush)
-        res["rows" if rows else "gather"] = round(ms, 4)
+        res["rows%d" % rows if rows else "gather"] = round(ms, 4)
         outs[rows] = (o14.float(), o7.float())
     lib.mnc_roi_warp_set_rows(0)
     d14 = (outs[0][0] - outs[1][0]).abs().max().item()
