@@ -70,6 +70,10 @@ class Detector:
         return out
 
     def _detect(self, data, info, hw, sc):
+        # every 32nd call: did any activation outgrow the exponents frozen at calibration?
+        self._calls = getattr(self, "_calls", 0) + 1
+        if self._calls % 32 == 0:
+            self.engine.range_ok()
         if self.use_graph:
             return self.engine.detect_graphed(data, info, hw, sc)
         return self.engine.detect(data, info, hw, sc)
@@ -190,6 +194,9 @@ class Detector:
             n = ops.record_layout(B, ROIS_PER_IMAGE)[3]
             args = (self._d_in[:B], info.to(dev, non_blocking=True), hw.to(dev, non_blocking=True),
                     sc.to(dev, non_blocking=True))
+            self._calls = getattr(self, "_calls", 0) + 1
+            if self._calls % 32 == 0:
+                self.engine.range_ok()
             if self.use_graph:
                 self.engine.detect_graphed(*args, rec=st["d_rec"])
             else:

@@ -92,6 +92,10 @@ class MNCEngine:
         self.cls_heads = (self._fc_w(cls_w), cls_b.contiguous())
         self._buf = {}
         self._amax = torch.zeros(2, dtype=torch.int32, device=dev)
+        # running max |value| of every tri-plane activation tensor (float bits, one slot per exponent
+        # key): written by the producing kernels on every call, read by range_ok()
+        self._amax_all = torch.zeros(128, dtype=torch.int32, device=dev)
+        self._amax_slot = {}
         # the box branch (fc6 on the 7x7 features: tensor-bound) is issued on a side stream so that
         # the mask branch's small / HBM-bound kernels (mask_pred, sigmoid + resize, MaskPooling) run
         # under it instead of in front of it; in a captured graph the fork becomes parallel branches
@@ -132,7 +136,8 @@ class MNCEngine:
         max |value|, choose the exponent that puts it at 2^12 (fp16 has 16x headroom above, the
         e4m3 planes saturate gracefully), relaunch if it changed."""
         if not self._calibrating:
-            fn(self.exp[exp_key], None)
+            slot = self._amax_slot.setdefault(exp_key, len(self._amax_slot))
+            fn(self.exp[exp_key], self._amax_all[slot:slot + 1] if slot < 128 else None)
             return
         slot = self._amax[:1]
         slot.zero_()
@@ -143,6 +148,26 @@ class MNCEngine:
         self.exp[exp_key] = e
         if e != e0:
             fn(e, None)
+
+    def range_ok(self, reset=True):
+        """Were the frozen exponents still adequate for everything computed since the last check?
+        One small D2H read.  A tensor whose maximum left the fp16 range of its exponent (value *
+        2^exp > 6e4: the main operand saturates) makes this return False and un-calibrates the
+        engine: the next forward measures the exponents again (and graphs are re-captured)."""
+        if not self.tri or not self._amax_slot:
+            return True
+        amax = self._amax_all.cpu().view(torch.float32)
+        bad = [k for k, i in self._amax_slot.items()
+               if i < 128 and float(amax[i]) * 2.0 ** self.exp.get(k, 0) > 6.0e4]
+        if reset:
+            self._amax_all.zero_()
+        if bad:
+            self._calibrated = False
+            if hasattr(self, "_graphs"):
+                self._graphs.clear()
+            self.last_range_violation = bad
+            return False
+        return True
 
     def _f32_buf(self, key, *shape):
         t = self._buf.get(key)

@@ -131,3 +131,34 @@ def test_detector_stream_equals_blocking_calls():
         assert got[4] == w_[4] == 1.6
         n += 1
     assert n == 4
+
+
+def test_exponent_range_monitor_recalibrates():
+    """The tri-plane exponents are frozen on the first forward; an input 200x larger saturates the
+    fp16 operands, which range_ok() must detect (the producing kernels keep a running max) and the
+    next forward must repair by measuring the exponents again."""
+    from mnc_b200 import weights as Wt
+    from mnc_b200.engine import MNCEngine
+    from oracle import oracle as O
+    w = Wt.make_weights(Wt.TINY_ARCH)
+    eng = MNCEngine(w)
+    blob, info = O.prep_blob(O.synthetic_image(1, 224, 320))
+    data, im_info = torch.from_numpy(blob).cuda(), torch.from_numpy(info).cuda()
+    eng.forward(data, im_info)
+    assert eng.range_ok()
+    exp_before = dict(eng.exp)
+    big = data * 200.0
+    eng.forward(big, im_info)                   # computed with stale exponents: saturated
+    assert not eng.range_ok() and eng.last_range_violation
+    out = eng.forward(big, im_info, keep_intermediate=True)    # recalibrates first
+    assert eng.range_ok()
+    assert any(eng.exp[k] < exp_before[k] for k in exp_before)
+    # and the result is right again: stage-1 head on the engine's own features vs the oracle
+    from mnc_b200 import dense
+    n = int(out["roi_counts"][0])
+    got14 = dense.merge(out["_feat14"])[:n].permute(0, 3, 1, 2).cpu().numpy()
+    with torch.no_grad():
+        h = O.head_forward(w, got14)
+    # (linear outputs: at 200x the softmax is saturated and amplifies 1e-5 of a logit)
+    assert util.rel_err(out["bbox_pred"][:n].cpu().numpy(), h["bbox_pred"]) < 1e-3
+    assert util.rel_err(out["_mask_logits"][:n, :441].cpu().numpy(), h["mask_pred"]) < 1e-3
