@@ -208,7 +208,7 @@ def workload_config(args, world):
             "l2": "inputs larger than L2: every step streams 1.13 GB of weights and > 5 GB of "
                   "activations through the 126 MB L2, nothing of a step survives to the next",
             "weights": "seeded random init (mnc_b200/weights.py), fp32 -> fp16 + 2 x e4m3 planes "
-                       "(halo-kernel layers: split bf16)"}
+                       "(every conv3x3 / inner product; conv1_1, K = 27: split bf16)"}
 
 
 def median_ms(fn, iters=20, warm=3, flush=None):
@@ -317,6 +317,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-overlap-heads", action="store_true",
                     help="A/B: issue the box branch in line instead of on the side stream")
+    ap.add_argument("--halo-split", action="store_true",
+                    help="A/B: the halo kernel (Cout <= 128 convs) on split-bf16 operands")
     ap.add_argument("--dump-igemm", default=None,
                     help="write the ordered list of tensor-core launches of one step "
                          "(shape, algorithmic FLOPs / bytes) as JSON, for scripts/ncu_tc_summary.py")
@@ -342,6 +344,9 @@ def main():
     dev = torch.device("cuda", local)
     B = args.batch
     w = Wt.make_weights(Wt.FULL_ARCH)
+    if args.halo_split:
+        from mnc_b200 import engine as _eng
+        _eng.MNCEngine.HALO_TRI = False
     det = Detector(w, device=dev, max_batch=B, height=H, width=W, use_graph=not args.no_graph)
     eng = det.engine
     eng.overlap_heads = not args.no_overlap_heads
@@ -412,13 +417,17 @@ def main():
         comm_ms = median_ms(lambda: mdist.all_gather_records(rec, out), iters=10)
 
     # ------------------------------------------------------------- eager pass: per-kernel roofline
+    # (single stream: with the box branch forked to the side stream two fc6 launches share the GPU
+    # and the events around each would count the overlap twice)
     dense.timer = dense.KernelTimer()
     launches0 = _lib.launch_count
     n_eager = 3
+    overlap_saved, eng.overlap_heads = eng.overlap_heads, False
     for _ in range(n_eager):
         step(graph=False)
     pipe.drain()
     torch.cuda.synchronize()
+    eng.overlap_heads = overlap_saved
     launches_per_step = (_lib.launch_count - launches0) // n_eager
     ktimer, dense.timer = dense.timer, None
     if args.dump_igemm and rank == 0:
@@ -540,8 +549,8 @@ def main():
         "tensor_work_factor": work / flops_step,
         "frac_tensor_pipe": (work / flops_step) * ach / peak_tf,
         "note": "fp32-parity arithmetic: launches with tri-plane operands issue one fp16 MMA + two "
-                "FP8 MMAs (double rate) per algorithmic MAC = 2 bf16-equivalent units, the three "
-                "halo-kernel layers (Cout <= 128) and conv1_1 three bf16 MMAs = 3 units; frac counts "
+                "FP8 MMAs (double rate) per algorithmic MAC = 2 bf16-equivalent units (conv1_1, not in "
+                "this kernel's launch list, three bf16 MMAs); frac counts "
                 "algorithmic FLOPs only, frac_tensor_pipe counts issued tensor work; per-launch "
                 "times from CUDA events around each launch in an eager pass of the same step",
     }

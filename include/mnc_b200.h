@@ -130,6 +130,12 @@ int mnc_conv1_1(const float* data_nchw, int batch, int H, int W, const float* we
  * weight.reshape(64, 27) (k = c*9 + ky*3 + kx), columns 27..31 zero.  Cout is 64. */
 int mnc_conv1_1_tc(const float* data_nchw, int batch, int H, int W, const void* w_stacked,
                    const float* bias, void* out_hi, void* out_lo, void* stream);
+/* General form: out_mode 0 = split-bf16 (out0 hi, out1 lo), 4 = tri-plane (out0 fp16, out1 e4m3
+ * residual, out2 e4m3 copy; values scaled by out_scale, a power of two).  amax (optional, device)
+ * receives atomicMax of |output| as float bits. */
+int mnc_conv1_1_tc2(const float* data_nchw, int batch, int H, int W, const void* w_stacked,
+                    const float* bias, int out_mode, void* out0, void* out1, void* out2,
+                    float out_scale, unsigned int* amax, void* stream);
 
 /* 2x2 stride-2 ceil-mode max pooling on split NHWC (pooling_layer.cu:11-47, pooling_layer.cpp:90-93). */
 int mnc_maxpool2x2_split(const void* in_hi, const void* in_lo, int batch, int H, int W, int C,

@@ -655,21 +655,31 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
 // their own ring of stages.
 constexpr int kHaloTH = 16, kHaloTW = 8;
 constexpr int kHaloRows = (kHaloTH + 2) * (kHaloTW + 2);          // 180 pixels
-constexpr int kHaloPlaneBytes = kHaloRows * 128;                   // 23040
+constexpr int kHaloPlaneBytes = kHaloRows * 128;                   // 23040 (2-byte plane of 64 channels)
 constexpr int kHaloPlanePad = (kHaloPlaneBytes + 1023) / 1024 * 1024;  // 23552
-constexpr int kHaloABytes = 2 * kHaloPlanePad;                     // hi + lo
+constexpr int kHaloPlane8Bytes = kHaloRows * 64;                   // 11520 (1-byte plane)
+constexpr int kHaloPlane8Pad = (kHaloPlane8Bytes + 1023) / 1024 * 1024;  // 12288
 constexpr int kHaloNA = 2;
 
-template <int BN>
+// PM 0: A = [hi | lo] bf16 planes, B per tap = [hi | lo]; three products as two instructions
+//       (stacked N, two accumulator column blocks).
+// PM 1: A = [h (fp16) | l | c (e4m3, 64-byte rows, SWIZZLE_64B)], B per tap = [h | c | l]; per
+//       64 channels 4 fp16 MMAs + 4 FP8 MMAs into ONE accumulator block.  The shifted-window
+//       descriptors work for the one-byte planes as well (start + (ky*10+kx)*64 B, SBO 640 B:
+//       scripts/exp/umma_offset_sw64_fp8_test.cu, all 9 windows exact on B200).
+template <int BN, int PM>
 struct HaloCfg {
-  static constexpr int kBBytes = BN * 128;                        // one plane of one tap's weights
-  static constexpr int kBStage = 2 * kBBytes;
-  static constexpr int kNB = (192 * 1024 - kHaloNA * kHaloABytes) / kBStage;
-  // accumulators: two column blocks per tile ([hi*hi + lo*hi | hi*lo]), double-buffered
-  static constexpr int kTmemCols = (4 * BN <= 256) ? 256 : 512;
+  static constexpr int kABytes = (PM == 0) ? 2 * kHaloPlanePad : kHaloPlanePad + 2 * kHaloPlane8Pad;
+  static constexpr int kATx = (PM == 0) ? 2 * kHaloPlaneBytes : kHaloPlaneBytes + 2 * kHaloPlane8Bytes;
+  static constexpr int kBBytes = BN * 128;                        // one 2-byte plane of one tap's weights
+  static constexpr int kBStage = 2 * kBBytes;                     // PM 1: h (kBBytes) + c + l (kBBytes/2 each)
+  static constexpr int kNB = (192 * 1024 - kHaloNA * kABytes) / kBStage;
+  // accumulators: PM 0 two column blocks per tile ([hi*hi + lo*hi | hi*lo]), PM 1 one; double-buffered
+  static constexpr int kAccCols = (PM == 0) ? 2 * BN : BN;
+  static constexpr int kTmemCols = (2 * kAccCols <= 128) ? 128 : (2 * kAccCols <= 256 ? 256 : 512);
   static constexpr int kStagingBytes = 2 * 2 * 128 * 64;
   static constexpr int kBarrierBytes = 1024;
-  static constexpr int kRingBytes = kHaloNA * kHaloABytes + kNB * kBStage;
+  static constexpr int kRingBytes = kHaloNA * kABytes + kNB * kBStage;
   static constexpr int kSmemBytes = kRingBytes + 1024 + kBarrierBytes + kStagingBytes;
 };
 
@@ -682,20 +692,22 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t smem_addr, uint
   return d;
 }
 
-template <int BN>
+template <int BN, int PM>
 __global__ void __launch_bounds__(BN == 64 ? 384 : 256, 1)
 conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                    const __grid_constant__ CUtensorMap tm_a_x,
                     const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                    const __grid_constant__ CUtensorMap tm_b_x,
                     const __grid_constant__ CUtensorMap tm_o_hi, const __grid_constant__ CUtensorMap tm_o_lo,
                     const __grid_constant__ CUtensorMap tm_o_x, const IgemmArgs p) {
-  using Cfg = HaloCfg<BN>;
+  using Cfg = HaloCfg<BN, PM>;
   constexpr int TH = kHaloTH, TW = kHaloTW, NB = Cfg::kNB;
   constexpr int kNG = (BN == 64) ? 2 : 1;   // epilogue warp groups (warps 4..7 [, 8..11])
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* a_ring = smem;
-  uint8_t* b_ring = smem + kHaloNA * kHaloABytes;
+  uint8_t* b_ring = smem + kHaloNA * Cfg::kABytes;
   uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + Cfg::kRingBytes);
   uint64_t* a_empty = a_full + kHaloNA;
   uint64_t* b_full = a_empty + kHaloNA;
@@ -716,6 +728,10 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
     ptx::prefetch_tmap(&tm_a_lo);
     ptx::prefetch_tmap(&tm_b_hi);
     ptx::prefetch_tmap(&tm_b_lo);
+    if (PM == 1) {
+      ptx::prefetch_tmap(&tm_a_x);
+      ptx::prefetch_tmap(&tm_b_x);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kHaloNA; ++s) {
@@ -747,11 +763,14 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
         const Tile tl = decode_tile<1>(p, t, 0, TH, TW, BN);
         for (int kc = 0; kc < kchunks; ++kc) {
           ptx::mbar_wait(&a_empty[as], aph ^ 1);
-          uint8_t* sa = a_ring + as * kHaloABytes;
-          ptx::mbar_arrive_expect_tx_w(&a_full[as], 2 * kHaloPlaneBytes);
+          uint8_t* sa = a_ring + as * Cfg::kABytes;
+          ptx::mbar_arrive_expect_tx_w(&a_full[as], Cfg::kATx);
           ptx::tma_load_4d_w(sa, &tm_a_hi, &a_full[as], kc * 64, tl.w0 - 1, tl.h0 - 1, tl.img);
           ptx::tma_load_4d_w(sa + kHaloPlanePad, &tm_a_lo, &a_full[as], kc * 64, tl.w0 - 1,
-                           tl.h0 - 1, tl.img);
+                             tl.h0 - 1, tl.img);
+          if (PM == 1)
+            ptx::tma_load_4d_w(sa + kHaloPlanePad + kHaloPlane8Pad, &tm_a_x, &a_full[as], kc * 64,
+                               tl.w0 - 1, tl.h0 - 1, tl.img);
           if (++as == kHaloNA) {
             as = 0;
             aph ^= 1;
@@ -761,8 +780,13 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
             uint8_t* sb = b_ring + bs * Cfg::kBStage;
             ptx::mbar_arrive_expect_tx_w(&b_full[bs], Cfg::kBStage);
             ptx::tma_load_2d_w(sb, &tm_b_hi, &b_full[bs], tap * p.Cin + kc * 64, tl.n0);
-            ptx::tma_load_2d_w(sb + Cfg::kBBytes, &tm_b_lo, &b_full[bs], tap * p.Cin + kc * 64,
-                             tl.n0);
+            if (PM == 0) {
+              ptx::tma_load_2d_w(sb + Cfg::kBBytes, &tm_b_lo, &b_full[bs], tap * p.Cin + kc * 64, tl.n0);
+            } else {
+              ptx::tma_load_2d_w(sb + Cfg::kBBytes, &tm_b_lo, &b_full[bs], tap * p.Cin + kc * 64, tl.n0);
+              ptx::tma_load_2d_w(sb + Cfg::kBBytes + Cfg::kBBytes / 2, &tm_b_x, &b_full[bs],
+                                 tap * p.Cin + kc * 64, tl.n0);
+            }
             if (++bs == NB) {
               bs = 0;
               bph ^= 1;
@@ -774,14 +798,16 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer
     {  // whole warp, warp-uniform arguments; one lane is elected inside each issue (ptx.cuh)
-      // The per-instruction overhead of tcgen05.mma (~40 cycles) matters at these small N, so
+      // PM 0: the per-instruction overhead of tcgen05.mma (~40 cycles) matters at these small N, so
       // the three split-precision products are issued as two instructions: the hi and lo weight
       // planes sit back to back in the stage, so A_hi x [B_hi | B_lo] is ONE N = 2*BN MMA into
       // columns [0, 2BN), and A_lo x B_hi accumulates into columns [0, BN).  The epilogue adds
       // the two column blocks.
       constexpr uint32_t idesc1 = ptx::umma_idesc_bf16_m128(2 * BN);
       constexpr uint32_t idesc2 = ptx::umma_idesc_bf16_m128(BN);
-      constexpr uint32_t kSbo = (TW + 2) * 128;  // one halo row
+      constexpr uint32_t idesc_f = ptx::umma_idesc_fmt0_m128(BN);   // PM 1: fp16 / e4m3, N = BN
+      constexpr uint32_t kSbo = (TW + 2) * 128;  // one halo row of a 2-byte plane
+      constexpr uint32_t kSbo8 = (TW + 2) * 64;  // ... of a 1-byte plane
       int as = 0, bs = 0, local = 0;
       uint32_t aph = 0, bph = 0;
       for (int t = first; t < total_tiles; t += stride, ++local) {
@@ -789,34 +815,52 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
         const uint32_t acc_phase = (local >> 1) & 1;
         ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * (2 * BN);
+        const uint32_t tmem_d = tmem_base + acc * Cfg::kAccCols;
         for (int kc = 0; kc < kchunks; ++kc) {
           ptx::mbar_wait(&a_full[as], aph);
           ptx::tc_fence_after();
-          const uint32_t a_hi0 = ptx::smem_u32(a_ring + as * kHaloABytes);
-          const uint32_t a_lo0 = a_hi0 + kHaloPlanePad;
+          const uint32_t a_hi0 = ptx::smem_u32(a_ring + as * Cfg::kABytes);
+          const uint32_t a_lo0 = a_hi0 + kHaloPlanePad;                    // PM 1: the residual plane
+          const uint32_t a_c0 = a_lo0 + kHaloPlane8Pad;                    // PM 1: the copy plane
           for (int tap = 0; tap < 9; ++tap) {
             ptx::mbar_wait(&b_full[bs], bph);
             ptx::tc_fence_after();
             // shifted window (reading all taps from offset 0 instead is no faster: the windows cost
-            // nothing extra; what bounds the Cout = 64 layer is shared-memory bandwidth -- per
-            // 16-wide k slice the two MMAs read 14 KB of operands in 96 tensor cycles, and the
-            // TMA fills add 194 KB per tile: ~5450 cycles of 128 B/clk against 3456 of MMA)
-            const uint32_t woff = ((tap / 3) * (TW + 2) + (tap % 3)) * 128;
-            // descriptor low words (start address >> 4); + 2 per 16-element k slice
-            const uint32_t la_hi = ptx::desc_lo(a_hi0 + woff);
-            const uint32_t la_lo = ptx::desc_lo(a_lo0 + woff);
-            const uint32_t lb = ptx::desc_lo(ptx::smem_u32(b_ring + bs * Cfg::kBStage));  // [hi | lo]
-            // (all eight MMAs of a tap from one asm block -- one election, half the instructions
-            // between UTCHMMAs -- measured 17 % SLOWER on conv1_2; ptx::umma_halo_tap_w is kept
-            // for the record)
+            // nothing extra; what bounds the Cout = 64 layer is shared-memory bandwidth)
+            const uint32_t wpix = (tap / 3) * (TW + 2) + (tap % 3);
+            const uint32_t lb = ptx::desc_lo(ptx::smem_u32(b_ring + bs * Cfg::kBStage));
+            if (PM == 0) {
+              // descriptor low words (start address >> 4); + 2 per 16-element k slice
+              const uint32_t la_hi = ptx::desc_lo(a_hi0 + wpix * 128);
+              const uint32_t la_lo = ptx::desc_lo(a_lo0 + wpix * 128);
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              const uint32_t accum = (kc > 0 || tap > 0 || kk > 0) ? 1u : 0u;
-              ptx::umma_bf16_ss_w32<ptx::desc_hi_sw128_sbo(kSbo), ptx::kDescHiSw128>(
-                  tmem_d, la_hi + 2 * kk, lb + 2 * kk, idesc1, accum);
-              ptx::umma_bf16_ss_w32<ptx::desc_hi_sw128_sbo(kSbo), ptx::kDescHiSw128>(
-                  tmem_d, la_lo + 2 * kk, lb + 2 * kk, idesc2, 1u);
+              for (int kk = 0; kk < 4; ++kk) {
+                const uint32_t accum = (kc > 0 || tap > 0 || kk > 0) ? 1u : 0u;
+                ptx::umma_bf16_ss_w32<ptx::desc_hi_sw128_sbo(kSbo), ptx::kDescHiSw128>(
+                    tmem_d, la_hi + 2 * kk, lb + 2 * kk, idesc1, accum);
+                ptx::umma_bf16_ss_w32<ptx::desc_hi_sw128_sbo(kSbo), ptx::kDescHiSw128>(
+                    tmem_d, la_lo + 2 * kk, lb + 2 * kk, idesc2, 1u);
+              }
+            } else {
+              const uint32_t la_h = ptx::desc_lo(a_hi0 + wpix * 128);
+              const uint32_t la_l = ptx::desc_lo(a_lo0 + wpix * 64);
+              const uint32_t la_c = ptx::desc_lo(a_c0 + wpix * 64);
+              const uint32_t lb_c = lb + (Cfg::kBBytes >> 4);                         // copy plane of B
+              const uint32_t lb_l = lb_c + (Cfg::kBBytes >> 5);                       // residual plane of B
+              // corrections (FP8, K = 32): residual x copy, copy x residual
+#pragma unroll
+              for (int kk = 0; kk < 2; ++kk) {
+                const uint32_t accum = (kc > 0 || tap > 0 || kk > 0) ? 1u : 0u;
+                ptx::umma_f8_ss_w32<ptx::desc_hi_sw64_sbo(kSbo8), ptx::kDescHiSw64>(
+                    tmem_d, la_l + 2 * kk, lb_c + 2 * kk, idesc_f, accum);
+                ptx::umma_f8_ss_w32<ptx::desc_hi_sw64_sbo(kSbo8), ptx::kDescHiSw64>(
+                    tmem_d, la_c + 2 * kk, lb_l + 2 * kk, idesc_f, 1u);
+              }
+              // main product (fp16, K = 16)
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                ptx::umma_bf16_ss_w32<ptx::desc_hi_sw128_sbo(kSbo), ptx::kDescHiSw128>(
+                    tmem_d, la_h + 2 * kk, lb + 2 * kk, idesc_f, 1u);
             }
             ptx::umma_commit_w(&b_empty[bs]);
             if (++bs == NB) {
@@ -834,8 +878,8 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
       }
     }
   } else if (warp >= 4) {
-    run_epilogue<TH, TW, BN, 1, true, kNG>(p, &tm_o_hi, &tm_o_lo, &tm_o_x, staging, tfull_bar,
-                                           tempty_bar, tmem_base, 0, first, stride, total_tiles);
+    run_epilogue<TH, TW, BN, 1, PM == 0, kNG>(p, &tm_o_hi, &tm_o_lo, &tm_o_x, staging, tfull_bar,
+                                              tempty_bar, tmem_base, 0, first, stride, total_tiles);
   }
 
   ptx::tc_fence_before();
@@ -870,7 +914,8 @@ constexpr int kC11Threads = 640;   // 4 control + 8 epilogue + 8 producer warps
 __global__ void __launch_bounds__(kC11Threads, 1)
 conv1_1_tc_kernel(const float* __restrict__ data, int B, int H, int W,
                   const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_o_hi,
-                  const __grid_constant__ CUtensorMap tm_o_lo, const IgemmArgs p) {
+                  const __grid_constant__ CUtensorMap tm_o_lo, const __grid_constant__ CUtensorMap tm_o_x,
+                  const IgemmArgs p) {
   constexpr int BN = 64;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -947,7 +992,7 @@ conv1_1_tc_kernel(const float* __restrict__ data, int B, int H, int W,
       }
     }
   } else if (warp >= 4 && warp < 12) {
-    run_epilogue<1, 128, BN, 1, true, 2>(p, &tm_o_hi, &tm_o_lo, &tm_o_lo, staging, tfull_bar,
+    run_epilogue<1, 128, BN, 1, true, 2>(p, &tm_o_hi, &tm_o_lo, &tm_o_x, staging, tfull_bar,
                                          tempty_bar, tmem_base, 0, first, stride, total_tiles);
   } else if (warp >= 12) {
     // -------------------------------------------------------------- A producers (128 threads)
@@ -1133,18 +1178,18 @@ static int launch_igemm(const Maps& m, const IgemmArgs& a, int max_ctas, cudaStr
   return e == cudaSuccess ? MNC_OK : MNC_ERR_CUDA;
 }
 
-template <int BN>
+template <int BN, int PM>
 static int launch_halo(const Maps& m, const IgemmArgs& a, int max_ctas, cudaStream_t stream) {
-  using Cfg = HaloCfg<BN>;
-  auto kern = conv_halo_tc_kernel<BN>;
+  using Cfg = HaloCfg<BN, PM>;
+  auto kern = conv_halo_tc_kernel<BN, PM>;
   static SmemGrant grant;
   if (!ensure_dynamic_smem(kern, Cfg::kSmemBytes, grant)) return MNC_ERR_CUDA;
   const int total = a.tiles_n * a.batch * a.tiles_h * a.tiles_w;
   int grid = sm_count();
   if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
   if (total < grid) grid = total;
-  kern<<<grid, BN == 64 ? 384 : 256, Cfg::kSmemBytes, stream>>>(m.a[0], m.a[1], m.b[0], m.b[1],
-                                                              m.o[0], m.o[1], m.o[2], a);
+  kern<<<grid, BN == 64 ? 384 : 256, Cfg::kSmemBytes, stream>>>(m.a[0], m.a[1], m.a[2], m.b[0], m.b[1],
+                                                              m.b[2], m.o[0], m.o[1], m.o[2], a);
   return cudaGetLastError() == cudaSuccess ? MNC_OK : MNC_ERR_CUDA;
 }
 
@@ -1213,7 +1258,7 @@ extern "C" int mnc_igemm_tc2(int in_fmt, const void* a0, const void* a1, const v
     return MNC_ERR_ARG;
   const bool conv = (taps == 9);
   if (bn == 0) bn = (Cout <= 64) ? 64 : (Cout <= 128 ? 128 : 256);
-  const bool halo = in_fmt == 0 && conv && g_igemm_halo && (bn == 64 || bn == 128) && split_k == 1;
+  const bool halo = conv && g_igemm_halo && (bn == 64 || bn == 128) && split_k == 1;
   const int TH = conv ? (halo ? kHaloTH : 8) : 1, TW = conv ? (halo ? kHaloTW : 16) : 128;
   if (bn != 64 && bn != 128 && bn != 192 && bn != 256) return MNC_ERR_ARG;
   const bool bk_forced = (bk != 0);
@@ -1298,8 +1343,12 @@ extern "C" int mnc_igemm_tc2(int in_fmt, const void* a0, const void* a1, const v
   if (in_fmt == 1 && (rc = make_wgt_map(&m.b[2], w2, Cout, ktot, bn / cl, bk, 1)) != MNC_OK) return rc;
   if (halo) {
     a.k_steps = 9 * (Cin / 64);
-    if (bn == 64) return launch_halo<64>(m, a, max_ctas, stream);
-    return launch_halo<128>(m, a, max_ctas, stream);
+    if (in_fmt == 1) {
+      if (bn == 64) return launch_halo<64, 1>(m, a, max_ctas, stream);
+      return launch_halo<128, 1>(m, a, max_ctas, stream);
+    }
+    if (bn == 64) return launch_halo<64, 0>(m, a, max_ctas, stream);
+    return launch_halo<128, 0>(m, a, max_ctas, stream);
   }
 
 #define MNC_LAUNCH_PM(TH_, TW_, BN_, BK_, PM_)                                      \
@@ -1343,13 +1392,17 @@ extern "C" int mnc_igemm_tc(const void* a_hi, const void* a_lo, int batch, int H
 
 // conv1_1 on the tensor cores.  w_stacked: bf16 [128][32] = rows 0..63 the hi plane, 64..127 the lo
 // plane of weight.reshape(64, 27) (k = c*9 + ky*3 + kx), columns 27..31 zero.
-extern "C" int mnc_conv1_1_tc(const float* data_nchw, int batch, int H, int W, const void* w_stacked,
-                              const float* bias, void* out_hi, void* out_lo, void* stream_) {
+// out_mode 0: split-bf16 planes (out0 = hi, out1 = lo); 4: tri-plane (out0 = fp16, out1 = e4m3
+// residual, out2 = e4m3 copy) scaled by out_scale.  amax (optional, device): atomicMax(|output|).
+extern "C" int mnc_conv1_1_tc2(const float* data_nchw, int batch, int H, int W, const void* w_stacked,
+                               const float* bias, int out_mode, void* out0, void* out1, void* out2,
+                               float out_scale, unsigned int* amax, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (batch <= 0 || H <= 0 || W <= 0) return MNC_ERR_ARG;
-  if ((reinterpret_cast<uintptr_t>(out_hi) | reinterpret_cast<uintptr_t>(out_lo) |
+  if (batch <= 0 || H <= 0 || W <= 0 || (out_mode != 0 && out_mode != 4)) return MNC_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(out0) | reinterpret_cast<uintptr_t>(out1) |
        reinterpret_cast<uintptr_t>(w_stacked)) % 16 != 0)
     return MNC_ERR_ARG;
+  if (out_mode == 4 && (out2 == nullptr || reinterpret_cast<uintptr_t>(out2) % 16 != 0)) return MNC_ERR_ARG;
   IgemmArgs a;
   a.batch = batch * H;   // one-row images
   a.H = 1;
@@ -1363,30 +1416,40 @@ extern "C" int mnc_conv1_1_tc(const float* data_nchw, int batch, int H, int W, c
   a.k_steps = 1;
   a.split_k = 1;
   a.relu = 1;
-  a.out_mode = 0;
+  a.out_mode = out_mode;
   a.bias = bias;
-  a.out_hi = static_cast<__nv_bfloat16*>(out_hi);
-  a.out_lo = static_cast<__nv_bfloat16*>(out_lo);
+  a.out_hi = static_cast<__nv_bfloat16*>(out0);
+  a.out_lo = static_cast<__nv_bfloat16*>(out1);
   a.out_f32 = nullptr;
   a.out_pix_stride = 64;
   a.out_ch_offset = 0;
   a.split_stride = 0;
   a.vec_ok = 1;
   a.tma_store = 1;
-  a.out_x = nullptr;
+  a.out_x = static_cast<uint8_t*>(out2);
   a.acc_scale = 1.0f;
-  a.out_scale = 1.0f;
-  a.amax = nullptr;
-  CUtensorMap tb, to_hi, to_lo;
+  a.out_scale = out_scale;
+  a.amax = amax;
+  CUtensorMap tb, to_hi, to_lo, to_x;
   int rc;
+  const int eb = (out_mode == 4) ? 1 : 2;
   if ((rc = make_wgt_map(&tb, w_stacked, 128, 32, 128, 32)) != MNC_OK) return rc;
-  if ((rc = make_out_map(&to_hi, out_hi, a.batch, 1, W, 64, 64, 1, 128)) != MNC_OK) return rc;
-  if ((rc = make_out_map(&to_lo, out_lo, a.batch, 1, W, 64, 64, 1, 128)) != MNC_OK) return rc;
+  if ((rc = make_out_map(&to_hi, out0, a.batch, 1, W, 64, 64, 1, 128, 2)) != MNC_OK) return rc;
+  if ((rc = make_out_map(&to_lo, out1, a.batch, 1, W, 64, 64, 1, 128, eb)) != MNC_OK) return rc;
+  to_x = to_lo;
+  if (out_mode == 4 && (rc = make_out_map(&to_x, out2, a.batch, 1, W, 64, 64, 1, 128, 1)) != MNC_OK) return rc;
   static SmemGrant grant;
   if (!ensure_dynamic_smem(conv1_1_tc_kernel, kC11Smem, grant)) return MNC_ERR_CUDA;
   const int total = a.batch * a.tiles_w;
   int grid = sm_count();
   if (total < grid) grid = total;
-  conv1_1_tc_kernel<<<grid, kC11Threads, kC11Smem, stream>>>(data_nchw, batch, H, W, tb, to_hi, to_lo, a);
+  conv1_1_tc_kernel<<<grid, kC11Threads, kC11Smem, stream>>>(data_nchw, batch, H, W, tb, to_hi, to_lo,
+                                                             to_x, a);
   return cudaGetLastError() == cudaSuccess ? MNC_OK : MNC_ERR_CUDA;
+}
+
+extern "C" int mnc_conv1_1_tc(const float* data_nchw, int batch, int H, int W, const void* w_stacked,
+                              const float* bias, void* out_hi, void* out_lo, void* stream_) {
+  return mnc_conv1_1_tc2(data_nchw, batch, H, W, w_stacked, bias, 0, out_hi, out_lo, nullptr, 1.0f,
+                         nullptr, stream_);
 }

@@ -369,6 +369,21 @@ __device__ __forceinline__ void umma_bf16_ss_w32(uint32_t tmem_d, uint32_t desc_
       "r"(desc_a_lo), "r"(desc_b_lo), "r"(idesc), "r"(accumulate), "n"(kHiA), "n"(kHiB)
       : "memory");
 }
+// kind::f8f6f4 flavour of umma_bf16_ss_w32 (descriptor low words + compile-time high words).
+template <uint32_t kHiA, uint32_t kHiB>
+__device__ __forceinline__ void umma_f8_ss_w32(uint32_t tmem_d, uint32_t desc_a_lo, uint32_t desc_b_lo,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %6};\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], da, db, %3, p;\n\t}"
+      ::"r"(tmem_d),
+      "r"(desc_a_lo), "r"(desc_b_lo), "r"(idesc), "r"(accumulate), "n"(kHiA), "n"(kHiB)
+      : "memory");
+}
 // One filter tap of the halo kernel = four 16-wide k slices x {A_hi x [B_hi|B_lo] (idesc1),
 // A_lo x B_hi (idesc2)}: eight MMAs issued from ONE asm block -- one election, the three descriptor
 // low words + TMEM address + the two instruction descriptors cross into uniform registers once, the
@@ -415,6 +430,7 @@ __device__ __forceinline__ void umma_halo_tap_w(uint32_t tmem_d, uint32_t la_hi,
 constexpr uint32_t kDescHiSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);
 constexpr uint32_t kDescHiSw64 = (512u >> 4) | (1u << 14) | (4u << 29);
 constexpr uint32_t desc_hi_sw128_sbo(uint32_t sbo_bytes) { return (sbo_bytes >> 4) | (1u << 14) | (2u << 29); }
+constexpr uint32_t desc_hi_sw64_sbo(uint32_t sbo_bytes) { return (sbo_bytes >> 4) | (1u << 14) | (4u << 29); }
 __device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr) { return (smem_addr & 0x3FFFFu) >> 4; }
 
 // K-major, 128-byte-swizzled operand tile (rows of 64 bf16 = 128 B, 8-row atoms of

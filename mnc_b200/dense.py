@@ -267,13 +267,20 @@ def conv1_1_weight_to_tc(weight):
     return sp.reshape(128, 32).contiguous()
 
 
-def conv1_1_tc(data, w_stacked, bias, out):
+def conv1_1_tc(data, w_stacked, bias, out, out_exp=0, amax=None):
+    """out: split bf16 [2, B, H, W, 64] or Tri (written with exponent out_exp)."""
     b, c, H, W = data.shape
     assert c == 3 and data.dtype == torch.float32 and data.is_contiguous()
     assert w_stacked.dtype == torch.bfloat16 and tuple(w_stacked.shape) == (128, 32)
-    rc = lib.mnc_conv1_1_tc(ptr(data), c_int(b), c_int(H), c_int(W), ptr(w_stacked), ptr(bias),
-                            ptr(out[0]), ptr(out[1]), cur_stream())
-    check(rc, "mnc_conv1_1_tc")
+    if isinstance(out, Tri):
+        out.exp = int(out_exp)
+        mode, op = 4, (out.h, out.l, out.c)
+    else:
+        mode, op = 0, (out[0], out[1], None)
+    rc = lib.mnc_conv1_1_tc2(ptr(data), c_int(b), c_int(H), c_int(W), ptr(w_stacked), ptr(bias),
+                             c_int(mode), ptr(op[0]), ptr(op[1]), ptr(op[2]),
+                             ctypes.c_float(2.0 ** out_exp), ptr(amax), cur_stream())
+    check(rc, "mnc_conv1_1_tc2")
 
 
 def maxpool2x2(a, batch, H, W, C, out):

@@ -31,15 +31,17 @@ def _ceil_half(x):
     return (x + 1) // 2
 
 
-HALO_MAX_COUT = 128    # 3x3 convs with Cout <= 128 run the halo kernel (split-bf16 operands)
+HALO_MAX_COUT = 128    # 3x3 convs with Cout <= 128 run the halo kernel
 
 
 class MNCEngine:
     # "f16f8": precision mode 1 on every launch of the per-tap / inner-product kernel -- tri-plane
     # operands, fp16 main product + two FP8 correction products (2 tensor-work units per MAC);
     # "bf16x3": split-bf16 operands everywhere (3 units per MAC).  The halo kernel (Cout <= 128)
-    # and conv1_1 use split-bf16 operands in both.
+    # has both modes as well (HALO_TRI False keeps it on split-bf16 operands under "f16f8");
+    # conv1_1 (K = 27) computes in split bf16 in both and writes the format its consumer reads.
     DEFAULT_PRECISION = "f16f8"
+    HALO_TRI = True
 
     def __init__(self, weights, device="cuda", impl="tc", sm_count=None, precision=None):
         """weights: {caffe name: (weight, bias)} fp32 tensors in Caffe layouts (see weights.py)."""
@@ -47,6 +49,7 @@ class MNCEngine:
         self.impl = impl
         self.precision = (precision or self.DEFAULT_PRECISION) if impl == "tc" else "bf16x3"
         self.tri = self.precision == "f16f8"
+        self.halo_tri = self.HALO_TRI
         self.fuse_pool = True
         # per-tensor exponents of the tri-plane activations, measured on the first forward
         self.exp = {}
@@ -65,10 +68,12 @@ class MNCEngine:
         # 64-channel conv1_1 runs on the tensor cores (stacked hi/lo weight tile, K padded to 32)
         self.conv1_1_tc = (dense.conv1_1_weight_to_tc(w["conv1_1"][0])
                            if impl == "tc" and w["conv1_1"][0].shape[0] == 64 else None)
+        if self.conv1_1_tc is None:
+            self.halo_tri = False      # only the tensor-core conv1_1 writes tri-plane output
         self.convs = []
         for name in TRUNK_NAMES[1:] + ["rpn_conv_3x3"]:
             if name in w:   # the CFM test net has no RPN (proposals are an input)
-                tri = self.tri and w[name][0].shape[0] > HALO_MAX_COUT
+                tri = self._conv_in_tri(w[name][0].shape[0])
                 cw = dense.conv_weight_to_tri(w[name][0]) if tri else dense.conv_weight_to_split(w[name][0])
                 self.convs.append((name, cw, w[name][1]))
         self.trunk_convs = [c for c in self.convs if c[0] != "rpn_conv_3x3"]
@@ -272,7 +277,7 @@ class MNCEngine:
     # ------------------------------------------------------------------ trunk
     def _conv_in_tri(self, cout):
         """Does the conv with `cout` output channels read tri-plane operands?"""
-        return self.tri and cout > HALO_MAX_COUT
+        return self.tri and (cout > HALO_MAX_COUT or self.halo_tri)
 
     def trunk(self, data):
         """conv1_1 .. conv5_3 (test.prototxt:19-387).  data fp32 (B,3,H,W) -> NHWC conv5_3 in the
@@ -290,8 +295,10 @@ class MNCEngine:
         first_next = couts[0] if couts else 0
         x = self._pp_buf(cur, self._conv_in_tri(first_next), "conv1_1", B, H, W, ch[0])
         if isinstance(x, dense.Tri):
-            raise NotImplementedError("conv1_1 feeds a halo-kernel layer in every supported net")
-        if self.conv1_1_tc is not None:
+            d = data.contiguous()
+            self._scaled("conv1_1", lambda e, amax: dense.conv1_1_tc(
+                d, self.conv1_1_tc, self.conv1_1[1], x, out_exp=e, amax=amax))
+        elif self.conv1_1_tc is not None:
             dense.conv1_1_tc(data.contiguous(), self.conv1_1_tc, self.conv1_1[1], x)
         else:
             dense.conv1_1(data, self.conv1_1[0], self.conv1_1[1], x)

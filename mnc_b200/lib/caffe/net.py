@@ -107,7 +107,7 @@ class Net(object):
                 host = {"mask_prob": o["mask_prob"].view(R, -1), "cls_prob": o["cls_prob"],
                         "seg_cls_prob": o["seg_cls_prob"], "bbox_pred": o["bbox_pred"]}
             conv5 = o["_conv5_3"]
-            _, B, H5, W5, C5 = conv5.shape
+            B, H5, W5, C5 = tuple(conv5.shape)[-4:]   # split bf16 [2, B, H, W, C] or dense.Tri
             c5 = torch.empty((B, C5, H5, W5), dtype=torch.float32, device=dev)
             dense.split_to_nchw(conv5, B, H5, W5, C5, c5)
             host["conv5_3"] = c5
@@ -138,7 +138,7 @@ class Net(object):
             o = self._engine.forward(d, info, keep_intermediate=True)
             n = int(o["roi_counts"][0].item())
             conv5 = o["_conv5_3"]
-            _, B, H5, W5, C5 = conv5.shape
+            B, H5, W5, C5 = tuple(conv5.shape)[-4:]   # split bf16 [2, B, H, W, C] or dense.Tri
             c5 = torch.empty((B, C5, H5, W5), dtype=torch.float32, device=dev)
             dense.split_to_nchw(conv5, B, H5, W5, C5, c5)
             host = {

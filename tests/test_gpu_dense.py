@@ -125,6 +125,13 @@ def test_conv1_1_tensor_core_form(B, H, W):
     simt = torch.zeros_like(out)
     dense.conv1_1(data, w, b, simt)
     assert relerr(dense.merge(out), dense.merge(simt).double()) < 1e-4
+    # tri-plane output (what the precision-mode-1 halo kernel reads) + the running max |output|
+    ot = dense.tri_alloc((B, H, W, 64), "cuda")
+    amax = torch.zeros(1, dtype=torch.int32, device="cuda")
+    dense.conv1_1_tc(data, dense.conv1_1_weight_to_tc(w), b, ot, out_exp=dense.exp_for(float(ref.max())),
+                     amax=amax)
+    assert relerr(ot.float(), ref) < 1e-4
+    assert abs(float(amax.view(torch.float32)) - float(ref.max())) < 1e-4 * float(ref.max())
 
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout,bn", [(1, 75, 125, 64, 128, 128), (2, 37, 53, 64, 64, 64),
@@ -147,3 +154,17 @@ def test_conv3x3_with_fused_ceil_mode_pool(B, H, W, Cin, Cout, bn):
     dense.igemm(xs, B, H, W, Cin, ws, Cout, 9, bias=b, relu=True, out=pooled, bn=bn, pool=True)
     want = F.max_pool2d(dense.merge(full).permute(0, 3, 1, 2), 2, 2, ceil_mode=True).permute(0, 2, 3, 1)
     assert torch.equal(dense.merge(pooled), want)
+    # precision mode 1 (halo kernel for bn <= 128, per-tap kernel above), tri-plane in and out
+    if Cout % 16 != 0:     # tri-plane rows are 16-byte aligned in every plane: Cout % 16 == 0
+        with pytest.raises(Exception, match="MNC_ERR_ARG"):
+            dense.igemm2(dense.tri_from_f32(x.permute(0, 2, 3, 1).contiguous()), B, H, W, Cin,
+                         dense.conv_weight_to_tri(w), Cout, 9, bias=b, relu=True,
+                         out=dense.tri_alloc((B, Ho, Wo, Cout), "cuda"), pool=True, bn=bn)
+        return
+    ref = F.max_pool2d(F.relu(F.conv2d(x.double(), w.double(), b.double(), padding=1)), 2, 2,
+                       ceil_mode=True).permute(0, 2, 3, 1)
+    xt, wt = dense.tri_from_f32(x.permute(0, 2, 3, 1).contiguous()), dense.conv_weight_to_tri(w)
+    pt = dense.tri_alloc((B, Ho, Wo, Cout), "cuda")
+    dense.igemm2(xt, B, H, W, Cin, wt, Cout, 9, bias=b, relu=True, out=pt, pool=True,
+                 out_exp=dense.exp_for(float(ref.max())), bn=bn)
+    assert relerr(pt.float(), ref) < 1e-4

@@ -125,9 +125,18 @@ def test_pixels_to_outputs_free_running(arch, H, W):
     rois = out["rois"][:n].cpu().numpy()
     i, j = _match_rois(rois, blobs["rois"])
     assert len(i) >= want_n - 6, "only %d of %d RoIs found in the oracle's list" % (len(i), want_n)
-    # rank agreement: paired RoIs appear in the same relative order, except where two scores
-    # within ~1e-6 of each other swap (bounded)
-    assert (np.diff(j) <= 0).sum() <= 3, np.where(np.diff(j) <= 0)[0]
+    # rank agreement: paired RoIs appear in the same relative order, except where two proposals
+    # whose ORACLE scores lie within the engine's score tolerance swap places (random-init RPN
+    # scores of neighbouring proposals are ~1e-5 apart); the swaps are few
+    inv = np.where(np.diff(j) <= 0)[0]
+    assert len(inv) <= 12, inv
+    if len(inv):
+        _, mid = O.proposal_layer_forward(blobs["rpn_cls_prob_reshape"], blobs["rpn_bbox_pred"],
+                                          np.asarray(im_info)[:1], return_intermediate=True)
+        sc = mid["sorted_scores"][mid["nms_keep"]]          # score of every oracle RoI, descending
+        assert len(sc) == want_n
+        gap = np.abs(sc[j[inv]] - sc[j[inv + 1]])
+        assert gap.max() < 0.2 * TOL, (inv, gap)
     for name, tol in (("mask_proposal", 5 * TOL), ("seg_cls_prob", 5 * TOL), ("cls_prob", 5 * TOL)):
         g = out[name][:n].cpu().numpy()[i]
         assert np.abs(g - blobs[name][j]).max() < tol, name

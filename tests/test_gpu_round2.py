@@ -81,10 +81,16 @@ def test_precision_modes_agree_on_full_arch():
     na, nb = int(a["roi_counts"][0]), int(b["roi_counts"][0])
     assert na == nb and na > 50
     ra, rb = a["rois"][:na].cpu().numpy(), b["rois"][:nb].cpu().numpy()
-    same = np.abs(ra - rb).max(axis=1) < 0.05
-    assert same.mean() > 0.95          # a near-tie may reorder a few proposals between the modes
+    # a near-tie may swap or replace a few proposals between the modes (which shifts every later
+    # position): pair the lists by coordinates
+    d = np.abs(ra[:, None, 1:] - rb[None, :, 1:]).max(axis=2)
+    jb = d.argmin(axis=1)
+    ia = np.where(d[np.arange(na), jb] < 0.05)[0]
+    jb = jb[ia]
+    assert len(ia) >= 0.97 * na and len(set(jb)) == len(jb)
+    assert (np.diff(jb) <= 0).sum() <= 0.03 * na
     for k in ("mask_proposal", "seg_cls_prob", "cls_prob"):
-        assert np.abs(a[k][:na].cpu().numpy()[same] - b[k][:nb].cpu().numpy()[same]).max() < 1e-3, k
+        assert np.abs(a[k][:na].cpu().numpy()[ia] - b[k][:nb].cpu().numpy()[jb]).max() < 1e-3, k
 
 
 def test_graph_replay_equals_eager():
