@@ -319,6 +319,8 @@ def main():
                     help="A/B: issue the box branch in line instead of on the side stream")
     ap.add_argument("--halo-split", action="store_true",
                     help="A/B: the halo kernel (Cout <= 128 convs) on split-bf16 operands")
+    ap.add_argument("--halo-single", action="store_true",
+                    help="A/B: the halo kernel with one CTA per tile instead of CTA pairs")
     ap.add_argument("--dump-igemm", default=None,
                     help="write the ordered list of tensor-core launches of one step "
                          "(shape, algorithmic FLOPs / bytes) as JSON, for scripts/ncu_tc_summary.py")
@@ -347,6 +349,8 @@ def main():
     if args.halo_split:
         from mnc_b200 import engine as _eng
         _eng.MNCEngine.HALO_TRI = False
+    if args.halo_single:
+        dense.set_halo_pair(0)
     det = Detector(w, device=dev, max_batch=B, height=H, width=W, use_graph=not args.no_graph)
     eng = det.engine
     eng.overlap_heads = not args.no_overlap_heads

@@ -98,6 +98,8 @@ int mnc_roi_warp_tri(const float* feat_nhwc, int C, int H, int W, const float* r
  * M = 256 MMA per instruction, each CTA holds its 128 pixel rows and half of the weight tile;
  * 1 = single-CTA 128-row tiles. */
 int mnc_igemm_set_cluster(int cluster_size);
+/* A/B switch: CTA pairs (cta_group::2, M = 256) in the halo kernel's precision mode 1 (default on). */
+int mnc_igemm_set_halo_pair(int on);
 /* K elements per pipeline stage: 64 (SWIZZLE_128B), 32 (SWIZZLE_64B, twice the stages) or
  * 0 = default (64; the 192-wide Cout tile always uses 32).  bn also accepts 192. */
 int mnc_igemm_set_block_k(int bk);

@@ -198,20 +198,54 @@ __device__ __forceinline__ void run_epilogue(const IgemmArgs& p, const CUtensorM
         // whole image rows of the pixel tile (TW = 16: two rows, TW = 8: four), so the pool window
         // of an even (row, column) is lanes {l, l^1, l^TW, l^(TW+1)}: two shuffles per channel.
         // Each of the 4 lanes of a window then stores 8 of the chunk's 32 channels.
-        const int part = (lane & 1) | (((lane / TW) & 1) << 1);
+        // The 4 lanes of a window end up with 8 channels each by a reduce-scatter: exchange halves
+        // with the x neighbour (16 shuffles), then quarters with the y neighbour (8) -- 24 shuffles
+        // and 24 max per chunk instead of 64 + 64 for all-channels-everywhere.
+        const bool odd_x = (lane & 1) != 0;
+        const bool odd_y = ((lane / TW) & 1) != 0;
+        const int part = (odd_x ? 2 : 0) | (odd_y ? 1 : 0);   // this lane stores channels part*8 .. +7
         const int hl = (row / TW) & ~1;   // tile-local top row / left column of this lane's window
         const int wl = (row % TW) & ~1;
-        float m[8];
+        float bv[32];
+        if (p.bias != nullptr && ch0 + 32 <= p.Cout && (reinterpret_cast<uintptr_t>(p.bias + ch0) & 15) == 0) {
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + ch0) + j4);
+            bv[4 * j4] = b4.x;
+            bv[4 * j4 + 1] = b4.y;
+            bv[4 * j4 + 2] = b4.z;
+            bv[4 * j4 + 3] = b4.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            bv[j] = (p.bias != nullptr && ch0 + j < p.Cout) ? __ldg(p.bias + ch0 + j) : 0.f;
+        }
+        float x[32];
+        float mx = 0.f;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(r[j]) * asc;
-          if (p.bias != nullptr && ch0 + j < p.Cout) x += __ldg(p.bias + ch0 + j);
-          if (p.relu) x = fmaxf(x, 0.f);
-          if (!valid) x = -3.402823466e+38f;
-          else amx = fmaxf(amx, fabsf(x));
-          x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 1));
-          x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, TW));
-          if ((j >> 3) == part) m[j & 7] = x;
+          x[j] = __uint_as_float(r[j]) * asc + bv[j];
+          if (p.relu) x[j] = fmaxf(x[j], 0.f);
+          mx = fmaxf(mx, fabsf(x[j]));
+        }
+        if (valid) amx = fmaxf(amx, mx);
+        if (!__all_sync(0xffffffffu, valid)) {   // ragged tile: rows outside the image never win
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = valid ? x[j] : -3.402823466e+38f;
+        }
+        float y[16], m[8];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float keep = odd_x ? x[j + 16] : x[j];
+          const float send = odd_x ? x[j] : x[j + 16];
+          y[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 1));
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float keep = odd_y ? y[j + 8] : y[j];
+          const float send = odd_y ? y[j] : y[j + 8];
+          m[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, TW));
         }
         const int hp = (h0 + hl) >> 1;
         const int wp = (w0 + wl) >> 1;
@@ -667,13 +701,18 @@ constexpr int kHaloNA = 2;
 //       64 channels 4 fp16 MMAs + 4 FP8 MMAs into ONE accumulator block.  The shifted-window
 //       descriptors work for the one-byte planes as well (start + (ky*10+kx)*64 B, SBO 640 B:
 //       scripts/exp/umma_offset_sw64_fp8_test.cu, all 9 windows exact on B200).
-template <int BN, int PM>
+// CL 2 (PM 1 only): a CTA pair computes two pixel tiles against one Cout tile with M = 256
+// cta_group::2 MMAs; each CTA brings in its own halo box and HALF of every tap's weights, so the
+// weight fills and the tensor core's B-operand reads per CTA halve (these layers are bound by
+// shared-memory bandwidth, profiles/README.md finding 11).
+template <int BN, int PM, int CL = 1>
 struct HaloCfg {
   static constexpr int kABytes = (PM == 0) ? 2 * kHaloPlanePad : kHaloPlanePad + 2 * kHaloPlane8Pad;
   static constexpr int kATx = (PM == 0) ? 2 * kHaloPlaneBytes : kHaloPlaneBytes + 2 * kHaloPlane8Bytes;
-  static constexpr int kBBytes = BN * 128;                        // one 2-byte plane of one tap's weights
+  static constexpr int kBBytes = (BN / CL) * 128;                 // one 2-byte plane of one tap's weights
   static constexpr int kBStage = 2 * kBBytes;                     // PM 1: h (kBBytes) + c + l (kBBytes/2 each)
-  static constexpr int kNB = (192 * 1024 - kHaloNA * kABytes) / kBStage;
+  static constexpr int kNBfit = (192 * 1024 - kHaloNA * kABytes) / kBStage;
+  static constexpr int kNB = kNBfit > 12 ? 12 : kNBfit;
   // accumulators: PM 0 two column blocks per tile ([hi*hi + lo*hi | hi*lo]), PM 1 one; double-buffered
   static constexpr int kAccCols = (PM == 0) ? 2 * BN : BN;
   static constexpr int kTmemCols = (2 * kAccCols <= 128) ? 128 : (2 * kAccCols <= 256 ? 256 : 512);
@@ -683,16 +722,7 @@ struct HaloCfg {
   static constexpr int kSmemBytes = kRingBytes + 1024 + kBarrierBytes + kStagingBytes;
 };
 
-__device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
-  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
-  d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
-  return d;
-}
-
-template <int BN, int PM>
+template <int BN, int PM, int CL>
 __global__ void __launch_bounds__(BN == 64 ? 384 : 256, 1)
 conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                     const __grid_constant__ CUtensorMap tm_a_x,
@@ -700,9 +730,12 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
                     const __grid_constant__ CUtensorMap tm_b_x,
                     const __grid_constant__ CUtensorMap tm_o_hi, const __grid_constant__ CUtensorMap tm_o_lo,
                     const __grid_constant__ CUtensorMap tm_o_x, const IgemmArgs p) {
-  using Cfg = HaloCfg<BN, PM>;
+  static_assert(CL == 1 || PM == 1, "CTA pairs: precision mode 1 only");
+  using Cfg = HaloCfg<BN, PM, CL>;
   constexpr int TH = kHaloTH, TW = kHaloTW, NB = Cfg::kNB;
   constexpr int kNG = (BN == 64) ? 2 : 1;   // epilogue warp groups (warps 4..7 [, 8..11])
+  constexpr bool kPair = (CL == 2);
+  constexpr uint16_t kMask = static_cast<uint16_t>((1u << CL) - 1u);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -719,9 +752,11 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = p.tiles_n * p.batch * p.tiles_h * p.tiles_w;
+  const int spatial_tiles = p.batch * p.tiles_h * p.tiles_w;
+  const int total_tiles = p.tiles_n * ((spatial_tiles + CL - 1) / CL);
   const int kchunks = p.Cin / 64;
-  const int first = blockIdx.x, stride = gridDim.x;
+  const int rank = kPair ? static_cast<int>(ptx::cluster_ctarank()) : 0;
+  const int first = blockIdx.x / CL, stride = gridDim.x / CL;   // work items are owned by clusters
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm_a_hi);
@@ -734,6 +769,8 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
     }
   }
   if (warp == 1 && lane == 0) {
+    // pair: the leader's full barriers count both CTAs' bytes; the leader's commits release the
+    // empty barriers of both CTAs; the leader's tempty collects both epilogues
     for (int s = 0; s < kHaloNA; ++s) {
       ptx::mbar_init(&a_full[s], 1);
       ptx::mbar_init(&a_empty[s], 1);
@@ -744,13 +781,19 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tfull_bar[a], 1);
-      ptx::mbar_init(&tempty_bar[a], 128 * kNG);
+      ptx::mbar_init(&tempty_bar[a], 128 * kNG * CL);
     }
     ptx::fence_barrier_init();
   }
-  if (warp == 2) ptx::tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  if (warp == 2) {
+    if (kPair)
+      ptx::tmem_alloc_2sm<Cfg::kTmemCols>(tmem_slot);
+    else
+      ptx::tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  }
   ptx::tc_fence_before();
   __syncthreads();
+  if (kPair) ptx::cluster_sync_all();  // peers' barriers are initialised before any remote arrive
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -760,17 +803,27 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       for (int t = first; t < total_tiles; t += stride) {
-        const Tile tl = decode_tile<1>(p, t, 0, TH, TW, BN);
+        const Tile tl = decode_tile<CL>(p, t, rank, TH, TW, BN);
+        const int nrow = tl.n0 + rank * (BN / CL);    // this CTA's share of the Cout tile
         for (int kc = 0; kc < kchunks; ++kc) {
           ptx::mbar_wait(&a_empty[as], aph ^ 1);
           uint8_t* sa = a_ring + as * Cfg::kABytes;
-          ptx::mbar_arrive_expect_tx_w(&a_full[as], Cfg::kATx);
-          ptx::tma_load_4d_w(sa, &tm_a_hi, &a_full[as], kc * 64, tl.w0 - 1, tl.h0 - 1, tl.img);
-          ptx::tma_load_4d_w(sa + kHaloPlanePad, &tm_a_lo, &a_full[as], kc * 64, tl.w0 - 1,
-                             tl.h0 - 1, tl.img);
-          if (PM == 1)
-            ptx::tma_load_4d_w(sa + kHaloPlanePad + kHaloPlane8Pad, &tm_a_x, &a_full[as], kc * 64,
-                               tl.w0 - 1, tl.h0 - 1, tl.img);
+          if (!kPair || rank == 0) ptx::mbar_arrive_expect_tx_w(&a_full[as], CL * Cfg::kATx);
+          if (kPair) {
+            const uint32_t bar = ptx::mapa_u32(ptx::smem_u32(&a_full[as]), 0);
+            ptx::tma_load_4d_2sm_w(sa, &tm_a_hi, bar, kc * 64, tl.w0 - 1, tl.h0 - 1, tl.img);
+            ptx::tma_load_4d_2sm_w(sa + kHaloPlanePad, &tm_a_lo, bar, kc * 64, tl.w0 - 1, tl.h0 - 1,
+                                   tl.img);
+            ptx::tma_load_4d_2sm_w(sa + kHaloPlanePad + kHaloPlane8Pad, &tm_a_x, bar, kc * 64,
+                                   tl.w0 - 1, tl.h0 - 1, tl.img);
+          } else {
+            ptx::tma_load_4d_w(sa, &tm_a_hi, &a_full[as], kc * 64, tl.w0 - 1, tl.h0 - 1, tl.img);
+            ptx::tma_load_4d_w(sa + kHaloPlanePad, &tm_a_lo, &a_full[as], kc * 64, tl.w0 - 1,
+                               tl.h0 - 1, tl.img);
+            if (PM == 1)
+              ptx::tma_load_4d_w(sa + kHaloPlanePad + kHaloPlane8Pad, &tm_a_x, &a_full[as], kc * 64,
+                                 tl.w0 - 1, tl.h0 - 1, tl.img);
+          }
           if (++as == kHaloNA) {
             as = 0;
             aph ^= 1;
@@ -778,14 +831,18 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
           for (int tap = 0; tap < 9; ++tap) {
             ptx::mbar_wait(&b_empty[bs], bph ^ 1);
             uint8_t* sb = b_ring + bs * Cfg::kBStage;
-            ptx::mbar_arrive_expect_tx_w(&b_full[bs], Cfg::kBStage);
-            ptx::tma_load_2d_w(sb, &tm_b_hi, &b_full[bs], tap * p.Cin + kc * 64, tl.n0);
-            if (PM == 0) {
-              ptx::tma_load_2d_w(sb + Cfg::kBBytes, &tm_b_lo, &b_full[bs], tap * p.Cin + kc * 64, tl.n0);
+            if (!kPair || rank == 0) ptx::mbar_arrive_expect_tx_w(&b_full[bs], CL * Cfg::kBStage);
+            const int kcol = tap * p.Cin + kc * 64;
+            if (kPair) {
+              const uint32_t bar = ptx::mapa_u32(ptx::smem_u32(&b_full[bs]), 0);
+              ptx::tma_load_2d_2sm_w(sb, &tm_b_hi, bar, kcol, nrow);
+              ptx::tma_load_2d_2sm_w(sb + Cfg::kBBytes, &tm_b_lo, bar, kcol, nrow);
+              ptx::tma_load_2d_2sm_w(sb + Cfg::kBBytes + Cfg::kBBytes / 2, &tm_b_x, bar, kcol, nrow);
             } else {
-              ptx::tma_load_2d_w(sb + Cfg::kBBytes, &tm_b_lo, &b_full[bs], tap * p.Cin + kc * 64, tl.n0);
-              ptx::tma_load_2d_w(sb + Cfg::kBBytes + Cfg::kBBytes / 2, &tm_b_x, &b_full[bs],
-                                 tap * p.Cin + kc * 64, tl.n0);
+              ptx::tma_load_2d_w(sb, &tm_b_hi, &b_full[bs], kcol, nrow);
+              ptx::tma_load_2d_w(sb + Cfg::kBBytes, &tm_b_lo, &b_full[bs], kcol, nrow);
+              if (PM == 1)
+                ptx::tma_load_2d_w(sb + Cfg::kBBytes + Cfg::kBBytes / 2, &tm_b_x, &b_full[bs], kcol, nrow);
             }
             if (++bs == NB) {
               bs = 0;
@@ -795,8 +852,8 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
         }
       }
     }
-  } else if (warp == 1) {
-    // -------------------------------------------------------------- MMA issuer
+  } else if (warp == 1 && rank == 0) {
+    // -------------------------------------------------------------- MMA issuer (pair: leader only)
     {  // whole warp, warp-uniform arguments; one lane is elected inside each issue (ptx.cuh)
       // PM 0: the per-instruction overhead of tcgen05.mma (~40 cycles) matters at these small N, so
       // the three split-precision products are issued as two instructions: the hi and lo weight
@@ -805,9 +862,15 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
       // the two column blocks.
       constexpr uint32_t idesc1 = ptx::umma_idesc_bf16_m128(2 * BN);
       constexpr uint32_t idesc2 = ptx::umma_idesc_bf16_m128(BN);
-      constexpr uint32_t idesc_f = ptx::umma_idesc_fmt0_m128(BN);   // PM 1: fp16 / e4m3, N = BN
+      constexpr uint32_t idesc_f1 = ptx::umma_idesc_fmt0_m128(BN);   // PM 1: fp16 / e4m3, N = BN
+      // pair: M = 256 (m_dim field = M >> 4 at bit 24)
+      constexpr uint32_t idesc_f = kPair ? ((idesc_f1 & ~(0x1Fu << 24)) | ((256u >> 4) << 24)) : idesc_f1;
       constexpr uint32_t kSbo = (TW + 2) * 128;  // one halo row of a 2-byte plane
       constexpr uint32_t kSbo8 = (TW + 2) * 64;  // ... of a 1-byte plane
+      constexpr uint64_t kHiA16 = static_cast<uint64_t>(ptx::desc_hi_sw128_sbo(kSbo)) << 32;
+      constexpr uint64_t kHiA8 = static_cast<uint64_t>(ptx::desc_hi_sw64_sbo(kSbo8)) << 32;
+      constexpr uint64_t kHiB16 = static_cast<uint64_t>(ptx::kDescHiSw128) << 32;
+      constexpr uint64_t kHiB8 = static_cast<uint64_t>(ptx::kDescHiSw64) << 32;
       int as = 0, bs = 0, local = 0;
       uint32_t aph = 0, bph = 0;
       for (int t = first; t < total_tiles; t += stride, ++local) {
@@ -851,42 +914,64 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
 #pragma unroll
               for (int kk = 0; kk < 2; ++kk) {
                 const uint32_t accum = (kc > 0 || tap > 0 || kk > 0) ? 1u : 0u;
-                ptx::umma_f8_ss_w32<ptx::desc_hi_sw64_sbo(kSbo8), ptx::kDescHiSw64>(
-                    tmem_d, la_l + 2 * kk, lb_c + 2 * kk, idesc_f, accum);
-                ptx::umma_f8_ss_w32<ptx::desc_hi_sw64_sbo(kSbo8), ptx::kDescHiSw64>(
-                    tmem_d, la_c + 2 * kk, lb_l + 2 * kk, idesc_f, 1u);
+                if (kPair) {
+                  ptx::umma_f8_ss_2sm_w(tmem_d, kHiA8 | (la_l + 2 * kk), kHiB8 | (lb_c + 2 * kk), idesc_f, accum);
+                  ptx::umma_f8_ss_2sm_w(tmem_d, kHiA8 | (la_c + 2 * kk), kHiB8 | (lb_l + 2 * kk), idesc_f, 1u);
+                } else {
+                  ptx::umma_f8_ss_w32<ptx::desc_hi_sw64_sbo(kSbo8), ptx::kDescHiSw64>(
+                      tmem_d, la_l + 2 * kk, lb_c + 2 * kk, idesc_f, accum);
+                  ptx::umma_f8_ss_w32<ptx::desc_hi_sw64_sbo(kSbo8), ptx::kDescHiSw64>(
+                      tmem_d, la_c + 2 * kk, lb_l + 2 * kk, idesc_f, 1u);
+                }
               }
               // main product (fp16, K = 16)
 #pragma unroll
-              for (int kk = 0; kk < 4; ++kk)
-                ptx::umma_bf16_ss_w32<ptx::desc_hi_sw128_sbo(kSbo), ptx::kDescHiSw128>(
-                    tmem_d, la_h + 2 * kk, lb + 2 * kk, idesc_f, 1u);
+              for (int kk = 0; kk < 4; ++kk) {
+                if (kPair)
+                  ptx::umma_f16_ss_2sm_w(tmem_d, kHiA16 | (la_h + 2 * kk), kHiB16 | (lb + 2 * kk), idesc_f, 1u);
+                else
+                  ptx::umma_bf16_ss_w32<ptx::desc_hi_sw128_sbo(kSbo), ptx::kDescHiSw128>(
+                      tmem_d, la_h + 2 * kk, lb + 2 * kk, idesc_f, 1u);
+              }
             }
-            ptx::umma_commit_w(&b_empty[bs]);
+            if (kPair)
+              ptx::umma_commit_2sm_w(&b_empty[bs], kMask);   // frees the stage in both CTAs
+            else
+              ptx::umma_commit_w(&b_empty[bs]);
             if (++bs == NB) {
               bs = 0;
               bph ^= 1;
             }
           }
-          ptx::umma_commit_w(&a_empty[as]);
+          if (kPair)
+            ptx::umma_commit_2sm_w(&a_empty[as], kMask);
+          else
+            ptx::umma_commit_w(&a_empty[as]);
           if (++as == kHaloNA) {
             as = 0;
             aph ^= 1;
           }
         }
-        ptx::umma_commit_w(&tfull_bar[acc]);
+        if (kPair)
+          ptx::umma_commit_2sm_w(&tfull_bar[acc], kMask);     // both epilogues may drain
+        else
+          ptx::umma_commit_w(&tfull_bar[acc]);
       }
     }
   } else if (warp >= 4) {
-    run_epilogue<TH, TW, BN, 1, PM == 0, kNG>(p, &tm_o_hi, &tm_o_lo, &tm_o_x, staging, tfull_bar,
-                                              tempty_bar, tmem_base, 0, first, stride, total_tiles);
+    run_epilogue<TH, TW, BN, CL, PM == 0, kNG>(p, &tm_o_hi, &tm_o_lo, &tm_o_x, staging, tfull_bar,
+                                               tempty_bar, tmem_base, rank, first, stride, total_tiles);
   }
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (kPair) ptx::cluster_sync_all();  // no CTA leaves while a peer may still signal its barriers
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    if (kPair)
+      ptx::tmem_dealloc_2sm<Cfg::kTmemCols>(tmem_base);
+    else
+      ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
 }
 
@@ -1178,19 +1263,34 @@ static int launch_igemm(const Maps& m, const IgemmArgs& a, int max_ctas, cudaStr
   return e == cudaSuccess ? MNC_OK : MNC_ERR_CUDA;
 }
 
-template <int BN, int PM>
+template <int BN, int PM, int CL>
 static int launch_halo(const Maps& m, const IgemmArgs& a, int max_ctas, cudaStream_t stream) {
-  using Cfg = HaloCfg<BN, PM>;
-  auto kern = conv_halo_tc_kernel<BN, PM>;
+  using Cfg = HaloCfg<BN, PM, CL>;
+  auto kern = conv_halo_tc_kernel<BN, PM, CL>;
   static SmemGrant grant;
   if (!ensure_dynamic_smem(kern, Cfg::kSmemBytes, grant)) return MNC_ERR_CUDA;
-  const int total = a.tiles_n * a.batch * a.tiles_h * a.tiles_w;
+  const int spatial = a.batch * a.tiles_h * a.tiles_w;
+  const int total = a.tiles_n * ((spatial + CL - 1) / CL);
   int grid = sm_count();
   if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
-  if (total < grid) grid = total;
-  kern<<<grid, BN == 64 ? 384 : 256, Cfg::kSmemBytes, stream>>>(m.a[0], m.a[1], m.a[2], m.b[0], m.b[1],
-                                                              m.b[2], m.o[0], m.o[1], m.o[2], a);
-  return cudaGetLastError() == cudaSuccess ? MNC_OK : MNC_ERR_CUDA;
+  if (total * CL < grid) grid = total * CL;
+  grid = (grid / CL) * CL;
+  if (grid < CL) grid = CL;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(BN == 64 ? 384 : 256);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, m.a[0], m.a[1], m.a[2], m.b[0], m.b[1], m.b[2],
+                                     m.o[0], m.o[1], m.o[2], a);
+  return e == cudaSuccess ? MNC_OK : MNC_ERR_CUDA;
 }
 
 }  // namespace mnc
@@ -1200,6 +1300,7 @@ using namespace mnc;
 // Cluster size used by mnc_igemm_tc launches (1 or 2).  2 = pairs of CTAs along the pixel/row
 // dimension share each weight tile through TMA multicast (halves weight traffic from L2).
 static int g_igemm_cluster = 2;
+static int g_halo_pair = 1;
 static int g_igemm_bk = 0;  // 0 = per-shape default
 static int g_igemm_halo = 1;  // halo-reuse kernel for 3x3 convs with Cout tiles <= 128
 extern "C" int mnc_igemm_set_halo(int on) {
@@ -1214,6 +1315,11 @@ extern "C" int mnc_igemm_set_tma_store(int on) {
 extern "C" int mnc_igemm_set_cluster(int cl) {
   if (cl != 1 && cl != 2) return MNC_ERR_ARG;
   g_igemm_cluster = cl;
+  return MNC_OK;
+}
+// A/B switch: CTA pairs in the halo kernel (precision mode 1; on by default, off = one CTA per tile)
+extern "C" int mnc_igemm_set_halo_pair(int on) {
+  g_halo_pair = on ? 1 : 0;
   return MNC_OK;
 }
 
@@ -1336,19 +1442,24 @@ extern "C" int mnc_igemm_tc2(int in_fmt, const void* a0, const void* a1, const v
       return MNC_ERR_DRIVER;
     a.tma_store = 1;
   }
-  const int cl = halo ? 1 : g_igemm_cluster;
+  // halo kernel: CTA pairs exist for precision mode 1 only
+  const int cl = halo ? ((in_fmt == 1 && g_igemm_cluster == 2 && g_halo_pair) ? 2 : 1) : g_igemm_cluster;
   if ((rc = make_wgt_map(&m.b[0], w0, Cout, ktot, bn / cl, bk, 2)) != MNC_OK) return rc;
   if ((rc = make_wgt_map(&m.b[1], w1, Cout, ktot, bn / cl, bk, in_fmt ? 1 : 2)) != MNC_OK) return rc;
   m.b[2] = m.b[1];
   if (in_fmt == 1 && (rc = make_wgt_map(&m.b[2], w2, Cout, ktot, bn / cl, bk, 1)) != MNC_OK) return rc;
   if (halo) {
     a.k_steps = 9 * (Cin / 64);
-    if (in_fmt == 1) {
-      if (bn == 64) return launch_halo<64, 1>(m, a, max_ctas, stream);
-      return launch_halo<128, 1>(m, a, max_ctas, stream);
+    if (in_fmt == 1 && cl == 2) {
+      if (bn == 64) return launch_halo<64, 1, 2>(m, a, max_ctas, stream);
+      return launch_halo<128, 1, 2>(m, a, max_ctas, stream);
     }
-    if (bn == 64) return launch_halo<64, 0>(m, a, max_ctas, stream);
-    return launch_halo<128, 0>(m, a, max_ctas, stream);
+    if (in_fmt == 1) {
+      if (bn == 64) return launch_halo<64, 1, 1>(m, a, max_ctas, stream);
+      return launch_halo<128, 1, 1>(m, a, max_ctas, stream);
+    }
+    if (bn == 64) return launch_halo<64, 0, 1>(m, a, max_ctas, stream);
+    return launch_halo<128, 0, 1>(m, a, max_ctas, stream);
   }
 
 #define MNC_LAUNCH_PM(TH_, TW_, BN_, BK_, PM_)                                      \

@@ -232,6 +232,11 @@ def set_cluster(cl):
     check(lib.mnc_igemm_set_cluster(c_int(cl)), "mnc_igemm_set_cluster")
 
 
+def set_halo_pair(on):
+    """A/B: CTA pairs in the halo kernel's precision mode 1 (default on)."""
+    check(lib.mnc_igemm_set_halo_pair(c_int(int(on))), "mnc_igemm_set_halo_pair")
+
+
 def set_block_k(bk):
     """K elements per pipeline stage of the tensor-core launches: 64, 32 or 0 (= per-shape default)."""
     check(lib.mnc_igemm_set_block_k(c_int(bk)), "mnc_igemm_set_block_k")

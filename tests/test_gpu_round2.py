@@ -58,6 +58,41 @@ def test_pair_and_single_cta_agree_in_both_modes(M, N, K):
         assert util.rel_err(o.cpu().numpy(), ref.cpu().numpy()) < 3e-5
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout,pool", [(1, 16, 8, 64, 64, False), (3, 37, 53, 64, 64, True),
+                                                 (1, 75, 125, 64, 128, False), (2, 30, 21, 128, 128, True),
+                                                 (1, 16, 24, 64, 80, False)])
+def test_halo_kernel_pair_and_single_cta_agree(B, H, W, Cin, Cout, pool):
+    """Halo kernel, precision mode 1: the CTA-pair form (M = 256, each CTA holds half of every
+    tap's weights) and the single-CTA form produce the same bits in all three output planes --
+    odd tile counts (a pair with a dummy tile), ragged tiles, Cout tails, fused pooling."""
+    from mnc_b200 import dense
+    g = torch.Generator(device="cuda").manual_seed(H * W + Cout)
+    x = torch.relu(torch.randn(B, H, W, Cin, device="cuda", generator=g))
+    w = torch.randn(Cout, Cin, 3, 3, device="cuda", generator=g) / (9 * Cin) ** 0.5
+    b = torch.randn(Cout, device="cuda", generator=g) * 0.1
+    xt, wt = dense.tri_from_f32(x), dense.conv_weight_to_tri(w)
+    Ho, Wo = ((H + 1) // 2, (W + 1) // 2) if pool else (H, W)
+    outs = {}
+    try:
+        for pair in (1, 0):
+            dense.set_halo_pair(pair)
+            o = dense.tri_alloc((B, Ho, Wo, Cout), "cuda")
+            for t in (o.h, o.l, o.c):
+                t.zero_()
+            dense.igemm2(xt, B, H, W, Cin, wt, Cout, 9, bias=b, relu=True, out=o, pool=pool, out_exp=9)
+            outs[pair] = o
+    finally:
+        dense.set_halo_pair(1)
+    torch.cuda.synchronize()
+    for pl in ("h", "l", "c"):
+        assert torch.equal(getattr(outs[1], pl), getattr(outs[0], pl)), pl
+    import torch.nn.functional as F
+    ref = F.relu(F.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), b.double(), padding=1))
+    if pool:
+        ref = F.max_pool2d(ref, 2, 2, ceil_mode=True)
+    assert util.rel_err(outs[1].float().cpu().numpy(), ref.permute(0, 2, 3, 1).cpu().numpy()) < 1e-4
+
+
 def _engine_outputs(eng, data, im_info):
     out = eng.forward(data, im_info, keep_intermediate=True)
     torch.cuda.synchronize()
