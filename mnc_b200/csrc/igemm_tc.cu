@@ -206,30 +206,12 @@ __device__ __forceinline__ void run_epilogue(const IgemmArgs& p, const CUtensorM
         const int part = (odd_x ? 2 : 0) | (odd_y ? 1 : 0);   // this lane stores channels part*8 .. +7
         const int hl = (row / TW) & ~1;   // tile-local top row / left column of this lane's window
         const int wl = (row % TW) & ~1;
-        float bv[32];
-        if (p.bias != nullptr && ch0 + 32 <= p.Cout && (reinterpret_cast<uintptr_t>(p.bias + ch0) & 15) == 0) {
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + ch0) + j4);
-            bv[4 * j4] = b4.x;
-            bv[4 * j4 + 1] = b4.y;
-            bv[4 * j4 + 2] = b4.z;
-            bv[4 * j4 + 3] = b4.w;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            bv[j] = (p.bias != nullptr && ch0 + j < p.Cout) ? __ldg(p.bias + ch0 + j) : 0.f;
-        }
+        // max commutes with the monotone epilogue  x -> relu(x * scale + bias)  (scale > 0), so the
+        // window maximum is taken on the RAW accumulators and the epilogue arithmetic runs on the 8
+        // surviving channels of each lane only (bit-identical: fma and max are monotone / exact)
         float x[32];
-        float mx = 0.f;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          x[j] = __uint_as_float(r[j]) * asc + bv[j];
-          if (p.relu) x[j] = fmaxf(x[j], 0.f);
-          mx = fmaxf(mx, fabsf(x[j]));
-        }
-        if (valid) amx = fmaxf(amx, mx);
+        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(r[j]);
         if (!__all_sync(0xffffffffu, valid)) {   // ragged tile: rows outside the image never win
 #pragma unroll
           for (int j = 0; j < 32; ++j) x[j] = valid ? x[j] : -3.402823466e+38f;
@@ -255,6 +237,23 @@ __device__ __forceinline__ void run_epilogue(const IgemmArgs& p, const CUtensorM
             chp < p.Cout) {
           const long long ppix = (static_cast<long long>(img) * Ho + hp) * Wo + wp;
           const long long poff = ppix * p.out_pix_stride + p.out_ch_offset + chp;
+          float bv[8];
+          if (p.bias != nullptr && chp + 8 <= p.Cout && (reinterpret_cast<uintptr_t>(p.bias + chp) & 15) == 0) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + chp));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + chp) + 1);
+            bv[0] = b0.x, bv[1] = b0.y, bv[2] = b0.z, bv[3] = b0.w;
+            bv[4] = b1.x, bv[5] = b1.y, bv[6] = b1.z, bv[7] = b1.w;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              bv[j] = (p.bias != nullptr && chp + j < p.Cout) ? __ldg(p.bias + chp + j) : 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            m[j] = m[j] * asc + bv[j];
+            if (p.relu) m[j] = fmaxf(m[j], 0.f);
+            if (chp + j < p.Cout) amx = fmaxf(amx, fabsf(m[j]));   // max |pooled output|
+          }
           if (p.out_mode == 5) {
             uint32_t hw[4], lw[2], cw[2];
 #pragma unroll
@@ -723,7 +722,7 @@ struct HaloCfg {
 };
 
 template <int BN, int PM, int CL>
-__global__ void __launch_bounds__(BN == 64 ? 384 : 256, 1)
+__global__ void __launch_bounds__(384, 1)
 conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                     const __grid_constant__ CUtensorMap tm_a_x,
                     const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
@@ -733,7 +732,10 @@ conv_halo_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
   static_assert(CL == 1 || PM == 1, "CTA pairs: precision mode 1 only");
   using Cfg = HaloCfg<BN, PM, CL>;
   constexpr int TH = kHaloTH, TW = kHaloTW, NB = Cfg::kNB;
-  constexpr int kNG = (BN == 64) ? 2 : 1;   // epilogue warp groups (warps 4..7 [, 8..11])
+  // two epilogue warp groups (warps 4..7, 8..11) drain alternate 32-column chunks: with one
+  // group a single warp per scheduler carried 4 chunks per tile at BN = 128 and the epilogue, not
+  // the MMA, set the pace (r02 ncu: the MMA warp waited on tempty)
+  constexpr int kNG = 2;
   constexpr bool kPair = (CL == 2);
   constexpr uint16_t kMask = static_cast<uint16_t>((1u << CL) - 1u);
   extern __shared__ uint8_t smem_raw[];
@@ -1278,7 +1280,7 @@ static int launch_halo(const Maps& m, const IgemmArgs& a, int max_ctas, cudaStre
   if (grid < CL) grid = CL;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(BN == 64 ? 384 : 256);
+  cfg.blockDim = dim3(384);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];

@@ -16,3 +16,6 @@ except Exception as e:
     print("ERR", e)
     print(open("gpurun_out/r02_bench_final.err").read()[-3000:])
 EOF2
+# launch list of two bench steps (per-kernel durations, cold-cache and serialised: shares only)
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --nvtx --nvtx-include "timed/" -c 400 --csv --log-file gpurun_out/r02_launches_final.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-micro --no-graph > /dev/null 2>&1
+python scripts/launch_summary.py gpurun_out/r02_launches_final.csv > gpurun_out/r02_launches_final_summary.txt 2>&1; head -30 gpurun_out/r02_launches_final_summary.txt
