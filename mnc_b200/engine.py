@@ -107,6 +107,21 @@ class MNCEngine:
         self.overlap_heads = True
         self._side = None
 
+    def clone_state(self):
+        """A second engine over the SAME weights and exponents with its own activation buffers,
+        scratch, range-monitor slots, side stream and CUDA graphs: lets two steps be in flight on
+        two streams (the second step's kernels fill the first one's wave tails and its
+        low-occupancy proposal phase).  Clone after the first forward (the clone inherits the
+        calibration; both share the exponent dictionary)."""
+        import copy
+        e = copy.copy(self)
+        e._buf = {}
+        e._amax = torch.zeros_like(self._amax)
+        e._amax_all = torch.zeros_like(self._amax_all)
+        e._side = None
+        e._graphs = {}
+        return e
+
     def _fc_w(self, w, chw=None):
         return dense.fc_weight_to_tri(w, chw) if self.tri else dense.fc_weight_to_split(w, chw)
 
@@ -564,7 +579,10 @@ class MNCEngine:
         msz = o["mask_proposal"].shape[-1] * o["mask_proposal"].shape[-2]
         need = ops.record_layout(B, n, msz, o["seg_cls_prob"].shape[-1])[3]
         if rec is None:
+            fresh = "record" not in self._buf or self._buf["record"].numel() < need
             rec = self._f32_buf("record", need)
+            if fresh:
+                rec.zero_()          # the padding after counts[B] is never written by the kernel
         valid = self._buf.get("valid")
         if valid is None or valid.numel() < B * 2 * n:
             valid = torch.empty(B * 2 * n, dtype=torch.uint8, device=self.device)

@@ -155,6 +155,38 @@ def test_graph_replay_equals_eager():
         assert torch.equal(e, g_)
 
 
+def test_two_steps_in_flight_agree():
+    """MNCEngine.clone_state: a second engine state over the same weights; two steps issued
+    back to back on two streams (graph replays) produce the same record as one alone."""
+    from mnc_b200 import weights as Wt
+    from mnc_b200.engine import MNCEngine
+    from oracle import oracle as O
+    w = Wt.make_weights(Wt.TINY_ARCH)
+    eng = MNCEngine(w)
+    ims = [O.synthetic_image(5 + i, 224, 320) for i in range(2)]
+    blobs = [O.prep_blob(im) for im in ims]
+    data = torch.from_numpy(np.concatenate([b[0] for b in blobs])).cuda()
+    im_info = torch.from_numpy(np.concatenate([b[1] for b in blobs])).cuda()
+    im_hw = torch.tensor([[224., 320.]] * 2, device="cuda")
+    im_scale = torch.ones(2, device="cuda")
+    eng.detect_graphed(data, im_info, im_hw, im_scale)
+    torch.cuda.synchronize()
+    want = eng.last_record.clone()
+    eng2 = eng.clone_state()
+    assert eng2.exp is eng.exp and eng2._buf is not eng._buf
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for s, e in ((s1, eng), (s2, eng2)):          # capture the clone's graph, warm both
+        with torch.cuda.stream(s):
+            e.detect_graphed(data, im_info, im_hw, im_scale)
+    torch.cuda.synchronize()
+    for _ in range(3):
+        for s, e in ((s1, eng), (s2, eng2)):
+            with torch.cuda.stream(s):
+                e.detect_graphed(data, im_info, im_hw, im_scale)
+    torch.cuda.synchronize()
+    assert torch.equal(eng.last_record, want) and torch.equal(eng2.last_record, want)
+
+
 def test_detector_stream_equals_blocking_calls():
     from mnc_b200 import weights as Wt
     from mnc_b200.api import Detector
