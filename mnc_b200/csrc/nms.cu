@@ -167,6 +167,125 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const int* __restri
   if (tid == 0) num_out[prob] = s_num;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Capped NMS (max_keep << n, the ProposalLayer case: 6000 candidates, 300 survivors,
+// proposal_layer.py:147-152) WITHOUT the n x n/64 suppression matrix.  The greedy result only ever
+// consults IoU(kept box, later candidate): at most n * max_keep pairs plus the 64 x 64 triangle
+// inside each 64-candidate block -- ~1.3 M pairs for 6000 / 300 against the 18 M of the full upper
+// triangle that nms_mask_kernel builds (and 5 M against 50 M for configs[4]'s 10 000 boxes).  So:
+// one CTA per problem walks the candidates in blocks of 64, keeps the kept boxes in shared memory,
+// and per block
+//   A. all warps: lanes = candidates (two 32-lane halves), warp pairs stride over the kept list
+//      (broadcast 16-byte shared-memory reads) and over the block's own rows; suppression bits are
+//      collected with __ballot_sync (same disjoint-box shortcut and devIoU expression as above);
+//   B. thread 0 resolves the block serially from the 64 diagonal words -- one iteration per KEPT
+//      box -- and appends the survivors to the kept list; the next block's boxes were prefetched
+//      into registers during A.
+// It stops at max_keep survivors.  Same keep list as nms_mask + nms_scan (tests compare them on
+// clustered and sparse boxes); only 1 SM per image is busy, so in the pipelined engine the other
+// in-flight batch's tensor kernels run beside it instead of waiting for a full-GPU mask launch.
+constexpr int kLazyThreads = 1024;
+constexpr int kLazyGroups = kLazyThreads / 64;   // warp pairs striding over kept boxes / block rows
+
+__device__ __forceinline__ bool nms_suppresses(const float* a, const float (&cb)[4], float thresh) {
+  // a: the earlier (row) box, cb: the later (column) box -- argument order of nms_kernel.cu:66-71
+  const bool disjoint = (min(a[2], cb[2]) - max(a[0], cb[0]) + 1 <= 0.f) ||
+                        (min(a[3], cb[3]) - max(a[1], cb[1]) + 1 <= 0.f);
+  if (disjoint && !(thresh < 0.f)) return false;   // interS == 0: 0 / x > thresh is false
+  return dev_iou(a, cb) > thresh;
+}
+
+__global__ void __launch_bounds__(kLazyThreads)
+nms_lazy_kernel(const float* __restrict__ boxes, int box_stride, long long problem_stride,
+                const int* __restrict__ counts, int n_max, float thresh, int max_keep,
+                int* __restrict__ keep_out, int keep_stride, int* __restrict__ num_out) {
+  extern __shared__ float4 kept_box[];             // max_keep entries
+  __shared__ float4 cand[2][64];
+  __shared__ uint32_t sup_bits[2];                 // candidates suppressed by an earlier kept box
+  __shared__ uint32_t diag_half[64][2];            // bit j of row i: candidate i suppresses j (j > i)
+  __shared__ int s_num;
+  const int prob = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int half = warp & 1, grp = warp >> 1;
+  const int c = half * 32 + lane;                  // this thread's candidate within the block
+  const int n = min(counts ? counts[prob] : n_max, n_max);
+  const float* pb = boxes + prob * problem_stride;
+  int* keep = keep_out + static_cast<long long>(prob) * keep_stride;
+  if (tid == 0) {
+    s_num = 0;
+    sup_bits[0] = sup_bits[1] = 0u;
+  }
+  if (tid < 64) {
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid < n) {
+      const float* s = pb + static_cast<long long>(tid) * box_stride;
+      b = make_float4(s[0], s[1], s[2], s[3]);
+    }
+    cand[0][tid] = b;
+  }
+  __syncthreads();
+  const int blocks = (n + 63) / 64;
+  for (int blk = 0; blk < blocks; ++blk) {
+    const int r0 = blk * 64, buf = blk & 1;
+    const int num = s_num;
+    // prefetch the next block's boxes (the last warp pair; the loads complete under phase A)
+    float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool fetch = grp == kLazyGroups - 1 && blk + 1 < blocks;
+    if (fetch && r0 + 64 + c < n) {
+      const float* s = pb + static_cast<long long>(r0 + 64 + c) * box_stride;
+      nxt = make_float4(s[0], s[1], s[2], s[3]);
+    }
+    // ---- phase A
+    const float4 cv = cand[buf][c];
+    const float cb[4] = {cv.x, cv.y, cv.z, cv.w};
+    const bool c_ok = r0 + c < n;
+    bool sup = false;
+    for (int k = grp; k < num; k += kLazyGroups)
+      sup |= nms_suppresses(reinterpret_cast<const float*>(&kept_box[k]), cb, thresh);
+    const uint32_t sb = __ballot_sync(0xffffffffu, sup && c_ok);
+    if (lane == 0 && sb) atomicOr(&sup_bits[half], sb);
+#pragma unroll
+    for (int q = 0; q < 64 / kLazyGroups; ++q) {
+      const int i = grp * (64 / kLazyGroups) + q;  // row of the diagonal tile
+      bool s = false;
+      if (c_ok && c > i) s = nms_suppresses(reinterpret_cast<const float*>(&cand[buf][i]), cb, thresh);
+      const uint32_t bits = __ballot_sync(0xffffffffu, s);
+      if (lane == 0) diag_half[i][half] = bits;
+    }
+    if (fetch) cand[buf ^ 1][c] = nxt;
+    __syncthreads();
+    // ---- phase B
+    if (tid == 0) {
+      unsigned long long cur = static_cast<unsigned long long>(sup_bits[0]) |
+                               (static_cast<unsigned long long>(sup_bits[1]) << 32);
+      const int rows = min(64, n - r0);
+      const unsigned long long rowmask = rows == 64 ? ~0ull : ((1ull << rows) - 1ull);
+      unsigned long long avail = ~cur & rowmask;
+      int nk = num;
+      while (avail && nk < max_keep) {
+        const int i = __ffsll(static_cast<long long>(avail)) - 1;
+        keep[nk] = r0 + i;
+        kept_box[nk] = cand[buf][i];
+        ++nk;
+        cur |= static_cast<unsigned long long>(diag_half[i][0]) |
+               (static_cast<unsigned long long>(diag_half[i][1]) << 32);
+        avail = ~cur & rowmask & ~((2ull << i) - 1ull);   // alive candidates after i
+      }
+      s_num = nk;
+      sup_bits[0] = sup_bits[1] = 0u;
+    }
+    __syncthreads();
+    if (s_num >= max_keep) break;
+  }
+  if (tid == 0) num_out[prob] = s_num;
+}
+
+// 1: mnc_nms_sorted uses nms_lazy_kernel when max_keep is small against n (default); 0: always the
+// mask + scan pair (A/B and cross-check switch, mnc_nms_set_lazy).
+static int g_nms_lazy = 1;
+constexpr int kLazyMaxKeep = 2048;   // kept boxes in shared memory: 32 KB
+constexpr int kLazyMinN = 1024;
+
 // Bitonic sort in shared memory, one CTA per problem, n <= 32768: (key desc, index asc).
 // Keys are mapped to order-preserving uint32 (0 is reserved for invalid / padding entries).
 __device__ __forceinline__ uint32_t f32_sort_key(float f) {
@@ -421,6 +540,8 @@ static inline int check_launch() { return cudaGetLastError() == cudaSuccess ? MN
 
 using namespace mnc;
 
+static bool nms_takes_lazy_path(int n_max, int max_keep);
+
 extern "C" long long mnc_nms_workspace_bytes(int n_max, int problems) {
   const long long col_blocks = (n_max + 63) / 64;
   return static_cast<long long>(problems) * col_blocks * n_max * 8;
@@ -435,6 +556,12 @@ extern "C" int mnc_nms_sorted(const float* boxes, int box_stride, long long prob
   const int col_blocks = (n_max + 63) / 64;
   if (col_blocks * 8 > 48 * 1024) return MNC_ERR_ARG;
   if (max_keep <= 0 || max_keep > n_max) max_keep = n_max;
+  if (nms_takes_lazy_path(n_max, max_keep)) {
+    nms_lazy_kernel<<<problems, kLazyThreads, max_keep * sizeof(float4), stream>>>(
+        boxes, box_stride, problem_stride, counts, n_max, thresh, max_keep, keep_out, keep_stride,
+        num_out);
+    return check_launch();
+  }
   dim3 grid(col_blocks, col_blocks, problems);
   nms_mask_kernel<<<grid, 128, 0, stream>>>(boxes, box_stride, problem_stride, counts, n_max,
                                             thresh, static_cast<unsigned long long*>(workspace));
@@ -442,6 +569,21 @@ extern "C" int mnc_nms_sorted(const float* boxes, int box_stride, long long prob
       static_cast<const unsigned long long*>(workspace), counts, n_max, max_keep, keep_out,
       keep_stride, num_out);
   return check_launch();
+}
+
+static bool nms_takes_lazy_path(int n_max, int max_keep) {
+  if (max_keep <= 0 || max_keep > n_max) max_keep = n_max;
+  return g_nms_lazy && n_max >= kLazyMinN && max_keep <= kLazyMaxKeep && max_keep * 4 <= n_max;
+}
+
+extern "C" int mnc_nms_sorted_launches(int n_max, int max_keep) {
+  return nms_takes_lazy_path(n_max, max_keep) ? 1 : 2;
+}
+
+extern "C" int mnc_nms_set_lazy(int on) {
+  const int prev = g_nms_lazy;
+  g_nms_lazy = on ? 1 : 0;
+  return prev;
 }
 
 extern "C" int mnc_rank_sort_desc(const float* keys, long long outer_stride,

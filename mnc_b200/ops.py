@@ -7,6 +7,7 @@ import ctypes
 
 import torch
 
+from . import _lib
 from ._lib import lib, ptr, cur_stream, check, c_int, c_ll, c_float
 
 c_double = ctypes.c_double
@@ -78,7 +79,15 @@ def nms_sorted(boxes, counts, thresh, max_keep):
     check(lib.mnc_nms_sorted(ptr(boxes), c_int(stride), c_ll(n_max * stride), ptr(counts),
                              c_int(n_max), c_int(problems), c_float(thresh), c_int(mk), ptr(ws),
                              ptr(keep), c_int(mk), ptr(num), cur_stream()), "mnc_nms_sorted")
+    # the launch-count table books 2 kernels (mask + scan); the capped form is a single launch
+    _lib.launch_count -= 2 - lib.mnc_nms_sorted_launches(c_int(n_max), c_int(mk))
     return keep, num
+
+
+def nms_set_lazy(on):
+    """A/B and cross-check switch: False forces the suppression-matrix NMS (nms_mask + nms_scan)
+    where mnc_nms_sorted would pick the capped form.  Returns the previous setting."""
+    return bool(lib.mnc_nms_set_lazy(c_int(1 if on else 0)))
 
 
 # ----------------------------------------------------------------------------- proposal pieces

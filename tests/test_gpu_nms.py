@@ -127,3 +127,63 @@ def test_topk_sort_is_prefix_of_full_order(n, k, tie_levels):
     # no `valid` array: everything takes part
     order, cnt = ops.topk_sort_desc(torch.from_numpy(s).cuda(), n, P, k, outer_stride=n)
     assert np.array_equal(order[0].cpu().numpy()[:min(k, n)], O.order_desc(s[0])[:k])
+
+
+def _clustered_boxes(n, seed, clusters=40):
+    """RPN-like candidates: many near-duplicates around a few centres (heavy suppression, so the
+    capped NMS has to walk most of the list before it has max_keep survivors)."""
+    rng = np.random.default_rng(seed)
+    cx = rng.uniform(50, 950, clusters)
+    cy = rng.uniform(50, 550, clusters)
+    sz = np.exp(rng.uniform(np.log(40), np.log(300), clusters))
+    k = rng.integers(0, clusters, n)
+    w = sz[k] * np.exp(rng.normal(0, 0.15, n))
+    h = sz[k] * np.exp(rng.normal(0, 0.15, n))
+    x = cx[k] + rng.normal(0, 6, n)
+    y = cy[k] + rng.normal(0, 6, n)
+    b = np.stack([x - w / 2, y - h / 2, x + w / 2, y + h / 2], axis=1)
+    b[:, 0::2] = np.clip(b[:, 0::2], 0, 999)
+    b[:, 1::2] = np.clip(b[:, 1::2], 0, 599)
+    return b.astype(np.float32)
+
+
+@pytest.mark.parametrize("n_max,max_keep,kind", [(6000, 300, "clustered"), (6000, 300, "sparse"),
+                                                 (10000, 300, "sparse"), (1024 + 17, 100, "clustered"),
+                                                 (4096, 1, "clustered"), (2500, 600, "clustered")])
+def test_capped_nms_equals_mask_scan_and_oracle(n_max, max_keep, kind):
+    """mnc_nms_sorted's capped form (nms_lazy_kernel: no suppression matrix, kept boxes in shared
+    memory) == the mask + scan pair == the oracle, with per-problem counts (full, ragged last block,
+    one box, empty)."""
+    import torch
+    from mnc_b200 import ops
+    from mnc_b200._lib import lib
+    from oracle import oracle as O
+    counts = [n_max, n_max - 37, 1, 0, 65]
+    P = len(counts)
+    boxes = np.zeros((P, n_max, 4), dtype=np.float32)
+    for p in range(P):
+        boxes[p] = (_clustered_boxes(n_max, 7 + p) if kind == "clustered"
+                    else util.random_boxes(n_max, seed=7 + p))
+    oracle_check = kind == "clustered"
+    if oracle_check:    # problem 0 is also held to the (FMA-free) oracle: keep IoUs off the threshold
+        boxes[0] = util.nudge_off_threshold(boxes[0], 0.7)
+    tb = torch.from_numpy(boxes).cuda()
+    tc = torch.tensor(counts, dtype=torch.int32).cuda()
+    assert lib.mnc_nms_sorted_launches(n_max, max_keep) == 1     # these sizes take the capped form
+    prev = ops.nms_set_lazy(True)
+    try:
+        k1, n1 = ops.nms_sorted(tb, tc, 0.7, max_keep)
+        ops.nms_set_lazy(False)
+        assert lib.mnc_nms_sorted_launches(n_max, max_keep) == 2
+        k0, n0 = ops.nms_sorted(tb, tc, 0.7, max_keep)
+    finally:
+        ops.nms_set_lazy(prev)
+    k1, n1, k0, n0 = k1.cpu().numpy(), n1.cpu().numpy(), k0.cpu().numpy(), n0.cpu().numpy()
+    assert np.array_equal(n1, n0)
+    for p in range(P):
+        assert np.array_equal(k1[p, :n1[p]], k0[p, :n0[p]])
+        if p == 0 and oracle_check:
+            want = O.nms_sorted(boxes[p, :counts[p]], 0.7)[:max_keep]
+            assert n1[p] == len(want) and np.array_equal(k1[p, :n1[p]], want)
+    if kind == "clustered" and max_keep > 1:
+        assert n1[0] < counts[0]                                 # suppression did happen
