@@ -311,6 +311,12 @@ int mnc_mv_device(const float* boxes, const float* masks, int nb, int box_dim, i
                   const int* cand_begin, const int* cand_end, const int* n_res, int max_results,
                   int batch, const int* im_hw, int* bbox_ws, float* out_mask, int* out_box,
                   void* stream);
+/* mv_device finds each result's tight box in two passes (every 4th pixel of every 4th row, then
+ * exactly the pixels outside the box the first pass found): same boxes as one full sweep of the
+ * region.  mnc_mv_set_two_pass(0) selects the single sweep (cross-check / A-B switch); returns the
+ * previous setting.  mnc_mv_device_launches(): kernels per mnc_mv_device call (5 / 4). */
+int mnc_mv_set_two_pass(int on);
+int mnc_mv_device_launches(void);
 
 /* ---------------------------------------------------------------------------------------------
  * Input preparation on the device ("next" row 1): prep_im_for_blob +

@@ -177,14 +177,24 @@ __global__ void mv_init_bbox_kernel(int* __restrict__ bbox, int total, int* __re
   }
 }
 
-// grid (chunks, max_results, batch); 256 threads.
+// grid (chunks, max_results, batch); 256 threads.  Launched twice per call:
+//   pass 1 (stride 4, refine 0): every 4th pixel of every 4th row -- 1/16 of the evaluations --
+//           gives an inner bounding box (each of its four sides comes from a real "on" pixel);
+//   pass 2 (stride 1, refine 1): all pixels EXCEPT those inside the box pass 1 left in `bbox`
+//           (a pixel inside a box spanned by "on" pixels cannot move the final box), i.e. only the
+//           border between the search region and the aggregate's support is evaluated exactly.
+// The result is the same tight box as a full sweep; a voted mask fills most of its box, so the
+// border is a small fraction of the region.  When the image's masks are in [0,1] and the weights
+// >= 0 (unit[img]) the search region is first cut down from the union of the candidate boxes to
+// the columns / rows whose covering weight  sum_i w_i [x_i0 <= w <= x_i1]  can exceed the threshold
+// at all (render <= 1, so agg(h, w) <= that sum; same 1e-4 margin as agg_exceeds_unit).
 __global__ void __launch_bounds__(256)
 mv_aggregate_kernel(const float* __restrict__ boxes, const float* __restrict__ masks, int nb,
                     int box_dim, int mask_size, const int* __restrict__ cand_inds,
                     const float* __restrict__ cand_weights, long long cand_img_stride,
                     const int* __restrict__ cand_begin, const int* __restrict__ cand_end,
                     const int* __restrict__ n_res, int max_results, const int* __restrict__ im_hw,
-                    const int* __restrict__ unit, int* __restrict__ bbox) {
+                    const int* __restrict__ unit, int* __restrict__ bbox, int stride, int refine) {
   extern __shared__ unsigned char smraw[];
   const int img = blockIdx.z, t = blockIdx.y;
   if (t >= n_res[img]) return;
@@ -197,16 +207,25 @@ mv_aggregate_kernel(const float* __restrict__ boxes, const float* __restrict__ m
   const float* pboxes = boxes + static_cast<long long>(img) * nb * box_dim;
   const float* pmasks = masks + static_cast<long long>(img) * nb * mask_size * mask_size;
   const int rt = img * max_results + t;
+  // pass 2: the box pass 1 found (read before any of this pass's updates matter: every value this
+  // word ever holds is a side of a box spanned by "on" pixels, so any snapshot is safe to skip)
+  int in_x0 = INT_MAX, in_y0 = INT_MAX, in_x1 = INT_MIN, in_y1 = INT_MIN;
+  if (refine) {
+    in_x0 = bbox[rt * 4 + 0];
+    in_y0 = bbox[rt * 4 + 1];
+    in_x1 = bbox[rt * 4 + 2];
+    in_y1 = bbox[rt * 4 + 3];
+  }
   load_cands(cl, pboxes, box_dim, cand_inds + img * cand_img_stride,
              cand_weights + img * cand_img_stride, cand_begin[rt], cand_end[rt], mask_size);
   const int H = im_hw[img * 2 + 0], W = im_hw[img * 2 + 1];
   // union region of the candidate boxes (a superset of every pixel with a non-zero render)
-  __shared__ int reg[4];
+  __shared__ int reg[4], core[4];
   if (threadIdx.x == 0) {
-    reg[0] = INT_MAX;
-    reg[1] = INT_MAX;
-    reg[2] = INT_MIN;
-    reg[3] = INT_MIN;
+    reg[0] = core[0] = INT_MAX;
+    reg[1] = core[1] = INT_MAX;
+    reg[2] = core[2] = INT_MIN;
+    reg[3] = core[3] = INT_MIN;
   }
   __syncthreads();
   {
@@ -226,17 +245,60 @@ mv_aggregate_kernel(const float* __restrict__ boxes, const float* __restrict__ m
     }
   }
   __syncthreads();
-  const int rx0 = max(reg[0], 0), ry0 = max(reg[1], 0);
-  const int rx1 = min(reg[2], W - 1), ry1 = min(reg[3], H - 1);
+  int rx0 = max(reg[0], 0), ry0 = max(reg[1], 0);
+  int rx1 = min(reg[2], W - 1), ry1 = min(reg[3], H - 1);
   if (cl.n == 0 || rx1 < rx0 || ry1 < ry0) return;
-  const int rw = rx1 - rx0 + 1, rh = ry1 - ry0 + 1;
-  const long long npix = static_cast<long long>(rw) * rh;
   const bool unit_range = unit[img] != 0;
+  if (unit_range) {
+    // columns, then rows, whose covering weight can reach the threshold
+    int lo = INT_MAX, hi = INT_MIN;
+    for (int w = rx0 + threadIdx.x; w <= rx1; w += blockDim.x) {
+      float u = 0.f;
+      for (int i = 0; i < cl.n; ++i) {
+        const float4 b = cl.box[i];
+        if (!(w < b.x || w > b.z)) u += cl.wgt[i];
+      }
+      if (u * 1.0001f > kBinarizeThresh) {
+        lo = min(lo, w);
+        hi = max(hi, w);
+      }
+    }
+    if (lo != INT_MAX) {
+      atomicMin(&core[0], lo);
+      atomicMax(&core[2], hi);
+    }
+    lo = INT_MAX;
+    hi = INT_MIN;
+    for (int h = ry0 + threadIdx.x; h <= ry1; h += blockDim.x) {
+      float u = 0.f;
+      for (int i = 0; i < cl.n; ++i) {
+        const float4 b = cl.box[i];
+        if (!(h < b.y || h > b.w)) u += cl.wgt[i];
+      }
+      if (u * 1.0001f > kBinarizeThresh) {
+        lo = min(lo, h);
+        hi = max(hi, h);
+      }
+    }
+    if (lo != INT_MAX) {
+      atomicMin(&core[1], lo);
+      atomicMax(&core[3], hi);
+    }
+    __syncthreads();
+    if (core[0] == INT_MAX || core[1] == INT_MAX) return;   // nowhere can the sum exceed 0.4
+    rx0 = core[0];
+    ry0 = core[1];
+    rx1 = core[2];
+    ry1 = core[3];
+  }
+  const int gw = (rx1 - rx0) / stride + 1, gh = (ry1 - ry0) / stride + 1;
+  const long long npix = static_cast<long long>(gw) * gh;
   int bx0 = INT_MAX, by0 = INT_MAX, bx1 = INT_MIN, by1 = INT_MIN;
   for (long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; p < npix;
        p += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int h = ry0 + static_cast<int>(p / rw);
-    const int w = rx0 + static_cast<int>(p % rw);
+    const int h = ry0 + static_cast<int>(p / gw) * stride;
+    const int w = rx0 + static_cast<int>(p % gw) * stride;
+    if (w >= in_x0 && w <= in_x1 && h >= in_y0 && h <= in_y1) continue;   // inside pass 1's box
     // reduce_mask_col/row, mv_kernel.cu:114-142 (strict >)
     const bool on = unit_range ? agg_exceeds_unit(cl, pmasks, mask_size, h, w)
                                : agg_at(cl, pmasks, mask_size, h, w) > kBinarizeThresh;
@@ -514,6 +576,16 @@ static inline int check_launch() { return cudaGetLastError() == cudaSuccess ? MN
 
 using namespace mnc;
 
+// 1 (default): coarse pass + exact border pass; 0: one full sweep of the region (A/B and
+// cross-check switch, mnc_mv_set_two_pass).  Identical results.
+static int g_mv_two_pass = 1;
+extern "C" int mnc_mv_set_two_pass(int on) {
+  const int prev = g_mv_two_pass;
+  g_mv_two_pass = on ? 1 : 0;
+  return prev;
+}
+extern "C" int mnc_mv_device_launches() { return g_mv_two_pass ? 5 : 4; }
+
 extern "C" int mnc_mv_device(const float* boxes, const float* masks, int nb, int box_dim,
                              int mask_size, const int* cand_inds, const float* cand_weights,
                              long long cand_img_stride, const int* cand_begin, const int* cand_end,
@@ -533,10 +605,15 @@ extern "C" int mnc_mv_device(const float* boxes, const float* masks, int nb, int
   mv_range_kernel<<<dim3(32, batch), 256, 0, stream>>>(
       masks, static_cast<long long>(nb) * mask_size * mask_size, cand_weights, cand_img_stride,
       cand_begin, cand_end, n_res, max_results, unit);
+  if (g_mv_two_pass) {
+    mv_aggregate_kernel<<<dim3(4, max_results, batch), 256, smem, stream>>>(
+        boxes, masks, nb, box_dim, mask_size, cand_inds, cand_weights, cand_img_stride, cand_begin,
+        cand_end, n_res, max_results, im_hw, unit, bbox_ws, 4, 0);
+  }
   const int chunks = 24;
   mv_aggregate_kernel<<<dim3(chunks, max_results, batch), 256, smem, stream>>>(
       boxes, masks, nb, box_dim, mask_size, cand_inds, cand_weights, cand_img_stride, cand_begin,
-      cand_end, n_res, max_results, im_hw, unit, bbox_ws);
+      cand_end, n_res, max_results, im_hw, unit, bbox_ws, 1, g_mv_two_pass);
   mv_finalize_kernel<<<dim3(max_results, batch), 256, smem, stream>>>(
       boxes, masks, nb, box_dim, mask_size, cand_inds, cand_weights, cand_img_stride, cand_begin,
       cand_end, n_res, max_results, im_hw, bbox_ws, out_mask, out_box);

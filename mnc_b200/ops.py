@@ -381,10 +381,17 @@ def mask_voting(boxes, masks, scores, im_hw, max_per_image=100, nms_thresh=0.3, 
                             ptr(cand_w), c_ll(max_results * nb), ptr(cand_begin), ptr(cand_end),
                             ptr(n_res), c_int(max_results), c_int(B), ptr(im_hw), ptr(bbox_ws),
                             ptr(out_mask), ptr(out_box), cur_stream()), "mnc_mv_device")
+    _lib.launch_count += lib.mnc_mv_device_launches() - 4      # the table books the 4-kernel form
     return dict(n_res=n_res, class_bar=class_bar, res_score=res_score, res_class=res_cls,
                 res_box_idx=res_idx, result_mask=out_mask, result_box=out_box,
                 cand_inds=cand_inds, cand_weights=cand_w, cand_begin=cand_begin, cand_end=cand_end,
                 overflow=overflow, order=order, keep=keep, num_keep=num)
+
+
+def mv_set_two_pass(on):
+    """A/B and cross-check switch of mnc_mv_device: False = one full sweep of each result's region
+    instead of the coarse pass + exact border pass.  Returns the previous setting."""
+    return bool(lib.mnc_mv_set_two_pass(c_int(1 if on else 0)))
 
 
 def mask_voting_checked(boxes, masks, scores, im_hw, max_per_image=100, box_valid=None, **kw):

@@ -93,3 +93,49 @@ def test_gpu_mask_voting_matches_oracle(nb, H, W, seed):
             assert np.array_equal(lb[c][:, 4], lb_o[c][:, 4])
             assert np.array_equal(lb[c][:, :4], lb_o[c][:, :4])
             assert util.rel_err(lm[c], lm_o[c]) < 1e-3
+
+
+@pytest.mark.parametrize("unit_range", [True, False])
+def test_mv_two_pass_equals_full_sweep(unit_range):
+    """mnc_mv_device's coarse pass + exact border pass (and, for masks in [0,1], the search region
+    cut down to the columns / rows whose covering weight can reach 0.4) gives the same tight boxes
+    and voted masks as one full sweep of the candidates' union region -- batched, blob-shaped and
+    noise masks, one image with nothing above the threshold."""
+    from mnc_b200 import ops
+    B, nb, H, W = 3, 300, 375, 500
+    rng = np.random.default_rng(77)
+    boxes = np.zeros((B, nb, 4), np.float32)
+    masks = np.zeros((B, nb, 1, 21, 21), np.float32)
+    scores = np.zeros((B, nb, 21), np.float32)
+    yy, xx = np.mgrid[0:21, 0:21]
+    for b in range(B):
+        bx, mk, sc = _voting_inputs(nb, H, W, 90 + b)
+        # clustered boxes (jittered copies of 12 objects) so that voting lists are long
+        src = rng.integers(0, 12, nb)
+        bx = bx[src] + rng.normal(0, 4, (nb, 4)).astype(np.float32)
+        bx[:, 0::2] = np.clip(np.sort(bx[:, 0::2], axis=1), 0, W - 1)
+        bx[:, 1::2] = np.clip(np.sort(bx[:, 1::2], axis=1), 0, H - 1)
+        if b == 0:      # blob masks: high in a centred ellipse, low outside
+            r = rng.uniform(5, 9, nb)[:, None, None]
+            mk = (1.0 / (1.0 + np.exp(((xx - 10) ** 2 + (yy - 10) ** 2) ** 0.5 - r)))[:, None].astype(np.float32)
+        elif b == 2:    # nothing ever exceeds the threshold
+            mk = np.full_like(mk, 0.2)
+        if not unit_range:
+            mk = mk * 1.3 - 0.15                     # values outside [0,1]: full-sum predicate
+        boxes[b], masks[b], scores[b] = bx, mk, sc
+    args = (torch.from_numpy(boxes).cuda(), torch.from_numpy(masks).cuda(),
+            torch.from_numpy(scores).cuda(),
+            torch.tensor([[H, W]] * B, dtype=torch.int32).cuda())
+    prev = ops.mv_set_two_pass(True)
+    try:
+        r2 = ops.mask_voting(*args)
+        ops.mv_set_two_pass(False)
+        r1 = ops.mask_voting(*args)
+    finally:
+        ops.mv_set_two_pass(prev)
+    n = r1["n_res"].cpu().numpy()
+    assert np.array_equal(n, r2["n_res"].cpu().numpy()) and n.min() > 5
+    assert torch.equal(r1["result_box"], r2["result_box"])
+    assert torch.equal(r1["result_mask"], r2["result_mask"])
+    rb = r1["result_box"][0, :n[0]].cpu().numpy()
+    assert (rb[:, 2] > rb[:, 0]).any()                # blob image: real (non-default) boxes
