@@ -325,6 +325,11 @@ def main():
                          "with its own activation buffers and CUDA graph over the shared weights)")
     ap.add_argument("--halo-single", action="store_true",
                     help="A/B: the halo kernel with one CTA per tile instead of CTA pairs")
+    ap.add_argument("--nms-matrix", action="store_true",
+                    help="A/B: proposal NMS through the n x n/64 suppression matrix (nms_mask + nms_scan) "
+                         "instead of the capped form")
+    ap.add_argument("--mv-full-sweep", action="store_true",
+                    help="A/B: mask voting finds the tight boxes by one full sweep instead of two passes")
     ap.add_argument("--dump-igemm", default=None,
                     help="write the ordered list of tensor-core launches of one step "
                          "(shape, algorithmic FLOPs / bytes) as JSON, for scripts/ncu_tc_summary.py")
@@ -355,6 +360,10 @@ def main():
         _eng.MNCEngine.HALO_TRI = False
     if args.halo_single:
         dense.set_halo_pair(0)
+    if args.nms_matrix:
+        ops.nms_set_lazy(False)
+    if args.mv_full_sweep:
+        ops.mv_set_two_pass(False)
     det = Detector(w, device=dev, max_batch=B, height=H, width=W, use_graph=not args.no_graph)
     eng = det.engine
     eng.overlap_heads = not args.no_overlap_heads
