@@ -634,7 +634,8 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None,
         "dtype": "f16+2xf8 (fp16 main product + two e4m3 correction products on tcgen05, fp32 "
-                 "accumulate, fp32-parity; Cout<=128 convs: bf16x3)",
+                 "accumulate, fp32-parity; conv1_1, K = 27: bf16x3)" if not args.halo_split else
+                 "f16+2xf8 (Cout > 128 convs, inner products), bf16x3 (Cout <= 128 convs)",
         "data": "synthetic", "config": workload_config(args, world),
         "e2e": {"value": e2e_pinned, "unit": "images/s", "h2d_bytes_per_step": det.h2d_bytes,
                 "d2h_bytes_per_step": det.d2h_bytes,

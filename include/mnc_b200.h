@@ -255,6 +255,9 @@ int mnc_roi_warp_nchw(const float* feat, int C, int H, int W, const float* rois,
  * channel pairs interleaved, packed fp32x2 arithmetic); 0 = per-tap gathers through L1 (round-1
  * kernel; other pooled sizes always use it).  Returns the previous value. */
 int mnc_roi_warp_set_stage(int on);
+/* Launch shape of the row-walk kernel: threads per CTA (multiple of 32, <= 256) and channels per
+ * CTA (default 128 / 32: every warp of the CTA owns planes; scripts/gpu_roi_walk_shape_ab.py). */
+int mnc_roi_warp_set_walk_shape(int threads, int channels_per_cta);
 /* Fused engine form (mnc_roi_warp_split / mnc_roi_warp_tri): 0 (default) = per-cell gathers,
  * 1 = row walk (bit-identical outputs, 2.5x fewer loads, measured no faster:
  * scripts/gpu_roi_rows_ab.py).  Returns the previous value. */

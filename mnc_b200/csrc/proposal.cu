@@ -178,22 +178,35 @@ __global__ void stage_bridge_kernel(const float* __restrict__ rois,
   ro[4] = o[3];
 }
 
-// Row softmax (Caffe order of operations), one thread per row, cols <= 64.
-__global__ void softmax_rows_kernel(const float* __restrict__ in, int in_stride, int rows,
-                                    int cols, float* __restrict__ out, int out_stride) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= rows) return;
+// Row softmax (softmax_layer.cu:86-120 order of operations), one WARP per row, cols <= 64: lanes
+// hold the columns (two each), the row maximum is a shuffle reduction (max is order-independent),
+// the exponentials are evaluated in parallel, and the denominator is accumulated in COLUMN ORDER
+// -- the order of the reference's channel-sum loop -- by every lane from shuffled values, so the
+// result equals the one-thread-per-row evaluation bit for bit while the 4 launches per step drop
+// from ~16 us (a serial chain of dependent global accesses) to launch latency.
+__global__ void __launch_bounds__(128)
+softmax_rows_kernel(const float* __restrict__ in, int in_stride, int rows, int cols,
+                    float* __restrict__ out, int out_stride) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;                       // warp-uniform
   const float* x = in + static_cast<long long>(r) * in_stride;
   float* y = out + static_cast<long long>(r) * out_stride;
-  float m = x[0];
-  for (int c = 1; c < cols; ++c) m = fmaxf(m, x[c]);
+  const bool ok0 = lane < cols, ok1 = lane + 32 < cols;
+  const float x0 = ok0 ? x[lane] : 0.f, x1 = ok1 ? x[lane + 32] : 0.f;
+  const float kNegInf = __int_as_float(0xff800000);
+  float m = fmaxf(ok0 ? x0 : kNegInf, ok1 ? x1 : kNegInf);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  const float e0 = ok0 ? expf(__fsub_rn(x0, m)) : 0.f;
+  const float e1 = ok1 ? expf(__fsub_rn(x1, m)) : 0.f;
   float s = 0.f;
   for (int c = 0; c < cols; ++c) {
-    const float e = expf(__fsub_rn(x[c], m));
-    y[c] = e;
-    s = __fadd_rn(s, e);
+    const float v = __shfl_sync(0xffffffffu, c < 32 ? e0 : e1, c & 31);
+    s = __fadd_rn(s, v);
   }
-  for (int c = 0; c < cols; ++c) y[c] = __fdiv_rn(y[c], s);
+  if (ok0) y[lane] = __fdiv_rn(e0, s);
+  if (ok1) y[lane + 32] = __fdiv_rn(e1, s);
 }
 
 // boxes_out[i] = clip(rois[i][1:5] / im_scale, im_shape)  -- tools/demo.py:92-95
@@ -328,7 +341,8 @@ extern "C" int mnc_stage_bridge(const float* rois, const float* bbox_pred, int b
 extern "C" int mnc_softmax_rows(const float* in, int in_stride, int rows, int cols, float* out,
                                 int out_stride, void* stream) {
   if (rows <= 0) return MNC_OK;
-  softmax_rows_kernel<<<(rows + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  if (cols <= 0 || cols > 64) return MNC_ERR_ARG;
+  softmax_rows_kernel<<<(rows + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(
       in, in_stride, rows, cols, out, out_stride);
   return check_launch();
 }

@@ -386,7 +386,8 @@ roi_warp_rowwalk_kernel(const float* __restrict__ feat, int C, int H, int W,
   __syncthreads();
   const int HW = H * W;
   const int nch = min(ch_per_cta, C - cbase);
-  for (int c = (warp * PPW + sub) * CH; c < nch; c += 8 * PPW * CH) {
+  const int nwarps = blockDim.x >> 5;
+  for (int c = (warp * PPW + sub) * CH; c < nch; c += nwarps * PPW * CH) {
     const float* plane = feat + (static_cast<long long>(g.level) * C + cbase + c) * HW;
     float* o = out + (static_cast<long long>(r) * C + cbase + c) * PP + pw;
     int koff[CH];                                   // plane offsets (a channel tail re-reads plane 0)
@@ -1162,6 +1163,16 @@ extern "C" int mnc_roi_warp_set_stage(int on) {
   return prev;
 }
 
+static int g_roi_walk_threads = 128, g_roi_walk_cpc = 32;
+// A/B knob of the row-walk ROIWarping kernel: threads per CTA (multiple of 32, <= 256) and
+// channels per CTA.
+extern "C" int mnc_roi_warp_set_walk_shape(int threads, int channels_per_cta) {
+  if (threads < 32 || threads > 256 || threads % 32 || channels_per_cta < 4) return MNC_ERR_ARG;
+  g_roi_walk_threads = threads;
+  g_roi_walk_cpc = channels_per_cta;
+  return MNC_OK;
+}
+
 extern "C" int mnc_roi_warp_nchw(const float* feat, int C, int H, int W, const float* rois, int R,
                                  int pooled_h, int pooled_w, float spatial_scale, float* out,
                                  void* stream) {
@@ -1175,12 +1186,16 @@ extern "C" int mnc_roi_warp_nchw(const float* feat, int C, int H, int W, const f
   const bool stage = g_roi_stage && (reinterpret_cast<uintptr_t>(out) % 16 == 0) &&
                      static_cast<long long>(H) * W * 5 <= kStageFloats;
   if (g_roi_stage == 2 && pooled_h == pooled_w && (pooled_h == 28 || pooled_h == 14)) {
-    const int cpc = 32;
+    // one pass of the CTA's warps covers threads/32 * (planes per warp) channels: 32 channels per
+    // CTA = 4 warps (28x28: 8 planes per lane; 14x14: 2 plane groups x 4), so 128 threads keep
+    // every warp of the CTA busy (with 256, half of them only waited at the barrier and held
+    // their scheduler slots until the CTA retired)
+    const int cpc = g_roi_walk_cpc, threads = g_roi_walk_threads;
     dim3 wgrid(R, (C + cpc - 1) / cpc);
     if (pooled_h == 28)
-      roi_warp_rowwalk_kernel<28><<<wgrid, 256, 0, s>>>(feat, C, H, W, rois, spatial_scale, cpc, out);
+      roi_warp_rowwalk_kernel<28><<<wgrid, threads, 0, s>>>(feat, C, H, W, rois, spatial_scale, cpc, out);
     else
-      roi_warp_rowwalk_kernel<14><<<wgrid, 256, 0, s>>>(feat, C, H, W, rois, spatial_scale, cpc, out);
+      roi_warp_rowwalk_kernel<14><<<wgrid, threads, 0, s>>>(feat, C, H, W, rois, spatial_scale, cpc, out);
     return check_launch();
   }
   // (14x14: 784 taps per channel against a ~440-float window -- staging does not pay, measured)
