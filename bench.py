@@ -328,6 +328,8 @@ def main():
     ap.add_argument("--nms-matrix", action="store_true",
                     help="A/B: proposal NMS through the n x n/64 suppression matrix (nms_mask + nms_scan) "
                          "instead of the capped form")
+    ap.add_argument("--nms-single-cta", action="store_true",
+                    help="A/B: the capped proposal NMS on one CTA per image instead of a cluster of 8")
     ap.add_argument("--mv-full-sweep", action="store_true",
                     help="A/B: mask voting finds the tight boxes by one full sweep instead of two passes")
     ap.add_argument("--dump-igemm", default=None,
@@ -361,7 +363,9 @@ def main():
     if args.halo_single:
         dense.set_halo_pair(0)
     if args.nms_matrix:
-        ops.nms_set_lazy(False)
+        ops.nms_set_lazy(0)
+    if args.nms_single_cta:
+        ops.nms_set_lazy(1)
     if args.mv_full_sweep:
         ops.mv_set_two_pass(False)
     det = Detector(w, device=dev, max_batch=B, height=H, width=W, use_graph=not args.no_graph)

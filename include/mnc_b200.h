@@ -179,9 +179,11 @@ int mnc_nms_sorted(const float* boxes, int box_stride, long long problem_stride,
                    int* keep_out, int keep_stride, int* num_out, void* stream);
 /* When max_keep is small against n_max (n_max >= 1024, max_keep <= 2048, 4*max_keep <= n_max: the
  * ProposalLayer's 6000 -> 300, lib/pylayer/proposal_layer.py:147-152) mnc_nms_sorted runs a capped
- * greedy NMS that never builds the suppression matrix (one CTA per problem, kept boxes in shared
- * memory; workspace unused) -- same keep list.  mnc_nms_set_lazy(0) forces the mask + scan pair
- * (cross-check / A-B switch); returns the previous setting. */
+ * greedy NMS that never builds the suppression matrix (candidates walked in blocks of 64 against
+ * the kept boxes held in shared memory; workspace unused) -- same keep list.
+ * mnc_nms_set_lazy(mode): 2 (default) = a thread-block cluster of 8 CTAs per problem, 1 = one CTA
+ * per problem, 0 = always the mask + scan pair (cross-check / A-B switch); returns the previous
+ * mode. */
 int mnc_nms_set_lazy(int on);
 /* number of kernels mnc_nms_sorted launches for these sizes (1: capped form, 2: mask + scan) */
 int mnc_nms_sorted_launches(int n_max, int max_keep);

@@ -395,6 +395,18 @@ mv_finalize_kernel(const float* __restrict__ boxes, const float* __restrict__ ma
 // One CTA per image.  From the per-class NMS keep lists pick the global score threshold
 // (mask_transform.py:242-244) and enumerate result instances in (class, score-rank) order
 // (:253-270).  kept entry e = (class c, k): original box index = order[c][keep[c][k]].
+//   1. all entries gathered in one round (keep -> order -> score: three dependent loads, every
+//      entry in flight at once instead of class by class);
+//   2. thresh = the min(total, max_per_image)-th largest score by a 4-pass byte-wise radix select on
+//      order-preserving keys (an all-pairs rank count was 2000 x 2000 compares on one SM);
+//   3. entries with score >= thresh are emitted in entry order by a ballot / prefix-count
+//      compaction (was a 2000-step loop of one thread); class_bar[p] = results before the end of
+//      class p's entries.
+__device__ __forceinline__ uint32_t vote_sort_key(float f) {
+  const uint32_t b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
 __global__ void __launch_bounds__(1024)
 vote_select_kernel(const float* __restrict__ scores, int nb, int ncls,
                    const int* __restrict__ order, const int* __restrict__ keep, int keep_stride,
@@ -408,12 +420,16 @@ vote_select_kernel(const float* __restrict__ scores, int nb, int ncls,
   const int cap = nprob * max_per_image;
   float* s_score = reinterpret_cast<float*>(smraw);      // cap
   int* s_orig = reinterpret_cast<int*>(s_score + cap);    // cap
-  int* s_flag = s_orig + cap;                             // cap
-  int* s_off = s_flag + cap;                              // nprob + 1
+  int* s_pref = s_orig + cap;                             // cap: class of the entry, later the
+                                                          //      number of flagged entries before it
+  int* s_off = s_pref + cap;                              // nprob + 1
   __shared__ float s_thresh;
-  __shared__ int s_total;
+  __shared__ int s_total, s_need, s_run;
+  __shared__ uint32_t s_prefix, s_hist[256];
+  __shared__ int s_warp[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* pscores = scores + static_cast<long long>(img) * nb * ncls;
-  if (threadIdx.x == 0) {
+  if (tid == 0) {
     int off = 0;
     for (int p = 0; p < nprob; ++p) {
       s_off[p] = off;
@@ -421,65 +437,91 @@ vote_select_kernel(const float* __restrict__ scores, int nb, int ncls,
     }
     s_off[nprob] = off;
     s_total = off;
+    s_run = 0;
   }
   __syncthreads();
   const int total = s_total;
-  for (int p = 0; p < nprob; ++p) {
-    const int prob = img * nprob + p;
-    const int cnt = s_off[p + 1] - s_off[p];
-    for (int k = threadIdx.x; k < cnt; k += blockDim.x) {
-      const int pos = keep[static_cast<long long>(prob) * keep_stride + k];
-      const int orig = order[static_cast<long long>(prob) * nb + pos];
-      s_orig[s_off[p] + k] = orig;
-      s_score[s_off[p] + k] = pscores[static_cast<long long>(orig) * ncls + (p + 1)];
-    }
-  }
-  __syncthreads();
   if (total == 0) {
-    if (threadIdx.x == 0) {
-      n_res[img] = 0;
-      for (int p = 0; p < nprob; ++p) class_bar[img * nprob + p] = 0;
-    }
+    if (tid == 0) n_res[img] = 0;
+    for (int p = tid; p < nprob; p += blockDim.x) class_bar[img * nprob + p] = 0;
     return;
   }
-  // thresh = sorted_desc[min(total, max_per_image) - 1]
-  const int want = min(total, max_per_image) - 1;
-  for (int e = threadIdx.x; e < total; e += blockDim.x) {
-    const float se = s_score[e];
-    int rank = 0;
-    for (int j = 0; j < total; ++j) {
-      const float sj = s_score[j];
-      rank += (sj > se || (sj == se && j < e)) ? 1 : 0;
-    }
-    if (rank == want) s_thresh = se;
+  for (int e = tid; e < total; e += blockDim.x) {
+    int p = 0;
+    while (e >= s_off[p + 1]) ++p;                        // class of entry e (nprob <= 20 steps)
+    const int prob = img * nprob + p;
+    const int pos = keep[static_cast<long long>(prob) * keep_stride + (e - s_off[p])];
+    const int orig = order[static_cast<long long>(prob) * nb + pos];
+    s_orig[e] = orig;
+    s_pref[e] = p;
+    s_score[e] = pscores[static_cast<long long>(orig) * ncls + (p + 1)];
   }
+  if (tid == 0) {
+    s_prefix = 0u;
+    s_need = min(total, max_per_image);                   // thresh = the s_need-th largest score
+  }
+  __syncthreads();
+  for (int pass = 3; pass >= 0; --pass) {
+    if (tid < 256) s_hist[tid] = 0u;
+    __syncthreads();
+    const uint32_t prefix = s_prefix;
+    const int sh = 8 * pass;
+    for (int e = tid; e < total; e += blockDim.x) {
+      const uint32_t key = vote_sort_key(s_score[e]);
+      if (pass == 3 || (key >> (sh + 8)) == (prefix >> (sh + 8))) atomicAdd(&s_hist[(key >> sh) & 255u], 1u);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int need = s_need, cum = 0, bin = 255;
+      for (; bin > 0; --bin) {
+        if (cum + static_cast<int>(s_hist[bin]) >= need) break;
+        cum += s_hist[bin];
+      }
+      s_prefix = prefix | (static_cast<uint32_t>(bin) << sh);
+      s_need = need - cum;
+    }
+    __syncthreads();
+  }
+  const uint32_t tkey = s_prefix;
+  for (int e = tid; e < total; e += blockDim.x)
+    if (vote_sort_key(s_score[e]) == tkey) s_thresh = s_score[e];   // same bits from every writer
   __syncthreads();
   const float thresh = s_thresh;
-  for (int e = threadIdx.x; e < total; e += blockDim.x) s_flag[e] = (s_score[e] >= thresh) ? 1 : 0;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int t = 0, p = 0;
-    int ovf = 0;
-    for (int e = 0; e < total; ++e) {
-      while (e >= s_off[p + 1]) {
-        class_bar[img * nprob + p] = t;
-        ++p;
-      }
-      if (s_flag[e]) {
-        if (t < max_results) {
-          res_box_idx[img * max_results + t] = s_orig[e];
-          res_class[img * max_results + t] = p + 1;
-          res_score[img * max_results + t] = s_score[e];
-          ++t;
-        } else {
-          ovf = 1;
-        }
+  // compaction in entry order; results beyond max_results are dropped and reported
+  for (int base = 0; base < total; base += blockDim.x) {
+    const int e = base + tid;
+    const bool flag = e < total && s_score[e] >= thresh;
+    const int cls = e < total ? s_pref[e] + 1 : 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, flag);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    int t = s_run;
+    for (int w = 0; w < warp; ++w) t += s_warp[w];
+    t += __popc(bal & ((1u << lane) - 1u));
+    if (e < total) s_pref[e] = t;                         // flagged entries before e
+    if (flag) {
+      if (t < max_results) {
+        res_box_idx[img * max_results + t] = s_orig[e];
+        res_class[img * max_results + t] = cls;
+        res_score[img * max_results + t] = s_score[e];
+      } else {
+        atomicExch(overflow, 1);
       }
     }
-    for (; p < nprob; ++p) class_bar[img * nprob + p] = t;
-    n_res[img] = t;
-    if (ovf) atomicExch(overflow, 1);
+    __syncthreads();
+    if (tid == 0) {
+      int tot = 0;
+      for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) tot += s_warp[w];
+      s_run += tot;
+    }
+    __syncthreads();
   }
+  const int flagged = s_run;
+  for (int p = tid; p < nprob; p += blockDim.x) {
+    const int end = s_off[p + 1];
+    class_bar[img * nprob + p] = min(end < total ? s_pref[end] : flagged, max_results);
+  }
+  if (tid == 0) n_res[img] = min(flagged, max_results);
 }
 
 // grid (max_results, batch), kMaxBoxes threads.  For result t with query box q = boxes[res_box_idx]:

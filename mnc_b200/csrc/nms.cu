@@ -11,6 +11,7 @@
 //    from device memory (counts are data dependent: they come from the min-size filter).
 // Semantics kept exactly: IoU with the +1 convention, suppress when IoU > thresh (strict),
 // boxes visited in the given (score-sorted) order.
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdlib>
@@ -192,6 +193,20 @@ __device__ __forceinline__ bool nms_suppresses(const float* a, const float (&cb)
   const bool disjoint = (min(a[2], cb[2]) - max(a[0], cb[0]) + 1 <= 0.f) ||
                         (min(a[3], cb[3]) - max(a[1], cb[1]) + 1 <= 0.f);
   if (disjoint && !(thresh < 0.f)) return false;   // interS == 0: 0 / x > thresh is false
+  // Decide devIoU(a, cb) > thresh without the IEEE division whenever the answer is not within
+  // rounding of the threshold: q = fl(I / U) differs from I / U by at most 2^-24 relative, so
+  // I > t*U*(1 + 1e-6) implies q > t and I < t*U*(1 - 1e-6) implies q < t (the margin also covers
+  // the rounding of t*U and of U itself).  Everything else -- U <= 0, NaNs, a ratio within 1e-6 of
+  // the threshold -- takes the reference expression, so the decision is always devIoU's.
+  const float width = max(min(a[2], cb[2]) - max(a[0], cb[0]) + 1, 0.f);
+  const float height = max(min(a[3], cb[3]) - max(a[1], cb[1]) + 1, 0.f);
+  const float inter = width * height;
+  const float uni = (a[2] - a[0] + 1) * (a[3] - a[1] + 1) + (cb[2] - cb[0] + 1) * (cb[3] - cb[1] + 1) - inter;
+  if (uni > 0.f && thresh >= 0.f) {
+    const float tu = thresh * uni;
+    if (inter > tu * 1.000001f) return true;
+    if (inter < tu * 0.999999f) return false;
+  }
   return dev_iou(a, cb) > thresh;
 }
 
@@ -280,9 +295,120 @@ nms_lazy_kernel(const float* __restrict__ boxes, int box_stride, long long probl
   if (tid == 0) num_out[prob] = s_num;
 }
 
+// The same walk spread over a thread-block CLUSTER of 8 CTAs (8 SMs) per problem: phase A is
+// compute-bound on one SM (64 x kept pair tests per block; 349 us for 8 x 6000 -> 300 with heavy
+// suppression, profiles/r02c_launches_summary.txt), so each CTA tests the block's 64 candidates
+// against every 8th part of the kept list and builds 8 of the 64 diagonal rows; the suppression
+// bits are OR-ed into, and the diagonal words stored to, EVERY CTA's shared memory through
+// distributed shared memory (double-buffered by block parity), one cluster barrier publishes them,
+// and then every CTA runs the same serial resolve on the same words -- so each keeps an identical
+// kept list locally and nothing has to be broadcast back.  CTA 0 writes the result.
+namespace cg = cooperative_groups;
+constexpr int kLazyClusterSize = 8;
+constexpr int kLazyClusterThreads = 256;
+constexpr int kLazyClusterGroups = kLazyClusterThreads / 64;   // warp pairs per CTA
+
+__global__ void __cluster_dims__(kLazyClusterSize, 1, 1) __launch_bounds__(kLazyClusterThreads)
+nms_lazy_cluster_kernel(const float* __restrict__ boxes, int box_stride, long long problem_stride,
+                        const int* __restrict__ counts, int n_max, float thresh, int max_keep,
+                        int* __restrict__ keep_out, int keep_stride, int* __restrict__ num_out) {
+  constexpr int S = kLazyClusterSize, G = kLazyClusterGroups;
+  constexpr int kRowsPerCta = 64 / S, kRowsPerGroup = kRowsPerCta / G;
+  static_assert(kRowsPerGroup >= 1 && kRowsPerGroup * G * S == 64, "diagonal rows must tile");
+  extern __shared__ float4 kept_box[];             // max_keep entries (every CTA holds the full list)
+  int* kept_idx = reinterpret_cast<int*>(kept_box + max_keep);   // their positions (written out at the end:
+                                                   // cluster.sync() carries a GPU-scope fence, which
+                                                   // would wait for global stores issued in the loop)
+  __shared__ float4 cand[2][64];
+  __shared__ uint32_t sup_bits[2][2];              // [block parity][half]
+  __shared__ uint32_t diag_half[2][64][2];         // [block parity][row][half]
+  __shared__ int s_num;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = static_cast<int>(cluster.block_rank());
+  const int prob = blockIdx.x / S;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int half = warp & 1, grp = warp >> 1;
+  const int c = half * 32 + lane;
+  const int n = min(counts ? counts[prob] : n_max, n_max);
+  const float* pb = boxes + prob * problem_stride;
+  int* keep = keep_out + static_cast<long long>(prob) * keep_stride;
+  if (tid == 0) {
+    s_num = 0;
+    sup_bits[0][0] = sup_bits[0][1] = sup_bits[1][0] = sup_bits[1][1] = 0u;
+  }
+  if (tid < 64) {
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid < n) {
+      const float* s = pb + static_cast<long long>(tid) * box_stride;
+      b = make_float4(s[0], s[1], s[2], s[3]);
+    }
+    cand[0][tid] = b;
+  }
+  cluster.sync();                                  // every CTA's words are zeroed before any peer ORs into them
+  const int blocks = (n + 63) / 64;
+  for (int blk = 0; blk < blocks; ++blk) {
+    const int r0 = blk * 64, buf = blk & 1;
+    const int num = s_num;
+    float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool fetch = grp == G - 1 && blk + 1 < blocks;
+    if (fetch && r0 + 64 + c < n) {
+      const float* s = pb + static_cast<long long>(r0 + 64 + c) * box_stride;
+      nxt = make_float4(s[0], s[1], s[2], s[3]);
+    }
+    // ---- phase A: this CTA's share of the kept list and of the diagonal rows
+    const float4 cv = cand[buf][c];
+    const float cb[4] = {cv.x, cv.y, cv.z, cv.w};
+    const bool c_ok = r0 + c < n;
+    bool sup = false;
+    for (int k = rank * G + grp; k < num; k += S * G)
+      sup |= nms_suppresses(reinterpret_cast<const float*>(&kept_box[k]), cb, thresh);
+    const uint32_t sb = __ballot_sync(0xffffffffu, sup && c_ok);
+    if (sb && lane < S) atomicOr(cluster.map_shared_rank(&sup_bits[buf][half], lane), sb);
+#pragma unroll
+    for (int q = 0; q < kRowsPerGroup; ++q) {
+      const int i = rank * kRowsPerCta + grp * kRowsPerGroup + q;
+      bool s = false;
+      if (c_ok && c > i) s = nms_suppresses(reinterpret_cast<const float*>(&cand[buf][i]), cb, thresh);
+      const uint32_t bits = __ballot_sync(0xffffffffu, s);
+      if (lane < S) *cluster.map_shared_rank(&diag_half[buf][i][half], lane) = bits;
+    }
+    if (fetch) cand[buf ^ 1][c] = nxt;
+    cluster.sync();                                // remote ORs / stores of this block are visible
+    // ---- phase B: the same serial resolve in every CTA
+    if (tid == 0) {
+      unsigned long long cur = static_cast<unsigned long long>(sup_bits[buf][0]) |
+                               (static_cast<unsigned long long>(sup_bits[buf][1]) << 32);
+      const int rows = min(64, n - r0);
+      const unsigned long long rowmask = rows == 64 ? ~0ull : ((1ull << rows) - 1ull);
+      unsigned long long avail = ~cur & rowmask;
+      int nk = num;
+      while (avail && nk < max_keep) {
+        const int i = __ffsll(static_cast<long long>(avail)) - 1;
+        kept_idx[nk] = r0 + i;
+        kept_box[nk] = cand[buf][i];
+        ++nk;
+        cur |= static_cast<unsigned long long>(diag_half[buf][i][0]) |
+               (static_cast<unsigned long long>(diag_half[buf][i][1]) << 32);
+        avail = ~cur & rowmask & ~((2ull << i) - 1ull);
+      }
+      s_num = nk;
+      // this parity's words are next written by peers in block blk + 2, i.e. after they passed the
+      // barrier of block blk + 1, which this CTA reaches only after this reset
+      sup_bits[buf][0] = sup_bits[buf][1] = 0u;
+    }
+    __syncthreads();
+    if (s_num >= max_keep) break;                  // identical in every CTA of the cluster
+  }
+  if (rank == 0) {
+    const int num = s_num;
+    for (int i = tid; i < num; i += blockDim.x) keep[i] = kept_idx[i];
+    if (tid == 0) num_out[prob] = num;
+  }
+}
+
 // 1: mnc_nms_sorted uses nms_lazy_kernel when max_keep is small against n (default); 0: always the
 // mask + scan pair (A/B and cross-check switch, mnc_nms_set_lazy).
-static int g_nms_lazy = 1;
+static int g_nms_lazy = 2;           // 2: the cluster form of the capped NMS (default), 1: one CTA per problem
 constexpr int kLazyMaxKeep = 2048;   // kept boxes in shared memory: 32 KB
 constexpr int kLazyMinN = 1024;
 
@@ -556,6 +682,13 @@ extern "C" int mnc_nms_sorted(const float* boxes, int box_stride, long long prob
   const int col_blocks = (n_max + 63) / 64;
   if (col_blocks * 8 > 48 * 1024) return MNC_ERR_ARG;
   if (max_keep <= 0 || max_keep > n_max) max_keep = n_max;
+  if (nms_takes_lazy_path(n_max, max_keep) && g_nms_lazy == 2) {
+    nms_lazy_cluster_kernel<<<problems * kLazyClusterSize, kLazyClusterThreads,
+                              max_keep * (sizeof(float4) + sizeof(int)), stream>>>(
+        boxes, box_stride, problem_stride, counts, n_max, thresh, max_keep, keep_out, keep_stride,
+        num_out);
+    return check_launch();
+  }
   if (nms_takes_lazy_path(n_max, max_keep)) {
     nms_lazy_kernel<<<problems, kLazyThreads, max_keep * sizeof(float4), stream>>>(
         boxes, box_stride, problem_stride, counts, n_max, thresh, max_keep, keep_out, keep_stride,
@@ -582,7 +715,7 @@ extern "C" int mnc_nms_sorted_launches(int n_max, int max_keep) {
 
 extern "C" int mnc_nms_set_lazy(int on) {
   const int prev = g_nms_lazy;
-  g_nms_lazy = on ? 1 : 0;
+  g_nms_lazy = on < 0 ? 0 : (on > 2 ? 2 : on);
   return prev;
 }
 

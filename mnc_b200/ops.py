@@ -84,10 +84,12 @@ def nms_sorted(boxes, counts, thresh, max_keep):
     return keep, num
 
 
-def nms_set_lazy(on):
-    """A/B and cross-check switch: False forces the suppression-matrix NMS (nms_mask + nms_scan)
-    where mnc_nms_sorted would pick the capped form.  Returns the previous setting."""
-    return bool(lib.mnc_nms_set_lazy(c_int(1 if on else 0)))
+def nms_set_lazy(mode):
+    """A/B and cross-check switch of the capped NMS mnc_nms_sorted picks when max_keep << n:
+    2 / True = thread-block-cluster form (default), 1 = one CTA per problem, 0 / False = always the
+    suppression-matrix pair (nms_mask + nms_scan).  Returns the previous mode (int)."""
+    mode = 2 if mode is True else (0 if mode is False else int(mode))
+    return int(lib.mnc_nms_set_lazy(c_int(mode)))
 
 
 # ----------------------------------------------------------------------------- proposal pieces
