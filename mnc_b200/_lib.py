@@ -34,15 +34,16 @@ c_ll = ctypes.c_longlong
 c_float = ctypes.c_float
 
 
-# kernels launched by each C-ABI entry point (for bench.py's `gpu_launches` claim)
-# (checked against the ncu launch list of a bench step, profiles/r02_launches_*.csv)
-_LAUNCHES = {"mnc_nms_sorted": 2, "mnc_mv_device": 4}
+# kernels launched by each C-ABI entry point (for bench.py's `gpu_launches` claim; checked against
+# the ncu launch list of a bench step, profiles/r02c_launches.csv).  Entry points whose kernel count
+# depends on their arguments report it themselves (`launches=`: mnc_nms_sorted_launches,
+# mnc_mv_device_launches).
 launch_count = 0
 
 
-def check(rc, what):
+def check(rc, what, launches=1):
     global launch_count
-    launch_count += _LAUNCHES.get(what, 1)
+    launch_count += launches
     if rc != MNC_OK:
         detail = ""
         if rc == 2:

@@ -7,7 +7,6 @@ import ctypes
 
 import torch
 
-from . import _lib
 from ._lib import lib, ptr, cur_stream, check, c_int, c_ll, c_float
 
 c_double = ctypes.c_double
@@ -78,9 +77,8 @@ def nms_sorted(boxes, counts, thresh, max_keep):
     num = _i32(problems, device=dev)
     check(lib.mnc_nms_sorted(ptr(boxes), c_int(stride), c_ll(n_max * stride), ptr(counts),
                              c_int(n_max), c_int(problems), c_float(thresh), c_int(mk), ptr(ws),
-                             ptr(keep), c_int(mk), ptr(num), cur_stream()), "mnc_nms_sorted")
-    # the launch-count table books 2 kernels (mask + scan); the capped form is a single launch
-    _lib.launch_count -= 2 - lib.mnc_nms_sorted_launches(c_int(n_max), c_int(mk))
+                             ptr(keep), c_int(mk), ptr(num), cur_stream()), "mnc_nms_sorted",
+          launches=lib.mnc_nms_sorted_launches(c_int(n_max), c_int(mk)))
     return keep, num
 
 
@@ -382,8 +380,8 @@ def mask_voting(boxes, masks, scores, im_hw, max_per_image=100, nms_thresh=0.3, 
     check(lib.mnc_mv_device(ptr(boxes), ptr(masks), c_int(nb), c_int(4), c_int(M), ptr(cand_inds),
                             ptr(cand_w), c_ll(max_results * nb), ptr(cand_begin), ptr(cand_end),
                             ptr(n_res), c_int(max_results), c_int(B), ptr(im_hw), ptr(bbox_ws),
-                            ptr(out_mask), ptr(out_box), cur_stream()), "mnc_mv_device")
-    _lib.launch_count += lib.mnc_mv_device_launches() - 4      # the table books the 4-kernel form
+                            ptr(out_mask), ptr(out_box), cur_stream()), "mnc_mv_device",
+          launches=lib.mnc_mv_device_launches())
     return dict(n_res=n_res, class_bar=class_bar, res_score=res_score, res_class=res_cls,
                 res_box_idx=res_idx, result_mask=out_mask, result_box=out_box,
                 cand_inds=cand_inds, cand_weights=cand_w, cand_begin=cand_begin, cand_end=cand_end,
