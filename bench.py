@@ -330,6 +330,9 @@ def main():
                          "instead of the capped form")
     ap.add_argument("--nms-single-cta", action="store_true",
                     help="A/B: the capped proposal NMS on one CTA per image instead of a cluster of 8")
+    ap.add_argument("--nms-mode", type=int, default=None, choices=[0, 1, 2, 3],
+                    help="A/B: capped proposal NMS form (3: cluster, 256-candidate rounds; 2: cluster, "
+                         "64-candidate rounds; 1: one CTA per image; 0: suppression matrix)")
     ap.add_argument("--mv-full-sweep", action="store_true",
                     help="A/B: mask voting finds the tight boxes by one full sweep instead of two passes")
     ap.add_argument("--dump-igemm", default=None,
@@ -366,6 +369,8 @@ def main():
         ops.nms_set_lazy(0)
     if args.nms_single_cta:
         ops.nms_set_lazy(1)
+    if args.nms_mode is not None:
+        ops.nms_set_lazy(args.nms_mode)
     if args.mv_full_sweep:
         ops.mv_set_two_pass(False)
     det = Detector(w, device=dev, max_batch=B, height=H, width=W, use_graph=not args.no_graph)

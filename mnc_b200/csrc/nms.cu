@@ -406,6 +406,135 @@ nms_lazy_cluster_kernel(const float* __restrict__ boxes, int box_stride, long lo
   }
 }
 
+// 256 candidates per round instead of 64 (mode 3).  The 64-candidate cluster form spends ~2 us per
+// round, most of it in the cluster barrier (a GPU-scope fence) and the hand-over to the serial
+// resolve -- 94 rounds for 6000 candidates; with 256-candidate rounds there are 24.  One thread per
+// candidate (256 threads per CTA, 8 suppression words per row): each CTA tests all 256 candidates
+// against every 8th kept box and builds 32 of the 256 diagonal rows (warps whose candidates all
+// precede a row skip it: the matrix is strictly upper triangular); its 1 KB slab of diagonal words
+// goes to the 7 peers with 16-byte distributed-shared-memory stores, suppression bits by remote
+// atomic OR; then the same serial resolve in every CTA, now over 8 words.
+constexpr int kWideBlock = 256;                  // candidates per round
+constexpr int kWideWords = kWideBlock / 32;      // suppression words per row
+constexpr int kWideRowsPerCta = kWideBlock / kLazyClusterSize;
+constexpr int kWideMaxKeep = 1024;               // 24.1 KB static + 20 B per kept box <= 48 KB
+
+__global__ void __cluster_dims__(kLazyClusterSize, 1, 1) __launch_bounds__(kWideBlock)
+nms_lazy_cluster_wide_kernel(const float* __restrict__ boxes, int box_stride, long long problem_stride,
+                             const int* __restrict__ counts, int n_max, float thresh, int max_keep,
+                             int* __restrict__ keep_out, int keep_stride, int* __restrict__ num_out) {
+  constexpr int S = kLazyClusterSize, CB = kWideBlock, NW = kWideWords, RPC = kWideRowsPerCta;
+  static_assert(CB == 256 && NW == 8 && RPC == 32, "one warp per suppression word, 32 rows per CTA");
+  extern __shared__ float4 kept_box[];             // max_keep entries (every CTA holds the full list)
+  int* kept_idx = reinterpret_cast<int*>(kept_box + max_keep);
+  __shared__ float4 cand[2][CB];
+  __shared__ __align__(16) uint32_t sup_bits[2][NW];      // [round parity][word]
+  __shared__ __align__(16) uint32_t diag[2][CB][NW];      // [round parity][row][word]
+  __shared__ int s_num;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = static_cast<int>(cluster.block_rank());
+  const int prob = blockIdx.x / S;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int c = tid;                               // this thread's candidate within the round
+  const int n = min(counts ? counts[prob] : n_max, n_max);
+  const float* pb = boxes + prob * problem_stride;
+  int* keep = keep_out + static_cast<long long>(prob) * keep_stride;
+  if (tid == 0) s_num = 0;
+  if (tid < 2 * NW) (&sup_bits[0][0])[tid] = 0u;
+  {
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < n) {
+      const float* s = pb + static_cast<long long>(c) * box_stride;
+      b = make_float4(s[0], s[1], s[2], s[3]);
+    }
+    cand[0][c] = b;
+  }
+  cluster.sync();                                  // every CTA's words are zeroed before any peer ORs into them
+  const int rounds = (n + CB - 1) / CB;
+  for (int blk = 0; blk < rounds; ++blk) {
+    const int r0 = blk * CB, buf = blk & 1;
+    const int num = s_num;
+    float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool fetch = blk + 1 < rounds;
+    if (fetch && r0 + CB + c < n) {
+      const float* s = pb + static_cast<long long>(r0 + CB + c) * box_stride;
+      nxt = make_float4(s[0], s[1], s[2], s[3]);
+    }
+    // ---- phase A: every 8th kept box, and 32 of the 256 diagonal rows
+    const float4 cv = cand[buf][c];
+    const float cb[4] = {cv.x, cv.y, cv.z, cv.w};
+    const bool c_ok = r0 + c < n;
+    bool sup = false;
+    for (int k = rank; k < num; k += S)
+      sup |= nms_suppresses(reinterpret_cast<const float*>(&kept_box[k]), cb, thresh);
+    const uint32_t sb = __ballot_sync(0xffffffffu, sup && c_ok);
+    if (sb && lane < S) atomicOr(cluster.map_shared_rank(&sup_bits[buf][warp], lane), sb);
+    const int row0 = rank * RPC;
+    for (int q = 0; q < RPC; ++q) {
+      const int i = row0 + q;
+      uint32_t bits = 0u;
+      if (i < 32 * warp + 31) {                    // warp-uniform: some candidate of this warp follows row i
+        bool s = false;
+        if (c_ok && c > i) s = nms_suppresses(reinterpret_cast<const float*>(&cand[buf][i]), cb, thresh);
+        bits = __ballot_sync(0xffffffffu, s);
+      }
+      if (lane == 0) diag[buf][i][warp] = bits;
+    }
+    if (fetch) cand[buf ^ 1][c] = nxt;
+    __syncthreads();                               // this CTA's slab of diagonal words is complete
+    {
+      // slab = rows row0 .. row0+31 = 64 uint4; 32 threads per peer, 2 uint4 each
+      const int peer = tid >> 5;
+      if (peer != rank) {
+        const uint4* src = reinterpret_cast<const uint4*>(&diag[buf][row0][0]);
+        uint4* dst = cluster.map_shared_rank(reinterpret_cast<uint4*>(&diag[buf][row0][0]), peer);
+        dst[lane] = src[lane];
+        dst[lane + 32] = src[lane + 32];
+      }
+    }
+    cluster.sync();                                // remote ORs / stores of this round are visible
+    // ---- phase B: the same serial resolve in every CTA
+    if (tid == 0) {
+      uint32_t cur[NW];
+#pragma unroll
+      for (int w = 0; w < NW; ++w) cur[w] = sup_bits[buf][w];
+      const int rows = min(CB, n - r0);
+      int nk = num;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) {
+        const int valid = min(max(rows - 32 * w, 0), 32);
+        const uint32_t rowmask = valid == 32 ? 0xffffffffu : ((1u << valid) - 1u);
+        while (nk < max_keep) {
+          const uint32_t alive = ~cur[w] & rowmask;
+          if (!alive) break;
+          const int ib = __ffs(static_cast<int>(alive)) - 1;
+          const int i = 32 * w + ib;
+          kept_idx[nk] = r0 + i;
+          kept_box[nk] = cand[buf][i];
+          ++nk;
+          const uint4 d0 = *reinterpret_cast<const uint4*>(&diag[buf][i][0]);
+          const uint4 d1 = *reinterpret_cast<const uint4*>(&diag[buf][i][4]);
+          cur[0] |= d0.x; cur[1] |= d0.y; cur[2] |= d0.z; cur[3] |= d0.w;
+          cur[4] |= d1.x; cur[5] |= d1.y; cur[6] |= d1.z; cur[7] |= d1.w;
+          cur[w] |= 1u << ib;                      // visited
+        }
+      }
+      s_num = nk;
+      // this parity's words are next written by peers in round blk + 2, i.e. after they passed the
+      // barrier of round blk + 1, which this CTA reaches only after this reset
+#pragma unroll
+      for (int w = 0; w < NW; ++w) sup_bits[buf][w] = 0u;
+    }
+    __syncthreads();
+    if (s_num >= max_keep) break;                  // identical in every CTA of the cluster
+  }
+  if (rank == 0) {
+    const int num = s_num;
+    for (int i = tid; i < num; i += blockDim.x) keep[i] = kept_idx[i];
+    if (tid == 0) num_out[prob] = num;
+  }
+}
+
 // 1: mnc_nms_sorted uses nms_lazy_kernel when max_keep is small against n (default); 0: always the
 // mask + scan pair (A/B and cross-check switch, mnc_nms_set_lazy).
 static int g_nms_lazy = 2;           // 2: the cluster form of the capped NMS (default), 1: one CTA per problem
@@ -682,7 +811,14 @@ extern "C" int mnc_nms_sorted(const float* boxes, int box_stride, long long prob
   const int col_blocks = (n_max + 63) / 64;
   if (col_blocks * 8 > 48 * 1024) return MNC_ERR_ARG;
   if (max_keep <= 0 || max_keep > n_max) max_keep = n_max;
-  if (nms_takes_lazy_path(n_max, max_keep) && g_nms_lazy == 2) {
+  if (nms_takes_lazy_path(n_max, max_keep) && g_nms_lazy == 3 && max_keep <= kWideMaxKeep) {
+    nms_lazy_cluster_wide_kernel<<<problems * kLazyClusterSize, kWideBlock,
+                                   max_keep * (sizeof(float4) + sizeof(int)), stream>>>(
+        boxes, box_stride, problem_stride, counts, n_max, thresh, max_keep, keep_out, keep_stride,
+        num_out);
+    return check_launch();
+  }
+  if (nms_takes_lazy_path(n_max, max_keep) && g_nms_lazy >= 2) {
     nms_lazy_cluster_kernel<<<problems * kLazyClusterSize, kLazyClusterThreads,
                               max_keep * (sizeof(float4) + sizeof(int)), stream>>>(
         boxes, box_stride, problem_stride, counts, n_max, thresh, max_keep, keep_out, keep_stride,
@@ -715,7 +851,7 @@ extern "C" int mnc_nms_sorted_launches(int n_max, int max_keep) {
 
 extern "C" int mnc_nms_set_lazy(int on) {
   const int prev = g_nms_lazy;
-  g_nms_lazy = on < 0 ? 0 : (on > 2 ? 2 : on);
+  g_nms_lazy = on < 0 ? 0 : (on > 3 ? 3 : on);
   return prev;
 }
 

@@ -82,11 +82,15 @@ def nms_sorted(boxes, counts, thresh, max_keep):
     return keep, num
 
 
+DEFAULT_NMS_MODE = 2
+
+
 def nms_set_lazy(mode):
     """A/B and cross-check switch of the capped NMS mnc_nms_sorted picks when max_keep << n:
-    2 / True = thread-block-cluster form (default), 1 = one CTA per problem, 0 / False = always the
-    suppression-matrix pair (nms_mask + nms_scan).  Returns the previous mode (int)."""
-    mode = 2 if mode is True else (0 if mode is False else int(mode))
+    3 = thread-block cluster, 256-candidate rounds; 2 = cluster, 64-candidate rounds; 1 = one CTA
+    per problem; 0 / False = always the suppression-matrix pair (nms_mask + nms_scan); True = the
+    library default.  Returns the previous mode (int)."""
+    mode = DEFAULT_NMS_MODE if mode is True else (0 if mode is False else int(mode))
     return int(lib.mnc_nms_set_lazy(c_int(mode)))
 
 
