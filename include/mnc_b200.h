@@ -260,6 +260,7 @@ int mnc_roi_warp_set_stage(int on);
 /* Launch shape of the row-walk kernel: threads per CTA (multiple of 32, <= 256) and channels per
  * CTA (default 128 / 32: every warp of the CTA owns planes; scripts/gpu_roi_walk_shape_ab.py). */
 int mnc_roi_warp_set_walk_shape(int threads, int channels_per_cta);
+int mnc_roi_warp_set_walk_planes14(int planes);   /* 14x14 row walk: planes per lane, 4 (default) or 8 */
 /* Fused engine form (mnc_roi_warp_split / mnc_roi_warp_tri): 0 (default) = per-cell gathers,
  * 1 = row walk (bit-identical outputs, 2.5x fewer loads, measured no faster:
  * scripts/gpu_roi_rows_ab.py).  Returns the previous value. */
@@ -322,6 +323,9 @@ int mnc_mv_device(const float* boxes, const float* masks, int nb, int box_dim, i
  * previous setting.  mnc_mv_device_launches(): kernels per mnc_mv_device call (5 / 4). */
 int mnc_mv_set_two_pass(int on);
 int mnc_mv_device_launches(void);
+/* A/B knob: pixel stride of the coarse pass and CTAs per result of the coarse / border pass
+ * (defaults 4, 4, 24). */
+int mnc_mv_set_shape(int stride, int chunks_coarse, int chunks_border);
 
 /* ---------------------------------------------------------------------------------------------
  * Input preparation on the device ("next" row 1): prep_im_for_blob +

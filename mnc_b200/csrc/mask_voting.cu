@@ -628,6 +628,19 @@ extern "C" int mnc_mv_set_two_pass(int on) {
 }
 extern "C" int mnc_mv_device_launches() { return g_mv_two_pass ? 5 : 4; }
 
+// launch shape of the two passes (A/B knob, scripts/gpu_mv_shape_ab.py): stride of the coarse pass,
+// CTAs per result of the coarse / the exact border pass
+static int g_mv_stride = 4, g_mv_chunks1 = 4, g_mv_chunks2 = 24;
+extern "C" int mnc_mv_set_shape(int stride, int chunks_coarse, int chunks_border) {
+  if (stride < 1 || stride > 64 || chunks_coarse < 1 || chunks_border < 1 || chunks_coarse > 1024 ||
+      chunks_border > 1024)
+    return MNC_ERR_ARG;
+  g_mv_stride = stride;
+  g_mv_chunks1 = chunks_coarse;
+  g_mv_chunks2 = chunks_border;
+  return MNC_OK;
+}
+
 extern "C" int mnc_mv_device(const float* boxes, const float* masks, int nb, int box_dim,
                              int mask_size, const int* cand_inds, const float* cand_weights,
                              long long cand_img_stride, const int* cand_begin, const int* cand_end,
@@ -648,11 +661,11 @@ extern "C" int mnc_mv_device(const float* boxes, const float* masks, int nb, int
       masks, static_cast<long long>(nb) * mask_size * mask_size, cand_weights, cand_img_stride,
       cand_begin, cand_end, n_res, max_results, unit);
   if (g_mv_two_pass) {
-    mv_aggregate_kernel<<<dim3(4, max_results, batch), 256, smem, stream>>>(
+    mv_aggregate_kernel<<<dim3(g_mv_chunks1, max_results, batch), 256, smem, stream>>>(
         boxes, masks, nb, box_dim, mask_size, cand_inds, cand_weights, cand_img_stride, cand_begin,
-        cand_end, n_res, max_results, im_hw, unit, bbox_ws, 4, 0);
+        cand_end, n_res, max_results, im_hw, unit, bbox_ws, g_mv_stride, 0);
   }
-  const int chunks = 24;
+  const int chunks = g_mv_two_pass ? g_mv_chunks2 : 24;
   mv_aggregate_kernel<<<dim3(chunks, max_results, batch), 256, smem, stream>>>(
       boxes, masks, nb, box_dim, mask_size, cand_inds, cand_weights, cand_img_stride, cand_begin,
       cand_end, n_res, max_results, im_hw, unit, bbox_ws, 1, g_mv_two_pass);

@@ -361,15 +361,14 @@ roi_warp28_stage_kernel(const float* __restrict__ feat, int C, int H, int W,
 // summed left to right, no FMA): bit-exact with the reference built with -fmad=false.
 // Stores: one 4 x P byte row segment per sample row, consecutive rows contiguous (whole plane
 // written once, streaming).  P = 14 packs two planes into one warp (lanes 0-13 and 16-29).
-template <int P>
+template <int P, int CH = ((P > 16) ? 8 : 4)>   // CH: planes walked together by one lane (ILP; the row
+                                                // bookkeeping and the 4 weights are shared; measured)
 __global__ void __launch_bounds__(256)
 roi_warp_rowwalk_kernel(const float* __restrict__ feat, int C, int H, int W,
                         const float* __restrict__ rois, float spatial_scale, int ch_per_cta,
                         float* __restrict__ out) {
   constexpr int PP = P * P;
   constexpr int PPW = (P <= 16) ? 2 : 1;          // plane groups per warp
-  constexpr int CH = (P > 16) ? 8 : 4;            // planes walked together by one lane (ILP; the row
-                                                  // bookkeeping and the 4 weights are shared; measured)
   __shared__ int4 tap_hq[P];                      // {lo (or -1: out of range), hi, bits(h), bits(l)}
   const int r = blockIdx.x;
   const int cbase = blockIdx.y * ch_per_cta;
@@ -1163,7 +1162,13 @@ extern "C" int mnc_roi_warp_set_stage(int on) {
   return prev;
 }
 
-static int g_roi_walk_threads = 128, g_roi_walk_cpc = 32;
+static int g_roi_walk_threads = 128, g_roi_walk_cpc = 32, g_roi_walk_ch14 = 4;
+// A/B knob: planes per lane of the 14x14 row walk (4 or 8)
+extern "C" int mnc_roi_warp_set_walk_planes14(int planes) {
+  if (planes != 4 && planes != 8) return MNC_ERR_ARG;
+  g_roi_walk_ch14 = planes;
+  return MNC_OK;
+}
 // A/B knob of the row-walk ROIWarping kernel: threads per CTA (multiple of 32, <= 256) and
 // channels per CTA.
 extern "C" int mnc_roi_warp_set_walk_shape(int threads, int channels_per_cta) {
@@ -1194,6 +1199,8 @@ extern "C" int mnc_roi_warp_nchw(const float* feat, int C, int H, int W, const f
     dim3 wgrid(R, (C + cpc - 1) / cpc);
     if (pooled_h == 28)
       roi_warp_rowwalk_kernel<28><<<wgrid, threads, 0, s>>>(feat, C, H, W, rois, spatial_scale, cpc, out);
+    else if (g_roi_walk_ch14 == 8)
+      roi_warp_rowwalk_kernel<14, 8><<<wgrid, threads, 0, s>>>(feat, C, H, W, rois, spatial_scale, cpc, out);
     else
       roi_warp_rowwalk_kernel<14><<<wgrid, threads, 0, s>>>(feat, C, H, W, rois, spatial_scale, cpc, out);
     return check_launch();
