@@ -317,14 +317,14 @@ int mnc_mv_device(const float* boxes, const float* masks, int nb, int box_dim, i
                   const int* cand_begin, const int* cand_end, const int* n_res, int max_results,
                   int batch, const int* im_hw, int* bbox_ws, float* out_mask, int* out_box,
                   void* stream);
-/* mv_device finds each result's tight box in two passes (every 4th pixel of every 4th row, then
+/* mv_device finds each result's tight box in two passes (every 6th pixel of every 6th row, then
  * exactly the pixels outside the box the first pass found): same boxes as one full sweep of the
  * region.  mnc_mv_set_two_pass(0) selects the single sweep (cross-check / A-B switch); returns the
  * previous setting.  mnc_mv_device_launches(): kernels per mnc_mv_device call (5 / 4). */
 int mnc_mv_set_two_pass(int on);
 int mnc_mv_device_launches(void);
 /* A/B knob: pixel stride of the coarse pass and CTAs per result of the coarse / border pass
- * (defaults 4, 4, 24). */
+ * (defaults 6, 2, 16: the best of the shapes measured, scripts/gpu_mv_shape_ab.py). */
 int mnc_mv_set_shape(int stride, int chunks_coarse, int chunks_border);
 
 /* ---------------------------------------------------------------------------------------------

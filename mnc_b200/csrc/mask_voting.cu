@@ -178,7 +178,7 @@ __global__ void mv_init_bbox_kernel(int* __restrict__ bbox, int total, int* __re
 }
 
 // grid (chunks, max_results, batch); 256 threads.  Launched twice per call:
-//   pass 1 (stride 4, refine 0): every 4th pixel of every 4th row -- 1/16 of the evaluations --
+//   pass 1 (stride 6, refine 0): every 6th pixel of every 6th row -- 1/36 of the evaluations --
 //           gives an inner bounding box (each of its four sides comes from a real "on" pixel);
 //   pass 2 (stride 1, refine 1): all pixels EXCEPT those inside the box pass 1 left in `bbox`
 //           (a pixel inside a box spanned by "on" pixels cannot move the final box), i.e. only the
@@ -630,7 +630,7 @@ extern "C" int mnc_mv_device_launches() { return g_mv_two_pass ? 5 : 4; }
 
 // launch shape of the two passes (A/B knob, scripts/gpu_mv_shape_ab.py): stride of the coarse pass,
 // CTAs per result of the coarse / the exact border pass
-static int g_mv_stride = 4, g_mv_chunks1 = 4, g_mv_chunks2 = 24;
+static int g_mv_stride = 6, g_mv_chunks1 = 2, g_mv_chunks2 = 16;   // measured best of 12 shapes (profiles/r02e_mv_shape_roi14_ab.json)
 extern "C" int mnc_mv_set_shape(int stride, int chunks_coarse, int chunks_border) {
   if (stride < 1 || stride > 64 || chunks_coarse < 1 || chunks_border < 1 || chunks_coarse > 1024 ||
       chunks_border > 1024)

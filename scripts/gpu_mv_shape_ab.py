@@ -35,7 +35,7 @@ for stride, c1, c2 in shapes:
     same = bool(torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1]))
     res["mv_stride%d_c%d_c%d" % (stride, c1, c2)] = {"voting_ms": round(ms, 4), "identical": same}
     print(stride, c1, c2, round(ms, 4), same, flush=True)
-lib.mnc_mv_set_shape(4, 4, 24)
+lib.mnc_mv_set_shape(6, 2, 16)
 ops.mv_set_two_pass(False)
 res["mv_full_sweep"] = {"voting_ms": round(bench.median_ms(lambda: ops.mask_voting(boxes, masks, scores, hw_i, box_valid=valid), iters=10), 4)}
 ops.mv_set_two_pass(True)
