@@ -227,9 +227,14 @@ def igemm(a, batch, H, W, cin, w, cout, taps, bias=None, relu=False, out=None, o
         check(rc, "mnc_igemm_simt")
 
 
+cluster_size = 2      # CTAs per work item of igemm_tc_kernel (tracked for the engine's split-K model)
+
+
 def set_cluster(cl):
     """Thread-block-cluster size of the tensor-core launches (1 or 2, default 2)."""
+    global cluster_size
     check(lib.mnc_igemm_set_cluster(c_int(cl)), "mnc_igemm_set_cluster")
+    cluster_size = cl
 
 
 def set_halo_pair(on):

@@ -208,9 +208,9 @@ class MNCEngine:
         # Cout tile: 192 for the wide layers -- at M = 2400, N = 4096 it gives 19 x 22 = 418 tiles
         # (220 CTA-pair items = 2.97 waves of 74 pairs), against 2.16 (-> 3) waves at 256
         bn = bn or (64 if N <= 64 else (128 if N <= 128 else (192 if N >= 1024 else 256)))
-        tiles = math.ceil(M / 128) * math.ceil(N / bn)
         k_steps = K // 64
-        split = self._pick_split(tiles, k_steps) if self.impl == "tc" else 1
+        split = (self._pick_split(math.ceil(M / 128), math.ceil(N / bn), k_steps, out_elems=M * N)
+                 if self.impl == "tc" else 1)
         a4 = a.view(1, 1, M, K) if tri_in else a.view(2, 1, 1, M, K)
         tri_out = isinstance(out, dense.Tri)
         ek = exp_key or key
@@ -245,18 +245,28 @@ class MNCEngine:
             dense.splitk_reduce(part, split, M * N, M, N, bias=bias, relu=relu, out=out,
                                 out_f32=out_f32, out_row_stride=out_stride, out_ch_offset=out_ch_offset)
 
-    def _pick_split(self, tiles, k_steps, max_split=32):
+    def _pick_split(self, tiles_m, tiles_n, k_steps, max_split=32, out_elems=0):
         """Split-K only when the launch cannot fill the GPU (e.g. fc6_maskest: 19 row tiles,
-        K = 100352).  A wave-quantisation-driven split (608 tiles -> 4.1 waves) was measured and
-        rejected: the extra fp32 partial reduce costs what the shorter tail saves
-        (profiles/README.md).  When splitting, the factor minimises waves x k-steps-per-CTA:
-        19 tiles x 8 = 152 work items on 148 SMs ran as two waves (0.47 ms); x 7 = 133 is one."""
-        if tiles >= self.sms * 0.7 or k_steps < 16:
+        K = 100352; every FC at batch 1).  A wave-quantisation-driven split (608 tiles -> 4.1 waves)
+        was measured and rejected: the extra fp32 partial reduce costs what the shorter tail saves
+        (profiles/README.md).  When splitting, the factor minimises waves x k-steps-per-item, counted
+        the way the kernel schedules: a work item is a CTA PAIR (two adjacent 128-row tiles x one
+        Cout tile x one split) and there are sms/2 of them in flight (igemm_tc.cu launch_igemm).
+        (Counting single tiles against 148 SMs picked 15 splits for fc6_maskest = 150 items = three
+        waves of 74, the last with 2 items; and 2 splits for fc6 at batch 1 = 88 items = two waves,
+        i.e. no gain at all.)"""
+        cl = dense.cluster_size
+        slots = max(1, self.sms // cl)
+        items = math.ceil(tiles_m / cl) * tiles_n
+        if items >= slots * 0.7 or k_steps < 16:
             return 1
+        # cost in k-step times (~0.45 us for a pair item): each split adds a launch-side constant and
+        # one fp32 copy of the output to write and re-read (M*N*8 B at ~5 TB/s)
+        per_split = 0.5 + out_elems * 1.7e-6
         best, best_cost = 1, None
         for s in range(1, min(max_split, max(1, k_steps // 8)) + 1):
-            waves = math.ceil(tiles * s / self.sms)
-            cost = waves * math.ceil(k_steps / s) + 0.5 * s      # + partial-sum traffic per split
+            waves = math.ceil(items * s / slots)
+            cost = waves * math.ceil(k_steps / s) + per_split * s
             if best_cost is None or cost < best_cost:
                 best, best_cost = s, cost
         return best
@@ -268,8 +278,9 @@ class MNCEngine:
             dense.igemm(x, B, H, W, cin, wgt, cout, 9, bias=bias, relu=True, out=out, impl=self.impl)
             return
         bn = 64 if cout <= 64 else (128 if cout <= 128 else 256)
-        tiles = B * math.ceil(H / 8) * math.ceil(W / 16) * math.ceil(cout / bn)
-        split = 1 if pool else self._pick_split(tiles, 9 * cin // 64, max_split=4)
+        split = 1 if pool else self._pick_split(B * math.ceil(H / 8) * math.ceil(W / 16),
+                                                math.ceil(cout / bn), 9 * cin // 64, max_split=4,
+                                                out_elems=B * H * W * cout)
         tri_out = isinstance(out, dense.Tri)
         if split == 1:
             def run(e, amax):
