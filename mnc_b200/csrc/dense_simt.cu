@@ -121,6 +121,7 @@ splitk_reduce_kernel(const float* __restrict__ partial, int splits, long long sp
     float v[4] = {0.f, 0.f, 0.f, 0.f};
     const float* p = partial + r * cols + c4;
     if (vec) {
+#pragma unroll 8   // loads of 8 splits in flight (a 32-way split was 32 dependent L2 round trips)
       for (int s = 0; s < splits; ++s) {  // fixed order: deterministic
         const float4 x = __ldcs(reinterpret_cast<const float4*>(p + s * split_stride));
         v[0] += x.x;

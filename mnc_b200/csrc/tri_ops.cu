@@ -56,6 +56,7 @@ splitk_reduce_tri_kernel(const float* __restrict__ partial, int splits, long lon
     const long long row = i / c4;
     const int col = static_cast<int>(i - row * c4) * 4;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8   // loads of 8 splits in flight; the sum keeps its split order
     for (int s = 0; s < splits; ++s) {
       const float4 v = __ldg(reinterpret_cast<const float4*>(partial + s * split_stride + row * cols + col));
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
