@@ -116,18 +116,30 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_time(weights, images, warmup):
-    """The CPU oracle, one image per step: `warmup` untimed images, then `images` timed ones.
-    Returns the per-image seconds."""
+def cpu_reference_time(weights, images, warmup, budget_s=45.0):
+    """The CPU oracle, one image per step: `warmup` untimed images, then up to `images` timed ones.
+    Bounded: once `budget_s` seconds have gone by the remaining warm-ups are skipped and the loop
+    stops after the next timed image (a loaded host must not stall the GPU bench).  Returns the
+    per-image seconds (>= 1 entry)."""
     from oracle import oracle as O
     times = []
-    for it in range(warmup + images):
+    t_start = time.perf_counter()
+    it = 0
+    warm_left = warmup
+    while len(times) < images:
+        over = time.perf_counter() - t_start > budget_s
+        if over and times:
+            break
         im = O.synthetic_image(it, H, W)
+        it += 1
         t0 = time.perf_counter()
         O.im_detect(weights, im)
         dt = time.perf_counter() - t0
-        if it >= warmup:
-            times.append(dt)
+        if warm_left > 0 and not over and dt < budget_s / 3:
+            warm_left -= 1
+            continue
+        warm_left = 0
+        times.append(dt)
     return times
 
 
@@ -156,10 +168,37 @@ def _emit(line):
     os.write(_JSON_FD if _JSON_FD is not None else 1, (json.dumps(line) + "\n").encode())
 
 
+_T0 = time.perf_counter()
+
+
+def _log(msg):
+    """Progress marker on stderr (stdout carries only the JSON line)."""
+    sys.stderr.write("[bench %7.1fs] %s\n" % (time.perf_counter() - _T0, msg))
+    sys.stderr.flush()
+
+
+def usable_cores():
+    """Threads the CPU arm may use: physical cores, capped by the process's affinity mask and by
+    the cgroup CPU quota (a box that hands this container 8 CPUs must not get 64 OpenMP threads)."""
+    n = physical_cores()
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(float(quota) / float(period))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
 def _pin_cpu_threads():
     """One software thread per physical core, before torch / OpenMP start (torchrun pins
     OMP_NUM_THREADS to 1 for its workers; oversubscribing SMT siblings made this arm swing 6x)."""
-    n = physical_cores()
+    n = usable_cores()
     os.environ["OMP_NUM_THREADS"] = str(n)
     os.environ["MKL_NUM_THREADS"] = str(n)
     os.environ.setdefault("OMP_PROC_BIND", "spread")
@@ -180,8 +219,9 @@ def run_reference(args, rank):
     w = Wt.make_weights(Wt.FULL_ARCH)
     images = max(5, min(args.steps, 8))
     warm = max(2, min(args.warmup, 3))
-    times = cpu_reference_time(w, images, warm)
+    times = cpu_reference_time(w, images, warm, budget_s=90.0)
     st = _summ(times)
+    images = len(times)
     v = 1.0 / st["median_s"]
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus,
@@ -356,6 +396,7 @@ def main():
     from mnc_b200.api import Detector
 
     rank, world, local = mdist.init_from_env()
+    _log("imports done; rank %d of %d" % (rank, world))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     B = args.batch
@@ -373,6 +414,7 @@ def main():
         ops.nms_set_lazy(args.nms_mode)
     if args.mv_full_sweep:
         ops.mv_set_two_pass(False)
+    _log("weights made; building the engine")
     det = Detector(w, device=dev, max_batch=B, height=H, width=W, use_graph=not args.no_graph)
     eng = det.engine
     eng.overlap_heads = not args.no_overlap_heads
@@ -442,6 +484,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    _log("warm-up done (%d streams); timed region" % n_str)
     # ------------------------------------------------------------- timed region (device resident)
     sampler = ClockSampler(local)
     if rank == 0:
@@ -479,6 +522,7 @@ def main():
         out = pipe.recv[0]
         comm_ms = median_ms(lambda: mdist.all_gather_records(rec, out), iters=10)
 
+    _log("timed region done: %.2f ms per step; eager pass" % (total_ms / args.steps))
     # ------------------------------------------------------------- eager pass: per-kernel roofline
     # (single stream: with the box branch forked to the side stream two fc6 launches share the GPU
     # and the events around each would count the overlap twice)
@@ -498,6 +542,7 @@ def main():
         with open(args.dump_igemm, "w") as f:
             json.dump({"steps": 1, "launches": ktimer.manifest[-per:]}, f)
 
+    _log("forward + voting")
     # ------------------------------------------------------------- forward + gpu_mask_voting
     # (the published 0.33 s/img covers im_detect only, tools/demo.py:144-147; BASELINE.md asks for
     # both numbers)
@@ -523,6 +568,7 @@ def main():
     vote_value = world * B * args.steps / (float(tv.item()) / 1000.0)
     n_instances = [int(x) for x in vr["n_res"].cpu().numpy()]
 
+    _log("e2e (host buffers)")
     # ------------------------------------------------------------- e2e: host buffers in and out
     # the reference's callers hand im_detect the raw uint8 image (tools/demo.py:143-146); so does
     # this: uint8 BGR frames in host memory -> boxes / masks / scores in host memory (+ the
@@ -555,6 +601,7 @@ def main():
     e2e_pageable = e2e_run(u8, True)       # a plain numpy array, as cv2.imread returns
     e2e_sync = e2e_run(u8_pinned, False)   # one blocking im_detect_images call per step
 
+    _log("batch-1 latency")
     # ------------------------------------------------------------- batch-1 latency (configs[0])
     lat1 = None
     if world == 1:
@@ -620,6 +667,7 @@ def main():
 
     micro, roof_warp = None, None
     if world == 1 and not args.no_micro:
+        _log("microbenchmarks (configs[3] / configs[4])")
         micro = microbench(hbm)
         rw = micro["roi_warp_P28"]
         roof_warp = {"kernel": "roi_warp_nchw_kernel (ROIWarping layer form, 2000 RoIs, 28x28, "
@@ -631,11 +679,12 @@ def main():
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         torch.set_num_threads(ncpu)
+        _log("cpu baseline (oracle on %d host threads, <= 5 images, 45 s budget)" % ncpu)
         times = cpu_reference_time(w, 5, 2)
         st = _summ(times)
         cpu = {"value": 1.0 / st["median_s"], "unit": "images/s", "cores": ncpu, "kind": "port",
-               "sample": "5 images (600x1000, 300 RoIs/stage) after 2 warm-up images, oracle port "
-                         "(torch CPU fp32 conv/FC + numpy layers + C kernels); 1 / median",
+               "sample": "%d images (600x1000, 300 RoIs/stage) after <= 2 warm-up images (45 s budget), oracle port "
+                         "(torch CPU fp32 conv/FC + numpy layers + C kernels); 1 / median" % len(times),
                "per_image_s": st}
 
     line = {
@@ -681,6 +730,7 @@ def main():
         "wall_s_timed_region": t_wall,
     }
     _emit(line)
+    _log("done")
     if world > 1:
         dist.destroy_process_group()
 
