@@ -34,6 +34,31 @@ def _ceil_half(x):
 HALO_MAX_COUT = 128    # 3x3 convs with Cout <= 128 run the halo kernel
 
 
+def pick_split_k(tiles_m, tiles_n, k_steps, sms, cluster=2, max_split=32, out_elems=0):
+    """Split-K only when the launch cannot fill the GPU (e.g. fc6_maskest: 19 row tiles,
+    K = 100352; every FC at batch 1).  A wave-quantisation-driven split (608 tiles -> 4.1 waves)
+    was measured and rejected: the extra fp32 partial reduce costs what the shorter tail saves
+    (profiles/README.md).  When splitting, the factor minimises waves x k-steps-per-item, counted
+    the way the kernel schedules: a work item is a CTA PAIR (two adjacent 128-row tiles x one
+    Cout tile x one split) and there are sms/2 of them in flight (igemm_tc.cu launch_igemm).
+    (Counting single tiles against 148 SMs picked 15 splits for fc6_maskest = 150 items = three
+    waves of 74, the last with 2 items; and 2 splits for fc6 at batch 1 = 88 items = two waves,
+    i.e. no gain at all.)  Cost unit: one k-step of a pair item (~0.45 us); each split adds a
+    launch-side constant and one fp32 copy of the output to write and re-read (M*N*8 B at ~5 TB/s)."""
+    slots = max(1, sms // cluster)
+    items = math.ceil(tiles_m / cluster) * tiles_n
+    if items >= slots * 0.7 or k_steps < 16:
+        return 1
+    per_split = 0.5 + out_elems * 1.7e-6
+    best, best_cost = 1, None
+    for s in range(1, min(max_split, max(1, k_steps // 8)) + 1):
+        waves = math.ceil(items * s / slots)
+        cost = waves * math.ceil(k_steps / s) + per_split * s
+        if best_cost is None or cost < best_cost:
+            best, best_cost = s, cost
+    return best
+
+
 class MNCEngine:
     # "f16f8": precision mode 1 on every launch of the per-tap / inner-product kernel -- tri-plane
     # operands, fp16 main product + two FP8 correction products (2 tensor-work units per MAC);
@@ -246,30 +271,8 @@ class MNCEngine:
                                 out_f32=out_f32, out_row_stride=out_stride, out_ch_offset=out_ch_offset)
 
     def _pick_split(self, tiles_m, tiles_n, k_steps, max_split=32, out_elems=0):
-        """Split-K only when the launch cannot fill the GPU (e.g. fc6_maskest: 19 row tiles,
-        K = 100352; every FC at batch 1).  A wave-quantisation-driven split (608 tiles -> 4.1 waves)
-        was measured and rejected: the extra fp32 partial reduce costs what the shorter tail saves
-        (profiles/README.md).  When splitting, the factor minimises waves x k-steps-per-item, counted
-        the way the kernel schedules: a work item is a CTA PAIR (two adjacent 128-row tiles x one
-        Cout tile x one split) and there are sms/2 of them in flight (igemm_tc.cu launch_igemm).
-        (Counting single tiles against 148 SMs picked 15 splits for fc6_maskest = 150 items = three
-        waves of 74, the last with 2 items; and 2 splits for fc6 at batch 1 = 88 items = two waves,
-        i.e. no gain at all.)"""
-        cl = dense.cluster_size
-        slots = max(1, self.sms // cl)
-        items = math.ceil(tiles_m / cl) * tiles_n
-        if items >= slots * 0.7 or k_steps < 16:
-            return 1
-        # cost in k-step times (~0.45 us for a pair item): each split adds a launch-side constant and
-        # one fp32 copy of the output to write and re-read (M*N*8 B at ~5 TB/s)
-        per_split = 0.5 + out_elems * 1.7e-6
-        best, best_cost = 1, None
-        for s in range(1, min(max_split, max(1, k_steps // 8)) + 1):
-            waves = math.ceil(items * s / slots)
-            cost = waves * math.ceil(k_steps / s) + per_split * s
-            if best_cost is None or cost < best_cost:
-                best, best_cost = s, cost
-        return best
+        """Split-K factor of one tensor-core launch: see pick_split_k."""
+        return pick_split_k(tiles_m, tiles_n, k_steps, self.sms, dense.cluster_size, max_split, out_elems)
 
     def _conv(self, x, B, H, W, cin, wgt, cout, bias, out, key, pool=False):
         """3x3 conv + bias + ReLU (+ fused 2x2 ceil-mode max pool) -> `out` (split-bf16 or Tri),

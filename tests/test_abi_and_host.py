@@ -389,3 +389,60 @@ def test_sbd_ground_truth_cache(tmp_path):
     stamp = (cache / "bicycle_mask_gt.pkl").stat().st_mtime_ns
     check_voc_sds_cache(str(cache), str(tmp_path / "nowhere"), ["im_a"], names)   # complete: not rebuilt
     assert (cache / "bicycle_mask_gt.pkl").stat().st_mtime_ns == stamp
+
+
+def test_split_k_model_counts_cta_pair_work_items():
+    """engine.pick_split_k: the factor is chosen in the kernel's own scheduling unit (CTA-pair work
+    items on sms/2 slots, igemm_tc.cu launch_igemm), not single tiles on all SMs."""
+    import math
+    from mnc_b200.engine import pick_split_k
+
+    def pick(M, N, K, bn, **kw):
+        return pick_split_k(math.ceil(M / 128), math.ceil(N / bn), K // 64, 148, 2, out_elems=M * N, **kw)
+
+    def waves(M, N, bn, s):
+        return math.ceil(M / 256) * math.ceil(N / bn) * s / 74.0
+
+    # launches that fill the GPU are never split (fc6 / fc7 at the benchmarked batch 8)
+    assert pick(2400, 4096, 25088, 192) == 1 and pick(2400, 4096, 4096, 192) == 1
+    # fc6_maskest at batch 8: 10 row pairs -> 7 splits = 70 items = one wave (15 was three waves)
+    s = pick(2400, 256, 100352, 256)
+    assert s == 7 and waves(2400, 256, 256, s) <= 1.0
+    # batch 1: fc6 (2 row pairs x 22 Cout tiles) -> 5 splits = 220 items = 2.97 waves
+    s = pick(300, 4096, 25088, 192)
+    assert s == 5 and 2.9 < waves(300, 4096, 192, s) <= 3.0
+    # tiny K is never split; the conv path caps the factor at 4
+    assert pick(300, 441, 256, 256) == 1
+    assert pick_split_k(20, 2, 72, 148, 2, max_split=4, out_elems=2394 * 512) <= 4
+    # single-CTA scheduling (cluster 1) keeps the old counting
+    assert pick_split_k(19, 1, 1568, 148, 1, out_elems=2400 * 256) in range(2, 33)
+
+
+def test_bench_cpu_arm_is_bounded_and_counts_usable_cores(monkeypatch):
+    """bench.py's CPU arm: the thread count honours the affinity mask / cgroup quota and the image
+    loop stops at its time budget with at least one timed image."""
+    import sys
+    import types
+    import bench
+    n = bench.usable_cores()
+    assert 1 <= n <= bench.physical_cores()
+    assert n <= len(__import__("os").sched_getaffinity(0))
+    calls = []
+    clock = [0.0]
+    fake = types.SimpleNamespace(synthetic_image=lambda it, H, W: it,
+                                 im_detect=lambda w, im: (calls.append(im), clock.__setitem__(0, clock[0] + 20.0)))
+    import oracle
+    monkeypatch.setattr(oracle, "oracle", fake, raising=False)
+    monkeypatch.setitem(sys.modules, "oracle.oracle", fake)
+    monkeypatch.setattr(bench.time, "perf_counter", lambda: clock[0])
+    times = bench.cpu_reference_time(None, images=5, warmup=2, budget_s=45.0)
+    # every image "takes" 20 s: slower than budget / 3, so no image is spent on warm-up, and the loop
+    # stops once the 45 s budget is exceeded: images at t = 0, 20, 40 are timed, the 4th never starts
+    assert len(times) == 3 and all(abs(t - 20.0) < 1e-9 for t in times) and len(calls) == 3
+    clock[0] = 0.0
+    fast = types.SimpleNamespace(synthetic_image=lambda it, H, W: it,
+                                 im_detect=lambda w, im: clock.__setitem__(0, clock[0] + 1.0))
+    monkeypatch.setitem(sys.modules, "oracle.oracle", fast)
+    monkeypatch.setattr(oracle, "oracle", fast, raising=False)
+    times = bench.cpu_reference_time(None, images=5, warmup=2, budget_s=45.0)
+    assert len(times) == 5                       # 2 warm-ups + 5 timed images fit the budget
