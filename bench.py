@@ -380,6 +380,11 @@ def main():
                          "(shape, algorithmic FLOPs / bytes) as JSON, for scripts/ncu_tc_summary.py")
     args = ap.parse_args()
     _claim_stdout()
+    # a run that is still going after 5 minutes leaves the Python stacks of all threads on stderr
+    # (the default line takes ~20 s on a warm box; one run of the round stalled without a trace)
+    import faulthandler
+    faulthandler.enable()
+    faulthandler.dump_traceback_later(300, repeat=False, exit=False)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
