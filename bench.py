@@ -234,7 +234,7 @@ def run_reference(args, rank):
                          "per_image_s": st},
         "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference has no runnable CPU path (BASELINE.md section 2); oracle port timed on "
-                "%d physical cores (torch CPU fp32 conv/FC + numpy layers + C/OpenMP kernels); "
+                "%d host threads = usable cores of this container (torch CPU fp32 conv/FC + numpy layers + C/OpenMP kernels); "
                 "steps/warmup clamped to keep the run bounded" % ncpu,
     }
     _emit(line)
